@@ -1,0 +1,170 @@
+/* libmtl_b200 -- C ABI of the B200-native meta-transfer training step.
+ *
+ * The reference (audioku/meta-transfer-learning) has no FFI layer: its hot path is Python calling
+ * PyTorch.  This header is therefore the boundary a maintainer would bind with ctypes (see
+ * INTEGRATION.md) to replace, per entry point, the reference code cited beside it.  Paths are
+ * relative to the reference tree.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error; mtl_last_error() gives the message
+ *     (thread-local).  Nothing here falls back to the CPU: without a CUDA device every compute
+ *     entry point fails with MTL_ERR_CUDA.
+ *   - all data pointers are DEVICE pointers owned by the caller (fp32 unless stated); the library
+ *     never allocates device memory and never synchronises: every call only enqueues kernels on
+ *     the given stream (cudaStream_t passed as void*), so a whole meta-step can be captured in a
+ *     CUDA graph.
+ *   - activations are NHWC inside the VGG front-end; (rows, features) row-major elsewhere.
+ */
+#ifndef MTL_B200_H
+#define MTL_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MTL_ABI_VERSION 1
+
+/* GEMM engines (mtl_session_set_gemm_mode / mtl_gemm `mode`) */
+#define MTL_GEMM_SIMT_FP32 0 /* CUDA-core fp32, exact                        */
+#define MTL_GEMM_TC_TF32 1   /* tcgen05.mma kind::tf32, TMA + TMEM           */
+#define MTL_GEMM_TC_3XTF32 2 /* tcgen05 with hi/lo split operands (~fp32)    */
+
+const char* mtl_last_error(void);
+int mtl_abi_version(void);
+
+/* ------------------------------------------------------------------ model layout / session
+ * utils/functions.py:307-351 (init_transformer_model), modules/encoder.py:20-51,
+ * modules/decoder.py:19-53, models/asr/transformer.py:22-76: the parameter set.  A session fixes the
+ * hyper-parameters, derives the flat parameter arena (tensors in model.parameters() order, each
+ * start padded to 64 floats) and remembers the activation record of the last forward pass. */
+typedef struct mtl_model_cfg {
+  int n_enc, n_dec, d_model, n_heads, d_k, d_v, d_inner, rank, vocab, n_freq;
+} mtl_model_cfg;
+typedef struct mtl_session mtl_session;
+
+int mtl_session_create(const mtl_model_cfg* cfg, mtl_session** out);
+void mtl_session_destroy(mtl_session* s);
+int mtl_session_set_gemm_mode(mtl_session* s, int mode);
+long long mtl_param_arena_floats(const mtl_session* s);
+int mtl_param_count(const mtl_session* s);
+int mtl_param_info(const mtl_session* s, int idx, long long* offset_floats, long long* numel);
+/* bytes of workspace one forward+backward of a (B, T frames, n = max target length + 1) batch needs */
+long long mtl_workspace_bytes(mtl_session* s, int B, int T, int n);
+
+/* One batch as SpectrogramDataset.sample / AudioDataLoader deliver it (utils/data_loader.py:245-321):
+ * x (B,1,F,T) fp32 zero padded, lens (B) int32 RAW frame counts, trg (B,L) int64 PAD=0.
+ * n = 1 + max_b #non-PAD targets (the reference derives it inside Decoder.preprocess,
+ * modules/decoder.py:55-69; the host knows it before the H2D copy).
+ * Optional outputs (device, may be NULL): hyp_out/gold_out (B*n int32), ce_out (8 floats:
+ * loss, n_valid, n_correct, ...). */
+typedef struct mtl_batch {
+  const float* x;
+  const int* lens;
+  const long long* trg;
+  int B, T, L, n;
+  int* hyp_out;
+  int* gold_out;
+  float* ce_out;
+} mtl_batch;
+
+/* Transformer.forward (models/asr/transformer.py:120-149) + calculate_metrics CE
+ * (utils/metrics.py:68-126).  pe_enc / pe_dec are the PositionalEncoding buffers
+ * (modules/common_layers.py:86-108), row-major (max_len, d_model).
+ * On return *pred_out points at the logits inside the workspace, (B*n) rows of *ldp_out floats,
+ * the first `vocab` of each row valid. */
+int mtl_asr_forward(mtl_session* s, const float* theta, const float* pe_enc, const float* pe_dec,
+                    void* workspace, long long workspace_bytes, const mtl_batch* batch, float dropout,
+                    unsigned long long seed, float label_smoothing, void* stream, float** pred_out,
+                    int* ldp_out);
+/* loss.backward() for the pass last run by mtl_asr_forward on this session; gradients are
+ * ACCUMULATED into `grad` (same layout as theta), scaled by loss_scale
+ * (trainer/asr/transient_trainer.py:198-199,226-227).  If dpred_ext != NULL it is used as the
+ * gradient w.r.t. the logits ((B*n) x ld_ext) instead of the fused CE gradient. */
+int mtl_asr_backward(mtl_session* s, const float* theta, float* grad, float loss_scale,
+                     const float* dpred_ext, int ld_ext, void* stream);
+
+/* ------------------------------------------------------------------ meta-step pieces
+ * trainer/asr/transient_trainer.py:178-237 for ONE task, is_copy_grad=True:
+ *   grad <- d CE(theta; train)            (:188-199)
+ *   [clip_grad_norm_(grad, max_norm)]     (:205-206)
+ *   theta <- theta - lr*grad              (:207, SGD)
+ *   grad += d [CE(theta; val) * val_scale]   (:215-227; NO zero_grad in between, so the train
+ *                                          gradient stays in .grad -- the reference's behaviour)
+ *   copy_grad += grad                     (:229, models/asr/transformer.py:219-224)
+ *   theta <- theta0                       (:237)
+ * results (device, 16 floats): [0..7] train CE block, [8..15] val CE block. */
+typedef struct mtl_meta_hparams {
+  float lr;            /* inner SGD lr (args.lr)                 */
+  float val_scale;     /* 1/N                                    */
+  int clip;            /* args.clip                              */
+  float max_norm;      /* args.max_norm                          */
+  float dropout;       /* args.dropout                           */
+  float label_smoothing;
+  unsigned long long seed;
+} mtl_meta_hparams;
+int mtl_meta_task(mtl_session* s, float* theta, const float* theta0, float* grad, float* copy_grad,
+                  const float* pe_enc, const float* pe_dec, void* workspace, long long workspace_bytes,
+                  const mtl_batch* train, const mtl_batch* val, const mtl_meta_hparams* hp,
+                  float* results16, void* stream);
+/* transient_trainer.py:248-255: grad <- copy_grad; [clip]; theta <- Adam(theta, grad).
+ * adam_state (device): int step, float step_size, float bc2_sqrt, pad (16 bytes). */
+int mtl_meta_finish(float* theta, float* grad, const float* copy_grad, float* adam_m, float* adam_v,
+                    void* adam_state, float meta_lr, int clip, float max_norm, float* scratch1032,
+                    long long n, void* stream);
+
+/* ------------------------------------------------------------------ flat-arena ops
+ * models/asr/transformer.py:204-240 (zero/add/from_copy_grad), deepcopy(state_dict) /
+ * load_state_dict (transient_trainer.py:160,237), torch.optim.SGD / Adam, clip_grad_norm_. */
+int mtl_arena_zero(float* p, long long n, void* stream);
+int mtl_arena_copy(float* dst, const float* src, long long n, void* stream);
+int mtl_arena_axpy(float* y, const float* x, float a, long long n, void* stream);
+int mtl_arena_sgd(float* p, const float* g, float lr, long long n, void* stream);
+int mtl_arena_clip(float* g, long long n, float max_norm, float* scratch1032, void* stream);
+int mtl_arena_adam(float* p, const float* g, float* m, float* v, void* adam_state, float lr, float b1,
+                   float b2, float eps, long long n, void* stream);
+
+/* ------------------------------------------------------------------ single operators (unit-test surface) */
+/* nn.Linear / its two backward contractions: C = epi(alpha*op(A)op(B)+bias)+beta*C, row-major.
+ * transA: A stored (K,M); transB: B stored (N,K).  epi: 0 none, 1 relu, 2 relu-backward (aux). */
+int mtl_gemm(int mode, int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda,
+             const float* B, int ldb, float beta, float* C, int ldc, const float* bias, int epi,
+             const float* aux, int split_k, void* stream);
+/* LayerNorm(dropout(y)+res)*rowmask (+pe)  -- modules/common_layers.py:129-131,303-304 */
+int mtl_ln_fwd(const float* y, const float* res, const float* gamma, const float* beta,
+               const float* rowmask, const float* pe, int pe_period, float drop_p,
+               unsigned long long seed, unsigned site, float* out, float* xhat, float* rstd, int M,
+               int d, void* stream);
+int mtl_ln_bwd(const float* dout, const float* xhat, const float* rstd, const float* gamma,
+               const float* rowmask, float drop_p, unsigned long long seed, unsigned site, float* dy,
+               float* dres, int dres_accumulate, float* dgamma, float* dbeta, int M, int d,
+               void* stream);
+/* ScaledDotProductAttention (modules/common_layers.py:317-331) on (B*T, H*dk) projections */
+int mtl_attn_fwd(const float* q, const float* k, const float* v, const unsigned char* keypad, int B,
+                 int H, int Tq, int Tk, int dk, int causal, float drop_p, unsigned long long seed,
+                 unsigned site, float* o, float* lse, void* stream);
+int mtl_attn_bwd(const float* q, const float* k, const float* v, const unsigned char* keypad,
+                 const float* o, const float* lse, const float* d_o, int B, int H, int Tq, int Tk,
+                 int dk, int causal, float drop_p, unsigned long long seed, unsigned site,
+                 float* delta, float* dq, float* dkk, float* dv, void* stream);
+/* F.cross_entropy(ignore_index=0) + topk(1)  -- utils/metrics.py:96-126, transformer.py:146 */
+int mtl_ce_fwd(const float* logits, int ld, const int* gold, int M, int V, float smoothing,
+               float* row_lse, float* row_loss, int* hyp, float* out8, void* stream);
+int mtl_ce_bwd(const float* logits, int ld, const int* gold, const float* row_lse, const float* out8,
+               float scale, float smoothing, float* dlogits, int M, int V, void* stream);
+/* VGG front-end pieces (models/asr/transformer.py:47-59,136-138), NHWC */
+int mtl_conv1_fwd(const float* x, const float* w, const float* b, float* out, int B, int F, int T,
+                  int Cout, void* stream);
+int mtl_conv3x3_relu_fwd(int mode, const float* x, const float* w, const float* b, float* col,
+                         float* wg, float* out, int B, int F, int T, int Cin, int Cout, void* stream);
+int mtl_maxpool2_fwd(const float* x, float* out, int B, int F, int T, int C, void* stream);
+int mtl_maxpool2_relu_bwd(const float* x, const float* dpool, float* dx, int B, int F, int T, int C,
+                          void* stream);
+int mtl_dec_preprocess(const long long* trg, int B, int L, int n, int* seq_in, int* seq_out,
+                       float* rowmask, unsigned char* keypad, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MTL_B200_H */

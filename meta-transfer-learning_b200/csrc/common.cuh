@@ -1,0 +1,108 @@
+// Shared device/host helpers for libmtl_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#define MTL_OK 0
+#define MTL_ERR_CUDA -1
+#define MTL_ERR_ARG -2
+#define MTL_ERR_WORKSPACE -3
+
+void mtl_set_error(const char* fmt, ...);
+
+#define MTL_CHECK_CUDA(expr)                                                                  \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      mtl_set_error("%s:%d CUDA error %s: %s", __FILE__, __LINE__, cudaGetErrorName(_e),      \
+                    cudaGetErrorString(_e));                                                  \
+      return MTL_ERR_CUDA;                                                                    \
+    }                                                                                         \
+  } while (0)
+
+#define MTL_CHECK_LAUNCH() MTL_CHECK_CUDA(cudaGetLastError())
+
+#define MTL_REQUIRE(cond, msg)                                                \
+  do {                                                                        \
+    if (!(cond)) {                                                            \
+      mtl_set_error("%s:%d invalid argument: %s", __FILE__, __LINE__, msg);   \
+      return MTL_ERR_ARG;                                                     \
+    }                                                                         \
+  } while (0)
+
+#define MTL_TRY(expr)            \
+  do {                           \
+    int _r = (expr);             \
+    if (_r != MTL_OK) return _r; \
+  } while (0)
+
+static inline int mtl_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+#ifdef __CUDACC__
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Block-wide sum for blockDim.x <= 1024 (multiple of 32). `red` must hold 32 floats.
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  float r = (threadIdx.x < nw) ? red[threadIdx.x] : 0.f;
+  if (w == 0) r = warp_sum(r);
+  if (threadIdx.x == 0) red[0] = r;
+  __syncthreads();
+  return red[0];
+}
+
+// ---- Philox4x32-10 counter-based RNG (dropout masks; recomputed in backward) ----
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0;
+    key.y += W1;
+  }
+  return ctr;
+}
+
+// Keep-decision for element `idx` of dropout site `site` (seed identifies the pass).
+// One Philox block serves 4 consecutive elements.  Returns the scale to apply (0 or 1/(1-p)).
+__device__ __forceinline__ float dropout_scale(unsigned long long seed, uint32_t site,
+                                               unsigned long long idx, float p, float inv_keep) {
+  uint4 c = make_uint4((uint32_t)(idx >> 2), (uint32_t)(idx >> 34), site, 0u);
+  uint4 r = philox4x32_10(c, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  uint32_t sel = (uint32_t)(idx & 3ull);
+  uint32_t v = sel == 0 ? r.x : (sel == 1 ? r.y : (sel == 2 ? r.z : r.w));
+  // uniform in [0,1): keep iff u >= p
+  float u = (float)(v >> 8) * (1.0f / 16777216.0f);
+  return u >= p ? inv_keep : 0.f;
+}
+#endif
+
+// Dropout descriptor passed to kernels (p == 0 disables).
+struct MtlDrop {
+  float p;
+  float inv_keep;
+  unsigned long long seed;
+  uint32_t site;
+};
+static inline MtlDrop mtl_nodrop() { MtlDrop d; d.p = 0.f; d.inv_keep = 1.f; d.seed = 0; d.site = 0; return d; }
+static inline MtlDrop mtl_drop(float p, unsigned long long seed, uint32_t site) {
+  MtlDrop d; d.p = p; d.inv_keep = p > 0.f ? 1.f / (1.f - p) : 1.f; d.seed = seed; d.site = site; return d;
+}

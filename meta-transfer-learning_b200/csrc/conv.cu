@@ -1,0 +1,276 @@
+// VGG front-end support kernels on NHWC activations ([B, F(freq), T(time), C]).
+// Reference: models/asr/transformer.py:47-59 (Conv2d 3x3 s1 p1 + ReLU x2, MaxPool2d(2,2), twice) and
+// :136-138 (view(B, C*F, T).transpose(1,2) -> feature index c*F'+f).
+// The 64->64, 64->128, 128->128 convolutions run as GEMMs over (tap, channel)-ordered patches
+// (im2col3x3 + weight re-layout here, contraction in gemm_*.cu); conv1 (C_in = 1, K = 9) is a
+// direct memory-bound kernel.
+#include "kernels.h"
+
+// ------------------------------------------------------------------ conv1: 1 -> Cout, direct
+__global__ void __launch_bounds__(256) conv1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                        const float* __restrict__ bias, float* __restrict__ out,
+                                                        int B, int F, int T, int Cout) {
+  extern __shared__ float sw[];               // [9][Cout] + bias[Cout]
+  for (int i = threadIdx.x; i < 9 * Cout; i += blockDim.x) { int co = i / 9, tap = i % 9; sw[tap * Cout + co] = w[i]; }
+  for (int i = threadIdx.x; i < Cout; i += blockDim.x) sw[9 * Cout + i] = bias[i];
+  __syncthreads();
+  const int cg = Cout >> 2;
+  const size_t total = (size_t)B * F * T * cg;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % cg) * 4;
+    const size_t p = i / cg;
+    const int t = (int)(p % T), f = (int)((p / T) % F);
+    const size_t img = (p / ((size_t)F * T)) * (size_t)F * T;
+    float4 acc = *reinterpret_cast<const float4*>(sw + 9 * Cout + c4);
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int ff = f + kh - 1;
+      if (ff < 0 || ff >= F) continue;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int tt = t + kw - 1;
+        if (tt < 0 || tt >= T) continue;
+        const float xv = x[img + (size_t)ff * T + tt];
+        const float4 wv = *reinterpret_cast<const float4*>(sw + (kh * 3 + kw) * Cout + c4);
+        acc.x += xv * wv.x; acc.y += xv * wv.y; acc.z += xv * wv.z; acc.w += xv * wv.w;
+      }
+    }
+    acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f);
+    *reinterpret_cast<float4*>(out + p * Cout + c4) = acc;
+  }
+}
+int k_conv1_fwd(const float* x, const float* w, const float* b, float* out, int B, int F, int T, int Cout,
+                cudaStream_t s) {
+  MTL_REQUIRE(Cout % 4 == 0, "conv1 Cout % 4");
+  size_t total = (size_t)B * F * T * (Cout / 4);
+  if (!total) return MTL_OK;
+  int grid = (int)((total + 255) / 256); if (grid > 148 * 16) grid = 148 * 16;
+  conv1_fwd_kernel<<<grid, 256, (size_t)10 * Cout * sizeof(float), s>>>(x, w, b, out, B, F, T, Cout);
+  MTL_CHECK_LAUNCH();
+  return MTL_OK;
+}
+
+// dw[co,tap] += sum_p dout[p,co] * x[p+tap] ; db[co] += sum_p dout[p,co].   dout is the gradient
+// w.r.t. the PRE-ReLU output (relu mask already applied by the caller).
+__global__ void __launch_bounds__(256) conv1_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dout,
+                                                          float* __restrict__ dw, float* __restrict__ db, int B,
+                                                          int F, int T, int Cout, int pix_per_block) {
+  extern __shared__ float red[];              // [lanes][Cout][10]
+  const int lanes = blockDim.x / Cout;
+  const int co = threadIdx.x % Cout, sub = threadIdx.x / Cout;
+  const size_t P = (size_t)B * F * T;
+  const size_t p0 = (size_t)blockIdx.x * pix_per_block;
+  const size_t p1 = p0 + pix_per_block < P ? p0 + pix_per_block : P;
+  float acc[10];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) acc[i] = 0.f;
+  if (sub < lanes) {
+    for (size_t p = p0 + sub; p < p1; p += lanes) {
+      const float g = dout[p * Cout + co];
+      const int t = (int)(p % T), f = (int)((p / T) % F);
+      const size_t img = (p / ((size_t)F * T)) * (size_t)F * T;
+      acc[9] += g;
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        const int ff = f + kh - 1;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const int tt = t + kw - 1;
+          const bool ok = ff >= 0 && ff < F && tt >= 0 && tt < T;
+          const float xv = ok ? x[img + (size_t)ff * T + tt] : 0.f;
+          acc[kh * 3 + kw] += g * xv;
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 10; ++i) red[((size_t)sub * Cout + co) * 10 + i] = acc[i];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < Cout * 10; i += blockDim.x) {
+    float t = 0.f;
+    for (int l = 0; l < lanes; ++l) t += red[(size_t)l * Cout * 10 + i];
+    const int c = i / 10, k = i % 10;
+    if (k < 9) atomicAdd(dw + c * 9 + k, t); else atomicAdd(db + c, t);
+  }
+}
+int k_conv1_wgrad(const float* x, const float* dout, float* dw, float* db, int B, int F, int T, int Cout,
+                  cudaStream_t s) {
+  MTL_REQUIRE(Cout <= 256 && 256 % Cout == 0, "conv1 Cout must divide 256");
+  size_t P = (size_t)B * F * T;
+  if (!P) return MTL_OK;
+  int ppb = 512;
+  int grid = mtl_cdiv((long long)P, ppb);
+  size_t smem = (size_t)(256 / Cout) * Cout * 10 * sizeof(float);
+  conv1_wgrad_kernel<<<grid, 256, smem, s>>>(x, dout, dw, db, B, F, T, Cout, ppb);
+  MTL_CHECK_LAUNCH();
+  return MTL_OK;
+}
+
+// ------------------------------------------------------------------ im2col (3x3, pad 1) on NHWC
+__global__ void __launch_bounds__(256) im2col3x3_kernel(const float4* __restrict__ x, float4* __restrict__ col,
+                                                        int B, int F, int T, int C4) {
+  const size_t total = (size_t)B * F * T * 9 * C4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4);
+    const int tap = (int)((i / C4) % 9);
+    const size_t p = i / ((size_t)9 * C4);
+    const int t = (int)(p % T), f = (int)((p / T) % F);
+    const size_t bimg = p / ((size_t)F * T);
+    const int ff = f + tap / 3 - 1, tt = t + tap % 3 - 1;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ff >= 0 && ff < F && tt >= 0 && tt < T) v = x[((bimg * F + ff) * T + tt) * C4 + c];
+    col[i] = v;
+  }
+}
+int k_im2col3x3(const float* x, float* col, int B, int F, int T, int C, cudaStream_t s) {
+  MTL_REQUIRE(C % 4 == 0, "im2col C % 4");
+  size_t total = (size_t)B * F * T * 9 * (C / 4);
+  if (!total) return MTL_OK;
+  size_t g = (total + 255) / 256; if (g > 148 * 32) g = 148 * 32;
+  im2col3x3_kernel<<<(int)g, 256, 0, s>>>((const float4*)x, (float4*)col, B, F, T, C / 4);
+  MTL_CHECK_LAUNCH();
+  return MTL_OK;
+}
+
+// ------------------------------------------------------------------ weight layouts
+__global__ void conv_w_fwd_layout_kernel(const float* __restrict__ w, float* __restrict__ wg, int Cout, int Cin) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;          // over wg [Cout][9][Cin]
+  if (i >= Cout * 9 * Cin) return;
+  int ci = i % Cin, tap = (i / Cin) % 9, co = i / (9 * Cin);
+  wg[i] = w[((size_t)co * Cin + ci) * 9 + tap];
+}
+__global__ void conv_w_dgrad_layout_kernel(const float* __restrict__ w, float* __restrict__ wd, int Cout, int Cin) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;          // over wd [Cin][9][Cout]
+  if (i >= Cout * 9 * Cin) return;
+  int co = i % Cout, tap = (i / Cout) % 9, ci = i / (9 * Cout);
+  wd[i] = w[((size_t)co * Cin + ci) * 9 + (8 - tap)];       // flipped taps: (2-kh, 2-kw)
+}
+__global__ void conv_wgrad_scatter_kernel(const float* __restrict__ dwg, float* __restrict__ dw, int Cout, int Cin) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;          // over dw [Cout][Cin][9]
+  if (i >= Cout * 9 * Cin) return;
+  int tap = i % 9, ci = (i / 9) % Cin, co = i / (9 * Cin);
+  dw[i] += dwg[((size_t)co * 9 + tap) * Cin + ci];
+}
+int k_conv_w_fwd_layout(const float* w, float* wg, int Cout, int Cin, cudaStream_t s) {
+  conv_w_fwd_layout_kernel<<<mtl_cdiv(Cout * 9 * Cin, 256), 256, 0, s>>>(w, wg, Cout, Cin);
+  MTL_CHECK_LAUNCH(); return MTL_OK;
+}
+int k_conv_w_dgrad_layout(const float* w, float* wd, int Cout, int Cin, cudaStream_t s) {
+  conv_w_dgrad_layout_kernel<<<mtl_cdiv(Cout * 9 * Cin, 256), 256, 0, s>>>(w, wd, Cout, Cin);
+  MTL_CHECK_LAUNCH(); return MTL_OK;
+}
+int k_conv_wgrad_scatter(const float* dwg, float* dw, int Cout, int Cin, cudaStream_t s) {
+  conv_wgrad_scatter_kernel<<<mtl_cdiv(Cout * 9 * Cin, 256), 256, 0, s>>>(dwg, dw, Cout, Cin);
+  MTL_CHECK_LAUNCH(); return MTL_OK;
+}
+
+// ------------------------------------------------------------------ 2x2 max-pool (floor) on NHWC
+__global__ void __launch_bounds__(256) maxpool2_fwd_kernel(const float4* __restrict__ x, float4* __restrict__ out,
+                                                           int B, int F, int T, int C4) {
+  const int F2 = F / 2, T2 = T / 2;
+  const size_t total = (size_t)B * F2 * T2 * C4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4);
+    const size_t p = i / C4;
+    const int t2 = (int)(p % T2), f2 = (int)((p / T2) % F2);
+    const size_t b = p / ((size_t)F2 * T2);
+    const size_t base = ((b * F + 2 * f2) * T + 2 * t2) * C4 + c;
+    float4 a = x[base], bb = x[base + C4], cc = x[base + (size_t)T * C4], d = x[base + (size_t)T * C4 + C4];
+    float4 r;
+    r.x = fmaxf(fmaxf(a.x, bb.x), fmaxf(cc.x, d.x)); r.y = fmaxf(fmaxf(a.y, bb.y), fmaxf(cc.y, d.y));
+    r.z = fmaxf(fmaxf(a.z, bb.z), fmaxf(cc.z, d.z)); r.w = fmaxf(fmaxf(a.w, bb.w), fmaxf(cc.w, d.w));
+    out[i] = r;
+  }
+}
+int k_maxpool2_fwd(const float* x, float* out, int B, int F, int T, int C, cudaStream_t s) {
+  MTL_REQUIRE(C % 4 == 0, "pool C % 4");
+  size_t total = (size_t)B * (F / 2) * (T / 2) * (C / 4);
+  if (!total) return MTL_OK;
+  size_t g = (total + 255) / 256; if (g > 148 * 16) g = 148 * 16;
+  maxpool2_fwd_kernel<<<(int)g, 256, 0, s>>>((const float4*)x, (float4*)out, B, F, T, C / 4);
+  MTL_CHECK_LAUNCH();
+  return MTL_OK;
+}
+// Gradient of relu -> maxpool w.r.t. the pre-ReLU conv output, given x = post-ReLU activation.
+// The window's gradient goes to its first maximum in scan order (PyTorch max_pool2d picks the
+// first index whose value is strictly greater); relu'(x) = [x > 0].
+__device__ __forceinline__ float pool_route(float v00, float v01, float v10, float v11, int me, float g) {
+  float m = v00; int am = 0;
+  if (v01 > m) { m = v01; am = 1; }
+  if (v10 > m) { m = v10; am = 2; }
+  if (v11 > m) { m = v11; am = 3; }
+  float mine = me == 0 ? v00 : (me == 1 ? v01 : (me == 2 ? v10 : v11));
+  return (am == me && mine > 0.f) ? g : 0.f;
+}
+__global__ void __launch_bounds__(256) maxpool2_relu_bwd_kernel(const float4* __restrict__ x,
+                                                                const float4* __restrict__ dpool,
+                                                                float4* __restrict__ dx, int B, int F, int T, int C4) {
+  const int F2 = F / 2, T2 = T / 2;
+  const size_t total = (size_t)B * F * T * C4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4);
+    const size_t p = i / C4;
+    const int t = (int)(p % T), f = (int)((p / T) % F);
+    const size_t b = p / ((size_t)F * T);
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int f2 = f >> 1, t2 = t >> 1;
+    if (f2 < F2 && t2 < T2) {
+      const size_t base = ((b * F + 2 * f2) * T + 2 * t2) * C4 + c;
+      float4 a = x[base], bb = x[base + C4], cc = x[base + (size_t)T * C4], d = x[base + (size_t)T * C4 + C4];
+      float4 g = dpool[((b * F2 + f2) * T2 + t2) * C4 + c];
+      const int me = (f & 1) * 2 + (t & 1);
+      r.x = pool_route(a.x, bb.x, cc.x, d.x, me, g.x); r.y = pool_route(a.y, bb.y, cc.y, d.y, me, g.y);
+      r.z = pool_route(a.z, bb.z, cc.z, d.z, me, g.z); r.w = pool_route(a.w, bb.w, cc.w, d.w, me, g.w);
+    }
+    dx[i] = r;
+  }
+}
+int k_maxpool2_relu_bwd(const float* x, const float* dpool, float* dx, int B, int F, int T, int C, cudaStream_t s) {
+  MTL_REQUIRE(C % 4 == 0, "pool C % 4");
+  size_t total = (size_t)B * F * T * (C / 4);
+  if (!total) return MTL_OK;
+  size_t g = (total + 255) / 256; if (g > 148 * 16) g = 148 * 16;
+  maxpool2_relu_bwd_kernel<<<(int)g, 256, 0, s>>>((const float4*)x, (const float4*)dpool, (float4*)dx, B, F, T, C / 4);
+  MTL_CHECK_LAUNCH();
+  return MTL_OK;
+}
+
+// ------------------------------------------------------------------ (B,F4,T4,C) <-> (B,T4,C*F4)
+__global__ void __launch_bounds__(256) feat_transpose_kernel(const float* __restrict__ p4, float* __restrict__ feat,
+                                                             int B, int F4, int T4, int C) {
+  const size_t total = (size_t)B * T4 * C * F4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int f = (int)(i % F4), c = (int)((i / F4) % C);
+    const size_t bt = i / ((size_t)F4 * C);
+    const int t = (int)(bt % T4);
+    const size_t b = bt / T4;
+    feat[i] = p4[((b * F4 + f) * T4 + t) * C + c];
+  }
+}
+__global__ void __launch_bounds__(256) feat_transpose_bwd_kernel(const float* __restrict__ dfeat,
+                                                                 float* __restrict__ dp4, int B, int F4, int T4, int C) {
+  const size_t total = (size_t)B * T4 * C * F4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C), t = (int)((i / C) % T4);
+    const size_t bf = i / ((size_t)C * T4);
+    const int f = (int)(bf % F4);
+    const size_t b = bf / F4;
+    dp4[i] = dfeat[((b * T4 + t) * C + c) * F4 + f];
+  }
+}
+int k_feat_transpose(const float* p4, float* feat, int B, int F4, int T4, int C, cudaStream_t s) {
+  size_t total = (size_t)B * T4 * C * F4;
+  if (!total) return MTL_OK;
+  size_t g = (total + 255) / 256; if (g > 148 * 16) g = 148 * 16;
+  feat_transpose_kernel<<<(int)g, 256, 0, s>>>(p4, feat, B, F4, T4, C);
+  MTL_CHECK_LAUNCH();
+  return MTL_OK;
+}
+int k_feat_transpose_bwd(const float* dfeat, float* dp4, int B, int F4, int T4, int C, cudaStream_t s) {
+  size_t total = (size_t)B * T4 * C * F4;
+  if (!total) return MTL_OK;
+  size_t g = (total + 255) / 256; if (g > 148 * 16) g = 148 * 16;
+  feat_transpose_bwd_kernel<<<(int)g, 256, 0, s>>>(dfeat, dp4, B, F4, T4, C);
+  MTL_CHECK_LAUNCH();
+  return MTL_OK;
+}

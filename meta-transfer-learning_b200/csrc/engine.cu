@@ -1,0 +1,782 @@
+// Host-side engine: parameter-arena layout, the whole-model forward/backward as a sequence of
+// kernel launches over a bump-allocated workspace, and the per-task meta-step composition.
+// Nothing here synchronises or allocates device memory, so a full meta-step is graph-capturable.
+//
+// Reference wiring restated by this file (relative to the reference tree):
+//   models/asr/transformer.py:47-59,120-149   VGG front-end, flatten, encoder, decoder, top-1
+//   modules/encoder.py:53-80,98-106           stem LN(Linear)+PE; [self-attn, FFN] x n_enc with row masks
+//   modules/decoder.py:71-115,311-323         preprocess, emb+PE+dropout, [self, cross, FFN] x n_dec, vocab proj
+//   modules/common_layers.py:122-132,276-331  FFN block, low-rank multi-head attention block
+//   utils/metrics.py:96-126                   CE loss
+//   trainer/asr/transient_trainer.py:178-255  per-task inner step / shared val pass / copy-grad / Adam
+#include "kernels.h"
+#include "../../include/mtl_b200.h"
+#include <stdarg.h>
+#include <new>
+#include <utility>
+#include <vector>
+
+// ----------------------------------------------------------------------------- error string
+static thread_local char g_err[1024] = "";
+void mtl_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+extern "C" const char* mtl_last_error(void) { return g_err; }
+extern "C" int mtl_abi_version(void) { return MTL_ABI_VERSION; }
+
+// ----------------------------------------------------------------------------- layout
+struct AttnP { size_t qa, qb_w, qb_b, ka, kb_w, kb_b, va, vb_w, vb_b, ln_w, ln_b, oa, ob_w, ob_b; };
+struct FfnP { size_t w1, b1, w2, b2, ln_w, ln_b; };
+struct Layout {
+  size_t in_w, in_b, lnin_w, lnin_b;
+  std::vector<AttnP> enc_sa;
+  std::vector<FfnP> enc_ff;
+  size_t emb;
+  std::vector<AttnP> dec_sa, dec_ca;
+  std::vector<FfnP> dec_ff;
+  size_t out_w;
+  size_t conv_w[4], conv_b[4];
+  std::vector<std::pair<size_t, size_t>> tensors;   // (offset, numel) in model.parameters() order
+  size_t total = 0;
+  size_t add(size_t numel) {
+    size_t off = (total + 63) & ~(size_t)63;
+    tensors.push_back(std::make_pair(off, numel));
+    total = off + numel;
+    return off;
+  }
+};
+
+static const int kConvCin[4] = {1, 64, 64, 128};
+static const int kConvCout[4] = {64, 64, 128, 128};
+
+static AttnP make_attn(Layout& L, const mtl_model_cfg& c) {   // common_layers.py:250-270 order
+  AttnP p;
+  size_t d = c.d_model, r = c.rank, hk = (size_t)c.n_heads * c.d_k, hv = (size_t)c.n_heads * c.d_v;
+  p.qa = L.add(r * d); p.qb_w = L.add(hk * r); p.qb_b = L.add(hk);
+  p.ka = L.add(r * d); p.kb_w = L.add(hk * r); p.kb_b = L.add(hk);
+  p.va = L.add(r * d); p.vb_w = L.add(hv * r); p.vb_b = L.add(hv);
+  p.ln_w = L.add(d); p.ln_b = L.add(d);
+  p.oa = L.add(r * hv); p.ob_w = L.add(d * r); p.ob_b = L.add(d);
+  return p;
+}
+static FfnP make_ffn(Layout& L, const mtl_model_cfg& c) {
+  FfnP p;
+  size_t d = c.d_model, f = c.d_inner;
+  p.w1 = L.add(f * d); p.b1 = L.add(f); p.w2 = L.add(d * f); p.b2 = L.add(d);
+  p.ln_w = L.add(d); p.ln_b = L.add(d);
+  return p;
+}
+static void build_layout(Layout& L, const mtl_model_cfg& c) {
+  size_t d = c.d_model;
+  size_t d_in = 128 * (size_t)((c.n_freq / 2) / 2);          // utils/functions.py:318-321
+  L.in_w = L.add(d * d_in); L.in_b = L.add(d); L.lnin_w = L.add(d); L.lnin_b = L.add(d);
+  for (int l = 0; l < c.n_enc; ++l) { L.enc_sa.push_back(make_attn(L, c)); L.enc_ff.push_back(make_ffn(L, c)); }
+  L.emb = L.add((size_t)c.vocab * d);
+  for (int l = 0; l < c.n_dec; ++l) {
+    L.dec_sa.push_back(make_attn(L, c));
+    L.dec_ca.push_back(make_attn(L, c));
+    L.dec_ff.push_back(make_ffn(L, c));
+  }
+  L.out_w = L.add((size_t)c.vocab * d);
+  for (int i = 0; i < 4; ++i) {
+    L.conv_w[i] = L.add((size_t)kConvCout[i] * kConvCin[i] * 9);
+    L.conv_b[i] = L.add(kConvCout[i]);
+  }
+  L.total = (L.total + 63) & ~(size_t)63;
+}
+
+// ----------------------------------------------------------------------------- activation records
+struct LowRankAct { const float* x; float* a; float* y; int M, K, N; size_t offA, offBw, offBb; };
+struct AttnAct {
+  LowRankAct q, k, v, o;
+  float *oh, *lse, *xhat, *rstd, *out;
+  const float *xq, *xkv;
+  int B, Tq, Tk, causal;
+  const unsigned char* keypad;
+  const float* rowmask;
+  MtlDrop drop_attn, drop_out;
+  AttnP p;
+};
+struct FfnAct {
+  const float* x;
+  float *f1, *f2, *xhat, *rstd, *out;
+  int M;
+  const float* rowmask;
+  MtlDrop drop;
+  FfnP p;
+};
+struct ConvAct { const float* x; float* col; float* y; int B, F, T, Cin, Cout, widx; };
+struct Pass {
+  bool valid = false;
+  mtl_batch b;
+  int B, T, F, F2, T2, F4, T4, n, Me, Md, d_in, ldp;
+  float *c1, *p2, *p4, *feat;
+  ConvAct cv[3];
+  float *enc_rowmask, *dec_rowmask;
+  unsigned char *enc_keypad, *dec_keypad;
+  float *h, *e0, *stem_xhat, *stem_rstd;
+  std::vector<AttnAct> enc_sa, dec_sa, dec_ca;
+  std::vector<FfnAct> enc_ff, dec_ff;
+  const float* enc_out;
+  int *seq_in, *seq_out, *hyp;
+  float* x0;
+  MtlDrop drop_emb;
+  const float* dec_last;
+  float *pred, *row_lse, *row_loss;
+  CeOut* ce;
+  float smoothing;
+  size_t ws_after_fwd;
+  uintptr_t ws_base;
+  size_t ws_cap;
+};
+
+struct mtl_session {
+  mtl_model_cfg cfg;
+  Layout L;
+  int mode = MTL_GEMM_SIMT_FP32;
+  Pass pass;
+};
+
+struct Bump {
+  uintptr_t base = 0;
+  size_t off = 0, cap = 0, peak = 0;
+  void* raw(size_t bytes) {
+    off = (off + 255) & ~(size_t)255;
+    void* p = (void*)(base + off);
+    off += bytes;
+    if (off > peak) peak = off;
+    return p;
+  }
+  float* f(size_t n) { return (float*)raw(n * sizeof(float)); }
+  int* i(size_t n) { return (int*)raw(n * sizeof(int)); }
+  unsigned char* u8(size_t n) { return (unsigned char*)raw(n); }
+};
+
+struct Run {
+  mtl_session* S;
+  cudaStream_t st;
+  bool dry;
+  Bump ws;
+  const float* theta;
+  float* grad;
+  float p_drop;
+  unsigned long long seed;
+  uint32_t site;
+  MtlDrop next_drop() { return p_drop > 0.f ? mtl_drop(p_drop, seed, site++) : mtl_nodrop(); }
+};
+
+#define K(call)                        \
+  do {                                 \
+    if (!R.dry) { MTL_TRY(call); }     \
+  } while (0)
+
+// ----------------------------------------------------------------------------- GEMM wrappers
+static int lin_fwd(Run& R, const float* x, int ldx, const float* W, const float* bias, float* y, int ldy, int M,
+                   int N, int Kd, int epi) {
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.A = x; g.lda = ldx; g.transA = 0; g.B = W; g.ldb = Kd; g.transB = 1; g.C = y; g.ldc = ldy;
+  g.M = M; g.N = N; g.K = Kd; g.alpha = 1.f; g.beta = 0.f; g.bias = bias; g.epi = epi; g.split_k = 1;
+  K(k_gemm(g, R.S->mode, R.st));
+  return MTL_OK;
+}
+// dx[M,K] = epi(dy[M,N] . W[N,K]) + beta*dx
+static int lin_dgrad(Run& R, const float* dy, int ldy, const float* W, float* dx, int ldx, int M, int N, int Kd,
+                     float beta, int epi, const float* aux) {
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.A = dy; g.lda = ldy; g.transA = 0; g.B = W; g.ldb = Kd; g.transB = 0; g.C = dx; g.ldc = ldx;
+  g.M = M; g.N = Kd; g.K = N; g.alpha = 1.f; g.beta = beta; g.epi = epi; g.aux = aux; g.split_k = 1;
+  K(k_gemm(g, R.S->mode, R.st));
+  return MTL_OK;
+}
+// dW[N,K] += dy[M,N]^T . x[M,K]
+static int lin_wgrad(Run& R, const float* dy, int ldy, const float* x, int ldx, float* dW, int M, int N, int Kd) {
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.A = dy; g.lda = ldy; g.transA = 1; g.B = x; g.ldb = ldx; g.transB = 0; g.C = dW; g.ldc = Kd;
+  g.M = N; g.N = Kd; g.K = M; g.alpha = 1.f; g.beta = 1.f; g.epi = EPI_NONE;
+  long long tiles = (long long)mtl_cdiv(N, 128) * mtl_cdiv(Kd, 64);
+  int split = (int)((296 + tiles - 1) / tiles);
+  int max_split = M / 256;
+  if (split > max_split) split = max_split;
+  if (split > 256) split = 256;
+  g.split_k = split > 1 ? split : 1;
+  K(k_gemm(g, R.S->mode, R.st));
+  return MTL_OK;
+}
+
+// ----------------------------------------------------------------------------- low-rank projection
+static int lowrank_fwd(Run& R, LowRankAct& A, const float* x, int M, int Kd, int N, int r, size_t offA,
+                       size_t offBw, size_t offBb) {
+  A.x = x; A.M = M; A.K = Kd; A.N = N; A.offA = offA; A.offBw = offBw; A.offBb = offBb;
+  A.a = R.ws.f((size_t)M * r);
+  A.y = R.ws.f((size_t)M * N);
+  MTL_TRY(lin_fwd(R, x, Kd, R.theta + offA, nullptr, A.a, r, M, r, Kd, EPI_NONE));
+  MTL_TRY(lin_fwd(R, A.a, r, R.theta + offBw, R.theta + offBb, A.y, N, M, N, r, EPI_NONE));
+  return MTL_OK;
+}
+// dx (+)= d/dx ; parameter grads accumulated.  dx may be null.
+static int lowrank_bwd(Run& R, const LowRankAct& A, const float* dy, float* dx, float beta_dx) {
+  const int r = R.S->cfg.rank;
+  size_t mark = R.ws.off;
+  float* da = R.ws.f((size_t)A.M * r);
+  MTL_TRY(lin_dgrad(R, dy, A.N, R.theta + A.offBw, da, r, A.M, A.N, r, 0.f, EPI_NONE, nullptr));
+  MTL_TRY(lin_wgrad(R, dy, A.N, A.a, r, R.grad + A.offBw, A.M, A.N, r));
+  K(k_colsum_acc(dy, A.M, A.N, A.N, R.grad + A.offBb, R.st));
+  MTL_TRY(lin_wgrad(R, da, r, A.x, A.K, R.grad + A.offA, A.M, r, A.K));
+  if (dx) MTL_TRY(lin_dgrad(R, da, r, R.theta + A.offA, dx, A.K, A.M, r, A.K, beta_dx, EPI_NONE, nullptr));
+  R.ws.off = mark;
+  return MTL_OK;
+}
+
+// ----------------------------------------------------------------------------- attention block
+static int attn_block_fwd(Run& R, AttnAct& A, const AttnP& p, const float* xq, const float* xkv, int B, int Tq,
+                          int Tk, const unsigned char* keypad, int causal, const float* rowmask) {
+  const mtl_model_cfg& c = R.S->cfg;
+  const int d = c.d_model, H = c.n_heads, dk = c.d_k, dv = c.d_v, r = c.rank;
+  const int Mq = B * Tq, Mk = B * Tk;
+  A.p = p; A.xq = xq; A.xkv = xkv; A.B = B; A.Tq = Tq; A.Tk = Tk; A.causal = causal; A.keypad = keypad;
+  A.rowmask = rowmask;
+  MTL_TRY(lowrank_fwd(R, A.q, xq, Mq, d, H * dk, r, p.qa, p.qb_w, p.qb_b));
+  MTL_TRY(lowrank_fwd(R, A.k, xkv, Mk, d, H * dk, r, p.ka, p.kb_w, p.kb_b));
+  MTL_TRY(lowrank_fwd(R, A.v, xkv, Mk, d, H * dv, r, p.va, p.vb_w, p.vb_b));
+  A.oh = R.ws.f((size_t)Mq * H * dv);
+  A.lse = R.ws.f((size_t)B * H * Tq);
+  A.drop_attn = R.next_drop();
+  AttnArgs a;
+  memset(&a, 0, sizeof(a));
+  a.q = A.q.y; a.k = A.k.y; a.v = A.v.y; a.o = A.oh; a.lse = A.lse; a.keypad = keypad;
+  a.B = B; a.H = H; a.Tq = Tq; a.Tk = Tk; a.dk = dk;
+  a.ldq = H * dk; a.ldk = H * dk; a.ldv = H * dv; a.ldo = H * dv;
+  a.causal = causal; a.inv_temp = 1.0f / sqrtf((float)dk); a.drop = A.drop_attn;
+  K(k_attn_fwd(a, R.st));
+  MTL_TRY(lowrank_fwd(R, A.o, A.oh, Mq, H * dv, d, r, p.oa, p.ob_w, p.ob_b));
+  A.xhat = R.ws.f((size_t)Mq * d);
+  A.rstd = R.ws.f(Mq);
+  A.out = R.ws.f((size_t)Mq * d);
+  A.drop_out = R.next_drop();
+  K(k_ln_fwd(A.o.y, xq, R.theta + p.ln_w, R.theta + p.ln_b, rowmask, nullptr, 1, A.drop_out, A.out, A.xhat,
+             A.rstd, Mq, d, R.st));
+  return MTL_OK;
+}
+// dout -> dxq (overwritten: residual + query-side grads); key/value-side grads ACCUMULATE into dxkv
+// (dxkv may alias dxq for self-attention).
+static int attn_block_bwd(Run& R, const AttnAct& A, const float* dout, float* dxq, float* dxkv) {
+  const mtl_model_cfg& c = R.S->cfg;
+  const int d = c.d_model, H = c.n_heads, dk = c.d_k, dv = c.d_v;
+  const int Mq = A.B * A.Tq, Mk = A.B * A.Tk;
+  size_t mark = R.ws.off;
+  float* do2 = R.ws.f((size_t)Mq * d);
+  float* d_oh = R.ws.f((size_t)Mq * H * dv);
+  float* dq = R.ws.f((size_t)Mq * H * dk);
+  float* dkk = R.ws.f((size_t)Mk * H * dk);
+  float* dvv = R.ws.f((size_t)Mk * H * dv);
+  float* delta = R.ws.f((size_t)A.B * H * A.Tq);
+  K(k_ln_bwd(dout, A.xhat, A.rstd, R.theta + A.p.ln_w, A.rowmask, A.drop_out, do2, dxq, 0, R.grad + A.p.ln_w,
+             R.grad + A.p.ln_b, Mq, d, R.st));
+  MTL_TRY(lowrank_bwd(R, A.o, do2, d_oh, 0.f));
+  AttnBwdArgs b;
+  memset(&b, 0, sizeof(b));
+  b.f.q = A.q.y; b.f.k = A.k.y; b.f.v = A.v.y; b.f.o = A.oh; b.f.lse = A.lse; b.f.keypad = A.keypad;
+  b.f.B = A.B; b.f.H = H; b.f.Tq = A.Tq; b.f.Tk = A.Tk; b.f.dk = dk;
+  b.f.ldq = H * dk; b.f.ldk = H * dk; b.f.ldv = H * dv; b.f.ldo = H * dv;
+  b.f.causal = A.causal; b.f.inv_temp = 1.0f / sqrtf((float)dk); b.f.drop = A.drop_attn;
+  b.d_o = d_oh; b.delta = delta; b.dq = dq; b.dk = dkk; b.dv = dvv;
+  K(k_attn_bwd(b, R.st));
+  MTL_TRY(lowrank_bwd(R, A.q, dq, dxq, 1.f));
+  MTL_TRY(lowrank_bwd(R, A.k, dkk, dxkv, 1.f));
+  MTL_TRY(lowrank_bwd(R, A.v, dvv, dxkv, 1.f));
+  R.ws.off = mark;
+  return MTL_OK;
+}
+
+// ----------------------------------------------------------------------------- FFN block
+static int ffn_block_fwd(Run& R, FfnAct& A, const FfnP& p, const float* x, int M, const float* rowmask) {
+  const mtl_model_cfg& c = R.S->cfg;
+  const int d = c.d_model, f = c.d_inner;
+  A.p = p; A.x = x; A.M = M; A.rowmask = rowmask;
+  A.f1 = R.ws.f((size_t)M * f);
+  A.f2 = R.ws.f((size_t)M * d);
+  A.xhat = R.ws.f((size_t)M * d);
+  A.rstd = R.ws.f(M);
+  A.out = R.ws.f((size_t)M * d);
+  MTL_TRY(lin_fwd(R, x, d, R.theta + p.w1, R.theta + p.b1, A.f1, f, M, f, d, EPI_RELU));
+  MTL_TRY(lin_fwd(R, A.f1, f, R.theta + p.w2, R.theta + p.b2, A.f2, d, M, d, f, EPI_NONE));
+  A.drop = R.next_drop();
+  K(k_ln_fwd(A.f2, x, R.theta + p.ln_w, R.theta + p.ln_b, rowmask, nullptr, 1, A.drop, A.out, A.xhat, A.rstd, M, d,
+             R.st));
+  return MTL_OK;
+}
+static int ffn_block_bwd(Run& R, const FfnAct& A, const float* dout, float* dx) {
+  const mtl_model_cfg& c = R.S->cfg;
+  const int d = c.d_model, f = c.d_inner, M = A.M;
+  size_t mark = R.ws.off;
+  float* df2 = R.ws.f((size_t)M * d);
+  float* df1 = R.ws.f((size_t)M * f);
+  K(k_ln_bwd(dout, A.xhat, A.rstd, R.theta + A.p.ln_w, A.rowmask, A.drop, df2, dx, 0, R.grad + A.p.ln_w,
+             R.grad + A.p.ln_b, M, d, R.st));
+  MTL_TRY(lin_wgrad(R, df2, d, A.f1, f, R.grad + A.p.w2, M, d, f));
+  K(k_colsum_acc(df2, M, d, d, R.grad + A.p.b2, R.st));
+  MTL_TRY(lin_dgrad(R, df2, d, R.theta + A.p.w2, df1, f, M, d, f, 0.f, EPI_RELU_BWD, A.f1));
+  MTL_TRY(lin_wgrad(R, df1, f, A.x, d, R.grad + A.p.w1, M, f, d));
+  K(k_colsum_acc(df1, M, f, f, R.grad + A.p.b1, R.st));
+  MTL_TRY(lin_dgrad(R, df1, f, R.theta + A.p.w1, dx, d, M, f, d, 1.f, EPI_NONE, nullptr));
+  R.ws.off = mark;
+  return MTL_OK;
+}
+
+// ----------------------------------------------------------------------------- 3x3 conv (+bias+ReLU) as GEMM
+static int conv_fwd(Run& R, ConvAct& A, const float* x, int B, int F, int T, int widx) {
+  const Layout& L = R.S->L;
+  A.x = x; A.B = B; A.F = F; A.T = T; A.Cin = kConvCin[widx]; A.Cout = kConvCout[widx]; A.widx = widx;
+  const size_t P = (size_t)B * F * T;
+  const int Kc = 9 * A.Cin;
+  A.col = R.ws.f(P * Kc);
+  float* wg = R.ws.f((size_t)A.Cout * Kc);
+  A.y = R.ws.f(P * A.Cout);
+  K(k_im2col3x3(x, A.col, B, F, T, A.Cin, R.st));
+  K(k_conv_w_fwd_layout(R.theta + L.conv_w[widx], wg, A.Cout, A.Cin, R.st));
+  MTL_TRY(lin_fwd(R, A.col, Kc, wg, R.theta + L.conv_b[widx], A.y, A.Cout, (int)P, A.Cout, Kc, EPI_RELU));
+  return MTL_OK;
+}
+// dy = gradient w.r.t. the pre-ReLU conv output.  dx (nullable) = gradient w.r.t. the conv input,
+// masked by relu_aux > 0 when relu_aux != null.
+static int conv_bwd(Run& R, const ConvAct& A, const float* dy, float* dx, const float* relu_aux) {
+  const Layout& L = R.S->L;
+  const size_t P = (size_t)A.B * A.F * A.T;
+  const int Kc = 9 * A.Cin;
+  size_t mark = R.ws.off;
+  float* dwg = R.ws.f((size_t)A.Cout * Kc);
+  K(k_zero(dwg, (size_t)A.Cout * Kc, R.st));
+  MTL_TRY(lin_wgrad(R, dy, A.Cout, A.col, Kc, dwg, (int)P, A.Cout, Kc));
+  K(k_conv_wgrad_scatter(dwg, R.grad + L.conv_w[A.widx], A.Cout, A.Cin, R.st));
+  K(k_colsum_acc(dy, (int)P, A.Cout, A.Cout, R.grad + L.conv_b[A.widx], R.st));
+  if (dx) {
+    const int Kg = 9 * A.Cout;
+    float* colg = R.ws.f(P * Kg);
+    float* wd = R.ws.f((size_t)A.Cin * Kg);
+    K(k_im2col3x3(dy, colg, A.B, A.F, A.T, A.Cout, R.st));
+    K(k_conv_w_dgrad_layout(R.theta + L.conv_w[A.widx], wd, A.Cout, A.Cin, R.st));
+    // dx[P,Cin] = colg[P,9Cout] . wd[Cin,9Cout]^T
+    GemmArgs g;
+    memset(&g, 0, sizeof(g));
+    g.A = colg; g.lda = Kg; g.transA = 0; g.B = wd; g.ldb = Kg; g.transB = 1; g.C = dx; g.ldc = A.Cin;
+    g.M = (int)P; g.N = A.Cin; g.K = Kg; g.alpha = 1.f; g.beta = 0.f;
+    g.epi = relu_aux ? EPI_RELU_BWD : EPI_NONE; g.aux = relu_aux; g.split_k = 1;
+    K(k_gemm(g, R.S->mode, R.st));
+  }
+  R.ws.off = mark;
+  return MTL_OK;
+}
+
+// ----------------------------------------------------------------------------- whole-model forward
+static int forward(Run& R, const mtl_batch& b, const float* pe_enc, const float* pe_dec, float smoothing) {
+  mtl_session* S = R.S;
+  const mtl_model_cfg& c = S->cfg;
+  const Layout& L = S->L;
+  Pass& P = S->pass;
+  P.valid = false;
+  MTL_REQUIRE(b.B > 0 && b.T > 0 && b.L > 0 && b.n >= 2, "empty batch");
+  P.b = b;
+  P.B = b.B; P.T = b.T; P.F = c.n_freq; P.F2 = P.F / 2; P.T2 = P.T / 2; P.F4 = P.F2 / 2; P.T4 = P.T2 / 2;
+  MTL_REQUIRE(P.T4 >= 1 && P.F4 >= 1, "input shorter than 4 frames / 4 bins");
+  P.n = b.n; P.Me = P.B * P.T4; P.Md = P.B * P.n; P.d_in = 128 * P.F4; P.ldp = (c.vocab + 3) & ~3;
+  P.smoothing = smoothing;
+  const int B = P.B, d = c.d_model, Tp = P.T4, n = P.n;
+  R.site = 0;
+
+  // ---- VGG front-end (transformer.py:47-59), NHWC
+  P.c1 = R.ws.f((size_t)B * P.F * P.T * 64);
+  K(k_conv1_fwd(b.x, R.theta + L.conv_w[0], R.theta + L.conv_b[0], P.c1, B, P.F, P.T, 64, R.st));
+  MTL_TRY(conv_fwd(R, P.cv[0], P.c1, B, P.F, P.T, 1));
+  P.p2 = R.ws.f((size_t)B * P.F2 * P.T2 * 64);
+  K(k_maxpool2_fwd(P.cv[0].y, P.p2, B, P.F, P.T, 64, R.st));
+  MTL_TRY(conv_fwd(R, P.cv[1], P.p2, B, P.F2, P.T2, 2));
+  MTL_TRY(conv_fwd(R, P.cv[2], P.cv[1].y, B, P.F2, P.T2, 3));
+  P.p4 = R.ws.f((size_t)B * P.F4 * P.T4 * 128);
+  K(k_maxpool2_fwd(P.cv[2].y, P.p4, B, P.F2, P.T2, 128, R.st));
+  P.feat = R.ws.f((size_t)P.Me * P.d_in);
+  K(k_feat_transpose(P.p4, P.feat, B, P.F4, P.T4, 128, R.st));
+
+  // ---- encoder (encoder.py:53-80)
+  P.enc_rowmask = R.ws.f(P.Me);
+  P.enc_keypad = R.ws.u8(P.Me);
+  K(k_enc_masks(b.lens, B, Tp, P.enc_rowmask, P.enc_keypad, R.st));
+  P.h = R.ws.f((size_t)P.Me * d);
+  P.e0 = R.ws.f((size_t)P.Me * d);
+  P.stem_xhat = R.ws.f((size_t)P.Me * d);
+  P.stem_rstd = R.ws.f(P.Me);
+  MTL_TRY(lin_fwd(R, P.feat, P.d_in, R.theta + L.in_w, R.theta + L.in_b, P.h, d, P.Me, d, P.d_in, EPI_NONE));
+  K(k_ln_fwd(P.h, nullptr, R.theta + L.lnin_w, R.theta + L.lnin_b, nullptr, pe_enc, Tp, mtl_nodrop(), P.e0,
+             P.stem_xhat, P.stem_rstd, P.Me, d, R.st));
+  const float* x = P.e0;
+  P.enc_sa.assign(c.n_enc, AttnAct());
+  P.enc_ff.assign(c.n_enc, FfnAct());
+  for (int l = 0; l < c.n_enc; ++l) {
+    MTL_TRY(attn_block_fwd(R, P.enc_sa[l], L.enc_sa[l], x, x, B, Tp, Tp, P.enc_keypad, 0, P.enc_rowmask));
+    x = P.enc_sa[l].out;
+    MTL_TRY(ffn_block_fwd(R, P.enc_ff[l], L.enc_ff[l], x, P.Me, P.enc_rowmask));
+    x = P.enc_ff[l].out;
+  }
+  P.enc_out = x;
+
+  // ---- decoder (decoder.py:71-115)
+  P.seq_in = R.ws.i(P.Md);
+  P.seq_out = R.ws.i(P.Md);
+  P.dec_rowmask = R.ws.f(P.Md);
+  P.dec_keypad = R.ws.u8(P.Md);
+  K(k_dec_preprocess(b.trg, B, b.L, n, P.seq_in, P.seq_out, P.dec_rowmask, P.dec_keypad, nullptr, R.st));
+  P.x0 = R.ws.f((size_t)P.Md * d);
+  P.drop_emb = R.next_drop();
+  K(k_embed_fwd(P.seq_in, R.theta + L.emb, pe_dec, P.drop_emb, P.x0, B, n, d, R.st));
+  x = P.x0;
+  P.dec_sa.assign(c.n_dec, AttnAct());
+  P.dec_ca.assign(c.n_dec, AttnAct());
+  P.dec_ff.assign(c.n_dec, FfnAct());
+  for (int l = 0; l < c.n_dec; ++l) {
+    MTL_TRY(attn_block_fwd(R, P.dec_sa[l], L.dec_sa[l], x, x, B, n, n, P.dec_keypad, 1, P.dec_rowmask));
+    x = P.dec_sa[l].out;
+    MTL_TRY(attn_block_fwd(R, P.dec_ca[l], L.dec_ca[l], x, P.enc_out, B, n, Tp, P.enc_keypad, 0, P.dec_rowmask));
+    x = P.dec_ca[l].out;
+    MTL_TRY(ffn_block_fwd(R, P.dec_ff[l], L.dec_ff[l], x, P.Md, P.dec_rowmask));
+    x = P.dec_ff[l].out;
+  }
+  P.dec_last = x;
+  P.pred = R.ws.f((size_t)P.Md * P.ldp);
+  MTL_TRY(lin_fwd(R, x, d, R.theta + L.out_w, nullptr, P.pred, P.ldp, P.Md, c.vocab, d, EPI_NONE));
+
+  // ---- CE + top-1 (metrics.py:126, transformer.py:146)
+  P.row_lse = R.ws.f(P.Md);
+  P.row_loss = R.ws.f(P.Md);
+  P.hyp = R.ws.i(P.Md);
+  P.ce = (CeOut*)R.ws.f(8);
+  K(k_ce_fwd(P.pred, P.ldp, P.seq_out, P.Md, c.vocab, smoothing, 0, P.row_lse, P.row_loss, P.hyp, P.ce, R.st));
+  if (!R.dry) {
+    if (b.hyp_out) MTL_CHECK_CUDA(cudaMemcpyAsync(b.hyp_out, P.hyp, sizeof(int) * P.Md, cudaMemcpyDeviceToDevice, R.st));
+    if (b.gold_out) MTL_CHECK_CUDA(cudaMemcpyAsync(b.gold_out, P.seq_out, sizeof(int) * P.Md, cudaMemcpyDeviceToDevice, R.st));
+    if (b.ce_out) MTL_CHECK_CUDA(cudaMemcpyAsync(b.ce_out, P.ce, sizeof(CeOut), cudaMemcpyDeviceToDevice, R.st));
+  }
+  P.ws_after_fwd = R.ws.off;
+  P.ws_base = R.ws.base;
+  P.ws_cap = R.ws.cap;
+  P.valid = !R.dry;
+  return MTL_OK;
+}
+
+// ----------------------------------------------------------------------------- whole-model backward
+static int backward(Run& R, float loss_scale, const float* dpred_ext, int ld_ext) {
+  mtl_session* S = R.S;
+  const mtl_model_cfg& c = S->cfg;
+  const Layout& L = S->L;
+  Pass& P = S->pass;
+  const int B = P.B, d = c.d_model, V = c.vocab;
+  float* dpred = R.ws.f((size_t)P.Md * P.ldp);
+  if (dpred_ext) {
+    if (!R.dry) {
+      MTL_CHECK_CUDA(cudaMemsetAsync(dpred, 0, sizeof(float) * (size_t)P.Md * P.ldp, R.st));
+      MTL_CHECK_CUDA(cudaMemcpy2DAsync(dpred, sizeof(float) * P.ldp, dpred_ext, sizeof(float) * ld_ext,
+                                       sizeof(float) * V, P.Md, cudaMemcpyDeviceToDevice, R.st));
+    }
+  } else {
+    K(k_ce_bwd(P.pred, P.ldp, P.seq_out, P.row_lse, P.ce, loss_scale, P.smoothing, 0, dpred, P.Md, V, R.st));
+  }
+  // vocab projection
+  MTL_TRY(lin_wgrad(R, dpred, P.ldp, P.dec_last, d, R.grad + L.out_w, P.Md, V, d));
+  float* gA = R.ws.f((size_t)P.Md * d);
+  float* gB = R.ws.f((size_t)P.Md * d);
+  MTL_TRY(lin_dgrad(R, dpred, P.ldp, R.theta + L.out_w, gA, d, P.Md, V, d, 0.f, EPI_NONE, nullptr));
+  float* gE1 = R.ws.f((size_t)P.Me * d);
+  float* gE2 = R.ws.f((size_t)P.Me * d);
+  K(k_zero(gE1, (size_t)P.Me * d, R.st));
+  for (int l = c.n_dec - 1; l >= 0; --l) {
+    MTL_TRY(ffn_block_bwd(R, P.dec_ff[l], gA, gB));
+    std::swap(gA, gB);
+    MTL_TRY(attn_block_bwd(R, P.dec_ca[l], gA, gB, gE1));
+    std::swap(gA, gB);
+    MTL_TRY(attn_block_bwd(R, P.dec_sa[l], gA, gB, gB));
+    std::swap(gA, gB);
+  }
+  K(k_embed_bwd(P.seq_in, gA, P.drop_emb, R.grad + L.emb, B, P.n, d, 0, R.st));
+  // encoder
+  for (int l = c.n_enc - 1; l >= 0; --l) {
+    MTL_TRY(ffn_block_bwd(R, P.enc_ff[l], gE1, gE2));
+    std::swap(gE1, gE2);
+    MTL_TRY(attn_block_bwd(R, P.enc_sa[l], gE1, gE2, gE2));
+    std::swap(gE1, gE2);
+  }
+  // stem: e0 = LN(h) + PE
+  float* dh = gE2;
+  K(k_ln_bwd(gE1, P.stem_xhat, P.stem_rstd, R.theta + L.lnin_w, nullptr, mtl_nodrop(), dh, nullptr, 0,
+             R.grad + L.lnin_w, R.grad + L.lnin_b, P.Me, d, R.st));
+  MTL_TRY(lin_wgrad(R, dh, d, P.feat, P.d_in, R.grad + L.in_w, P.Me, d, P.d_in));
+  K(k_colsum_acc(dh, P.Me, d, d, R.grad + L.in_b, R.st));
+  float* dfeat = R.ws.f((size_t)P.Me * P.d_in);
+  MTL_TRY(lin_dgrad(R, dh, d, R.theta + L.in_w, dfeat, P.d_in, P.Me, d, P.d_in, 0.f, EPI_NONE, nullptr));
+  // VGG front-end
+  float* dp4 = R.ws.f((size_t)B * P.F4 * P.T4 * 128);
+  K(k_feat_transpose_bwd(dfeat, dp4, B, P.F4, P.T4, 128, R.st));
+  float* dc4 = R.ws.f((size_t)B * P.F2 * P.T2 * 128);
+  K(k_maxpool2_relu_bwd(P.cv[2].y, dp4, dc4, B, P.F2, P.T2, 128, R.st));
+  float* dc3 = R.ws.f((size_t)B * P.F2 * P.T2 * 128);
+  MTL_TRY(conv_bwd(R, P.cv[2], dc4, dc3, P.cv[2].x /* = c3, post-ReLU */));
+  float* dp2 = R.ws.f((size_t)B * P.F2 * P.T2 * 64);
+  MTL_TRY(conv_bwd(R, P.cv[1], dc3, dp2, nullptr));
+  float* dc2 = R.ws.f((size_t)B * P.F * P.T * 64);
+  K(k_maxpool2_relu_bwd(P.cv[0].y, dp2, dc2, B, P.F, P.T, 64, R.st));
+  float* dc1 = R.ws.f((size_t)B * P.F * P.T * 64);
+  MTL_TRY(conv_bwd(R, P.cv[0], dc2, dc1, P.c1));
+  K(k_conv1_wgrad(P.b.x, dc1, R.grad + L.conv_w[0], R.grad + L.conv_b[0], B, P.F, P.T, 64, R.st));
+  return MTL_OK;
+}
+
+// ----------------------------------------------------------------------------- C ABI: session
+extern "C" int mtl_session_create(const mtl_model_cfg* cfg, mtl_session** out) {
+  MTL_REQUIRE(cfg && out, "null argument");
+  MTL_REQUIRE(cfg->n_enc >= 0 && cfg->n_dec >= 0 && cfg->d_model > 0 && cfg->d_model % 4 == 0 && cfg->d_model <= 1024,
+              "d_model must be a multiple of 4, <= 1024");
+  MTL_REQUIRE(cfg->d_k == cfg->d_v && (cfg->d_k == 32 || cfg->d_k == 64), "d_k == d_v in {32, 64}");
+  MTL_REQUIRE(cfg->rank > 0 && cfg->rank % 4 == 0, "rank must be a multiple of 4");
+  MTL_REQUIRE(cfg->d_inner > 0 && cfg->d_inner % 4 == 0, "d_inner must be a multiple of 4");
+  MTL_REQUIRE(cfg->vocab > 4 && cfg->n_freq >= 4 && cfg->n_heads > 0, "vocab / n_freq / n_heads");
+  mtl_session* s = new (std::nothrow) mtl_session();
+  MTL_REQUIRE(s, "out of host memory");
+  s->cfg = *cfg;
+  build_layout(s->L, s->cfg);
+  *out = s;
+  return MTL_OK;
+}
+extern "C" void mtl_session_destroy(mtl_session* s) { delete s; }
+extern "C" int mtl_session_set_gemm_mode(mtl_session* s, int mode) {
+  MTL_REQUIRE(s && mode >= 0 && mode <= 2, "gemm mode");
+  s->mode = mode;
+  return MTL_OK;
+}
+extern "C" long long mtl_param_arena_floats(const mtl_session* s) { return s ? (long long)s->L.total : -1; }
+extern "C" int mtl_param_count(const mtl_session* s) { return s ? (int)s->L.tensors.size() : -1; }
+extern "C" int mtl_param_info(const mtl_session* s, int idx, long long* off, long long* numel) {
+  MTL_REQUIRE(s && idx >= 0 && idx < (int)s->L.tensors.size() && off && numel, "param index");
+  *off = (long long)s->L.tensors[idx].first;
+  *numel = (long long)s->L.tensors[idx].second;
+  return MTL_OK;
+}
+
+static int dry_plan(mtl_session* s, int B, int T, int n, size_t* bytes) {
+  Run R;
+  R.S = s; R.st = 0; R.dry = true; R.theta = nullptr; R.grad = nullptr; R.p_drop = 0.f; R.seed = 0; R.site = 0;
+  R.ws.base = 0; R.ws.cap = ~(size_t)0;
+  mtl_batch b;
+  memset(&b, 0, sizeof(b));
+  b.B = B; b.T = T; b.L = n > 1 ? n - 1 : 1; b.n = n;
+  Pass saved = s->pass;
+  int rc = forward(R, b, nullptr, nullptr, 0.f);
+  if (rc == MTL_OK) rc = backward(R, 1.f, nullptr, 0);
+  s->pass = saved;
+  *bytes = R.ws.peak + 256;
+  return rc;
+}
+extern "C" long long mtl_workspace_bytes(mtl_session* s, int B, int T, int n) {
+  if (!s) return -1;
+  size_t bytes = 0;
+  if (dry_plan(s, B, T, n, &bytes) != MTL_OK) return -1;
+  return (long long)bytes;
+}
+
+static int check_ws(mtl_session* s, const mtl_batch* b, void* ws, long long ws_bytes) {
+  MTL_REQUIRE(ws && (((uintptr_t)ws) & 255u) == 0, "workspace must be 256B aligned");
+  size_t need = 0;
+  MTL_TRY(dry_plan(s, b->B, b->T, b->n, &need));
+  if ((long long)need > ws_bytes) {
+    mtl_set_error("workspace too small: need %zu bytes, have %lld", need, ws_bytes);
+    return MTL_ERR_WORKSPACE;
+  }
+  return MTL_OK;
+}
+
+extern "C" int mtl_asr_forward(mtl_session* s, const float* theta, const float* pe_enc, const float* pe_dec,
+                               void* workspace, long long workspace_bytes, const mtl_batch* batch, float dropout,
+                               unsigned long long seed, float label_smoothing, void* stream, float** pred_out,
+                               int* ldp_out) {
+  MTL_REQUIRE(s && theta && pe_enc && pe_dec && batch && batch->x && batch->lens && batch->trg, "null argument");
+  MTL_REQUIRE(dropout >= 0.f && dropout < 1.f, "dropout in [0,1)");
+  MTL_TRY(check_ws(s, batch, workspace, workspace_bytes));
+  Run R;
+  R.S = s; R.st = (cudaStream_t)stream; R.dry = false; R.theta = theta; R.grad = nullptr;
+  R.p_drop = dropout; R.seed = seed; R.site = 0;
+  R.ws.base = (uintptr_t)workspace; R.ws.cap = (size_t)workspace_bytes;
+  MTL_TRY(forward(R, *batch, pe_enc, pe_dec, label_smoothing));
+  if (pred_out) *pred_out = s->pass.pred;
+  if (ldp_out) *ldp_out = s->pass.ldp;
+  return MTL_OK;
+}
+
+extern "C" int mtl_asr_backward(mtl_session* s, const float* theta, float* grad, float loss_scale,
+                                const float* dpred_ext, int ld_ext, void* stream) {
+  MTL_REQUIRE(s && theta && grad, "null argument");
+  MTL_REQUIRE(s->pass.valid, "mtl_asr_backward without a preceding mtl_asr_forward");
+  Run R;
+  R.S = s; R.st = (cudaStream_t)stream; R.dry = false; R.theta = theta; R.grad = grad;
+  R.p_drop = 0.f; R.seed = 0; R.site = 0;
+  R.ws.base = s->pass.ws_base; R.ws.cap = s->pass.ws_cap; R.ws.off = s->pass.ws_after_fwd;
+  MTL_TRY(backward(R, loss_scale, dpred_ext, ld_ext));
+  s->pass.valid = false;
+  return MTL_OK;
+}
+
+// ----------------------------------------------------------------------------- C ABI: meta-step pieces
+extern "C" int mtl_meta_task(mtl_session* s, float* theta, const float* theta0, float* grad, float* copy_grad,
+                             const float* pe_enc, const float* pe_dec, void* workspace, long long workspace_bytes,
+                             const mtl_batch* train, const mtl_batch* val, const mtl_meta_hparams* hp,
+                             float* results16, void* stream) {
+  MTL_REQUIRE(s && theta && theta0 && grad && copy_grad && train && val && hp, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n = s->L.total;
+  // scratch for the clip coefficient lives at the very end of the workspace
+  const long long tail = (long long)((MTL_NORM_PARTIALS + 8) * sizeof(float) + 256);
+  MTL_REQUIRE(workspace_bytes > tail, "workspace too small");
+  const long long ws_main = (workspace_bytes - tail) & ~255LL;
+  float* scratch = (float*)((char*)workspace + ws_main);
+  mtl_batch tr = *train, va = *val;
+  if (results16) { tr.ce_out = results16; va.ce_out = results16 + 8; }
+  MTL_TRY(k_zero(grad, n, st));                                                     // inner_opt.zero_grad()
+  MTL_TRY(mtl_asr_forward(s, theta, pe_enc, pe_dec, workspace, ws_main, &tr, hp->dropout, hp->seed * 2ull + 0ull,
+                          hp->label_smoothing, stream, nullptr, nullptr));
+  MTL_TRY(mtl_asr_backward(s, theta, grad, 1.f, nullptr, 0, stream));              // tr_loss.backward()
+  if (hp->clip) {
+    MTL_TRY(k_clip_coef(grad, n, hp->max_norm, scratch, scratch + MTL_NORM_PARTIALS, st));
+    MTL_TRY(k_scale_by_dev(grad, scratch + MTL_NORM_PARTIALS + 1, n, st));
+  }
+  MTL_TRY(k_sgd(theta, grad, hp->lr, n, st));                                       // inner_opt.step()
+  MTL_TRY(mtl_asr_forward(s, theta, pe_enc, pe_dec, workspace, ws_main, &va, hp->dropout, hp->seed * 2ull + 1ull,
+                          hp->label_smoothing, stream, nullptr, nullptr));
+  MTL_TRY(mtl_asr_backward(s, theta, grad, hp->val_scale, nullptr, 0, stream));    // (val_loss/N).backward(), no zero_grad
+  MTL_TRY(k_axpy(copy_grad, grad, 1.f, n, st));                                     // model.add_copy_grad()
+  MTL_TRY(k_copy(theta, theta0, n, st));                                            // model.load_state_dict(weights_original)
+  return MTL_OK;
+}
+
+struct AdamState { int step; float step_size; float bc2_sqrt; float pad; };
+
+extern "C" int mtl_arena_adam(float* p, const float* g, float* m, float* v, void* adam_state, float lr, float b1,
+                              float b2, float eps, long long n, void* stream) {
+  MTL_REQUIRE(p && g && m && v && adam_state && n >= 0, "null argument");
+  AdamState* a = (AdamState*)adam_state;
+  cudaStream_t st = (cudaStream_t)stream;
+  MTL_TRY(k_adam_prep(&a->step, &a->step_size, lr, b1, b2, st));
+  MTL_TRY(k_adam(p, g, m, v, &a->step_size, b1, b2, eps, (size_t)n, st));
+  return MTL_OK;
+}
+extern "C" int mtl_arena_clip(float* g, long long n, float max_norm, float* scratch1032, void* stream) {
+  MTL_REQUIRE(g && scratch1032 && n >= 0, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  MTL_TRY(k_clip_coef(g, (size_t)n, max_norm, scratch1032, scratch1032 + MTL_NORM_PARTIALS, st));
+  MTL_TRY(k_scale_by_dev(g, scratch1032 + MTL_NORM_PARTIALS + 1, (size_t)n, st));
+  return MTL_OK;
+}
+extern "C" int mtl_meta_finish(float* theta, float* grad, const float* copy_grad, float* adam_m, float* adam_v,
+                               void* adam_state, float meta_lr, int clip, float max_norm, float* scratch1032,
+                               long long n, void* stream) {
+  MTL_REQUIRE(theta && grad && copy_grad && adam_m && adam_v && adam_state, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  MTL_TRY(k_copy(grad, copy_grad, (size_t)n, st));                                  // model.from_copy_grad()
+  if (clip) MTL_TRY(mtl_arena_clip(grad, n, max_norm, scratch1032, stream));
+  MTL_TRY(mtl_arena_adam(theta, grad, adam_m, adam_v, adam_state, meta_lr, 0.9f, 0.999f, 1e-8f, n, stream));
+  return MTL_OK;
+}
+extern "C" int mtl_arena_zero(float* p, long long n, void* stream) { return k_zero(p, (size_t)n, (cudaStream_t)stream); }
+extern "C" int mtl_arena_copy(float* d, const float* s, long long n, void* stream) { return k_copy(d, s, (size_t)n, (cudaStream_t)stream); }
+extern "C" int mtl_arena_axpy(float* y, const float* x, float a, long long n, void* stream) { return k_axpy(y, x, a, (size_t)n, (cudaStream_t)stream); }
+extern "C" int mtl_arena_sgd(float* p, const float* g, float lr, long long n, void* stream) { return k_sgd(p, g, lr, (size_t)n, (cudaStream_t)stream); }
+
+// ----------------------------------------------------------------------------- C ABI: single operators
+int k_gemm(const GemmArgs& g, int mode, cudaStream_t s) {
+  if (mode != MTL_GEMM_SIMT_FP32 && k_gemm_tc_eligible(g)) return k_gemm_tc(g, mode, s);
+  return k_gemm_simt(g, s);
+}
+extern "C" int mtl_gemm(int mode, int transA, int transB, int M, int N, int Kd, float alpha, const float* A, int lda,
+                        const float* B, int ldb, float beta, float* C, int ldc, const float* bias, int epi,
+                        const float* aux, int split_k, void* stream) {
+  MTL_REQUIRE(A && B && C, "null argument");
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.A = A; g.B = B; g.C = C; g.M = M; g.N = N; g.K = Kd; g.lda = lda; g.ldb = ldb; g.ldc = ldc;
+  g.transA = transA; g.transB = transB; g.alpha = alpha; g.beta = beta; g.bias = bias; g.epi = epi; g.aux = aux;
+  g.split_k = split_k;
+  return k_gemm(g, mode, (cudaStream_t)stream);
+}
+extern "C" int mtl_ln_fwd(const float* y, const float* res, const float* gamma, const float* beta,
+                          const float* rowmask, const float* pe, int pe_period, float drop_p,
+                          unsigned long long seed, unsigned site, float* out, float* xhat, float* rstd, int M, int d,
+                          void* stream) {
+  return k_ln_fwd(y, res, gamma, beta, rowmask, pe, pe_period, drop_p > 0.f ? mtl_drop(drop_p, seed, site) : mtl_nodrop(),
+                  out, xhat, rstd, M, d, (cudaStream_t)stream);
+}
+extern "C" int mtl_ln_bwd(const float* dout, const float* xhat, const float* rstd, const float* gamma,
+                          const float* rowmask, float drop_p, unsigned long long seed, unsigned site, float* dy,
+                          float* dres, int dres_accumulate, float* dgamma, float* dbeta, int M, int d, void* stream) {
+  return k_ln_bwd(dout, xhat, rstd, gamma, rowmask, drop_p > 0.f ? mtl_drop(drop_p, seed, site) : mtl_nodrop(), dy,
+                  dres, dres_accumulate, dgamma, dbeta, M, d, (cudaStream_t)stream);
+}
+static AttnArgs make_attn_args(const float* q, const float* k, const float* v, const unsigned char* keypad, int B,
+                               int H, int Tq, int Tk, int dk, int causal, float drop_p, unsigned long long seed,
+                               unsigned site, float* o, float* lse) {
+  AttnArgs a;
+  memset(&a, 0, sizeof(a));
+  a.q = q; a.k = k; a.v = v; a.o = o; a.lse = lse; a.keypad = keypad; a.B = B; a.H = H; a.Tq = Tq; a.Tk = Tk;
+  a.dk = dk; a.ldq = a.ldk = a.ldv = a.ldo = H * dk; a.causal = causal; a.inv_temp = 1.0f / sqrtf((float)dk);
+  a.drop = drop_p > 0.f ? mtl_drop(drop_p, seed, site) : mtl_nodrop();
+  return a;
+}
+extern "C" int mtl_attn_fwd(const float* q, const float* k, const float* v, const unsigned char* keypad, int B, int H,
+                            int Tq, int Tk, int dk, int causal, float drop_p, unsigned long long seed, unsigned site,
+                            float* o, float* lse, void* stream) {
+  return k_attn_fwd(make_attn_args(q, k, v, keypad, B, H, Tq, Tk, dk, causal, drop_p, seed, site, o, lse),
+                    (cudaStream_t)stream);
+}
+extern "C" int mtl_attn_bwd(const float* q, const float* k, const float* v, const unsigned char* keypad,
+                            const float* o, const float* lse, const float* d_o, int B, int H, int Tq, int Tk, int dk,
+                            int causal, float drop_p, unsigned long long seed, unsigned site, float* delta, float* dq,
+                            float* dkk, float* dv, void* stream) {
+  AttnBwdArgs b;
+  b.f = make_attn_args(q, k, v, keypad, B, H, Tq, Tk, dk, causal, drop_p, seed, site, (float*)o, (float*)lse);
+  b.d_o = d_o; b.delta = delta; b.dq = dq; b.dk = dkk; b.dv = dv;
+  return k_attn_bwd(b, (cudaStream_t)stream);
+}
+extern "C" int mtl_ce_fwd(const float* logits, int ld, const int* gold, int M, int V, float smoothing, float* row_lse,
+                          float* row_loss, int* hyp, float* out8, void* stream) {
+  return k_ce_fwd(logits, ld, gold, M, V, smoothing, 0, row_lse, row_loss, hyp, (CeOut*)out8, (cudaStream_t)stream);
+}
+extern "C" int mtl_ce_bwd(const float* logits, int ld, const int* gold, const float* row_lse, const float* out8,
+                          float scale, float smoothing, float* dlogits, int M, int V, void* stream) {
+  return k_ce_bwd(logits, ld, gold, row_lse, (const CeOut*)out8, scale, smoothing, 0, dlogits, M, V,
+                  (cudaStream_t)stream);
+}
+extern "C" int mtl_conv1_fwd(const float* x, const float* w, const float* b, float* out, int B, int F, int T, int Cout,
+                             void* stream) {
+  return k_conv1_fwd(x, w, b, out, B, F, T, Cout, (cudaStream_t)stream);
+}
+extern "C" int mtl_conv3x3_relu_fwd(int mode, const float* x, const float* w, const float* b, float* col, float* wg,
+                                    float* out, int B, int F, int T, int Cin, int Cout, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  MTL_TRY(k_im2col3x3(x, col, B, F, T, Cin, st));
+  MTL_TRY(k_conv_w_fwd_layout(w, wg, Cout, Cin, st));
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.A = col; g.lda = 9 * Cin; g.B = wg; g.ldb = 9 * Cin; g.transB = 1; g.C = out; g.ldc = Cout;
+  g.M = B * F * T; g.N = Cout; g.K = 9 * Cin; g.alpha = 1.f; g.bias = b; g.epi = EPI_RELU; g.split_k = 1;
+  return k_gemm(g, mode, st);
+}
+extern "C" int mtl_maxpool2_fwd(const float* x, float* out, int B, int F, int T, int C, void* stream) {
+  return k_maxpool2_fwd(x, out, B, F, T, C, (cudaStream_t)stream);
+}
+extern "C" int mtl_maxpool2_relu_bwd(const float* x, const float* dpool, float* dx, int B, int F, int T, int C,
+                                     void* stream) {
+  return k_maxpool2_relu_bwd(x, dpool, dx, B, F, T, C, (cudaStream_t)stream);
+}
+extern "C" int mtl_dec_preprocess(const long long* trg, int B, int L, int n, int* seq_in, int* seq_out, float* rowmask,
+                                  unsigned char* keypad, void* stream) {
+  return k_dec_preprocess(trg, B, L, n, seq_in, seq_out, rowmask, keypad, nullptr, (cudaStream_t)stream);
+}

@@ -1,0 +1,267 @@
+// LayerNorm(+dropout+residual+row-mask+PE) forward/backward, column sums, embedding gather/scatter,
+// decoder preprocessing and mask builders.  Warp-per-row, shuffle reductions.
+// Reference: modules/common_layers.py:129-131,303-304 (LN(dropout(branch)+x)), modules/encoder.py:72-73,
+// 101-104 (stem LN + PE, "*= non_pad_mask"), modules/decoder.py:55-69,86-96,314-321.
+#include "kernels.h"
+
+#define LN_MAXV 32   // d <= 1024
+#define LN_EPS 1e-5f
+
+__global__ void __launch_bounds__(128) ln_fwd_kernel(
+    const float* __restrict__ y, const float* __restrict__ res, const float* __restrict__ gamma,
+    const float* __restrict__ beta, const float* __restrict__ rowmask, const float* __restrict__ pe,
+    int pe_period, MtlDrop drop, float* __restrict__ out, float* __restrict__ xhat,
+    float* __restrict__ rstd_out, int M, int d) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (row >= M) return;
+  float z[LN_MAXV];
+  float sum = 0.f;
+  const size_t base = (size_t)row * d;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    int c = lane + i * 32;
+    float v = 0.f;
+    if (c < d) {
+      v = y[base + c];
+      if (drop.p > 0.f) v *= dropout_scale(drop.seed, drop.site, base + c, drop.p, drop.inv_keep);
+      if (res) v += res[base + c];
+    }
+    z[i] = v;
+    sum += v;
+  }
+  const float mean = warp_sum(sum) / (float)d;
+  float var = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    int c = lane + i * 32;
+    if (c < d) { float t = z[i] - mean; var += t * t; }
+  }
+  var = warp_sum(var) / (float)d;
+  const float rstd = rsqrtf(var + LN_EPS);
+  const float rm = rowmask ? rowmask[row] : 1.f;
+  const float* per = pe ? pe + (size_t)(row % pe_period) * d : nullptr;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    int c = lane + i * 32;
+    if (c < d) {
+      float xh = (z[i] - mean) * rstd;
+      float o = xh * gamma[c] + beta[c];
+      if (per) o += per[c];
+      xhat[base + c] = xh;
+      out[base + c] = o * rm;
+    }
+  }
+  if (lane == 0) rstd_out[row] = rstd;
+}
+
+int k_ln_fwd(const float* y, const float* res, const float* gamma, const float* beta, const float* rowmask,
+             const float* pe, int pe_period, MtlDrop drop, float* out, float* xhat, float* rstd, int M,
+             int d, cudaStream_t s) {
+  MTL_REQUIRE(d <= 32 * LN_MAXV, "layer norm width > 1024");
+  if (M == 0) return MTL_OK;
+  ln_fwd_kernel<<<mtl_cdiv(M, 4), 128, 0, s>>>(y, res, gamma, beta, rowmask, pe, pe_period > 0 ? pe_period : 1,
+                                              drop, out, xhat, rstd, M, d);
+  MTL_CHECK_LAUNCH();
+  return MTL_OK;
+}
+
+__global__ void __launch_bounds__(128) ln_bwd_kernel(
+    const float* __restrict__ dout, const float* __restrict__ xhat, const float* __restrict__ rstd,
+    const float* __restrict__ gamma, const float* __restrict__ rowmask, MtlDrop drop,
+    float* __restrict__ dy, float* __restrict__ dres, int dres_acc, int M, int d) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const size_t base = (size_t)row * d;
+  const float rm = rowmask ? rowmask[row] : 1.f;
+  float dxh[LN_MAXV], xh[LN_MAXV];
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    int c = lane + i * 32;
+    float a = 0.f, b = 0.f;
+    if (c < d) { a = dout[base + c] * rm * gamma[c]; b = xhat[base + c]; }
+    dxh[i] = a; xh[i] = b;
+    s1 += a; s2 += a * b;
+  }
+  s1 = warp_sum(s1) / (float)d;
+  s2 = warp_sum(s2) / (float)d;
+  const float r = rstd[row];
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    int c = lane + i * 32;
+    if (c < d) {
+      float dz = r * (dxh[i] - s1 - xh[i] * s2);
+      if (dres) dres[base + c] = dres_acc ? dres[base + c] + dz : dz;
+      if (dy) {
+        float sc = drop.p > 0.f ? dropout_scale(drop.seed, drop.site, base + c, drop.p, drop.inv_keep) : 1.f;
+        dy[base + c] = dz * sc;
+      }
+    }
+  }
+}
+
+// dgamma[c] += sum_m dout*rm*xhat ; dbeta[c] += sum_m dout*rm.  Block = 32 columns x 8 row-lanes.
+__global__ void __launch_bounds__(256) ln_param_grad_kernel(
+    const float* __restrict__ dout, const float* __restrict__ xhat, const float* __restrict__ rowmask,
+    float* __restrict__ dgamma, float* __restrict__ dbeta, int M, int d) {
+  __shared__ float sg[8][33], sb[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  float ag = 0.f, ab = 0.f;
+  if (c < d) {
+    for (int m = ty; m < M; m += 8) {
+      float rm = rowmask ? rowmask[m] : 1.f;
+      float g = dout[(size_t)m * d + c] * rm;
+      ag += g * xhat[(size_t)m * d + c];
+      ab += g;
+    }
+  }
+  sg[ty][tx] = ag; sb[ty][tx] = ab;
+  __syncthreads();
+  if (ty == 0 && c < d) {
+    float g = 0.f, b = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { g += sg[i][tx]; b += sb[i][tx]; }
+    dgamma[c] += g;
+    dbeta[c] += b;
+  }
+}
+
+int k_ln_bwd(const float* dout, const float* xhat, const float* rstd, const float* gamma, const float* rowmask,
+             MtlDrop drop, float* dy, float* dres, int dres_accumulate, float* dgamma, float* dbeta, int M,
+             int d, cudaStream_t s) {
+  MTL_REQUIRE(d <= 32 * LN_MAXV, "layer norm width > 1024");
+  if (M == 0) return MTL_OK;
+  ln_bwd_kernel<<<mtl_cdiv(M, 4), 128, 0, s>>>(dout, xhat, rstd, gamma, rowmask, drop, dy, dres,
+                                              dres_accumulate, M, d);
+  MTL_CHECK_LAUNCH();
+  ln_param_grad_kernel<<<mtl_cdiv(d, 32), 256, 0, s>>>(dout, xhat, rowmask, dgamma, dbeta, M, d);
+  MTL_CHECK_LAUNCH();
+  return MTL_OK;
+}
+
+// out[n] += sum_m x[m*ld + n].  Rows are split over gridDim.y slabs when M is large (atomic merge).
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, int M, int N, int ld,
+                                                     float* __restrict__ out, int rows_per_slab) {
+  __shared__ float sm[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  const int m0 = blockIdx.y * rows_per_slab;
+  const int m1 = min(M, m0 + rows_per_slab);
+  float a = 0.f;
+  if (c < N)
+    for (int m = m0 + ty; m < m1; m += 8) a += x[(size_t)m * ld + c];
+  sm[ty][tx] = a;
+  __syncthreads();
+  if (ty == 0 && c < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sm[i][tx];
+    if (gridDim.y == 1) out[c] += t; else atomicAdd(out + c, t);
+  }
+}
+int k_colsum_acc(const float* x, int M, int N, int ld, float* out, cudaStream_t s) {
+  if (M == 0 || N == 0) return MTL_OK;
+  int slabs = 1;
+  if (M > 4096) slabs = mtl_cdiv(M, 2048);
+  if (slabs > 512) slabs = 512;
+  int rps = mtl_cdiv(M, slabs);
+  colsum_kernel<<<dim3(mtl_cdiv(N, 32), slabs), 256, 0, s>>>(x, M, N, ld, out, rps);
+  MTL_CHECK_LAUNCH();
+  return MTL_OK;
+}
+
+// ---------------------------------------------------------------- embedding (+PE, dropout)
+__global__ void __launch_bounds__(256) embed_fwd_kernel(const int* __restrict__ tok, const float* __restrict__ E,
+                                                        const float* __restrict__ pe, MtlDrop drop,
+                                                        float* __restrict__ out, int rows, int n, int d) {
+  size_t total = (size_t)rows * d;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int row = (int)(i / d), c = (int)(i % d);
+    int pos = row % n;
+    float v = E[(size_t)tok[row] * d + c] * 1.0f + pe[(size_t)pos * d + c];   // x_logit_scale = 1 (decoder.py:53)
+    if (drop.p > 0.f) v *= dropout_scale(drop.seed, drop.site, i, drop.p, drop.inv_keep);
+    out[i] = v;
+  }
+}
+int k_embed_fwd(const int* tok, const float* E, const float* pe, MtlDrop drop, float* out, int B, int n, int d,
+                cudaStream_t s) {
+  size_t total = (size_t)B * n * d;
+  if (!total) return MTL_OK;
+  int grid = (int)((total + 255) / 256); if (grid > 148 * 16) grid = 148 * 16;
+  embed_fwd_kernel<<<grid, 256, 0, s>>>(tok, E, pe, drop, out, B * n, n, d);
+  MTL_CHECK_LAUNCH();
+  return MTL_OK;
+}
+__global__ void __launch_bounds__(256) embed_bwd_kernel(const int* __restrict__ tok, const float* __restrict__ dout,
+                                                        MtlDrop drop, float* __restrict__ dE, int rows, int d,
+                                                        int pad_id) {
+  size_t total = (size_t)rows * d;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int row = (int)(i / d), c = (int)(i % d);
+    int t = tok[row];
+    if (t == pad_id) continue;                       // nn.Embedding(padding_idx=PAD) (decoder.py:39)
+    float g = dout[i];
+    if (drop.p > 0.f) g *= dropout_scale(drop.seed, drop.site, i, drop.p, drop.inv_keep);
+    atomicAdd(dE + (size_t)t * d + c, g);
+  }
+}
+int k_embed_bwd(const int* tok, const float* dout, MtlDrop drop, float* dE, int B, int n, int d, int pad_id,
+                cudaStream_t s) {
+  size_t total = (size_t)B * n * d;
+  if (!total) return MTL_OK;
+  int grid = (int)((total + 255) / 256); if (grid > 148 * 16) grid = 148 * 16;
+  embed_bwd_kernel<<<grid, 256, 0, s>>>(tok, dout, drop, dE, B * n, d, pad_id);
+  MTL_CHECK_LAUNCH();
+  return MTL_OK;
+}
+
+// ---------------------------------------------------------------- decoder preprocess + masks
+// Decoder.preprocess (decoder.py:55-69): strip PAD(0); seq_in = <SOS> y, padded with EOS;
+// seq_out = y <EOS>, padded with PAD.  non_pad = seq_in != EOS (:86); key-pad = seq_in == EOS (:87).
+__global__ void dec_preprocess_kernel(const long long* __restrict__ trg, int B, int L, int n, int* seq_in,
+                                      int* seq_out, float* rowmask, unsigned char* keypad, int* overflow) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int PAD = 0, SOS = 1, EOS = 2;
+  int* si = seq_in + (size_t)b * n;
+  int* so = seq_out + (size_t)b * n;
+  for (int i = 0; i < n; ++i) { si[i] = EOS; so[i] = PAD; }
+  si[0] = SOS;
+  int cnt = 0;
+  for (int j = 0; j < L; ++j) {
+    int t = (int)trg[(size_t)b * L + j];
+    if (t == PAD) continue;
+    if (cnt + 1 < n) { si[cnt + 1] = t; so[cnt] = t; }
+    ++cnt;
+  }
+  if (cnt < n) so[cnt] = EOS; else if (overflow) atomicExch(overflow, 1);
+  for (int i = 0; i < n; ++i) {
+    bool e = si[i] == EOS;
+    rowmask[(size_t)b * n + i] = e ? 0.f : 1.f;
+    keypad[(size_t)b * n + i] = e ? 1 : 0;
+  }
+}
+int k_dec_preprocess(const long long* trg, int B, int L, int n, int* seq_in, int* seq_out, float* rowmask,
+                     unsigned char* keypad, int* overflow_flag, cudaStream_t s) {
+  if (B == 0) return MTL_OK;
+  dec_preprocess_kernel<<<mtl_cdiv(B, 64), 64, 0, s>>>(trg, B, L, n, seq_in, seq_out, rowmask, keypad, overflow_flag);
+  MTL_CHECK_LAUNCH();
+  return MTL_OK;
+}
+__global__ void enc_masks_kernel(const int* __restrict__ lens, int B, int Tp, float* rowmask, unsigned char* keypad) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * Tp) return;
+  int b = i / Tp, t = i % Tp;
+  bool valid = t < lens[b];
+  rowmask[i] = valid ? 1.f : 0.f;
+  keypad[i] = valid ? 0 : 1;
+}
+int k_enc_masks(const int* lens, int B, int Tp, float* rowmask, unsigned char* keypad, cudaStream_t s) {
+  if (B * Tp == 0) return MTL_OK;
+  enc_masks_kernel<<<mtl_cdiv(B * Tp, 256), 256, 0, s>>>(lens, B, Tp, rowmask, keypad);
+  MTL_CHECK_LAUNCH();
+  return MTL_OK;
+}

@@ -1,0 +1,272 @@
+"""-m gpu: the CUDA hot path (through the C ABI) against the CPU oracle (oracle/ref_asr.py, ref_meta.py)
+on the same seeded inputs, and against the golden vectors the live reference produced (tests/golden).
+
+Tolerances.  north_star: "within 1e-3 relative fp32 tolerance (bit-exact for argmax decode indices)".
+Per-tensor relative error = max|a-b| / max|b|.  The exact-fp32 engine (MTL_GEMM_MODE=0, default) is held
+to 1e-4; set MTL_GEMM_MODE=1/2 to run the same suite on the tcgen05 TF32 / 3xTF32 engines (1e-3 on
+outputs/loss, TOL_GRAD on gradients)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import mtl_b200
+from gpu_util import GEMM_MODE, dev, rel_err, spec_of, to_batch
+from oracle import make_golden as mg
+from oracle import ref_asr, ref_meta
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+TOL_OUT = {0: 1e-4, 1: 1e-3, 2: 1e-4}[GEMM_MODE]
+TOL_GRAD = {0: 2e-4, 1: 5e-3, 2: 2e-4}[GEMM_MODE]
+
+
+def _session(cfg):
+    return mtl_b200.Session(spec_of(cfg), gemm_mode=GEMM_MODE)
+
+
+def _fwd_bwd(s, params, batch, scale=1.0, dropout=0.0, seed=0):
+    theta, grad = s.new_arena(), s.new_arena()
+    s.load(theta, params)
+    out = s.forward(theta, to_batch(batch), dropout=dropout, seed=seed)
+    pred = out["pred"].clone()
+    s.backward(theta, grad, scale)
+    torch.cuda.synchronize()
+    return out, pred, s.views(grad)
+
+
+@pytest.mark.parametrize("ragged", [False, True])
+def test_small_fwd_bwd_vs_oracle(ragged):
+    cfg = ref_asr.SMALL
+    p = ref_asr.init_params(cfg, 2)
+    if ragged:
+        batch = ref_meta.synth_batch(cfg, 4, 41, 7, 10, lengths=[41, 30, 9, 5], tgt_lengths=[7, 5, 3, 1])
+    else:
+        batch = ref_meta.synth_batch(cfg, 4, 41, 7, 10)
+    loss_o, g_o, gold_o, hyp_o, pred_o = ref_meta.loss_and_grads(p, cfg, batch)
+    out, pred, grads = _fwd_bwd(_session(cfg), p, batch)
+    assert torch.equal(out["gold"].cpu().long(), gold_o)
+    keep = gold_o != 0
+    assert torch.equal(out["hyp"].cpu().long()[keep], hyp_o[keep])          # bit-exact decode indices
+    assert rel_err(pred, pred_o) < TOL_OUT
+    assert abs(float(out["ce"][0]) - loss_o) < TOL_OUT * abs(loss_o)
+    assert int(out["ce"][2]) == ref_asr.num_correct(pred_o, gold_o)
+    bad = {k: rel_err(grads[k], g_o[k]) for k in g_o if float(g_o[k].abs().max()) > 1e-7}
+    worst = max(bad, key=bad.get)
+    assert bad[worst] < TOL_GRAD, (worst, bad[worst])
+    for k in g_o:   # mathematically-zero gradients (key bias) stay negligible
+        if float(g_o[k].abs().max()) <= 1e-7:
+            assert float(grads[k].abs().max()) < 1e-6, k
+
+
+def test_small_golden_from_live_reference():
+    g = np.load(os.path.join(GOLD, "small_fwd_bwd.npz"))
+    cfg = ref_asr.SMALL
+    p = ref_asr.init_params(cfg, 21)
+    batch = ref_meta.synth_batch(cfg, 4, 41, 7, 2100, lengths=[41, 30, 9, 5], tgt_lengths=[7, 5, 3, 1])
+    out, pred, grads = _fwd_bwd(_session(cfg), p, batch)
+    assert np.array_equal(out["gold"].cpu().numpy(), g["gold"])
+    keep = g["gold"] != 0
+    assert np.array_equal(out["hyp"].cpu().numpy()[keep], g["hyp"][keep])
+    assert rel_err(pred, torch.from_numpy(g["pred"])) < TOL_OUT
+    assert abs(float(out["ce"][0]) - float(g["loss"])) < TOL_OUT * float(g["loss"])
+    assert int(out["ce"][2]) == int(g["num_correct"])
+    for name, _ in ref_asr.param_specs(cfg):
+        ref = torch.from_numpy(g["grad/" + name])
+        if float(ref.abs().max()) > 1e-7:
+            assert rel_err(grads[name], ref) < TOL_GRAD, name
+
+
+def test_loss_scale_and_accumulation_semantics():
+    """backward accumulates scale*grad into the arena (transient_trainer.py:198-199,226-227: no zero_grad
+    between the two backward calls)."""
+    cfg = ref_asr.SMALL
+    p = ref_asr.init_params(cfg, 5)
+    s = _session(cfg)
+    b1, b2 = ref_meta.synth_batch(cfg, 4, 41, 7, 1), ref_meta.synth_batch(cfg, 3, 30, 5, 2)
+    theta, grad = s.new_arena(), s.new_arena()
+    s.load(theta, p)
+    s.forward(theta, to_batch(b1)); s.backward(theta, grad, 1.0)
+    s.forward(theta, to_batch(b2)); s.backward(theta, grad, 1.0 / 3)
+    _, g1, *_ = ref_meta.loss_and_grads(p, cfg, b1)
+    _, g2, *_ = ref_meta.loss_and_grads(p, cfg, b2, 1.0 / 3)
+    v = s.views(grad)
+    for k in g1:
+        ref = g1[k] + g2[k]
+        if float(ref.abs().max()) > 1e-7:
+            assert rel_err(v[k], ref) < TOL_GRAD, k
+
+
+def test_external_dpred_backward_matches_fused_ce():
+    """Transformer.forward returns pred; a caller may push its own d(loss)/d(pred) (autograd drop-in)."""
+    cfg = ref_asr.SMALL
+    p = ref_asr.init_params(cfg, 6)
+    s = _session(cfg)
+    b = ref_meta.synth_batch(cfg, 4, 41, 7, 3, tgt_lengths=[7, 4, 6, 2])
+    theta, ga, gb = s.new_arena(), s.new_arena(), s.new_arena()
+    s.load(theta, p)
+    out = s.forward(theta, to_batch(b))
+    pred = out["pred"].clone().requires_grad_(True)
+    loss = torch.nn.functional.cross_entropy(pred.view(-1, cfg.vocab), out["gold"].view(-1).long(), ignore_index=0)
+    loss.backward()
+    s.backward(theta, ga, 1.0, dpred=pred.grad)
+    s.forward(theta, to_batch(b)); s.backward(theta, gb, 1.0)
+    assert rel_err(ga, gb) < 1e-5
+
+
+def _meta_run(s, p, steps, lr, meta_lr, clip=False, max_norm=400.0):
+    theta, theta0, grad, cg = (s.new_arena() for _ in range(4))
+    m, v, st = s.new_arena(), s.new_arena(), s.new_adam_state()
+    s.load(theta, p)
+    losses = []
+    for tasks, val in steps:
+        n = len(tasks)
+        res = torch.zeros(n, 16, device=dev())
+        s.copy(theta0, theta)
+        s.zero(cg)
+        vb = to_batch(val)
+        for i, tr in enumerate(tasks):
+            s.meta_task(theta, theta0, grad, cg, to_batch(tr), vb, lr, 1.0 / n, clip=clip, max_norm=max_norm,
+                        results=res[i])
+        assert torch.equal(theta, theta0), "theta not restored to theta0 after the task loop"
+        s.meta_finish(theta, grad, cg, m, v, st, meta_lr, clip=clip, max_norm=max_norm)
+        losses.append(float(res[:, 8].mean()))
+    torch.cuda.synchronize()
+    return losses, s.views(cg), s.views(theta)
+
+
+@pytest.mark.parametrize("clip", [False, True])
+def test_small_meta_steps_vs_oracle(clip):
+    cfg = ref_asr.SMALL
+    p = ref_asr.init_params(cfg, 3)
+    steps = []
+    for st in range(3):
+        tasks = [ref_meta.synth_batch(cfg, 4, 41, 7, 100 * st + i,
+                                      lengths=[41, 30, 9, 5] if (st == 1 and i == 0) else None,
+                                      tgt_lengths=[7, 5, 3, 1] if (st == 1 and i == 0) else None) for i in range(3)]
+        steps.append((tasks, ref_meta.synth_batch(cfg, 4, 41, 7, 100 * st + 50)))
+    po = {k: v.clone() for k, v in p.items()}
+    adam = ref_meta.AdamState()
+    ref_losses = []
+    for tasks, val in steps:
+        r = ref_meta.meta_step(po, adam, cfg, tasks, val, lr=1e-2, meta_lr=1e-3, clip=clip, max_norm=0.5)
+        ref_losses.append(r["loss"])
+    losses, cg, theta = _meta_run(_session(cfg), p, steps, 1e-2, 1e-3, clip=clip, max_norm=0.5)
+    for a, b in zip(losses, ref_losses):
+        assert abs(a - b) < max(TOL_OUT * abs(b), 2e-5), (losses, ref_losses)
+    for k in po:
+        ref = r["copy_grad"][k]
+        if float(ref.abs().max()) > 1e-7:
+            assert rel_err(cg[k], ref) < 5 * TOL_GRAD, k
+        d = (theta[k].cpu() - po[k]).abs()
+        if k.endswith("key_linear_b.bias"):          # zero-gradient tensor: Adam amplifies rounding noise
+            assert float(d.max()) <= 2.1 * 1e-3 * 3
+        else:                                         # Adam-normalised update: |step| <= meta_lr
+            assert float((d > 0.05 * 1e-3).float().mean()) <= 2e-3, k
+            assert float(d.max()) <= 2.1 * 1e-3 * 3, k
+
+
+def test_small_meta_golden_from_live_reference():
+    g = np.load(os.path.join(GOLD, "small_meta.npz"))
+    cfg, m = ref_asr.SMALL, mg.SMALL_META
+    p = ref_asr.init_params(cfg, m["seed"])
+    steps = [mg.small_tasks(st) for st in range(m["n_steps"])]
+    losses, cg, theta = _meta_run(_session(cfg), p, steps, m["lr"], m["meta_lr"])
+    for a, b in zip(losses, g["losses"]):
+        assert abs(a - b) < 2e-4
+    for name, _ in ref_asr.param_specs(cfg):
+        ref = torch.from_numpy(g["copy_grad/" + name])
+        if float(ref.abs().max()) > 1e-7:
+            assert rel_err(cg[name], ref) < 5 * TOL_GRAD, name
+
+
+@pytest.mark.timeout(900)
+def test_cfg2_fwd_bwd_golden_from_live_reference():
+    """BASELINE cfg 2 shapes (enc2/dec4/d512, B=8, T=101, L=32, ragged): loss, indices, pred samples and
+    per-tensor gradient norms/samples recorded from the live reference."""
+    g = np.load(os.path.join(GOLD, "cfg2_fwd_bwd.npz"))
+    cfg = ref_asr.CFG2
+    p = ref_asr.init_params(cfg, 31)
+    out, pred, grads = _fwd_bwd(_session(cfg), p, mg.cfg2_batch(3100, ragged=True))
+    assert np.array_equal(out["gold"].cpu().numpy(), g["gold"])
+    keep = g["gold"] != 0
+    assert np.array_equal(out["hyp"].cpu().numpy()[keep], g["hyp"][keep])
+    assert abs(float(out["ce"][0]) - float(g["loss"])) < TOL_OUT * float(g["loss"])
+    assert int(out["ce"][2]) == int(g["num_correct"])
+    flat = pred.reshape(-1).cpu()
+    ps = flat[torch.from_numpy(mg.pred_sample_idx(flat.numel()))]
+    assert rel_err(ps, torch.from_numpy(g["pred_samples"])) < TOL_OUT
+    assert abs(float(pred.double().norm()) - float(g["pred_norm"])) < TOL_OUT * float(g["pred_norm"])
+    for name, _ in ref_asr.param_specs(cfg):
+        gn = float(g["gnorm/" + name])
+        v = grads[name].cpu()
+        if gn > 1e-6:
+            assert abs(float(v.double().norm()) - gn) < TOL_GRAD * gn, name
+            s = v.reshape(-1)[torch.from_numpy(mg.sample_idx(v.numel()))]
+            assert float((s - torch.from_numpy(g["gsamp/" + name])).abs().max()) < TOL_GRAD * gn, name
+
+
+@pytest.mark.timeout(900)
+def test_cfg2_meta_step_golden_from_live_reference():
+    """One full cfg-2 meta-step (3 tasks x (8 train + 8 val)) vs the unchanged TransientTrainer."""
+    g = np.load(os.path.join(GOLD, "cfg2_meta.npz"))
+    cfg, m = ref_asr.CFG2, mg.CFG2_META
+    p = ref_asr.init_params(cfg, m["seed"])
+    tasks, val = mg.cfg2_tasks()
+    losses, cg, theta = _meta_run(_session(cfg), p, [(tasks, val)], m["lr"], m["meta_lr"])
+    assert abs(losses[0] - float(g["losses"][0])) < 2e-4 * float(g["losses"][0])
+    n_bad = n_tot = 0
+    for name, _ in ref_asr.param_specs(cfg):
+        gn = float(g["cgnorm/" + name])
+        idx = torch.from_numpy(mg.sample_idx(cg[name].numel()))
+        if gn > 1e-6:
+            assert abs(float(cg[name].double().norm()) - gn) < 5 * TOL_GRAD * gn, name
+            s = cg[name].reshape(-1).cpu()[idx]
+            assert float((s - torch.from_numpy(g["cgsamp/" + name])).abs().max()) < 5 * TOL_GRAD * gn, name
+        # first Adam step: delta = -meta_lr * g/(|g|+eps) -> sign agreement wherever |g| is not ~0
+        delta = (theta[name].cpu() - p[name]).reshape(-1)[idx]
+        ref_d = torch.from_numpy(g["dsamp/" + name])
+        big = torch.from_numpy(np.abs(g["cgsamp/" + name])) > 1e-6
+        n_bad += int(((delta - ref_d).abs() > 0.05 * m["meta_lr"])[big].sum())
+        n_tot += int(big.sum())
+    assert n_bad <= 0.002 * n_tot, (n_bad, n_tot)
+
+
+def test_full_size_properties_cfg2():
+    """Size-independent properties at BASELINE cfg-2 size: zero loss-scale gives exactly zero gradient
+    contribution; gradient is linear in the loss scale; meta_task restores theta bit-exactly and
+    copy_grad accumulates exactly what backward left in grad."""
+    cfg = ref_asr.CFG2
+    s = _session(cfg)
+    p = ref_asr.init_params(cfg, 7)
+    theta, theta0, grad, g2, cg = (s.new_arena() for _ in range(5))
+    s.load(theta, p)
+    s.copy(theta0, theta)
+    tr, va = to_batch(mg.cfg2_batch(1)), to_batch(mg.cfg2_batch(2))
+    s.forward(theta, tr); s.backward(theta, grad, 0.0)
+    assert float(grad.abs().max()) == 0.0
+    s.forward(theta, tr); s.backward(theta, grad, 1.0)
+    s.forward(theta, tr); s.backward(theta, g2, 0.25)
+    assert rel_err(g2 * 4, grad) < 1e-4
+    res = torch.zeros(16, device=dev())
+    s.meta_task(theta, theta0, g2, cg, tr, va, 1e-4, 1.0 / 3, results=res)
+    assert torch.equal(theta, theta0)
+    assert torch.equal(cg, g2)
+    assert float(res[0]) > 0 and float(res[8]) > 0 and int(res[1]) == 8 * 33
+
+
+def test_dropout_pass_is_deterministic_given_seed_and_unbiased():
+    cfg = ref_asr.SMALL
+    s = _session(cfg)
+    p = ref_asr.init_params(cfg, 8)
+    b = ref_meta.synth_batch(cfg, 4, 41, 7, 4)
+    o1, pred1, g1 = _fwd_bwd(s, p, b, dropout=0.1, seed=42)
+    g1 = {k: v.clone() for k, v in g1.items()}
+    o2, pred2, g2 = _fwd_bwd(s, p, b, dropout=0.1, seed=42)
+    assert torch.equal(pred1, pred2)
+    o3, pred3, _ = _fwd_bwd(s, p, b, dropout=0.1, seed=43)
+    assert not torch.equal(pred1, pred3)
+    o0, pred0, _ = _fwd_bwd(s, p, b, dropout=0.0)
+    assert 0.0 < rel_err(pred1, pred0) < 1.0
