@@ -111,7 +111,7 @@ int mtl_meta_task(mtl_session* s, float* theta, const float* theta0, float* grad
 /* transient_trainer.py:248-255: grad <- copy_grad; [clip]; theta <- Adam(theta, grad).
  * adam_state (device): int step, float step_size, float bc2_sqrt, pad (16 bytes). */
 int mtl_meta_finish(float* theta, float* grad, const float* copy_grad, float* adam_m, float* adam_v,
-                    void* adam_state, float meta_lr, int clip, float max_norm, float* scratch1032,
+                    void* adam_state, double meta_lr, int clip, float max_norm, float* scratch1032,
                     long long n, void* stream);
 
 /* ------------------------------------------------------------------ flat-arena ops
@@ -122,8 +122,8 @@ int mtl_arena_copy(float* dst, const float* src, long long n, void* stream);
 int mtl_arena_axpy(float* y, const float* x, float a, long long n, void* stream);
 int mtl_arena_sgd(float* p, const float* g, float lr, long long n, void* stream);
 int mtl_arena_clip(float* g, long long n, float max_norm, float* scratch1032, void* stream);
-int mtl_arena_adam(float* p, const float* g, float* m, float* v, void* adam_state, float lr, float b1,
-                   float b2, float eps, long long n, void* stream);
+int mtl_arena_adam(float* p, const float* g, float* m, float* v, void* adam_state, double lr, double b1,
+                   double b2, double eps, long long n, void* stream);
 
 /* ------------------------------------------------------------------ single operators (unit-test surface) */
 /* nn.Linear / its two backward contractions: C = epi(alpha*op(A)op(B)+bias)+beta*C, row-major.

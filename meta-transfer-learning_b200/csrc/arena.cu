@@ -44,10 +44,10 @@ struct SgdF { float* p; const float* g; float lr;
   __device__ void one(size_t i) { p[i] -= lr * g[i]; } };
 
 struct AdamF {
-  float* p; const float* g; float* m; float* v; const float* coef; float b1, b2, eps;
+  float* p; const float* g; float* m; float* v; const float* coef; float b2, omb1, omb2, eps;
   __device__ __forceinline__ void upd(float& pp, float gg, float& mm, float& vv, float step_size, float bc2s) {
-    mm = mm + (1.f - b1) * (gg - mm);                 // exp_avg.lerp_(grad, 1-beta1)
-    vv = vv * b2 + (1.f - b2) * gg * gg;              // exp_avg_sq.mul_(b2).addcmul_(g,g,1-b2)
+    mm = mm + omb1 * (gg - mm);                       // exp_avg.lerp_(grad, 1-beta1)
+    vv = vv * b2 + omb2 * gg * gg;                   // exp_avg_sq.mul_(b2).addcmul_(g,g,1-b2)
     float denom = sqrtf(vv) / bc2s + eps;
     pp = pp - step_size * (mm / denom);
   }
@@ -77,22 +77,23 @@ int k_copy(float* d, const float* src, size_t n, cudaStream_t s) { MTL_REQUIRE(a
 int k_axpy(float* y, const float* x, float a, size_t n, cudaStream_t s) { MTL_REQUIRE(al16(y) && al16(x), "arena not 16B aligned"); AxpyF f{y, x, a}; LAUNCH_EW(f, n, s); }
 int k_scale_by_dev(float* y, const float* c, size_t n, cudaStream_t s) { MTL_REQUIRE(al16(y), "arena not 16B aligned"); ScaleDevF f{y, c}; LAUNCH_EW(f, n, s); }
 int k_sgd(float* p, const float* g, float lr, size_t n, cudaStream_t s) { MTL_REQUIRE(al16(p) && al16(g), "arena not 16B aligned"); SgdF f{p, g, lr}; LAUNCH_EW(f, n, s); }
-int k_adam(float* p, const float* g, float* m, float* v, const float* coef, float b1, float b2, float eps,
+int k_adam(float* p, const float* g, float* m, float* v, const float* coef, double b1, double b2, double eps,
            size_t n, cudaStream_t s) {
   MTL_REQUIRE(al16(p) && al16(g) && al16(m) && al16(v), "arena not 16B aligned");
-  AdamF f{p, g, m, v, coef, b1, b2, eps};
+  // scalars are rounded to fp32 from double exactly as torch does for Python-float hyper-parameters
+  AdamF f{p, g, m, v, coef, (float)b2, (float)(1.0 - b1), (float)(1.0 - b2), (float)eps};
   LAUNCH_EW(f, n, s);
 }
 
-__global__ void adam_prep_kernel(int* step, float* coef, float lr, float b1, float b2) {
+__global__ void adam_prep_kernel(int* step, float* coef, double lr, double b1, double b2) {
   int t = *step + 1;
   *step = t;
-  double bc1 = 1.0 - pow((double)b1, (double)t);
-  double bc2 = 1.0 - pow((double)b2, (double)t);
-  coef[0] = (float)((double)lr / bc1);
+  double bc1 = 1.0 - pow(b1, (double)t);
+  double bc2 = 1.0 - pow(b2, (double)t);
+  coef[0] = (float)(lr / bc1);
   coef[1] = (float)sqrt(bc2);
 }
-int k_adam_prep(int* step_dev, float* coef2_dev, float lr, float b1, float b2, cudaStream_t s) {
+int k_adam_prep(int* step_dev, float* coef2_dev, double lr, double b1, double b2, cudaStream_t s) {
   adam_prep_kernel<<<1, 1, 0, s>>>(step_dev, coef2_dev, lr, b1, b2);
   MTL_CHECK_LAUNCH();
   return MTL_OK;

@@ -660,8 +660,8 @@ extern "C" int mtl_meta_task(mtl_session* s, float* theta, const float* theta0, 
 
 struct AdamState { int step; float step_size; float bc2_sqrt; float pad; };
 
-extern "C" int mtl_arena_adam(float* p, const float* g, float* m, float* v, void* adam_state, float lr, float b1,
-                              float b2, float eps, long long n, void* stream) {
+extern "C" int mtl_arena_adam(float* p, const float* g, float* m, float* v, void* adam_state, double lr, double b1,
+                              double b2, double eps, long long n, void* stream) {
   MTL_REQUIRE(p && g && m && v && adam_state && n >= 0, "null argument");
   AdamState* a = (AdamState*)adam_state;
   cudaStream_t st = (cudaStream_t)stream;
@@ -677,13 +677,13 @@ extern "C" int mtl_arena_clip(float* g, long long n, float max_norm, float* scra
   return MTL_OK;
 }
 extern "C" int mtl_meta_finish(float* theta, float* grad, const float* copy_grad, float* adam_m, float* adam_v,
-                               void* adam_state, float meta_lr, int clip, float max_norm, float* scratch1032,
+                               void* adam_state, double meta_lr, int clip, float max_norm, float* scratch1032,
                                long long n, void* stream) {
   MTL_REQUIRE(theta && grad && copy_grad && adam_m && adam_v && adam_state, "null argument");
   cudaStream_t st = (cudaStream_t)stream;
   MTL_TRY(k_copy(grad, copy_grad, (size_t)n, st));                                  // model.from_copy_grad()
   if (clip) MTL_TRY(mtl_arena_clip(grad, n, max_norm, scratch1032, stream));
-  MTL_TRY(mtl_arena_adam(theta, grad, adam_m, adam_v, adam_state, meta_lr, 0.9f, 0.999f, 1e-8f, n, stream));
+  MTL_TRY(mtl_arena_adam(theta, grad, adam_m, adam_v, adam_state, meta_lr, 0.9, 0.999, 1e-8, n, stream));
   return MTL_OK;
 }
 extern "C" int mtl_arena_zero(float* p, long long n, void* stream) { return k_zero(p, (size_t)n, (cudaStream_t)stream); }

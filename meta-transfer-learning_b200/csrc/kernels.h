@@ -19,9 +19,9 @@ int k_sgd(float* p, const float* g, float lr, size_t n, cudaStream_t s);        
 int k_clip_coef(const float* g, size_t n, float max_norm, float* partial, float* out2, cudaStream_t s);
 // Adam (torch.optim.Adam defaults).  state3 = {int step, float step_size, float bc2_sqrt} on
 // device; k_adam_prep increments step and refreshes the two floats so the step is graph-safe.
-int k_adam_prep(int* step_dev, float* coef2_dev, float lr, float b1, float b2, cudaStream_t s);
-int k_adam(float* p, const float* g, float* m, float* v, const float* coef2_dev, float b1, float b2,
-           float eps, size_t n, cudaStream_t s);
+int k_adam_prep(int* step_dev, float* coef2_dev, double lr, double b1, double b2, cudaStream_t s);
+int k_adam(float* p, const float* g, float* m, float* v, const float* coef2_dev, double b1, double b2,
+           double eps, size_t n, cudaStream_t s);
 
 // ----------------------------------------------------------------------------- gemm_simt.cu / gemm_tc.cu
 enum { EPI_NONE = 0, EPI_RELU = 1, EPI_RELU_BWD = 2 };

@@ -36,6 +36,7 @@ class MetaHParams(C.Structure):
 
 
 _P, _I, _F, _LL, _ULL, _U = C.c_void_p, C.c_int, C.c_float, C.c_longlong, C.c_ulonglong, C.c_uint
+_D = C.c_double
 
 # name -> (restype, argtypes); every symbol include/mtl_b200.h declares
 SIGNATURES = {
@@ -53,13 +54,13 @@ SIGNATURES = {
     "mtl_asr_backward": (_I, [_P, _P, _P, _F, _P, _I, _P]),
     "mtl_meta_task": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _LL, C.POINTER(CBatch), C.POINTER(CBatch),
                            C.POINTER(MetaHParams), _P, _P]),
-    "mtl_meta_finish": (_I, [_P, _P, _P, _P, _P, _P, _F, _I, _F, _P, _LL, _P]),
+    "mtl_meta_finish": (_I, [_P, _P, _P, _P, _P, _P, _D, _I, _F, _P, _LL, _P]),
     "mtl_arena_zero": (_I, [_P, _LL, _P]),
     "mtl_arena_copy": (_I, [_P, _P, _LL, _P]),
     "mtl_arena_axpy": (_I, [_P, _P, _F, _LL, _P]),
     "mtl_arena_sgd": (_I, [_P, _P, _F, _LL, _P]),
     "mtl_arena_clip": (_I, [_P, _LL, _F, _P, _P]),
-    "mtl_arena_adam": (_I, [_P, _P, _P, _P, _P, _F, _F, _F, _F, _LL, _P]),
+    "mtl_arena_adam": (_I, [_P, _P, _P, _P, _P, _D, _D, _D, _D, _LL, _P]),
     "mtl_gemm": (_I, [_I, _I, _I, _I, _I, _I, _F, _P, _I, _P, _I, _F, _P, _I, _P, _I, _P, _I, _P]),
     "mtl_ln_fwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _F, _ULL, _U, _P, _P, _P, _I, _I, _P]),
     "mtl_ln_bwd": (_I, [_P, _P, _P, _P, _P, _F, _ULL, _U, _P, _P, _I, _P, _P, _I, _I, _P]),

@@ -145,6 +145,7 @@ class Session:
         _l.check(self.lib.mtl_asr_forward(self._h, _ptr(theta), _ptr(self.pe_enc), _ptr(self.pe_dec), _ptr(ws),
                                           ws.numel(), C.byref(cb), float(dropout), int(seed), float(smoothing),
                                           _stream(), C.byref(pred_p), C.byref(ldp)))
+        self._live = (b, theta)               # keep the inputs alive until backward() has been enqueued
         off = pred_p.value - ws.data_ptr()
         flat = ws[off:off + B * n * ldp.value * 4].view(torch.float32)
         pred = flat.view(B, n, ldp.value)[:, :, :self.spec.vocab]

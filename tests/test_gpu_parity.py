@@ -175,7 +175,7 @@ def test_small_meta_golden_from_live_reference():
     steps = [mg.small_tasks(st) for st in range(m["n_steps"])]
     losses, cg, theta = _meta_run(_session(cfg), p, steps, m["lr"], m["meta_lr"])
     for a, b in zip(losses, g["losses"]):
-        assert abs(a - b) < 2e-4
+        assert abs(a - b) < 6e-4          # the reference prints the loss with 3 decimals
     for name, _ in ref_asr.param_specs(cfg):
         ref = torch.from_numpy(g["copy_grad/" + name])
         if float(ref.abs().max()) > 1e-7:
