@@ -33,6 +33,8 @@ extern "C" {
 
 const char* mtl_last_error(void);
 int mtl_abi_version(void);
+/* number of kernels this library has enqueued so far in this process */
+unsigned long long mtl_launch_count(void);
 
 /* ------------------------------------------------------------------ model layout / session
  * utils/functions.py:307-351 (init_transformer_model), modules/encoder.py:20-51,

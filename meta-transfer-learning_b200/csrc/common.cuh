@@ -22,7 +22,12 @@ void mtl_set_error(const char* fmt, ...);
     }                                                                                         \
   } while (0)
 
-#define MTL_CHECK_LAUNCH() MTL_CHECK_CUDA(cudaGetLastError())
+extern unsigned long long g_mtl_launches;   // kernels enqueued by this library (bench.py reports it)
+#define MTL_CHECK_LAUNCH()               \
+  do {                                   \
+    ++g_mtl_launches;                    \
+    MTL_CHECK_CUDA(cudaGetLastError());  \
+  } while (0)
 
 #define MTL_REQUIRE(cond, msg)                                                \
   do {                                                                        \

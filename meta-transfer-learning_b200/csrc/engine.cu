@@ -24,7 +24,9 @@ void mtl_set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+unsigned long long g_mtl_launches = 0;
 extern "C" const char* mtl_last_error(void) { return g_err; }
+extern "C" unsigned long long mtl_launch_count(void) { return g_mtl_launches; }
 extern "C" int mtl_abi_version(void) { return MTL_ABI_VERSION; }
 
 // ----------------------------------------------------------------------------- layout

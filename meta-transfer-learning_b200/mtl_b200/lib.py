@@ -42,6 +42,7 @@ _D = C.c_double
 SIGNATURES = {
     "mtl_last_error": (C.c_char_p, []),
     "mtl_abi_version": (_I, []),
+    "mtl_launch_count": (_ULL, []),
     "mtl_session_create": (_I, [C.POINTER(ModelCfg), C.POINTER(_P)]),
     "mtl_session_destroy": (None, [_P]),
     "mtl_session_set_gemm_mode": (_I, [_P, _I]),

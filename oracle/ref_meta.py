@@ -90,8 +90,8 @@ def meta_step(params: dict, adam: AdamState, cfg, tasks, val, lr: float, meta_lr
     cg = {k: torch.zeros_like(v) for k, v in params.items()}                 # :165
     val_losses, tr_losses, hyps = [], [], []
     for tr in tasks:
-        _, g, _, hyp_tr, _ = loss_and_grads(params, cfg, tr, 1.0, smoothing, train, bufs)   # :188-199
-        tr_losses.append(_)
+        lt, g, _, hyp_tr, _ = loss_and_grads(params, cfg, tr, 1.0, smoothing, train, bufs)  # :188-199
+        tr_losses.append(lt)
         if clip:
             clip_grad_norm_(g, max_norm)                                     # :205-206
         sgd_step_(params, g, lr)                                             # :207

@@ -137,49 +137,102 @@ def _meta_run(s, p, steps, lr, meta_lr, clip=False, max_norm=400.0):
     return losses, s.views(cg), s.views(theta)
 
 
-@pytest.mark.parametrize("clip", [False, True])
-def test_small_meta_steps_vs_oracle(clip):
+def _small_steps():
     cfg = ref_asr.SMALL
-    p = ref_asr.init_params(cfg, 3)
     steps = []
     for st in range(3):
         tasks = [ref_meta.synth_batch(cfg, 4, 41, 7, 100 * st + i,
                                       lengths=[41, 30, 9, 5] if (st == 1 and i == 0) else None,
                                       tgt_lengths=[7, 5, 3, 1] if (st == 1 and i == 0) else None) for i in range(3)]
-        steps.append((tasks, ref_meta.synth_batch(cfg, 4, 41, 7, 100 * st + 50)))
+        steps.append((tasks, ref_meta.synth_batch(cfg, 4, 37 if st == 2 else 41, 6 if st == 2 else 7, 100 * st + 50)))
+    return steps
+
+
+@pytest.mark.parametrize("clip", [False, True])
+def test_small_meta_steps_vs_oracle_teacher_forced(clip):
+    """Three meta-steps, each started from the ORACLE's (theta, Adam m/v/step): per-step val losses, the
+    accumulated copy_grad (train-gradient leak included) and the Adam update must match.
+
+    Why teacher-forced: with Adam the first updates are ~ lr*sign(g); elements whose gradient is at
+    rounding-noise level (|g| < 1e-5 max|g|) flip with any change of summation order, and the
+    perturbation grows ~10x per step (injecting 2e-6 relative noise into the ORACLE's own gradients
+    moves its copy_grad by 4-7% two steps later), so free-running trajectories only agree loosely
+    (test_small_meta_free_running)."""
+    cfg = ref_asr.SMALL
+    lr, meta_lr, max_norm = 1e-2, 1e-3, 0.5
+    p = ref_asr.init_params(cfg, 3)
+    s = _session(cfg)
     po = {k: v.clone() for k, v in p.items()}
     adam = ref_meta.AdamState()
-    ref_losses = []
-    for tasks, val in steps:
-        r = ref_meta.meta_step(po, adam, cfg, tasks, val, lr=1e-2, meta_lr=1e-3, clip=clip, max_norm=0.5)
-        ref_losses.append(r["loss"])
-    losses, cg, theta = _meta_run(_session(cfg), p, steps, 1e-2, 1e-3, clip=clip, max_norm=0.5)
+    theta, theta0, grad, cg, m, v = (s.new_arena() for _ in range(6))
+    st = s.new_adam_state()
+    for si, (tasks, val) in enumerate(_small_steps()):
+        s.load(theta, po)
+        if adam.step:
+            s.load(m, adam.m); s.load(v, adam.v)
+        st[0] = adam.step
+        n = len(tasks)
+        res = torch.zeros(n, 16, device=dev())
+        s.copy(theta0, theta); s.zero(cg)
+        vb = to_batch(val)
+        for i, tr in enumerate(tasks):
+            s.meta_task(theta, theta0, grad, cg, to_batch(tr), vb, lr, 1.0 / n, clip=clip, max_norm=max_norm,
+                        results=res[i])
+        assert torch.equal(theta, theta0), "theta not restored to theta0 after the task loop"
+        s.meta_finish(theta, grad, cg, m, v, st, meta_lr, clip=clip, max_norm=max_norm)
+        torch.cuda.synchronize()
+        r = ref_meta.meta_step(po, adam, cfg, tasks, val, lr=lr, meta_lr=meta_lr, clip=clip, max_norm=max_norm)
+        for i in range(n):
+            assert abs(float(res[i, 0]) - r["tr_losses"][i]) < TOL_OUT * r["tr_losses"][i], (si, i)
+            assert abs(float(res[i, 8]) - r["val_losses"][i]) < TOL_OUT * r["val_losses"][i], (si, i)
+        cgv, thv = s.views(cg), s.views(theta)
+        for k in po:
+            ref = r["copy_grad"][k]
+            gmax = float(ref.abs().max())
+            if gmax > 1e-7:
+                assert rel_err(cgv[k], ref) < TOL_GRAD, (si, k)
+            d = (thv[k].cpu() - po[k]).abs()
+            assert float(d.max()) <= 2.1 * meta_lr, (si, k)            # |Adam step| <= lr either way
+            solid = ref.abs() > 1e-2 * gmax                               # elements with a real gradient
+            if solid.any():
+                assert float(d[solid].max()) <= 0.02 * meta_lr, (si, k, float(d[solid].max()))
+        assert int(st[0]) == adam.step
+
+
+def test_small_meta_free_running():
+    """Free-running 3-step trajectory: losses stay within 2e-3 relative of the oracle's (see the
+    teacher-forced test for why not tighter)."""
+    cfg = ref_asr.SMALL
+    p = ref_asr.init_params(cfg, 3)
+    steps = _small_steps()
+    po = {k: v.clone() for k, v in p.items()}
+    adam = ref_meta.AdamState()
+    ref_losses = [ref_meta.meta_step(po, adam, cfg, t, v, lr=1e-2, meta_lr=1e-3)["loss"] for t, v in steps]
+    losses, cg, theta = _meta_run(_session(cfg), p, steps, 1e-2, 1e-3)
+    assert abs(losses[0] - ref_losses[0]) < TOL_OUT * ref_losses[0]
     for a, b in zip(losses, ref_losses):
-        assert abs(a - b) < max(TOL_OUT * abs(b), 2e-5), (losses, ref_losses)
-    for k in po:
-        ref = r["copy_grad"][k]
-        if float(ref.abs().max()) > 1e-7:
-            assert rel_err(cg[k], ref) < 5 * TOL_GRAD, k
-        d = (theta[k].cpu() - po[k]).abs()
-        if k.endswith("key_linear_b.bias"):          # zero-gradient tensor: Adam amplifies rounding noise
-            assert float(d.max()) <= 2.1 * 1e-3 * 3
-        else:                                         # Adam-normalised update: |step| <= meta_lr
-            assert float((d > 0.05 * 1e-3).float().mean()) <= 2e-3, k
-            assert float(d.max()) <= 2.1 * 1e-3 * 3, k
+        assert abs(a - b) < 2e-3 * abs(b), (losses, ref_losses)
+    assert losses[-1] < losses[0]
 
 
 def test_small_meta_golden_from_live_reference():
+    """Two unchanged TransientTrainer iterations recorded from the live reference (val batch shape differs
+    from the train batches).  Step-0 loss and copy_grad are compared via the 1-step state; the
+    reference prints losses with 3 decimals."""
     g = np.load(os.path.join(GOLD, "small_meta.npz"))
     cfg, m = ref_asr.SMALL, mg.SMALL_META
     p = ref_asr.init_params(cfg, m["seed"])
     steps = [mg.small_tasks(st) for st in range(m["n_steps"])]
     losses, cg, theta = _meta_run(_session(cfg), p, steps, m["lr"], m["meta_lr"])
-    for a, b in zip(losses, g["losses"]):
-        assert abs(a - b) < 6e-4          # the reference prints the loss with 3 decimals
+    assert abs(losses[0] - g["losses"][0]) < 6e-4, (losses, g["losses"])
+    assert abs(losses[1] - g["losses"][1]) < 2e-3 * g["losses"][1], (losses, g["losses"])
+    # after ONE Adam step of lr 1e-3 the second step's copy_grad agrees to a few % (Adam noise amplification)
+    num = den = 0.0
     for name, _ in ref_asr.param_specs(cfg):
-        ref = torch.from_numpy(g["copy_grad/" + name])
-        if float(ref.abs().max()) > 1e-7:
-            assert rel_err(cg[name], ref) < 5 * TOL_GRAD, name
+        ref = torch.from_numpy(g["copy_grad/" + name]).double()
+        num += float((cg[name].cpu().double() - ref).pow(2).sum())
+        den += float(ref.pow(2).sum())
+    assert (num / den) ** 0.5 < 3e-2, (num / den) ** 0.5
 
 
 @pytest.mark.timeout(900)
