@@ -180,17 +180,20 @@ def run_ours(args, rank, world, local_rank):
         tasks = [synth_task(spec, K_TRAIN, 1000 * i + rank * n_local + t) for t in range(n_local)]
         val = synth_task(spec, K_VALID, 1000 * i + 999)
         host.append(([tuple(t.pin_memory() for t in b) for b in tasks], tuple(t.pin_memory() for t in val)))
-    resident = [([mtl_b200.Batch.from_host(*b, device=dev) for b in tasks], mtl_b200.Batch.from_host(*val, device=dev))
-                for tasks, val in host]
-    results = torch.zeros(total_steps, n_local, 16, device=dev)
+    resident = [([tuple(t.to(dev) for t in b) for b in tasks], tuple(t.to(dev) for t in val)) for tasks, val in host]
+    n_tok = L_TOKENS + 1
+    stepper = mtl_b200.MetaStepper(s, n_local, n_lanes=args.lanes or n_local, use_graph=not args.no_graph)
+    all_results = torch.zeros(total_steps, n_local, 16, device=dev)
     torch.cuda.synchronize()
 
     def meta_step(i, tasks, val):
-        s.copy(theta0, theta)                                   # weights_original = deepcopy(state_dict)
-        s.zero(cg)                                              # model.zero_copy_grad()
-        for t, tr in enumerate(tasks):
-            s.meta_task(theta, theta0, grad, cg, tr, val, LR, 1.0 / n_total, dropout=DROPOUT,
-                        seed=(i * 1000 + rank * n_local + t), results=results[i, t])
+        # snapshot / reset of the weights (transient_trainer.py:160,237) are folded into the per-lane
+        # theta copies inside mtl_meta_tasks; theta itself only changes in the Adam step below
+        for t, b in enumerate(tasks):
+            stepper.load_task(t, *b, n=n_tok)                   # H2D (e2e) or D2D (resident) into the static slots
+        stepper.load_val(*val, n=n_tok)
+        res = stepper.run(theta, cg, LR, 1.0 / n_total, dropout=DROPOUT, seed=i * 64 + rank)
+        all_results[i].copy_(res, non_blocking=True)
         if dist is not None:
             dist.all_reduce(cg, op=dist.ReduceOp.SUM)           # the one exchange step
         s.meta_finish(theta, grad, cg, m, v, adam_state, META_LR)
@@ -218,7 +221,7 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms)
     clk = clocks.stop() if clocks else None
-    losses = results[args.warmup:, :, 8].mean(dim=1).tolist()
+    losses = all_results[args.warmup:, :, 8].mean(dim=1).tolist()
 
     # ---------------- end to end: host (pinned) batches in, losses out, every step
     h2d = sum(t.numel() * t.element_size() for b in host[0][0] for t in b) + \
@@ -228,10 +231,8 @@ def run_ours(args, rank, world, local_rank):
 
     def e2e_step(i):
         tasks, val = host[i]
-        vb = mtl_b200.Batch.from_host(*val, device=dev)
-        tb = [mtl_b200.Batch.from_host(*b, device=dev) for b in tasks]
-        meta_step(i, tb, vb)
-        host_res.copy_(results[i], non_blocking=True)
+        meta_step(i, tasks, val)
+        host_res.copy_(stepper.results, non_blocking=True)
         torch.cuda.current_stream().synchronize()               # the trainer prints the loss every step
         return float(host_res[:, 8].mean())
 
@@ -247,6 +248,7 @@ def run_ours(args, rank, world, local_rank):
     if dist is not None:
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
     ms_e2e = float(ms2)
+    graph_caps, graph_reps = s.graph_stats()
 
     # ---------------- roofline of the dominant kernel: conv.2 forward contraction (130088 x 64 x 576)
     roof = None
@@ -270,6 +272,7 @@ def run_ours(args, rank, world, local_rank):
             "e2e": {"value": u_total * args.steps / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
+            "cuda_graph": {"captures": graph_caps, "replays": graph_reps, "lanes": stepper.n_lanes},
             "clocks": clk,
             "roofline": roof,
             "cpu_baseline": cpu,
@@ -343,8 +346,10 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--gemm-mode", type=int, default=int(os.environ.get("MTL_GEMM_MODE", "0")))
+    ap.add_argument("--gemm-mode", type=int, default=int(os.environ.get("MTL_GEMM_MODE", "2")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="run the meta-step eagerly (no CUDA graph replay)")
+    ap.add_argument("--lanes", type=int, default=0, help="concurrent task lanes (default: one per task)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

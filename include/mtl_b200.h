@@ -110,6 +110,39 @@ int mtl_meta_task(mtl_session* s, float* theta, const float* theta0, float* grad
                   const float* pe_enc, const float* pe_dec, void* workspace, long long workspace_bytes,
                   const mtl_batch* train, const mtl_batch* val, const mtl_meta_hparams* hp,
                   float* results16, void* stream);
+/* ALL tasks of one meta-step (transient_trainer.py:155-237), tasks running concurrently:
+ *   copy_grad <- 0
+ *   task t (on lane t % n_lanes, own stream): theta_l <- theta (replaces deepcopy(state_dict) +
+ *     load_state_dict: theta itself is never modified); the mtl_meta_task body at theta_l;
+ *     copy_grad += grad_l, ordered task 0, 1, 2, ... by events so the fp32 sum has the reference's order.
+ * theta is left untouched; the caller all-reduces copy_grad when the tasks are sharded over GPUs
+ * and then calls mtl_meta_finish.  Dropout seed of task t, pass p (0 train, 1 val): hp.seed*128 + 2t + p.
+ * use_graph != 0 (needs seed_slot, 8 device bytes): the second call with identical pointers, shapes and
+ * hyper-parameters captures the whole step into a CUDA graph; later calls replay it (only hp.seed may
+ * differ -- it is patched into the graph), cutting ~1000 launches per task to one. */
+typedef struct mtl_lane {
+  float* theta;             /* adapted weights of the task running on this lane (arena-sized) */
+  float* grad;              /* its gradient (arena-sized)                                     */
+  void* workspace;          /* >= mtl_workspace_bytes(...) + 8 KiB, 256 B aligned              */
+  long long workspace_bytes;
+} mtl_lane;
+typedef struct mtl_meta_step_args {
+  const float* theta;
+  float* copy_grad;
+  const float* pe_enc;
+  const float* pe_dec;
+  int n_tasks;
+  const mtl_batch* train;   /* n_tasks training batches                                       */
+  const mtl_batch* val;     /* the shared validation batch (transient_trainer.py:168-169)     */
+  int n_lanes;
+  const mtl_lane* lanes;
+  mtl_meta_hparams hp;
+  float* results;           /* n_tasks x 16 floats (device), may be NULL                      */
+  unsigned long long* seed_slot;
+  int use_graph;
+} mtl_meta_step_args;
+int mtl_meta_tasks(mtl_session* s, const mtl_meta_step_args* args, void* stream);
+int mtl_graph_stats(const mtl_session* s, unsigned long long* captures, unsigned long long* replays);
 /* transient_trainer.py:248-255: grad <- copy_grad; [clip]; theta <- Adam(theta, grad).
  * adam_state (device): int step, float step_size, float bc2_sqrt, pad (16 bytes). */
 int mtl_meta_finish(float* theta, float* grad, const float* copy_grad, float* adam_m, float* adam_v,
@@ -158,8 +191,16 @@ int mtl_ce_bwd(const float* logits, int ld, const int* gold, const float* row_ls
 /* VGG front-end pieces (models/asr/transformer.py:47-59,136-138), NHWC */
 int mtl_conv1_fwd(const float* x, const float* w, const float* b, float* out, int B, int F, int T,
                   int Cout, void* stream);
+/* relu(conv3x3(x) + b): mode 0 = im2col (col: B*F*T*9*Cin floats) + fp32 GEMM; modes 1/2 = tcgen05 implicit GEMM
+ * through 4-D TMA boxes (col unused, may be NULL).  wg: Cout*9*Cin floats of scratch. */
 int mtl_conv3x3_relu_fwd(int mode, const float* x, const float* w, const float* b, float* col,
                          float* wg, float* out, int B, int F, int T, int Cin, int Cout, void* stream);
+/* Backward of y = conv3x3(x) + b given dy (gradient w.r.t. the pre-ReLU output): dw += , db += ,
+ * dx = (dgrad) masked by relu_aux > 0 when relu_aux != NULL (dx may be NULL). */
+long long mtl_conv3x3_bwd_scratch_floats(int mode, int B, int F, int T, int Cin, int Cout);
+int mtl_conv3x3_bwd(int mode, const float* x, const float* w, const float* dy, const float* relu_aux,
+                    float* dw, float* db, float* dx, float* scratch, int B, int F, int T, int Cin, int Cout,
+                    void* stream);
 int mtl_maxpool2_fwd(const float* x, float* out, int B, int F, int T, int C, void* stream);
 int mtl_maxpool2_relu_bwd(const float* x, const float* dpool, float* dx, int B, int F, int T, int C,
                           void* stream);

@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(AttnArgs a) {
       m[r] = mn;
       if (a.drop.p > 0.f && ok) {
         unsigned long long idx = (((unsigned long long)(b * a.H + h) * a.Tq + qi) * a.Tk + kj);
-        p *= dropout_scale(a.drop.seed, a.drop.site, idx, a.drop.p, a.drop.inv_keep);
+        p *= dropout_scale(mtl_eff_seed(a.drop), a.drop.site, idx, a.drop.p, a.drop.inv_keep);
       }
 #pragma unroll
       for (int v = 0; v < NV; ++v) acc[r][v] *= corr;
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(128) attn_dq_kernel(AttnBwdArgs a) {
       float p = ok ? __expf(s * f.inv_temp - lse[r]) : 0.f;
       if (f.drop.p > 0.f && ok) {
         unsigned long long idx = (((unsigned long long)(b * f.H + h) * f.Tq + qi) * f.Tk + kj);
-        dp *= dropout_scale(f.drop.seed, f.drop.site, idx, f.drop.p, f.drop.inv_keep);
+        dp *= dropout_scale(mtl_eff_seed(f.drop), f.drop.site, idx, f.drop.p, f.drop.inv_keep);
       }
       const float ds = p * (dp - dl[r]);
 #pragma unroll
@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(128) attn_dkv_kernel(AttnBwdArgs a) {
       float pd = p;
       if (f.drop.p > 0.f && ok) {
         unsigned long long idx = (((unsigned long long)(b * f.H + h) * f.Tq + qi) * f.Tk + kj);
-        float sc = dropout_scale(f.drop.seed, f.drop.site, idx, f.drop.p, f.drop.inv_keep);
+        float sc = dropout_scale(mtl_eff_seed(f.drop), f.drop.site, idx, f.drop.p, f.drop.inv_keep);
         pd = p * sc; dp *= sc;
       }
       const float ds = p * (dp - Ds[lane]);

@@ -100,14 +100,27 @@ __device__ __forceinline__ float dropout_scale(unsigned long long seed, uint32_t
 }
 #endif
 
-// Dropout descriptor passed to kernels (p == 0 disables).
+// Dropout descriptor passed to kernels (p == 0 disables).  The effective Philox seed is
+// seed (+ *seed_dev * seed_mul when seed_dev != null): a device-resident base lets a captured CUDA
+// graph draw fresh masks on every replay.
 struct MtlDrop {
   float p;
   float inv_keep;
   unsigned long long seed;
   uint32_t site;
+  const unsigned long long* seed_dev;
+  unsigned long long seed_mul;
 };
-static inline MtlDrop mtl_nodrop() { MtlDrop d; d.p = 0.f; d.inv_keep = 1.f; d.seed = 0; d.site = 0; return d; }
-static inline MtlDrop mtl_drop(float p, unsigned long long seed, uint32_t site) {
-  MtlDrop d; d.p = p; d.inv_keep = p > 0.f ? 1.f / (1.f - p) : 1.f; d.seed = seed; d.site = site; return d;
+static inline MtlDrop mtl_nodrop() {
+  MtlDrop d; d.p = 0.f; d.inv_keep = 1.f; d.seed = 0; d.site = 0; d.seed_dev = nullptr; d.seed_mul = 0; return d;
 }
+static inline MtlDrop mtl_drop(float p, unsigned long long seed, uint32_t site,
+                               const unsigned long long* seed_dev = nullptr, unsigned long long seed_mul = 0) {
+  MtlDrop d; d.p = p; d.inv_keep = p > 0.f ? 1.f / (1.f - p) : 1.f; d.seed = seed; d.site = site;
+  d.seed_dev = seed_dev; d.seed_mul = seed_mul; return d;
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned long long mtl_eff_seed(const MtlDrop& d) {
+  return d.seed_dev ? __ldg(d.seed_dev) * d.seed_mul + d.seed : d.seed;
+}
+#endif

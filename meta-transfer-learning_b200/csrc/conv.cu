@@ -151,6 +151,16 @@ __global__ void conv_wgrad_scatter_kernel(const float* __restrict__ dwg, float* 
   int tap = i % 9, ci = (i / 9) % Cin, co = i / (9 * Cin);
   dw[i] += dwg[((size_t)co * 9 + tap) * Cin + ci];
 }
+__global__ void conv_wgrad_scatter_t_kernel(const float* __restrict__ dwgT, float* __restrict__ dw, int Cout, int Cin) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;          // over dw [Cout][Cin][9]
+  if (i >= Cout * 9 * Cin) return;
+  int tap = i % 9, ci = (i / 9) % Cin, co = i / (9 * Cin);
+  dw[i] += dwgT[((size_t)tap * Cin + ci) * Cout + co];
+}
+int k_conv_wgrad_scatter_t(const float* dwgT, float* dw, int Cout, int Cin, cudaStream_t s) {
+  conv_wgrad_scatter_t_kernel<<<mtl_cdiv(Cout * 9 * Cin, 256), 256, 0, s>>>(dwgT, dw, Cout, Cin);
+  MTL_CHECK_LAUNCH(); return MTL_OK;
+}
 int k_conv_w_fwd_layout(const float* w, float* wg, int Cout, int Cin, cudaStream_t s) {
   conv_w_fwd_layout_kernel<<<mtl_cdiv(Cout * 9 * Cin, 256), 256, 0, s>>>(w, wg, Cout, Cin);
   MTL_CHECK_LAUNCH(); return MTL_OK;

@@ -135,11 +135,34 @@ struct Pass {
   size_t ws_cap;
 };
 
+// One lane = one concurrently running task of a meta-step: its own stream and activation record.
+struct Lane {
+  cudaStream_t st = nullptr;
+  cudaEvent_t done = nullptr;
+  Pass pass;
+};
+// A captured meta-step (all tasks, all lanes) keyed by every pointer / shape / hyper-parameter baked into it.
+struct GraphEntry {
+  std::vector<unsigned long long> key;
+  int seen = 0;                       // eager runs so far (capture happens on the second sighting)
+  cudaGraph_t graph = nullptr;        // kept alive: seed_node is a handle into it
+  cudaGraphExec_t exec = nullptr;
+  cudaGraphNode_t seed_node = nullptr;
+  unsigned long long kernels = 0;     // kernel nodes per replay (for mtl_launch_count)
+  unsigned long long last_use = 0;
+};
 struct mtl_session {
   mtl_model_cfg cfg;
   Layout L;
   int mode = MTL_GEMM_SIMT_FP32;
-  Pass pass;
+  Pass pass;                          // record of the plain mtl_asr_forward / mtl_meta_task API
+  std::vector<Lane> lanes;
+  cudaEvent_t ev_fork = nullptr;
+  cudaStream_t cap_st = nullptr;      // capture origin (the caller's stream may be the legacy stream, which cannot capture)
+  std::vector<cudaEvent_t> ev_axpy;
+  std::vector<GraphEntry> graphs;
+  unsigned long long tick = 0;
+  unsigned long long graph_replays = 0, graph_captures = 0;
 };
 
 struct Bump {
@@ -159,15 +182,18 @@ struct Bump {
 
 struct Run {
   mtl_session* S;
+  Pass* P;                                    // activation record this run fills / consumes
   cudaStream_t st;
   bool dry;
   Bump ws;
   const float* theta;
   float* grad;
   float p_drop;
-  unsigned long long seed;
+  unsigned long long seed;                    // effective seed = seed + (*seed_dev) * seed_mul
+  const unsigned long long* seed_dev = nullptr;
+  unsigned long long seed_mul = 0;
   uint32_t site;
-  MtlDrop next_drop() { return p_drop > 0.f ? mtl_drop(p_drop, seed, site++) : mtl_nodrop(); }
+  MtlDrop next_drop() { return p_drop > 0.f ? mtl_drop(p_drop, seed, site++, seed_dev, seed_mul) : mtl_nodrop(); }
 };
 
 #define K(call)                        \
@@ -337,12 +363,17 @@ static int conv_fwd(Run& R, ConvAct& A, const float* x, int B, int F, int T, int
   A.x = x; A.B = B; A.F = F; A.T = T; A.Cin = kConvCin[widx]; A.Cout = kConvCout[widx]; A.widx = widx;
   const size_t P = (size_t)B * F * T;
   const int Kc = 9 * A.Cin;
-  A.col = R.ws.f(P * Kc);
+  const bool implicit = R.S->mode != MTL_GEMM_SIMT_FP32;      // tcgen05 implicit GEMM: no patch matrix
+  A.col = implicit ? nullptr : R.ws.f(P * Kc);
   float* wg = R.ws.f((size_t)A.Cout * Kc);
   A.y = R.ws.f(P * A.Cout);
-  K(k_im2col3x3(x, A.col, B, F, T, A.Cin, R.st));
   K(k_conv_w_fwd_layout(R.theta + L.conv_w[widx], wg, A.Cout, A.Cin, R.st));
-  MTL_TRY(lin_fwd(R, A.col, Kc, wg, R.theta + L.conv_b[widx], A.y, A.Cout, (int)P, A.Cout, Kc, EPI_RELU));
+  if (implicit) {
+    K(k_conv3x3_tc(x, wg, R.theta + L.conv_b[widx], A.y, B, F, T, A.Cin, A.Cout, EPI_RELU, nullptr, R.S->mode, R.st));
+  } else {
+    K(k_im2col3x3(x, A.col, B, F, T, A.Cin, R.st));
+    MTL_TRY(lin_fwd(R, A.col, Kc, wg, R.theta + L.conv_b[widx], A.y, A.Cout, (int)P, A.Cout, Kc, EPI_RELU));
+  }
   return MTL_OK;
 }
 // dy = gradient w.r.t. the pre-ReLU conv output.  dx (nullable) = gradient w.r.t. the conv input,
@@ -351,25 +382,36 @@ static int conv_bwd(Run& R, const ConvAct& A, const float* dy, float* dx, const 
   const Layout& L = R.S->L;
   const size_t P = (size_t)A.B * A.F * A.T;
   const int Kc = 9 * A.Cin;
+  const bool implicit = R.S->mode != MTL_GEMM_SIMT_FP32;
   size_t mark = R.ws.off;
   float* dwg = R.ws.f((size_t)A.Cout * Kc);
   K(k_zero(dwg, (size_t)A.Cout * Kc, R.st));
-  MTL_TRY(lin_wgrad(R, dy, A.Cout, A.col, Kc, dwg, (int)P, A.Cout, Kc));
-  K(k_conv_wgrad_scatter(dwg, R.grad + L.conv_w[A.widx], A.Cout, A.Cin, R.st));
+  if (implicit) {
+    K(k_conv3x3_wgrad_tc(A.x, dy, dwg, A.B, A.F, A.T, A.Cin, A.Cout, R.S->mode, R.st));
+    K(k_conv_wgrad_scatter_t(dwg, R.grad + L.conv_w[A.widx], A.Cout, A.Cin, R.st));
+  } else {
+    MTL_TRY(lin_wgrad(R, dy, A.Cout, A.col, Kc, dwg, (int)P, A.Cout, Kc));
+    K(k_conv_wgrad_scatter(dwg, R.grad + L.conv_w[A.widx], A.Cout, A.Cin, R.st));
+  }
   K(k_colsum_acc(dy, (int)P, A.Cout, A.Cout, R.grad + L.conv_b[A.widx], R.st));
   if (dx) {
     const int Kg = 9 * A.Cout;
-    float* colg = R.ws.f(P * Kg);
     float* wd = R.ws.f((size_t)A.Cin * Kg);
-    K(k_im2col3x3(dy, colg, A.B, A.F, A.T, A.Cout, R.st));
     K(k_conv_w_dgrad_layout(R.theta + L.conv_w[A.widx], wd, A.Cout, A.Cin, R.st));
-    // dx[P,Cin] = colg[P,9Cout] . wd[Cin,9Cout]^T
-    GemmArgs g;
-    memset(&g, 0, sizeof(g));
-    g.A = colg; g.lda = Kg; g.transA = 0; g.B = wd; g.ldb = Kg; g.transB = 1; g.C = dx; g.ldc = A.Cin;
-    g.M = (int)P; g.N = A.Cin; g.K = Kg; g.alpha = 1.f; g.beta = 0.f;
-    g.epi = relu_aux ? EPI_RELU_BWD : EPI_NONE; g.aux = relu_aux; g.split_k = 1;
-    K(k_gemm(g, R.S->mode, R.st));
+    if (implicit) {
+      K(k_conv3x3_tc(dy, wd, nullptr, dx, A.B, A.F, A.T, A.Cout, A.Cin, relu_aux ? EPI_RELU_BWD : EPI_NONE, relu_aux,
+                     R.S->mode, R.st));
+    } else {
+      float* colg = R.ws.f(P * Kg);
+      K(k_im2col3x3(dy, colg, A.B, A.F, A.T, A.Cout, R.st));
+      // dx[P,Cin] = colg[P,9Cout] . wd[Cin,9Cout]^T
+      GemmArgs g;
+      memset(&g, 0, sizeof(g));
+      g.A = colg; g.lda = Kg; g.transA = 0; g.B = wd; g.ldb = Kg; g.transB = 1; g.C = dx; g.ldc = A.Cin;
+      g.M = (int)P; g.N = A.Cin; g.K = Kg; g.alpha = 1.f; g.beta = 0.f;
+      g.epi = relu_aux ? EPI_RELU_BWD : EPI_NONE; g.aux = relu_aux; g.split_k = 1;
+      K(k_gemm(g, R.S->mode, R.st));
+    }
   }
   R.ws.off = mark;
   return MTL_OK;
@@ -380,7 +422,7 @@ static int forward(Run& R, const mtl_batch& b, const float* pe_enc, const float*
   mtl_session* S = R.S;
   const mtl_model_cfg& c = S->cfg;
   const Layout& L = S->L;
-  Pass& P = S->pass;
+  Pass& P = *R.P;
   P.valid = false;
   MTL_REQUIRE(b.B > 0 && b.T > 0 && b.L > 0 && b.n >= 2, "empty batch");
   P.b = b;
@@ -474,7 +516,7 @@ static int backward(Run& R, float loss_scale, const float* dpred_ext, int ld_ext
   mtl_session* S = R.S;
   const mtl_model_cfg& c = S->cfg;
   const Layout& L = S->L;
-  Pass& P = S->pass;
+  Pass& P = *R.P;
   const int B = P.B, d = c.d_model, V = c.vocab;
   float* dpred = R.ws.f((size_t)P.Md * P.ldp);
   if (dpred_ext) {
@@ -551,7 +593,15 @@ extern "C" int mtl_session_create(const mtl_model_cfg* cfg, mtl_session** out) {
   *out = s;
   return MTL_OK;
 }
-extern "C" void mtl_session_destroy(mtl_session* s) { delete s; }
+extern "C" void mtl_session_destroy(mtl_session* s) {
+  if (!s) return;
+  for (auto& g : s->graphs) { if (g.exec) cudaGraphExecDestroy(g.exec); if (g.graph) cudaGraphDestroy(g.graph); }
+  for (auto& l : s->lanes) { if (l.done) cudaEventDestroy(l.done); if (l.st) cudaStreamDestroy(l.st); }
+  for (auto e : s->ev_axpy) cudaEventDestroy(e);
+  if (s->ev_fork) cudaEventDestroy(s->ev_fork);
+  if (s->cap_st) cudaStreamDestroy(s->cap_st);
+  delete s;
+}
 extern "C" int mtl_session_set_gemm_mode(mtl_session* s, int mode) {
   MTL_REQUIRE(s && mode >= 0 && mode <= 2, "gemm mode");
   s->mode = mode;
@@ -567,16 +617,16 @@ extern "C" int mtl_param_info(const mtl_session* s, int idx, long long* off, lon
 }
 
 static int dry_plan(mtl_session* s, int B, int T, int n, size_t* bytes) {
+  Pass scratch;
   Run R;
-  R.S = s; R.st = 0; R.dry = true; R.theta = nullptr; R.grad = nullptr; R.p_drop = 0.f; R.seed = 0; R.site = 0;
+  R.S = s; R.P = &scratch; R.st = 0; R.dry = true; R.theta = nullptr; R.grad = nullptr; R.p_drop = 0.f; R.seed = 0;
+  R.site = 0;
   R.ws.base = 0; R.ws.cap = ~(size_t)0;
   mtl_batch b;
   memset(&b, 0, sizeof(b));
   b.B = B; b.T = T; b.L = n > 1 ? n - 1 : 1; b.n = n;
-  Pass saved = s->pass;
   int rc = forward(R, b, nullptr, nullptr, 0.f);
   if (rc == MTL_OK) rc = backward(R, 1.f, nullptr, 0);
-  s->pass = saved;
   *bytes = R.ws.peak + 256;
   return rc;
 }
@@ -598,18 +648,41 @@ static int check_ws(mtl_session* s, const mtl_batch* b, void* ws, long long ws_b
   return MTL_OK;
 }
 
-extern "C" int mtl_asr_forward(mtl_session* s, const float* theta, const float* pe_enc, const float* pe_dec,
-                               void* workspace, long long workspace_bytes, const mtl_batch* batch, float dropout,
-                               unsigned long long seed, float label_smoothing, void* stream, float** pred_out,
-                               int* ldp_out) {
+// forward / backward of one batch on an explicit activation record
+struct SeedRef { unsigned long long seed; const unsigned long long* dev; unsigned long long mul; };
+static int run_forward(mtl_session* s, Pass* pass, const float* theta, const float* pe_enc, const float* pe_dec,
+                       void* workspace, long long workspace_bytes, const mtl_batch* batch, float dropout, SeedRef seed,
+                       float label_smoothing, cudaStream_t st) {
   MTL_REQUIRE(s && theta && pe_enc && pe_dec && batch && batch->x && batch->lens && batch->trg, "null argument");
   MTL_REQUIRE(dropout >= 0.f && dropout < 1.f, "dropout in [0,1)");
   MTL_TRY(check_ws(s, batch, workspace, workspace_bytes));
   Run R;
-  R.S = s; R.st = (cudaStream_t)stream; R.dry = false; R.theta = theta; R.grad = nullptr;
-  R.p_drop = dropout; R.seed = seed; R.site = 0;
+  R.S = s; R.P = pass; R.st = st; R.dry = false; R.theta = theta; R.grad = nullptr;
+  R.p_drop = dropout; R.seed = seed.seed; R.seed_dev = seed.dev; R.seed_mul = seed.mul; R.site = 0;
   R.ws.base = (uintptr_t)workspace; R.ws.cap = (size_t)workspace_bytes;
-  MTL_TRY(forward(R, *batch, pe_enc, pe_dec, label_smoothing));
+  return forward(R, *batch, pe_enc, pe_dec, label_smoothing);
+}
+static int run_backward(mtl_session* s, Pass* pass, const float* theta, float* grad, float loss_scale,
+                        const float* dpred_ext, int ld_ext, cudaStream_t st) {
+  MTL_REQUIRE(s && theta && grad, "null argument");
+  MTL_REQUIRE(pass->valid, "backward without a preceding forward");
+  Run R;
+  R.S = s; R.P = pass; R.st = st; R.dry = false; R.theta = theta; R.grad = grad;
+  R.p_drop = 0.f; R.seed = 0; R.site = 0;
+  R.ws.base = pass->ws_base; R.ws.cap = pass->ws_cap; R.ws.off = pass->ws_after_fwd;
+  MTL_TRY(backward(R, loss_scale, dpred_ext, ld_ext));
+  pass->valid = false;
+  return MTL_OK;
+}
+
+extern "C" int mtl_asr_forward(mtl_session* s, const float* theta, const float* pe_enc, const float* pe_dec,
+                               void* workspace, long long workspace_bytes, const mtl_batch* batch, float dropout,
+                               unsigned long long seed, float label_smoothing, void* stream, float** pred_out,
+                               int* ldp_out) {
+  MTL_REQUIRE(s, "null argument");
+  SeedRef sr = {seed, nullptr, 0};
+  MTL_TRY(run_forward(s, &s->pass, theta, pe_enc, pe_dec, workspace, workspace_bytes, batch, dropout, sr,
+                      label_smoothing, (cudaStream_t)stream));
   if (pred_out) *pred_out = s->pass.pred;
   if (ldp_out) *ldp_out = s->pass.ldp;
   return MTL_OK;
@@ -617,24 +690,16 @@ extern "C" int mtl_asr_forward(mtl_session* s, const float* theta, const float* 
 
 extern "C" int mtl_asr_backward(mtl_session* s, const float* theta, float* grad, float loss_scale,
                                 const float* dpred_ext, int ld_ext, void* stream) {
-  MTL_REQUIRE(s && theta && grad, "null argument");
-  MTL_REQUIRE(s->pass.valid, "mtl_asr_backward without a preceding mtl_asr_forward");
-  Run R;
-  R.S = s; R.st = (cudaStream_t)stream; R.dry = false; R.theta = theta; R.grad = grad;
-  R.p_drop = 0.f; R.seed = 0; R.site = 0;
-  R.ws.base = s->pass.ws_base; R.ws.cap = s->pass.ws_cap; R.ws.off = s->pass.ws_after_fwd;
-  MTL_TRY(backward(R, loss_scale, dpred_ext, ld_ext));
-  s->pass.valid = false;
-  return MTL_OK;
+  MTL_REQUIRE(s, "null argument");
+  return run_backward(s, &s->pass, theta, grad, loss_scale, dpred_ext, ld_ext, (cudaStream_t)stream);
 }
 
 // ----------------------------------------------------------------------------- C ABI: meta-step pieces
-extern "C" int mtl_meta_task(mtl_session* s, float* theta, const float* theta0, float* grad, float* copy_grad,
-                             const float* pe_enc, const float* pe_dec, void* workspace, long long workspace_bytes,
-                             const mtl_batch* train, const mtl_batch* val, const mtl_meta_hparams* hp,
-                             float* results16, void* stream) {
-  MTL_REQUIRE(s && theta && theta0 && grad && copy_grad && train && val && hp, "null argument");
-  cudaStream_t st = (cudaStream_t)stream;
+// One task on one stream: trainer/asr/transient_trainer.py:188-229 at the weights in `theta`
+// (grad <- dCE_train; [clip]; theta -= lr*grad; grad += d(CE_val*val_scale)).
+static int task_body(mtl_session* s, Pass* pass, float* theta, float* grad, const float* pe_enc, const float* pe_dec,
+                     void* workspace, long long workspace_bytes, const mtl_batch* train, const mtl_batch* val,
+                     const mtl_meta_hparams* hp, SeedRef seed_tr, SeedRef seed_va, float* results16, cudaStream_t st) {
   const size_t n = s->L.total;
   // scratch for the clip coefficient lives at the very end of the workspace
   const long long tail = (long long)((MTL_NORM_PARTIALS + 8) * sizeof(float) + 256);
@@ -644,19 +709,197 @@ extern "C" int mtl_meta_task(mtl_session* s, float* theta, const float* theta0, 
   mtl_batch tr = *train, va = *val;
   if (results16) { tr.ce_out = results16; va.ce_out = results16 + 8; }
   MTL_TRY(k_zero(grad, n, st));                                                     // inner_opt.zero_grad()
-  MTL_TRY(mtl_asr_forward(s, theta, pe_enc, pe_dec, workspace, ws_main, &tr, hp->dropout, hp->seed * 2ull + 0ull,
-                          hp->label_smoothing, stream, nullptr, nullptr));
-  MTL_TRY(mtl_asr_backward(s, theta, grad, 1.f, nullptr, 0, stream));              // tr_loss.backward()
+  MTL_TRY(run_forward(s, pass, theta, pe_enc, pe_dec, workspace, ws_main, &tr, hp->dropout, seed_tr,
+                      hp->label_smoothing, st));
+  MTL_TRY(run_backward(s, pass, theta, grad, 1.f, nullptr, 0, st));                 // tr_loss.backward()
   if (hp->clip) {
     MTL_TRY(k_clip_coef(grad, n, hp->max_norm, scratch, scratch + MTL_NORM_PARTIALS, st));
     MTL_TRY(k_scale_by_dev(grad, scratch + MTL_NORM_PARTIALS + 1, n, st));
   }
   MTL_TRY(k_sgd(theta, grad, hp->lr, n, st));                                       // inner_opt.step()
-  MTL_TRY(mtl_asr_forward(s, theta, pe_enc, pe_dec, workspace, ws_main, &va, hp->dropout, hp->seed * 2ull + 1ull,
-                          hp->label_smoothing, stream, nullptr, nullptr));
-  MTL_TRY(mtl_asr_backward(s, theta, grad, hp->val_scale, nullptr, 0, stream));    // (val_loss/N).backward(), no zero_grad
+  MTL_TRY(run_forward(s, pass, theta, pe_enc, pe_dec, workspace, ws_main, &va, hp->dropout, seed_va,
+                      hp->label_smoothing, st));
+  MTL_TRY(run_backward(s, pass, theta, grad, hp->val_scale, nullptr, 0, st));       // (val_loss/N).backward(), no zero_grad
+  return MTL_OK;
+}
+
+extern "C" int mtl_meta_task(mtl_session* s, float* theta, const float* theta0, float* grad, float* copy_grad,
+                             const float* pe_enc, const float* pe_dec, void* workspace, long long workspace_bytes,
+                             const mtl_batch* train, const mtl_batch* val, const mtl_meta_hparams* hp,
+                             float* results16, void* stream) {
+  MTL_REQUIRE(s && theta && theta0 && grad && copy_grad && train && val && hp, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n = s->L.total;
+  SeedRef s0 = {hp->seed * 2ull + 0ull, nullptr, 0}, s1 = {hp->seed * 2ull + 1ull, nullptr, 0};
+  MTL_TRY(task_body(s, &s->pass, theta, grad, pe_enc, pe_dec, workspace, workspace_bytes, train, val, hp, s0, s1,
+                    results16, st));
   MTL_TRY(k_axpy(copy_grad, grad, 1.f, n, st));                                     // model.add_copy_grad()
   MTL_TRY(k_copy(theta, theta0, n, st));                                            // model.load_state_dict(weights_original)
+  return MTL_OK;
+}
+
+// ---- all tasks of one meta-step, concurrently on internal streams, optionally replayed from a CUDA graph
+__global__ void set_u64_kernel(unsigned long long* slot, unsigned long long v) { *slot = v; }
+
+static int ensure_lanes(mtl_session* s, int n_lanes, int n_tasks) {
+  while ((int)s->lanes.size() < n_lanes) {
+    Lane l;
+    MTL_CHECK_CUDA(cudaStreamCreateWithFlags(&l.st, cudaStreamNonBlocking));
+    MTL_CHECK_CUDA(cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming));
+    s->lanes.push_back(l);
+  }
+  if (!s->ev_fork) MTL_CHECK_CUDA(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
+  if (!s->cap_st) MTL_CHECK_CUDA(cudaStreamCreateWithFlags(&s->cap_st, cudaStreamNonBlocking));
+  while ((int)s->ev_axpy.size() < n_tasks) {
+    cudaEvent_t e;
+    MTL_CHECK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    s->ev_axpy.push_back(e);
+  }
+  return MTL_OK;
+}
+
+static int meta_tasks_body(mtl_session* s, const mtl_meta_step_args* a, cudaStream_t st) {
+  const size_t n = s->L.total;
+  const bool dev_seed = a->seed_slot != nullptr;
+  if (dev_seed) {
+    set_u64_kernel<<<1, 1, 0, st>>>(a->seed_slot, a->hp.seed);
+    MTL_CHECK_LAUNCH();
+  }
+  MTL_TRY(k_zero(a->copy_grad, n, st));                                             // model.zero_copy_grad()
+  MTL_CHECK_CUDA(cudaEventRecord(s->ev_fork, st));
+  const int used = a->n_lanes < a->n_tasks ? a->n_lanes : a->n_tasks;
+  for (int l = 0; l < used; ++l) MTL_CHECK_CUDA(cudaStreamWaitEvent(s->lanes[l].st, s->ev_fork, 0));
+  for (int t = 0; t < a->n_tasks; ++t) {
+    const int l = t % a->n_lanes;
+    Lane& ln = s->lanes[l];
+    const mtl_lane& lb = a->lanes[l];
+    // adapted weights start from the shared theta (weights_original): the lane copy replaces
+    // deepcopy(state_dict) + load_state_dict (transient_trainer.py:160,237)
+    MTL_TRY(k_copy(lb.theta, a->theta, n, ln.st));
+    mtl_batch va = *a->val;
+    if (a->n_tasks > 1) { va.hyp_out = nullptr; va.gold_out = nullptr; }            // shared val batch: per-task outputs would race
+    SeedRef s0, s1;
+    const unsigned long long lo0 = (unsigned long long)t * 2ull, lo1 = lo0 + 1ull;
+    if (dev_seed) { s0 = {lo0, a->seed_slot, 128ull}; s1 = {lo1, a->seed_slot, 128ull}; }
+    else { s0 = {a->hp.seed * 128ull + lo0, nullptr, 0}; s1 = {a->hp.seed * 128ull + lo1, nullptr, 0}; }
+    MTL_TRY(task_body(s, &ln.pass, lb.theta, lb.grad, a->pe_enc, a->pe_dec, lb.workspace, lb.workspace_bytes,
+                      &a->train[t], &va, &a->hp, s0, s1, a->results ? a->results + 16 * t : nullptr, ln.st));
+    if (t > 0) MTL_CHECK_CUDA(cudaStreamWaitEvent(ln.st, s->ev_axpy[t - 1], 0));    // keep the reference's summation order
+    MTL_TRY(k_axpy(a->copy_grad, lb.grad, 1.f, n, ln.st));                          // model.add_copy_grad()
+    MTL_CHECK_CUDA(cudaEventRecord(s->ev_axpy[t], ln.st));
+  }
+  for (int l = 0; l < used; ++l) {
+    MTL_CHECK_CUDA(cudaEventRecord(s->lanes[l].done, s->lanes[l].st));
+    MTL_CHECK_CUDA(cudaStreamWaitEvent(st, s->lanes[l].done, 0));
+  }
+  return MTL_OK;
+}
+
+static void push_batch_key(std::vector<unsigned long long>& k, const mtl_batch& b) {
+  k.push_back((unsigned long long)(uintptr_t)b.x); k.push_back((unsigned long long)(uintptr_t)b.lens);
+  k.push_back((unsigned long long)(uintptr_t)b.trg);
+  k.push_back(((unsigned long long)(unsigned)b.B << 32) | (unsigned)b.T);
+  k.push_back(((unsigned long long)(unsigned)b.L << 32) | (unsigned)b.n);
+  k.push_back((unsigned long long)(uintptr_t)b.hyp_out); k.push_back((unsigned long long)(uintptr_t)b.gold_out);
+}
+static unsigned long long fbits(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
+
+extern "C" int mtl_meta_tasks(mtl_session* s, const mtl_meta_step_args* a, void* stream) {
+  MTL_REQUIRE(s && a && a->theta && a->copy_grad && a->pe_enc && a->pe_dec && a->train && a->val && a->lanes,
+              "null argument");
+  MTL_REQUIRE(a->n_tasks >= 1 && a->n_tasks <= 64 && a->n_lanes >= 1, "1 <= n_tasks <= 64, n_lanes >= 1");
+  for (int l = 0; l < a->n_lanes; ++l)
+    MTL_REQUIRE(a->lanes[l].theta && a->lanes[l].grad && a->lanes[l].workspace, "lane buffers");
+  cudaStream_t st = (cudaStream_t)stream;
+  MTL_TRY(ensure_lanes(s, a->n_lanes, a->n_tasks));
+  if (!a->use_graph || !a->seed_slot) return meta_tasks_body(s, a, st);
+
+  std::vector<unsigned long long> key;
+  key.push_back((unsigned long long)(uintptr_t)a->theta); key.push_back((unsigned long long)(uintptr_t)a->copy_grad);
+  key.push_back((unsigned long long)(uintptr_t)a->pe_enc); key.push_back((unsigned long long)(uintptr_t)a->pe_dec);
+  key.push_back(((unsigned long long)(unsigned)a->n_tasks << 32) | (unsigned)a->n_lanes);
+  for (int t = 0; t < a->n_tasks; ++t) push_batch_key(key, a->train[t]);
+  push_batch_key(key, *a->val);
+  for (int l = 0; l < a->n_lanes; ++l) {
+    key.push_back((unsigned long long)(uintptr_t)a->lanes[l].theta); key.push_back((unsigned long long)(uintptr_t)a->lanes[l].grad);
+    key.push_back((unsigned long long)(uintptr_t)a->lanes[l].workspace); key.push_back((unsigned long long)a->lanes[l].workspace_bytes);
+  }
+  key.push_back(fbits(a->hp.lr)); key.push_back(fbits(a->hp.val_scale)); key.push_back((unsigned long long)a->hp.clip);
+  key.push_back(fbits(a->hp.max_norm)); key.push_back(fbits(a->hp.dropout)); key.push_back(fbits(a->hp.label_smoothing));
+  key.push_back((unsigned long long)(uintptr_t)a->results); key.push_back((unsigned long long)(uintptr_t)a->seed_slot);
+  key.push_back((unsigned long long)s->mode);
+
+  GraphEntry* e = nullptr;
+  for (auto& g : s->graphs) if (g.key == key) { e = &g; break; }
+  if (!e) {
+    if (s->graphs.size() >= 16) {                                                   // evict the least recently used entry
+      size_t victim = 0;
+      for (size_t i = 1; i < s->graphs.size(); ++i) if (s->graphs[i].last_use < s->graphs[victim].last_use) victim = i;
+      if (s->graphs[victim].exec) cudaGraphExecDestroy(s->graphs[victim].exec);
+      if (s->graphs[victim].graph) cudaGraphDestroy(s->graphs[victim].graph);
+      s->graphs.erase(s->graphs.begin() + victim);
+    }
+    s->graphs.emplace_back();
+    e = &s->graphs.back();
+    e->key = key;
+  }
+  e->last_use = ++s->tick;
+  if (!e->exec) {
+    if (e->seen++ == 0) return meta_tasks_body(s, a, st);                           // first sighting: eager (also warms every kernel up)
+    // second sighting: capture.  ThreadLocal mode keeps other host threads (data prefetch) free to use CUDA.
+    MTL_CHECK_CUDA(cudaStreamBeginCapture(s->cap_st, cudaStreamCaptureModeThreadLocal));
+    const unsigned long long launches_before = g_mtl_launches;
+    int rc = meta_tasks_body(s, a, s->cap_st);
+    cudaGraph_t graph = nullptr;
+    cudaError_t ce = cudaStreamEndCapture(s->cap_st, &graph);
+    e->kernels = g_mtl_launches - launches_before;
+    g_mtl_launches = launches_before;
+    if (rc != MTL_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (ce != cudaSuccess || !graph) {
+      mtl_set_error("stream capture of the meta-step failed: %s", cudaGetErrorString(ce));
+      return MTL_ERR_CUDA;
+    }
+    size_t n_nodes = 0;
+    MTL_CHECK_CUDA(cudaGraphGetNodes(graph, nullptr, &n_nodes));
+    std::vector<cudaGraphNode_t> nodes(n_nodes);
+    MTL_CHECK_CUDA(cudaGraphGetNodes(graph, nodes.data(), &n_nodes));
+    for (size_t i = 0; i < n_nodes && !e->seed_node; ++i) {
+      cudaGraphNodeType ty;
+      if (cudaGraphNodeGetType(nodes[i], &ty) != cudaSuccess || ty != cudaGraphNodeTypeKernel) continue;
+      cudaKernelNodeParams kp;
+      if (cudaGraphKernelNodeGetParams(nodes[i], &kp) == cudaSuccess && kp.func == (void*)set_u64_kernel) e->seed_node = nodes[i];
+    }
+    cudaGraphExec_t exec = nullptr;
+    ce = cudaGraphInstantiate(&exec, graph, 0);
+    if (ce != cudaSuccess || !e->seed_node) {
+      if (exec) cudaGraphExecDestroy(exec);
+      cudaGraphDestroy(graph);
+      e->seed_node = nullptr;
+      mtl_set_error("graph instantiate failed: %s", ce != cudaSuccess ? cudaGetErrorString(ce) : "seed node not found");
+      return MTL_ERR_CUDA;
+    }
+    e->exec = exec;
+    e->graph = graph;
+    ++s->graph_captures;
+  }
+  // replay with this step's seed patched into the one kernel node that writes the device seed slot
+  unsigned long long* slot = a->seed_slot;
+  unsigned long long seed = a->hp.seed;
+  void* kargs[2] = {&slot, &seed};
+  cudaKernelNodeParams kp;
+  memset(&kp, 0, sizeof(kp));
+  kp.func = (void*)set_u64_kernel;
+  kp.gridDim = dim3(1, 1, 1); kp.blockDim = dim3(1, 1, 1); kp.sharedMemBytes = 0; kp.kernelParams = kargs; kp.extra = nullptr;
+  MTL_CHECK_CUDA(cudaGraphExecKernelNodeSetParams(e->exec, e->seed_node, &kp));
+  MTL_CHECK_CUDA(cudaGraphLaunch(e->exec, st));
+  g_mtl_launches += e->kernels;
+  ++s->graph_replays;
+  return MTL_OK;
+}
+extern "C" int mtl_graph_stats(const mtl_session* s, unsigned long long* captures, unsigned long long* replays) {
+  MTL_REQUIRE(s, "null argument");
+  if (captures) *captures = s->graph_captures;
+  if (replays) *replays = s->graph_replays;
   return MTL_OK;
 }
 
@@ -763,12 +1006,54 @@ extern "C" int mtl_conv1_fwd(const float* x, const float* w, const float* b, flo
 extern "C" int mtl_conv3x3_relu_fwd(int mode, const float* x, const float* w, const float* b, float* col, float* wg,
                                     float* out, int B, int F, int T, int Cin, int Cout, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  MTL_TRY(k_im2col3x3(x, col, B, F, T, Cin, st));
+  MTL_REQUIRE(x && w && b && wg && out, "null argument");
   MTL_TRY(k_conv_w_fwd_layout(w, wg, Cout, Cin, st));
+  if (mode != MTL_GEMM_SIMT_FP32) return k_conv3x3_tc(x, wg, b, out, B, F, T, Cin, Cout, EPI_RELU, nullptr, mode, st);
+  MTL_REQUIRE(col, "mode 0 needs the im2col buffer");
+  MTL_TRY(k_im2col3x3(x, col, B, F, T, Cin, st));
   GemmArgs g;
   memset(&g, 0, sizeof(g));
   g.A = col; g.lda = 9 * Cin; g.B = wg; g.ldb = 9 * Cin; g.transB = 1; g.C = out; g.ldc = Cout;
   g.M = B * F * T; g.N = Cout; g.K = 9 * Cin; g.alpha = 1.f; g.bias = b; g.epi = EPI_RELU; g.split_k = 1;
+  return k_gemm(g, mode, st);
+}
+extern "C" long long mtl_conv3x3_bwd_scratch_floats(int mode, int B, int F, int T, int Cin, int Cout) {
+  const long long P = (long long)B * F * T, wsz = (long long)Cout * 9 * Cin + 64;
+  return 2 * wsz + (mode == MTL_GEMM_SIMT_FP32 ? P * 9 * Cin + P * 9 * Cout + 128 : 0);
+}
+extern "C" int mtl_conv3x3_bwd(int mode, const float* x, const float* w, const float* dy, const float* relu_aux,
+                               float* dw, float* db, float* dx, float* scratch, int B, int F, int T, int Cin, int Cout,
+                               void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  MTL_REQUIRE(x && w && dy && dw && db && scratch, "null argument");
+  const size_t P = (size_t)B * F * T, wsz = ((size_t)Cout * 9 * Cin + 63) & ~(size_t)63;
+  float* dwg = scratch;
+  float* wd = scratch + wsz;
+  MTL_TRY(k_zero(dwg, wsz, st));
+  if (mode != MTL_GEMM_SIMT_FP32) {
+    MTL_TRY(k_conv3x3_wgrad_tc(x, dy, dwg, B, F, T, Cin, Cout, mode, st));
+    MTL_TRY(k_conv_wgrad_scatter_t(dwg, dw, Cout, Cin, st));
+  } else {
+    float* col = scratch + 2 * wsz;
+    MTL_TRY(k_im2col3x3(x, col, B, F, T, Cin, st));
+    GemmArgs g;
+    memset(&g, 0, sizeof(g));
+    g.A = dy; g.lda = Cout; g.transA = 1; g.B = col; g.ldb = 9 * Cin; g.transB = 0; g.C = dwg; g.ldc = 9 * Cin;
+    g.M = Cout; g.N = 9 * Cin; g.K = (int)P; g.alpha = 1.f; g.beta = 1.f; g.split_k = 64;
+    MTL_TRY(k_gemm(g, mode, st));
+    MTL_TRY(k_conv_wgrad_scatter(dwg, dw, Cout, Cin, st));
+  }
+  MTL_TRY(k_colsum_acc(dy, (int)P, Cout, Cout, db, st));
+  if (!dx) return MTL_OK;
+  MTL_TRY(k_conv_w_dgrad_layout(w, wd, Cout, Cin, st));
+  const int epi = relu_aux ? EPI_RELU_BWD : EPI_NONE;
+  if (mode != MTL_GEMM_SIMT_FP32) return k_conv3x3_tc(dy, wd, nullptr, dx, B, F, T, Cout, Cin, epi, relu_aux, mode, st);
+  float* colg = scratch + 2 * wsz + ((P * 9 * Cin + 63) & ~(size_t)63);
+  MTL_TRY(k_im2col3x3(dy, colg, B, F, T, Cout, st));
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.A = colg; g.lda = 9 * Cout; g.B = wd; g.ldb = 9 * Cout; g.transB = 1; g.C = dx; g.ldc = Cin;
+  g.M = (int)P; g.N = Cin; g.K = 9 * Cout; g.alpha = 1.f; g.epi = epi; g.aux = relu_aux; g.split_k = 1;
   return k_gemm(g, mode, st);
 }
 extern "C" int mtl_maxpool2_fwd(const float* x, float* out, int B, int F, int T, int C, void* stream) {

@@ -1,14 +1,22 @@
-// Blackwell tensor-core GEMM for the GemmArgs contract (kernels.h): TMA (cp.async.bulk.tensor, 128B
-// swizzle) stages fp32 operand tiles into shared memory, one elected thread issues
-// tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=BN, K=8 per instruction) with the accumulator in
-// tensor memory, and four epilogue warps drain TMEM with tcgen05.ld and apply the fused epilogue
-// (alpha, bias, ReLU, ReLU-backward mask, beta*C, or atomic split-K accumulation).
+// Blackwell tensor-core contraction for the GemmArgs contract (kernels.h) and for the VGG 3x3
+// convolutions as IMPLICIT GEMMs (no im2col buffer): TMA (cp.async.bulk.tensor, 128B swizzle) stages
+// fp32 operand tiles into shared memory, one elected thread issues tcgen05.mma.cta_group::1.kind::tf32
+// (M=128, N=BN, K=8 per instruction) with the accumulator in tensor memory, and four epilogue warps
+// drain TMEM with tcgen05.ld and apply the fused epilogue (alpha, bias, ReLU, ReLU-backward mask,
+// beta*C, or vectorised-atomic split-K accumulation).
 //
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
-// warps 2..5 = epilogue (TMEM lane quarter = warp_id % 4).  Two CTAs are co-resident per SM so one
-// tile's epilogue overlaps the other's main loop.
+// warps 2..5 = operand splitter (3xTF32 only) during the main loop, then epilogue
+// (TMEM lane quarter = warp_id % 4).
 //
-// Operand majors map onto UMMA shared-memory descriptors (SWIZZLE_128B, sm_100 descriptor version 1):
+// Precision modes
+//   TF32   : TMA delivers TFLOAT32-typed (rounded) tiles, one MMA per k-step.
+//   3xTF32 : TMA delivers raw fp32; the splitter warps rewrite every staged tile in place as
+//            hi = rna_tf32(a) and write lo = rna_tf32(a - hi) to a sibling buffer; three MMAs per k-step
+//            (lo*hi + hi*lo + hi*hi) accumulate in fp32 TMEM.  Per-operand residual <= 2^-22 |a| (unbiased)
+//            and the dropped lo*lo term is <= 2^-22 |a||b|: fp32-grade products.
+//
+// Operand majors map onto UMMA shared-memory descriptors (SWIZZLE_128B family, sm_100 descriptor v1):
 //   K-major  (A stored [M,K], B stored [N,K]):  TMA box {32 fp32 of K, rows}; rows are 128 B, 8-row
 //            swizzle atoms stacked every 1024 B (SBO = 1024); each K=8 step advances the start by 32 B.
 //   MN-major (A stored [K,M], B stored [K,N]):  TMA boxes {32 fp32 of M/N, 32 rows of K} with the
@@ -16,6 +24,14 @@
 //            SWIZZLE_128B_BASE32B), one 4096 B box per 32 columns (LBO = 4096), 4-row atoms every 512 B
 //            (SBO = 512); each K=8 step advances the start by 1024 B.
 // Out-of-range rows/columns/K are zero-filled by TMA, so ragged M, N, K need no special casing.
+//
+// Implicit convolution (NHWC activations [B,F,T,C], 3x3, stride 1, zero pad 1 -- models/asr/transformer.py:47-59)
+//   CONV_FWD  : C[pixel, co] = sum_{tap,ci} X[pixel + tap, ci] * Wg[co, tap*Cin + ci]   (also the dgrad, on dY with
+//               flipped taps).  The A tile of k-block (tap, 32-channel chunk) is ONE 4-D TMA box
+//               {32 c, BT t, 128/BT f, 1} fetched at the tap-shifted coordinate; the zero padding is TMA's
+//               out-of-bounds fill.  Tile rows are pixels in (f, t) order.
+//   CONV_WGRAD: dWgT[tap*Cin + ci, co] = sum_pixel X[pixel + tap, ci] * dY[pixel, co].  K runs over 32-pixel
+//               boxes {BT t, 32/BT f}; A boxes (MN-major) are tap-shifted X boxes, B boxes are dY boxes.
 #include "kernels.h"
 #include <cuda.h>
 #include <mutex>
@@ -35,6 +51,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // Bounded wait: a pipeline bug must trap (error reported to the host), never hang the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
@@ -57,6 +76,13 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_dst), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                            int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_dst), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -86,9 +112,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// round-to-nearest fp32 -> tf32 (10 explicit mantissa bits, low 13 bits zero)
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 
 // UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor bit layout): start>>4 [0,14), LBO>>4 [16,30),
-// SBO>>4 [32,46), version=1 [46,48), base_offset=0, layout_type=SWIZZLE_128B(2) [61,64).
+// SBO>>4 [32,46), version=1 [46,48), base_offset=0, layout_type [61,64).
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
                                               uint32_t layout_type) {
   uint64_t d = 0;
@@ -101,28 +136,37 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
 }
 // K-major tile: SWIZZLE_128B (2), 8-row atoms every 1024 B.
 __device__ __forceinline__ uint64_t desc_kmajor(uint32_t saddr) { return umma_desc(saddr, 16, 1024, 2); }
-// MN-major fp32/tf32 tile: the only legal layout is SWIZZLE_128B_BASE32B (1) -- 32 B swizzle granules,
-// atoms of 32 (MN) x 4 (K) elements = 512 B stacked along K (SBO = 512), 32-column groups 4096 B apart (LBO).
+// MN-major fp32/tf32 tile: SWIZZLE_128B_BASE32B (1) -- 32 B swizzle granules, atoms of 32 (MN) x 4 (K)
+// elements = 512 B stacked along K (SBO = 512), 32-column groups 4096 B apart (LBO).
 __device__ __forceinline__ uint64_t desc_mnmajor(uint32_t saddr) { return umma_desc(saddr, 4096, 512, 1); }
+
+enum { CONV_NONE = 0, CONV_FWD = 1, CONV_WGRAD = 2 };
 
 struct TcParams {
   GemmArgs g;
   int kb_total;      // number of 32-wide k-blocks
   int kb_per_split;  // k-blocks per blockIdx.z
   int vecC;          // C (and aux) rows are 16 B aligned
+  // implicit-convolution geometry (conv_mode != CONV_NONE)
+  int conv_mode;
+  int cF, cT, cCin;  // activation extents of the tap-shifted operand
+  int bt_log2;       // pixel box: (1 << bt_log2) time steps wide
+  int tiles_t, tiles_f;
 };
 
-template <int BN, int STAGES, bool A_MN, bool B_MN>
+template <int BN, int STAGES, bool A_MN, bool B_MN, bool SPLIT3>
 __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                       const __grid_constant__ CUtensorMap tmB, const TcParams P) {
   constexpr int B_STAGE_BYTES = BN * BK * 4;
-  constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  constexpr int HI_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  constexpr int STAGE_BYTES = HI_BYTES * (SPLIT3 ? 2 : 1);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // SWIZZLE_128B atoms need 1024 B alignment
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   uint64_t* empty = full + STAGES;
-  uint64_t* tmem_full = empty + STAGES;
+  uint64_t* ready = empty + STAGES;       // SPLIT3: splitter warps -> MMA issuer
+  uint64_t* tmem_full = ready + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
   const GemmArgs& g = P.g;
@@ -131,8 +175,17 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
   const int kb0 = blockIdx.z * P.kb_per_split;
   const int kb1 = min(P.kb_total, kb0 + P.kb_per_split);
 
+  // CONV_FWD: this CTA's 128 output pixels are the box (b, f0.., t0..)
+  int cb = 0, cf0 = 0, ct0 = 0;
+  if (P.conv_mode == CONV_FWD) {
+    const int tt = blockIdx.x % P.tiles_t, rem = blockIdx.x / P.tiles_t;
+    ct0 = tt << P.bt_log2;
+    cf0 = (rem % P.tiles_f) * (BM >> P.bt_log2);
+    cb = rem / P.tiles_f;
+  }
+
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&ready[s], 4); }
     mbar_init(tmem_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -154,19 +207,40 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
         mbar_wait(&empty[s], ph ^ 1);
-        mbar_expect_tx(&full[s], STAGE_BYTES);
+        mbar_expect_tx(&full[s], HI_BYTES);
         const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + A_STAGE_BYTES;
-        if (!A_MN) {
-          tma_load_2d(sa, &tmA, &full[s], kb * BK, m0);
-        } else {
+        if (P.conv_mode == CONV_NONE) {
+          if (!A_MN) {
+            tma_load_2d(sa, &tmA, &full[s], kb * BK, m0);
+          } else {
 #pragma unroll
-          for (int i = 0; i < BM / 32; ++i) tma_load_2d(sa + i * 4096, &tmA, &full[s], m0 + i * 32, kb * BK);
-        }
-        if (!B_MN) {
+            for (int i = 0; i < BM / 32; ++i) tma_load_2d(sa + i * 4096, &tmA, &full[s], m0 + i * 32, kb * BK);
+          }
+          if (!B_MN) {
+            tma_load_2d(sb, &tmB, &full[s], kb * BK, n0);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BN / 32; ++i) tma_load_2d(sb + i * 4096, &tmB, &full[s], n0 + i * 32, kb * BK);
+          }
+        } else if (P.conv_mode == CONV_FWD) {
+          const int cpb = P.cCin >> 5;                       // 32-channel chunks per tap
+          const int tap = kb / cpb, c0 = (kb - tap * cpb) << 5;
+          const int kh = tap / 3, kw = tap - kh * 3;
+          tma_load_4d(sa, &tmA, &full[s], c0, ct0 + kw - 1, cf0 + kh - 1, cb);
           tma_load_2d(sb, &tmB, &full[s], kb * BK, n0);
-        } else {
+        } else {                                             // CONV_WGRAD: k-block = 32-pixel box
+          const int tt = kb % P.tiles_t, rem = kb / P.tiles_t;
+          const int t0 = tt << P.bt_log2, f0 = (rem % P.tiles_f) * (32 >> P.bt_log2), b = rem / P.tiles_f;
 #pragma unroll
-          for (int i = 0; i < BN / 32; ++i) tma_load_2d(sb + i * 4096, &tmB, &full[s], n0 + i * 32, kb * BK);
+          for (int i = 0; i < BM / 32; ++i) {
+            const int mg = m0 + i * 32;
+            int tap = mg / P.cCin, c0 = mg - tap * P.cCin;
+            if (tap > 8) { tap = 0; c0 = P.cCin; }           // rows past 9*Cin: fully out of bounds -> zeros
+            const int kh = tap / 3, kw = tap - kh * 3;
+            tma_load_4d(sa + i * 4096, &tmA, &full[s], c0, t0 + kw - 1, f0 + kh - 1, b);
+          }
+#pragma unroll
+          for (int i = 0; i < BN / 32; ++i) tma_load_4d(sb + i * 4096, &tmB, &full[s], n0 + i * 32, t0, f0, b);
         }
       }
     }
@@ -180,23 +254,66 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
       for (int kb = kb0; kb < kb1; ++kb, ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait(&full[s], ph);
+        mbar_wait(SPLIT3 ? &ready[s] : &full[s], ph);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + A_STAGE_BYTES;
 #pragma unroll
         for (int k = 0; k < BK / 8; ++k) {
-          const uint64_t da = A_MN ? desc_mnmajor(sa + k * 1024) : desc_kmajor(sa + k * 32);
-          const uint64_t db = B_MN ? desc_mnmajor(sb + k * 1024) : desc_kmajor(sb + k * 32);
-          tc_mma_tf32(tmem_base, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          const uint32_t oa = A_MN ? k * 1024 : k * 32, ob = B_MN ? k * 1024 : k * 32;
+          const uint64_t da = A_MN ? desc_mnmajor(sa + oa) : desc_kmajor(sa + oa);
+          const uint64_t db = B_MN ? desc_mnmajor(sb + ob) : desc_kmajor(sb + ob);
+          const uint32_t acc0 = (it > 0 || k > 0) ? 1u : 0u;
+          if (SPLIT3) {
+            const uint64_t la = A_MN ? desc_mnmajor(sa + HI_BYTES + oa) : desc_kmajor(sa + HI_BYTES + oa);
+            const uint64_t lb = B_MN ? desc_mnmajor(sb + HI_BYTES + ob) : desc_kmajor(sb + HI_BYTES + ob);
+            tc_mma_tf32(tmem_base, la, db, idesc, acc0);     // small terms first
+            tc_mma_tf32(tmem_base, da, lb, idesc, 1u);
+            tc_mma_tf32(tmem_base, da, db, idesc, 1u);
+          } else {
+            tc_mma_tf32(tmem_base, da, db, idesc, acc0);
+          }
         }
         tc_commit(&empty[s]);          // frees the smem slot once these MMAs have read it
       }
       tc_commit(tmem_full);            // accumulator complete
     }
   } else {
+    if (SPLIT3) {
+      // ===================== operand splitter: a -> (hi in place, lo beside it) =====================
+      const int tid = threadIdx.x - 64;                      // 0..127
+      int it = 0;
+      for (int kb = kb0; kb < kb1; ++kb, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(&full[s], ph);
+        float4* hi = reinterpret_cast<float4*>(smem + s * STAGE_BYTES);
+        float4* lo = reinterpret_cast<float4*>(smem + s * STAGE_BYTES + HI_BYTES);
+#pragma unroll 4
+        for (int i = tid; i < HI_BYTES / 16; i += 128) {
+          const float4 a = hi[i];
+          float4 h, l;
+          h.x = tf32_rna(a.x); l.x = tf32_rna(a.x - h.x);
+          h.y = tf32_rna(a.y); l.y = tf32_rna(a.y - h.y);
+          h.z = tf32_rna(a.z); l.z = tf32_rna(a.z - h.z);
+          h.w = tf32_rna(a.w); l.w = tf32_rna(a.w - h.w);
+          hi[i] = h;
+          lo[i] = l;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to the MMA (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ready[s]);
+      }
+    }
     // ===================== epilogue: TMEM -> registers -> global =====================
     const int q = warp & 3;            // TMEM lane quarter this warp may access
-    const int row = m0 + q * 32 + lane;
+    const int r_in_tile = q * 32 + lane;
+    long long orow;                    // output row index, -1 = this lane has no row
+    if (P.conv_mode == CONV_FWD) {
+      const int f = cf0 + (r_in_tile >> P.bt_log2), t = ct0 + (r_in_tile & ((1 << P.bt_log2) - 1));
+      orow = (f < P.cF && t < P.cT) ? ((long long)cb * P.cF + f) * P.cT + t : -1;
+    } else {
+      orow = (m0 + r_in_tile < g.M) ? (long long)(m0 + r_in_tile) : -1;
+    }
     mbar_wait(tmem_full, 0);
     tc_fence_after();
 #pragma unroll 1
@@ -204,14 +321,21 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
       uint32_t r[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
       const int col0 = n0 + c * 32;
-      if (row < g.M && col0 < g.N) {
-        float* crow = g.C + (long long)row * g.ldc + col0;
+      if (orow >= 0 && col0 < g.N) {
+        float* crow = g.C + orow * g.ldc + col0;
         if (g.split_k > 1) {
+          if (P.vecC && col0 + 31 < g.N) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < g.N) atomicAdd(crow + j, g.alpha * __uint_as_float(r[j]));
+            for (int j = 0; j < 32; j += 4)
+              red_add_v4(crow + j, g.alpha * __uint_as_float(r[j]), g.alpha * __uint_as_float(r[j + 1]),
+                         g.alpha * __uint_as_float(r[j + 2]), g.alpha * __uint_as_float(r[j + 3]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < g.N) atomicAdd(crow + j, g.alpha * __uint_as_float(r[j]));
+          }
         } else {
-          const float* arow = g.epi == EPI_RELU_BWD ? g.aux + (long long)row * g.ldc + col0 : nullptr;
+          const float* arow = g.epi == EPI_RELU_BWD ? g.aux + orow * g.ldc + col0 : nullptr;
 #pragma unroll
           for (int j4 = 0; j4 < 32; j4 += 4) {
             float v[4];
@@ -277,34 +401,26 @@ EncodeTiledFn get_encode() {
 }
 
 struct MapKey {
-  const void* ptr; long long inner, outer, ld; int box_outer, dtype;
+  const void* ptr; long long d0, d1, d2, d3, ld; int b1, b2, flags;
   bool operator==(const MapKey& o) const {
-    return ptr == o.ptr && inner == o.inner && outer == o.outer && ld == o.ld && box_outer == o.box_outer && dtype == o.dtype;
+    return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && d3 == o.d3 && ld == o.ld && b1 == o.b1 &&
+           b2 == o.b2 && flags == o.flags;
   }
 };
 struct MapKeyHash {
   size_t operator()(const MapKey& k) const {
     size_t h = (size_t)k.ptr;
-    h = h * 1000003u ^ (size_t)k.inner; h = h * 1000003u ^ (size_t)k.outer; h = h * 1000003u ^ (size_t)k.ld;
-    h = h * 1000003u ^ (size_t)(k.box_outer * 4 + k.dtype);
+    h = h * 1000003u ^ (size_t)k.d0; h = h * 1000003u ^ (size_t)k.d1; h = h * 1000003u ^ (size_t)k.d2;
+    h = h * 1000003u ^ (size_t)k.d3; h = h * 1000003u ^ (size_t)k.ld;
+    h = h * 1000003u ^ (size_t)(k.b1 * 1024 + k.b2 * 8 + k.flags);
     return h;
   }
 };
 std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
 std::mutex g_maps_mu;
 
-// TMA data type for the fp32 operands: TFLOAT32 (default) lets the copy engine deliver TF32-formatted
-// values; MTL_TMA_FP32=1 selects plain FLOAT32 (the tensor core then ignores the low mantissa bits).
-int tma_dtype() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("MTL_TMA_FP32"); v = (e && e[0] == '1') ? 0 : 1; }
-  return v;
-}
-
-// 2-D map over a row-major fp32 matrix: `inner` contiguous elements, `outer` rows of stride ld; box {32, box_outer}.
-int make_map(const float* ptr, long long inner, long long outer, long long ld, int box_outer, bool mn_major,
-             CUtensorMap* out) {
-  MapKey key{ptr, inner, outer, ld, box_outer, tma_dtype() + (mn_major ? 2 : 0)};
+int encode_cached(const MapKey& key, int rank, const cuuint64_t* dims, const cuuint64_t* strides, const cuuint32_t* box,
+                  bool tf32_type, bool mn_major, CUtensorMap* out) {
   {
     std::lock_guard<std::mutex> lk(g_maps_mu);
     auto it = g_maps.find(key);
@@ -312,17 +428,14 @@ int make_map(const float* ptr, long long inner, long long outer, long long ld, i
   }
   EncodeTiledFn enc = get_encode();
   if (!enc) { mtl_set_error("cuTensorMapEncodeTiled unavailable (driver too old?)"); return MTL_ERR_CUDA; }
-  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-  cuuint32_t box[2] = {32, (cuuint32_t)box_outer};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(out, tma_dtype() ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr,
-                   dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(out, tf32_type ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank,
+                   (void*)key.ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    mtl_set_error("cuTensorMapEncodeTiled failed (%d) for ptr=%p inner=%lld outer=%lld ld=%lld", (int)r, (const void*)ptr,
-                  inner, outer, ld);
+    mtl_set_error("cuTensorMapEncodeTiled failed (%d) rank=%d ptr=%p dims=%lld,%lld,%lld,%lld ld=%lld box=%d,%d", (int)r,
+                  rank, key.ptr, key.d0, key.d1, key.d2, key.d3, key.ld, key.b1, key.b2);
     return MTL_ERR_CUDA;
   }
   std::lock_guard<std::mutex> lk(g_maps_mu);
@@ -331,11 +444,31 @@ int make_map(const float* ptr, long long inner, long long outer, long long ld, i
   return MTL_OK;
 }
 
-template <int BN, int STAGES, bool A_MN, bool B_MN>
+// 2-D map over a row-major fp32 matrix: `inner` contiguous elements, `outer` rows of stride ld; box {32, box_outer}.
+int make_map(const float* ptr, long long inner, long long outer, long long ld, int box_outer, bool mn_major,
+             bool tf32_type, CUtensorMap* out) {
+  MapKey key{ptr, inner, outer, 0, 0, ld, box_outer, 0, (tf32_type ? 1 : 0) + (mn_major ? 2 : 0)};
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {32, (cuuint32_t)box_outer};
+  return encode_cached(key, 2, dims, strides, box, tf32_type, mn_major, out);
+}
+// 4-D map over an NHWC activation [B,F,T,C]: dims (C,T,F,B), box {32, bt, bf, 1}.
+int make_map_nhwc(const float* ptr, int B, int F, int T, int C, int bt, int bf, bool mn_major, bool tf32_type,
+                  CUtensorMap* out) {
+  MapKey key{ptr, C, T, F, B, 0, bt, bf, 4 + (tf32_type ? 1 : 0) + (mn_major ? 2 : 0)};
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)T, (cuuint64_t)F, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)T * C * 4, (cuuint64_t)F * T * C * 4};
+  cuuint32_t box[4] = {32, (cuuint32_t)bt, (cuuint32_t)bf, 1};
+  return encode_cached(key, 4, dims, strides, box, tf32_type, mn_major, out);
+}
+
+template <int BN, int STAGES, bool A_MN, bool B_MN, bool SPLIT3>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& P, dim3 grid, cudaStream_t s) {
-  constexpr int SMEM = STAGES * (A_STAGE_BYTES + BN * BK * 4) + 1024 /*align slack*/ + 256 /*barriers*/;
+  constexpr int SMEM = STAGES * (A_STAGE_BYTES + BN * BK * 4) * (SPLIT3 ? 2 : 1) + 1024 /*align slack*/ + 256 /*barriers*/;
+  static_assert(SMEM <= 227 * 1024, "shared memory budget");
   static bool configured = false;
-  auto kern = gemm_tc_kernel<BN, STAGES, A_MN, B_MN>;
+  auto kern = gemm_tc_kernel<BN, STAGES, A_MN, B_MN, SPLIT3>;
   if (!configured) {
     MTL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     configured = true;
@@ -345,16 +478,54 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& P, dim3
   return MTL_OK;
 }
 
-template <int BN, int STAGES>
+template <int BN, bool SPLIT3>
 int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& P, dim3 grid,
                    cudaStream_t s) {
-  if (!a_mn && !b_mn) return launch<BN, STAGES, false, false>(ta, tb, P, grid, s);
-  if (!a_mn && b_mn) return launch<BN, STAGES, false, true>(ta, tb, P, grid, s);
-  if (a_mn && !b_mn) return launch<BN, STAGES, true, false>(ta, tb, P, grid, s);
-  return launch<BN, STAGES, true, true>(ta, tb, P, grid, s);
+  constexpr int STAGES = SPLIT3 ? (BN == 64 ? 4 : 3) : (BN == 64 ? 4 : 3);
+  if (!a_mn && !b_mn) return launch<BN, STAGES, false, false, SPLIT3>(ta, tb, P, grid, s);
+  if (!a_mn && b_mn) return launch<BN, STAGES, false, true, SPLIT3>(ta, tb, P, grid, s);
+  if (a_mn && !b_mn) return launch<BN, STAGES, true, false, SPLIT3>(ta, tb, P, grid, s);
+  return launch<BN, STAGES, true, true, SPLIT3>(ta, tb, P, grid, s);
+}
+int dispatch(int bn, bool split3, bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& P,
+             dim3 grid, cudaStream_t s) {
+  if (bn == 64) return split3 ? dispatch_major<64, true>(a_mn, b_mn, ta, tb, P, grid, s)
+                              : dispatch_major<64, false>(a_mn, b_mn, ta, tb, P, grid, s);
+  return split3 ? dispatch_major<128, true>(a_mn, b_mn, ta, tb, P, grid, s)
+                : dispatch_major<128, false>(a_mn, b_mn, ta, tb, P, grid, s);
 }
 
 inline bool al16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
+
+// Splits kb_total k-blocks over `want` CTAs (blockIdx.z); returns the grid depth and fills kb_per_split.
+int plan_split(TcParams& P, int want) {
+  int split = want > 1 ? want : 1;
+  if (split > 1) {
+    if (split > P.kb_total) split = P.kb_total;
+    P.kb_per_split = mtl_cdiv(P.kb_total, split);
+    split = mtl_cdiv(P.kb_total, P.kb_per_split);
+    P.g.split_k = 2;                   // atomic epilogue (also when the split collapsed to one slab)
+  } else {
+    P.kb_per_split = P.kb_total;
+    P.g.split_k = 1;
+  }
+  return split;
+}
+
+// pixel-box width (log2) minimising padded work for a rows-pixel box over an F x T plane
+int pick_bt_log2(int rows, int F, int T, int* tiles_t, int* tiles_f) {
+  int best = -1;
+  long long best_cost = 0;
+  for (int l = 3; (1 << l) <= rows; ++l) {            // bt >= 8: TMA inner extents stay >= 16 B anyway (channels are inner)
+    const int bt = 1 << l, bf = rows / bt;
+    if (bf > 256 || bt > 256) continue;
+    const long long cost = (long long)mtl_cdiv(T, bt) * bt * mtl_cdiv(F, bf) * bf;
+    if (best < 0 || cost < best_cost) { best = l; best_cost = cost; }
+  }
+  *tiles_t = mtl_cdiv(T, 1 << best);
+  *tiles_f = mtl_cdiv(F, rows >> best);
+  return best;
+}
 
 }  // namespace
 
@@ -366,31 +537,79 @@ bool k_gemm_tc_eligible(const GemmArgs& g) {
 }
 
 int k_gemm_tc(const GemmArgs& g, int precision_mode, cudaStream_t s) {
-  (void)precision_mode;
   MTL_REQUIRE(k_gemm_tc_eligible(g), "operands not TMA-compatible (16 B aligned base, leading dims % 4 == 0)");
+  const bool split3 = precision_mode == 2;
+  const bool tf = !split3;
   const bool a_mn = g.transA != 0;     // A stored [K,M]: M contiguous
   const bool b_mn = g.transB == 0;     // B stored [K,N]: N contiguous
   const int bn = g.N <= 64 ? 64 : 128;
   CUtensorMap ta, tb;
-  if (!a_mn) MTL_TRY(make_map(g.A, g.K, g.M, g.lda, BM, false, &ta)); else MTL_TRY(make_map(g.A, g.M, g.K, g.lda, 32, true, &ta));
-  if (!b_mn) MTL_TRY(make_map(g.B, g.K, g.N, g.ldb, bn, false, &tb)); else MTL_TRY(make_map(g.B, g.N, g.K, g.ldb, 32, true, &tb));
+  if (!a_mn) MTL_TRY(make_map(g.A, g.K, g.M, g.lda, BM, false, tf, &ta)); else MTL_TRY(make_map(g.A, g.M, g.K, g.lda, 32, true, tf, &ta));
+  if (!b_mn) MTL_TRY(make_map(g.B, g.K, g.N, g.ldb, bn, false, tf, &tb)); else MTL_TRY(make_map(g.B, g.N, g.K, g.ldb, 32, true, tf, &tb));
   TcParams P;
+  memset(&P, 0, sizeof(P));
   P.g = g;
+  P.conv_mode = CONV_NONE;
   P.kb_total = mtl_cdiv(g.K, BK);
-  int split = g.split_k > 1 ? g.split_k : 1;
-  if (split > 1) {
-    MTL_REQUIRE(g.beta == 1.f && g.epi == EPI_NONE && g.bias == nullptr, "split-K needs beta=1, no epilogue");
-    if (split > P.kb_total) split = P.kb_total;
-    P.kb_per_split = mtl_cdiv(P.kb_total, split);
-    split = mtl_cdiv(P.kb_total, P.kb_per_split);
-    P.g.split_k = 2;                   // atomic epilogue (also when the split collapsed to one slab)
-  } else {
-    P.kb_per_split = P.kb_total;
-    P.g.split_k = 1;
-  }
+  if (g.split_k > 1) MTL_REQUIRE(g.beta == 1.f && g.epi == EPI_NONE && g.bias == nullptr, "split-K needs beta=1, no epilogue");
+  const int split = plan_split(P, g.split_k);
   P.vecC = al16(g.C) && (g.ldc % 4 == 0) && (g.epi != EPI_RELU_BWD || al16(g.aux));
   dim3 grid(mtl_cdiv(g.M, BM), mtl_cdiv(g.N, bn), split);
   MTL_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "gemm grid too large");
-  if (bn == 64) return dispatch_major<64, 4>(a_mn, b_mn, ta, tb, P, grid, s);
-  return dispatch_major<128, 3>(a_mn, b_mn, ta, tb, P, grid, s);
+  return dispatch(bn, split3, a_mn, b_mn, ta, tb, P, grid, s);
+}
+
+// y[pixel, co] = epi(sum_{tap,ci} x[pixel+tap, ci] * wg[co, tap*Cin+ci] + bias[co])   (x NHWC [B,F,T,Cin], y [B*F*T, Cout])
+int k_conv3x3_tc(const float* x, const float* wg, const float* bias, float* y, int B, int F, int T, int Cin, int Cout,
+                 int epi, const float* aux, int precision_mode, cudaStream_t s) {
+  MTL_REQUIRE(Cin % 32 == 0 && Cout % 4 == 0 && al16(x) && al16(wg) && al16(y), "conv3x3_tc: Cin % 32, Cout % 4, 16 B alignment");
+  MTL_REQUIRE(epi != EPI_RELU_BWD || (aux && al16(aux)), "conv3x3_tc: aux");
+  const bool split3 = precision_mode == 2, tf = !split3;
+  const int bn = Cout <= 64 ? 64 : 128;
+  TcParams P;
+  memset(&P, 0, sizeof(P));
+  P.conv_mode = CONV_FWD;
+  P.cF = F; P.cT = T; P.cCin = Cin;
+  P.bt_log2 = pick_bt_log2(BM, F, T, &P.tiles_t, &P.tiles_f);
+  CUtensorMap ta, tb;
+  MTL_TRY(make_map_nhwc(x, B, F, T, Cin, 1 << P.bt_log2, BM >> P.bt_log2, false, tf, &ta));
+  MTL_TRY(make_map(wg, 9LL * Cin, Cout, 9LL * Cin, bn, false, tf, &tb));
+  GemmArgs& g = P.g;
+  g.A = x; g.B = wg; g.C = y; g.M = B * F * T; g.N = Cout; g.K = 9 * Cin; g.lda = Cin; g.ldb = 9 * Cin; g.ldc = Cout;
+  g.transA = 0; g.transB = 1; g.alpha = 1.f; g.beta = 0.f; g.bias = bias; g.epi = epi; g.aux = aux; g.split_k = 1;
+  P.kb_total = 9 * (Cin / 32);
+  P.kb_per_split = P.kb_total;
+  P.vecC = 1;
+  dim3 grid(B * P.tiles_f * P.tiles_t, mtl_cdiv(Cout, bn), 1);
+  return dispatch(bn, split3, false, false, ta, tb, P, grid, s);
+}
+
+// dwgT[tap*Cin+ci, co] += sum_pixel x[pixel+tap, ci] * dy[pixel, co]   (vectorised atomics; dwgT must be pre-zeroed or hold a running sum)
+int k_conv3x3_wgrad_tc(const float* x, const float* dy, float* dwgT, int B, int F, int T, int Cin, int Cout,
+                       int precision_mode, cudaStream_t s) {
+  MTL_REQUIRE(Cin % 32 == 0 && Cout % 32 == 0 && al16(x) && al16(dy) && al16(dwgT), "conv3x3_wgrad_tc: channels % 32, alignment");
+  const bool split3 = precision_mode == 2, tf = !split3;
+  const int bn = Cout <= 64 ? 64 : 128;
+  TcParams P;
+  memset(&P, 0, sizeof(P));
+  P.conv_mode = CONV_WGRAD;
+  P.cF = F; P.cT = T; P.cCin = Cin;
+  P.bt_log2 = pick_bt_log2(32, F, T, &P.tiles_t, &P.tiles_f);
+  const int bt = 1 << P.bt_log2, bf = 32 >> P.bt_log2;
+  CUtensorMap ta, tb;
+  MTL_TRY(make_map_nhwc(x, B, F, T, Cin, bt, bf, true, tf, &ta));
+  MTL_TRY(make_map_nhwc(dy, B, F, T, Cout, bt, bf, true, tf, &tb));
+  GemmArgs& g = P.g;
+  g.A = x; g.B = dy; g.C = dwgT; g.M = 9 * Cin; g.N = Cout; g.K = B * F * T; g.lda = Cin; g.ldb = Cout; g.ldc = Cout;
+  g.transA = 1; g.transB = 0; g.alpha = 1.f; g.beta = 1.f; g.bias = nullptr; g.epi = EPI_NONE; g.aux = nullptr;
+  P.kb_total = B * P.tiles_f * P.tiles_t;
+  const int mt = mtl_cdiv(g.M, BM), nt = mtl_cdiv(Cout, bn);
+  int want = mtl_cdiv(2 * 148, (long long)mt * nt);        // about two waves of CTAs
+  if (want > P.kb_total / 8) want = P.kb_total / 8 > 0 ? P.kb_total / 8 : 1;
+  const int split = plan_split(P, want > 1 ? want : 2);
+  P.g.split_k = 2;
+  P.vecC = 1;
+  dim3 grid(mt, nt, split);
+  MTL_REQUIRE(grid.z <= 65535, "conv wgrad grid too large");
+  return dispatch(bn, split3, true, true, ta, tb, P, grid, s);
 }

@@ -44,6 +44,13 @@ int k_gemm_tc(const GemmArgs& g, int precision_mode, cudaStream_t s);   // tcgen
 bool k_gemm_tc_eligible(const GemmArgs& g);
 // Dispatcher: mode 0 = SIMT fp32 (exact), 1 = tcgen05 TF32, 2 = tcgen05 3xTF32.
 int k_gemm(const GemmArgs& g, int mode, cudaStream_t s);
+// Implicit-GEMM 3x3 convolutions on NHWC activations (tcgen05; precision_mode 1 = TF32, 2 = 3xTF32):
+//   y[pixel,co] = epi(sum x[pixel+tap,ci] * wg[co, tap*Cin+ci] + bias[co])          (forward, and dgrad on dY with flipped taps)
+//   dwgT[tap*Cin+ci, co] += sum_pixel x[pixel+tap,ci] * dy[pixel,co]                  (weight gradient, atomics)
+int k_conv3x3_tc(const float* x, const float* wg, const float* bias, float* y, int B, int F, int T, int Cin, int Cout,
+                 int epi, const float* aux, int precision_mode, cudaStream_t s);
+int k_conv3x3_wgrad_tc(const float* x, const float* dy, float* dwgT, int B, int F, int T, int Cin, int Cout,
+                       int precision_mode, cudaStream_t s);
 
 // ----------------------------------------------------------------------------- norm_embed.cu
 // z = drop(y)*? + res ; xhat=(z-mean)*rstd ; out = (xhat*gamma+beta) [+ pe[row % pe_period]] ; out *= rowmask[row]
@@ -107,6 +114,7 @@ int k_im2col3x3(const float* x, float* col, int B, int F, int T, int C, cudaStre
 int k_conv_w_fwd_layout(const float* w, float* wg, int Cout, int Cin, cudaStream_t s);
 int k_conv_w_dgrad_layout(const float* w, float* wd, int Cout, int Cin, cudaStream_t s);
 int k_conv_wgrad_scatter(const float* dwg, float* dw, int Cout, int Cin, cudaStream_t s);  // dw[co,ci,kh,kw] += dwg[co,(tap,ci)]
+int k_conv_wgrad_scatter_t(const float* dwgT, float* dw, int Cout, int Cin, cudaStream_t s);  // dw[co,ci,kh,kw] += dwgT[(tap,ci),co]
 int k_maxpool2_fwd(const float* x, float* out, int B, int F, int T, int C, cudaStream_t s);
 // dx = (x>0 && x is the first max of its 2x2 window) ? dpool : 0
 int k_maxpool2_relu_bwd(const float* x, const float* dpool, float* dx, int B, int F, int T, int C, cudaStream_t s);

@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(128) ln_fwd_kernel(
     float v = 0.f;
     if (c < d) {
       v = y[base + c];
-      if (drop.p > 0.f) v *= dropout_scale(drop.seed, drop.site, base + c, drop.p, drop.inv_keep);
+      if (drop.p > 0.f) v *= dropout_scale(mtl_eff_seed(drop), drop.site, base + c, drop.p, drop.inv_keep);
       if (res) v += res[base + c];
     }
     z[i] = v;
@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(128) ln_bwd_kernel(
       float dz = r * (dxh[i] - s1 - xh[i] * s2);
       if (dres) dres[base + c] = dres_acc ? dres[base + c] + dz : dz;
       if (dy) {
-        float sc = drop.p > 0.f ? dropout_scale(drop.seed, drop.site, base + c, drop.p, drop.inv_keep) : 1.f;
+        float sc = drop.p > 0.f ? dropout_scale(mtl_eff_seed(drop), drop.site, base + c, drop.p, drop.inv_keep) : 1.f;
         dy[base + c] = dz * sc;
       }
     }
@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(256) embed_fwd_kernel(const int* __restrict__ 
     int row = (int)(i / d), c = (int)(i % d);
     int pos = row % n;
     float v = E[(size_t)tok[row] * d + c] * 1.0f + pe[(size_t)pos * d + c];   // x_logit_scale = 1 (decoder.py:53)
-    if (drop.p > 0.f) v *= dropout_scale(drop.seed, drop.site, i, drop.p, drop.inv_keep);
+    if (drop.p > 0.f) v *= dropout_scale(mtl_eff_seed(drop), drop.site, i, drop.p, drop.inv_keep);
     out[i] = v;
   }
 }
@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const int* __restrict__ 
     int t = tok[row];
     if (t == pad_id) continue;                       // nn.Embedding(padding_idx=PAD) (decoder.py:39)
     float g = dout[i];
-    if (drop.p > 0.f) g *= dropout_scale(drop.seed, drop.site, i, drop.p, drop.inv_keep);
+    if (drop.p > 0.f) g *= dropout_scale(mtl_eff_seed(drop), drop.site, i, drop.p, drop.inv_keep);
     atomicAdd(dE + (size_t)t * d + c, g);
   }
 }

@@ -5,4 +5,4 @@ There is no CPU fallback: every compute entry point raises if the library or a C
 missing."""
 from .lib import MtlError, get_lib, library_path  # noqa: F401
 from .spec import ModelSpec, param_specs  # noqa: F401
-from .session import Batch, Session  # noqa: F401
+from .session import Batch, MetaStepper, Session  # noqa: F401

@@ -35,6 +35,18 @@ class MetaHParams(C.Structure):
                 ("dropout", C.c_float), ("label_smoothing", C.c_float), ("seed", C.c_ulonglong)]
 
 
+class CLane(C.Structure):
+    _fields_ = [("theta", C.c_void_p), ("grad", C.c_void_p), ("workspace", C.c_void_p),
+                ("workspace_bytes", C.c_longlong)]
+
+
+class MetaStepArgs(C.Structure):
+    _fields_ = [("theta", C.c_void_p), ("copy_grad", C.c_void_p), ("pe_enc", C.c_void_p), ("pe_dec", C.c_void_p),
+                ("n_tasks", C.c_int), ("train", C.POINTER(CBatch)), ("val", C.POINTER(CBatch)),
+                ("n_lanes", C.c_int), ("lanes", C.POINTER(CLane)), ("hp", MetaHParams),
+                ("results", C.c_void_p), ("seed_slot", C.c_void_p), ("use_graph", C.c_int)]
+
+
 _P, _I, _F, _LL, _ULL, _U = C.c_void_p, C.c_int, C.c_float, C.c_longlong, C.c_ulonglong, C.c_uint
 _D = C.c_double
 
@@ -55,6 +67,8 @@ SIGNATURES = {
     "mtl_asr_backward": (_I, [_P, _P, _P, _F, _P, _I, _P]),
     "mtl_meta_task": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _LL, C.POINTER(CBatch), C.POINTER(CBatch),
                            C.POINTER(MetaHParams), _P, _P]),
+    "mtl_meta_tasks": (_I, [_P, C.POINTER(MetaStepArgs), _P]),
+    "mtl_graph_stats": (_I, [_P, C.POINTER(_ULL), C.POINTER(_ULL)]),
     "mtl_meta_finish": (_I, [_P, _P, _P, _P, _P, _P, _D, _I, _F, _P, _LL, _P]),
     "mtl_arena_zero": (_I, [_P, _LL, _P]),
     "mtl_arena_copy": (_I, [_P, _P, _LL, _P]),
@@ -71,6 +85,8 @@ SIGNATURES = {
     "mtl_ce_bwd": (_I, [_P, _I, _P, _P, _P, _F, _F, _P, _I, _I, _P]),
     "mtl_conv1_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "mtl_conv3x3_relu_fwd": (_I, [_I, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "mtl_conv3x3_bwd_scratch_floats": (_LL, [_I, _I, _I, _I, _I, _I]),
+    "mtl_conv3x3_bwd": (_I, [_I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "mtl_maxpool2_fwd": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "mtl_maxpool2_relu_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "mtl_dec_preprocess": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _P]),

@@ -54,7 +54,7 @@ class Batch:
 class Session:
     """A model layout + workspace bound to one CUDA device."""
 
-    def __init__(self, spec: ModelSpec, device="cuda", gemm_mode: int = 0):
+    def __init__(self, spec: ModelSpec, device="cuda", gemm_mode: int = 2):
         if not torch.cuda.is_available():
             raise _l.MtlError("libmtl_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = _l.get_lib()
@@ -176,6 +176,11 @@ class Session:
                                         _ptr(self.pe_enc), _ptr(self.pe_dec), _ptr(ws), ws.numel(),
                                         C.byref(ctr), C.byref(cva), C.byref(hp), _ptr(results), _stream()))
 
+    def graph_stats(self):
+        cap, rep = C.c_ulonglong(), C.c_ulonglong()
+        _l.check(self.lib.mtl_graph_stats(self._h, C.byref(cap), C.byref(rep)))
+        return int(cap.value), int(rep.value)
+
     def meta_finish(self, theta, grad, copy_grad, adam_m, adam_v, adam_state, meta_lr: float, clip: bool = False,
                     max_norm: float = 400.0):
         _l.check(self.lib.mtl_meta_finish(_ptr(theta), _ptr(grad), _ptr(copy_grad), _ptr(adam_m), _ptr(adam_v),
@@ -206,3 +211,102 @@ class Session:
     def adam(self, p, g, m, v, state, lr: float, b1=0.9, b2=0.999, eps=1e-8):
         _l.check(self.lib.mtl_arena_adam(_ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(state), float(lr), b1, b2, eps,
                                          p.numel(), _stream()))
+
+
+class MetaStepper:
+    """All tasks of one meta-step through ``mtl_meta_tasks``: tasks run concurrently on per-lane streams
+    and, once the same shapes have been seen twice, the whole step replays from a CUDA graph.
+
+    Owns what a graph bakes in: the per-lane adapted-weight / gradient arenas and workspaces, the device seed
+    slot, the results block and STATIC input slots (one set per distinct batch shape) into which every step's
+    batches are copied, so pointers never change between steps."""
+
+    def __init__(self, session: Session, n_tasks: int, n_lanes: Optional[int] = None, use_graph: bool = True):
+        self.s = session
+        self.n_tasks = int(n_tasks)
+        self.n_lanes = int(n_lanes or min(self.n_tasks, 8))
+        self.use_graph = bool(use_graph)
+        dev = session.device
+        self.lane_theta = [session.new_arena() for _ in range(self.n_lanes)]
+        self.lane_grad = [session.new_arena() for _ in range(self.n_lanes)]
+        self.lane_ws = [None] * self.n_lanes
+        self.seed_slot = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.results = torch.zeros(self.n_tasks, 16, dtype=torch.float32, device=dev)
+        self._slots = {}
+        self.train = [None] * self.n_tasks
+        self.val = None
+
+    # ------------------------------------------------------------------ static input slots
+    def _slot(self, who, B, F, T, L):
+        key = (who, B, F, T, L)
+        if key not in self._slots:
+            dev = self.s.device
+            self._slots[key] = (torch.zeros(B, 1, F, T, dtype=torch.float32, device=dev),
+                                torch.zeros(B, dtype=torch.int32, device=dev),
+                                torch.zeros(B, L, dtype=torch.int64, device=dev),
+                                torch.zeros(B * (L + 1), dtype=torch.int32, device=dev),     # hyp
+                                torch.zeros(B * (L + 1), dtype=torch.int32, device=dev))     # gold
+        return self._slots[key]
+
+    def _stage(self, who, x, lens, trg, n):
+        B, _, F, T = x.shape
+        L = trg.shape[1]
+        sx, sl, st, hyp, gold = self._slot(who, B, F, T, L)
+        sx.copy_(x, non_blocking=True)
+        sl.copy_(lens, non_blocking=True)
+        st.copy_(trg, non_blocking=True)
+        if n is None:
+            n = int((trg != 0).sum(dim=1).max().item()) + 1      # host tensors: no device sync
+        return Batch(sx, sl, st, n), hyp, gold
+
+    def load_task(self, t: int, x, lens, trg, n: Optional[int] = None):
+        """Copies task t's training batch (host pinned or device tensors) into its static slot."""
+        self.train[t] = self._stage(("tr", t), x, lens, trg, n)
+
+    def load_val(self, x, lens, trg, n: Optional[int] = None):
+        self.val = self._stage(("val",), x, lens, trg, n)
+
+    # ------------------------------------------------------------------ the step
+    def run(self, theta, copy_grad, lr: float, val_scale: float, clip: bool = False, max_norm: float = 400.0,
+            dropout: float = 0.0, smoothing: float = 0.0, seed: int = 0):
+        """copy_grad <- sum over tasks of [grad(train; theta) + val_scale * grad(val; theta - lr*grad_train)];
+        self.results[t] = [train CE block (8), val CE block (8)].  theta is not modified."""
+        s = self.s
+        B = max(max(b.B for b, _, _ in self.train), self.val[0].B)
+        T = max(max(b.x.shape[3] for b, _, _ in self.train), self.val[0].x.shape[3])
+        n = max(max(b.n for b, _, _ in self.train), self.val[0].n)
+        need = int(s.lib.mtl_workspace_bytes(s._h, B, T, n))
+        if need < 0:
+            _l.check(-2)
+        need += (1024 + 8) * 4 + 512
+        for l in range(self.n_lanes):
+            if self.lane_ws[l] is None or self.lane_ws[l].numel() < need:
+                self.lane_ws[l] = None
+                self.lane_ws[l] = torch.empty(need + (16 << 20), dtype=torch.uint8, device=s.device)
+        ctr = (_l.CBatch * self.n_tasks)()
+        for t, (b, hyp, gold) in enumerate(self.train):
+            ctr[t] = s._cbatch(b, hyp, gold)
+        cva = s._cbatch(self.val[0], self.val[1], self.val[2])
+        lanes = (_l.CLane * self.n_lanes)()
+        for l in range(self.n_lanes):
+            lanes[l].theta = self.lane_theta[l].data_ptr()
+            lanes[l].grad = self.lane_grad[l].data_ptr()
+            lanes[l].workspace = self.lane_ws[l].data_ptr()
+            lanes[l].workspace_bytes = self.lane_ws[l].numel()
+        a = _l.MetaStepArgs()
+        a.theta, a.copy_grad = theta.data_ptr(), copy_grad.data_ptr()
+        a.pe_enc, a.pe_dec = s.pe_enc.data_ptr(), s.pe_dec.data_ptr()
+        a.n_tasks, a.train, a.val = self.n_tasks, ctr, C.pointer(cva)
+        a.n_lanes, a.lanes = self.n_lanes, lanes
+        a.hp = _l.MetaHParams(float(lr), float(val_scale), int(bool(clip)), float(max_norm), float(dropout),
+                              float(smoothing), int(seed))
+        a.results = self.results.data_ptr()
+        a.seed_slot = self.seed_slot.data_ptr()
+        a.use_graph = int(self.use_graph)
+        _l.check(s.lib.mtl_meta_tasks(s._h, C.byref(a), _stream()))
+        return self.results
+
+    def train_outputs(self, t: int):
+        """(hyp, gold) int32 (B, n) of task t's TRAINING pass (what the trainer's CER is computed from)."""
+        b, hyp, gold = self.train[t]
+        return hyp[:b.B * b.n].view(b.B, b.n), gold[:b.B * b.n].view(b.B, b.n)

@@ -9,7 +9,7 @@ import mtl_b200
 from mtl_b200 import lib as L
 from oracle import ref_asr
 
-GEMM_MODE = int(os.environ.get("MTL_GEMM_MODE", "0"))
+GEMM_MODE = int(os.environ.get("MTL_GEMM_MODE", "2"))   # default = the tcgen05 3xTF32 engine
 
 
 def dev():
