@@ -98,6 +98,19 @@ __device__ __forceinline__ float dropout_scale(unsigned long long seed, uint32_t
   float u = (float)(v >> 8) * (1.0f / 16777216.0f);
   return u >= p ? inv_keep : 0.f;
 }
+// Same decisions for the 4 consecutive elements idx4 .. idx4+3 (idx4 % 4 == 0) from ONE Philox block.
+__device__ __forceinline__ float4 dropout_scale4(unsigned long long seed, uint32_t site,
+                                                 unsigned long long idx4, float p, float inv_keep) {
+  uint4 c = make_uint4((uint32_t)(idx4 >> 2), (uint32_t)(idx4 >> 34), site, 0u);
+  uint4 r = philox4x32_10(c, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const float k = 1.0f / 16777216.0f;
+  float4 o;
+  o.x = (float)(r.x >> 8) * k >= p ? inv_keep : 0.f;
+  o.y = (float)(r.y >> 8) * k >= p ? inv_keep : 0.f;
+  o.z = (float)(r.z >> 8) * k >= p ? inv_keep : 0.f;
+  o.w = (float)(r.w >> 8) * k >= p ? inv_keep : 0.f;
+  return o;
+}
 #endif
 
 // Dropout descriptor passed to kernels (p == 0 disables).  The effective Philox seed is

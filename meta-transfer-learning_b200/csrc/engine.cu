@@ -952,6 +952,19 @@ extern "C" int mtl_gemm(int mode, int transA, int transB, int M, int N, int Kd, 
   g.split_k = split_k;
   return k_gemm(g, mode, (cudaStream_t)stream);
 }
+// `reps` back-to-back launches of one GEMM (device-side timing of the kernel itself, without per-call host overhead)
+extern "C" int mtl_gemm_repeat(int reps, int mode, int transA, int transB, int M, int N, int Kd, const float* A, int lda,
+                               const float* B, int ldb, float beta, float* C, int ldc, int split_k, void* stream) {
+  MTL_REQUIRE(A && B && C && reps >= 1, "null argument");
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.A = A; g.B = B; g.C = C; g.M = M; g.N = N; g.K = Kd; g.lda = lda; g.ldb = ldb; g.ldc = ldc;
+  g.transA = transA; g.transB = transB; g.alpha = 1.f; g.beta = beta; g.split_k = split_k;
+  for (int i = 0; i < reps; ++i) MTL_TRY(k_gemm(g, mode, (cudaStream_t)stream));
+  return MTL_OK;
+}
+int k_gemm_tc_debug_stamps(long long* host32);
+extern "C" int mtl_debug_gemm_stamps(long long* host32) { return k_gemm_tc_debug_stamps(host32); }
 extern "C" int mtl_ln_fwd(const float* y, const float* res, const float* gamma, const float* beta,
                           const float* rowmask, const float* pe, int pe_period, float drop_p,
                           unsigned long long seed, unsigned site, float* out, float* xhat, float* rstd, int M, int d,

@@ -56,6 +56,9 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // Bounded wait: a pipeline bug must trap (error reported to the host), never hang the GPU.
+// debug stamps (MTL_GEMM_DBG=1): SM cycle counter at the main events of CTA (0,0,0)
+__device__ long long g_dbg[32];
+#define DBG_STAMP(i) do { if (P.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) g_dbg[i] = clock64(); } while (0)
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   const long long t0 = clock64();
@@ -122,6 +125,25 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// ---- thread-block-cluster helpers (cluster = the split-K group of one output tile)
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_saddr, uint32_t cta) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_saddr), "r"(cta));
+  return ra;
+}
+// 16-byte load from a shared::cluster address (own CTA's shared memory when the address was not mapa'd)
+__device__ __forceinline__ float4 ld_cluster_v4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
 // UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor bit layout): start>>4 [0,14), LBO>>4 [16,30),
 // SBO>>4 [32,46), version=1 [46,48), base_offset=0, layout_type [61,64).
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
@@ -152,6 +174,8 @@ struct TcParams {
   int cF, cT, cCin;  // activation extents of the tap-shifted operand
   int bt_log2;       // pixel box: (1 << bt_log2) time steps wide
   int tiles_t, tiles_f;
+  int dbg;
+  int cluster_k;     // > 1: grid.z CTAs form one cluster that splits K and reduces over distributed shared memory
 };
 
 template <int BN, int STAGES, bool A_MN, bool B_MN, bool SPLIT3>
@@ -174,6 +198,8 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
   const int kb0 = blockIdx.z * P.kb_per_split;
   const int kb1 = min(P.kb_total, kb0 + P.kb_per_split);
+  // cluster split-K (P.cluster_k > 1): the CTAs of one cluster (grid.z) own disjoint K slabs of ONE output tile;
+  // partial accumulators are pushed over DSMEM to the CTA that owns the row and summed there in a fixed order.
 
   // CONV_FWD: this CTA's 128 output pixels are the box (b, f0.., t0..)
   int cb = 0, cf0 = 0, ct0 = 0;
@@ -184,6 +210,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
     cb = rem / P.tiles_f;
   }
 
+  if (threadIdx.x == 0) DBG_STAMP(0);
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&ready[s], 4); }
     mbar_init(tmem_full, 1);
@@ -198,18 +225,21 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) DBG_STAMP(1);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
+      const int conv_mode = P.conv_mode, cCin = P.cCin, btl = P.bt_log2, tiles_t = P.tiles_t, tiles_f = P.tiles_f;
       int it = 0;
       for (int kb = kb0; kb < kb1; ++kb, ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
         mbar_wait(&empty[s], ph ^ 1);
+        if (it == 0) DBG_STAMP(2);
         mbar_expect_tx(&full[s], HI_BYTES);
         const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + A_STAGE_BYTES;
-        if (P.conv_mode == CONV_NONE) {
+        if (conv_mode == CONV_NONE) {
           if (!A_MN) {
             tma_load_2d(sa, &tmA, &full[s], kb * BK, m0);
           } else {
@@ -222,20 +252,20 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
 #pragma unroll
             for (int i = 0; i < BN / 32; ++i) tma_load_2d(sb + i * 4096, &tmB, &full[s], n0 + i * 32, kb * BK);
           }
-        } else if (P.conv_mode == CONV_FWD) {
-          const int cpb = P.cCin >> 5;                       // 32-channel chunks per tap
+        } else if (conv_mode == CONV_FWD) {
+          const int cpb = cCin >> 5;                         // 32-channel chunks per tap
           const int tap = kb / cpb, c0 = (kb - tap * cpb) << 5;
           const int kh = tap / 3, kw = tap - kh * 3;
           tma_load_4d(sa, &tmA, &full[s], c0, ct0 + kw - 1, cf0 + kh - 1, cb);
           tma_load_2d(sb, &tmB, &full[s], kb * BK, n0);
         } else {                                             // CONV_WGRAD: k-block = 32-pixel box
-          const int tt = kb % P.tiles_t, rem = kb / P.tiles_t;
-          const int t0 = tt << P.bt_log2, f0 = (rem % P.tiles_f) * (32 >> P.bt_log2), b = rem / P.tiles_f;
+          const int tt = kb % tiles_t, rem = kb / tiles_t;
+          const int t0 = tt << btl, f0 = (rem % tiles_f) * (32 >> btl), b = rem / tiles_f;
 #pragma unroll
           for (int i = 0; i < BM / 32; ++i) {
             const int mg = m0 + i * 32;
-            int tap = mg / P.cCin, c0 = mg - tap * P.cCin;
-            if (tap > 8) { tap = 0; c0 = P.cCin; }           // rows past 9*Cin: fully out of bounds -> zeros
+            int tap = mg / cCin, c0 = mg - tap * cCin;
+            if (tap > 8) { tap = 0; c0 = cCin; }             // rows past 9*Cin: fully out of bounds -> zeros
             const int kh = tap / 3, kw = tap - kh * 3;
             tma_load_4d(sa + i * 4096, &tmA, &full[s], c0, t0 + kw - 1, f0 + kh - 1, b);
           }
@@ -255,6 +285,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
         mbar_wait(SPLIT3 ? &ready[s] : &full[s], ph);
+        if (it == 0) DBG_STAMP(3);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + A_STAGE_BYTES;
 #pragma unroll
@@ -276,6 +307,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
         tc_commit(&empty[s]);          // frees the smem slot once these MMAs have read it
       }
       tc_commit(tmem_full);            // accumulator complete
+      DBG_STAMP(4);
     }
   } else {
     if (SPLIT3) {
@@ -304,78 +336,152 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
         if (lane == 0) mbar_arrive(&ready[s]);
       }
     }
-    // ===================== epilogue: TMEM -> registers -> global =====================
-    const int q = warp & 3;            // TMEM lane quarter this warp may access
-    const int r_in_tile = q * 32 + lane;
-    long long orow;                    // output row index, -1 = this lane has no row
-    if (P.conv_mode == CONV_FWD) {
-      const int f = cf0 + (r_in_tile >> P.bt_log2), t = ct0 + (r_in_tile & ((1 << P.bt_log2) - 1));
-      orow = (f < P.cF && t < P.cT) ? ((long long)cb * P.cF + f) * P.cT + t : -1;
-    } else {
-      orow = (m0 + r_in_tile < g.M) ? (long long)(m0 + r_in_tile) : -1;
-    }
+  }
+
+  // ===================== epilogue =====================
+  // Phase 1: every epilogue thread owns one accumulator row (TMEM lane) and parks it in a shared-memory staging
+  //          tile (row-major, padded).
+  // Phase 2: lanes run along COLUMNS (float4 each), so every warp instruction touches whole contiguous rows:
+  //          apply alpha / bias / ReLU / ReLU-mask / beta*C and write coalesced rows (or vectorised atomics).
+  //          With cluster split-K each CTA finishes rows [rank*128/CS, ...) of the tile and first sums the CS
+  //          partial tiles, pulling its peers' rows over distributed shared memory in a fixed order (deterministic).
+  constexpr int LDS = BN + 4;                       // staging row stride (floats): conflict-free float4 rows
+  float* stg = reinterpret_cast<float*>(smem);      // aliases the operand stages (dead once the accumulator is complete)
+  const int CS = P.cluster_k;
+  const int rank = CS > 1 ? (int)cluster_ctarank() : 0;
+  const int rows_per = BM / CS;
+  const int q = warp & 3;                           // TMEM lane quarter this warp may access
+  if (warp >= 2) {
     mbar_wait(tmem_full, 0);
     tc_fence_after();
+    if (threadIdx.x == 64) DBG_STAMP(5);
+    float* dst = stg + (q * 32 + lane) * LDS;
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
-      uint32_t r[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
-      const int col0 = n0 + c * 32;
-      if (orow >= 0 && col0 < g.N) {
-        float* crow = g.C + orow * g.ldc + col0;
-        if (g.split_k > 1) {
-          if (P.vecC && col0 + 31 < g.N) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              red_add_v4(crow + j, g.alpha * __uint_as_float(r[j]), g.alpha * __uint_as_float(r[j + 1]),
-                         g.alpha * __uint_as_float(r[j + 2]), g.alpha * __uint_as_float(r[j + 3]));
-          } else {
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(dst + c * 32 + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                   __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+    }
+    if (threadIdx.x == 64) DBG_STAMP(9);
+  }
+  if (CS > 1) cluster_sync_all();                   // every CTA's partial tile is staged
+  else if (warp >= 2) asm volatile("bar.sync 1, 128;" ::: "memory");
+  if (threadIdx.x == 64) DBG_STAMP(10);
+  if (warp >= 2) {
+    // Everything the loop needs lives in registers: re-reading kernel parameters from the constant bank inside the
+    // loop costs a dependent ~30-cycle load per field and, with one warp per scheduler, nothing hides it.
+    constexpr int LPR = BN / 4;                     // lanes per output row (float4 each)
+    constexpr int RPI = 32 / LPR;                   // rows per warp iteration
+    constexpr int STEP = 4 * RPI;                   // rows per iteration of the four epilogue warps
+    const int col_t = (lane % LPR) * 4, col = n0 + col_t;
+    const int N = g.N, M = g.M, ldc = g.ldc, epi = g.epi;
+    const float alpha = g.alpha, beta = g.beta;
+    float* const Cp = g.C;
+    const float* const auxp = g.aux;
+    const bool atomic = g.split_k > 1;
+    const bool vec = P.vecC && col + 3 < N;
+    const bool conv = P.conv_mode == CONV_FWD;
+    const int btl = P.bt_log2, btm = (1 << P.bt_log2) - 1, cF = P.cF, cT = P.cT;
+    float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (g.bias && !atomic) {
+      if (col + 0 < N) bias4.x = g.bias[col + 0];
+      if (col + 1 < N) bias4.y = g.bias[col + 1];
+      if (col + 2 < N) bias4.z = g.bias[col + 2];
+      if (col + 3 < N) bias4.w = g.bias[col + 3];
+    }
+    const float lo = epi == EPI_RELU ? 0.f : -INFINITY;   // branch-free ReLU
+    const int lr0 = q * RPI + lane / LPR;
+    const int r_first = rank * rows_per;            // first tile row this CTA finishes
+    uint32_t peer[8];                               // staging address of (row r_first + lr0, col_t) in every peer CTA
+    {
+      const uint32_t a0 = smem_u32(stg + (r_first + lr0) * LDS + col_t);
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < g.N) atomicAdd(crow + j, g.alpha * __uint_as_float(r[j]));
+      for (int s2 = 0; s2 < 8; ++s2) peer[s2] = (CS > 1 && s2 < CS) ? mapa_u32(a0, (uint32_t)s2) : a0;
+    }
+    if (col < N) {
+      if (!conv && vec && !atomic && epi != EPI_RELU_BWD && beta == 0.f) {
+        // hot path (every nn.Linear forward / dgrad): valid rows are a prefix of the tile
+        const int lim = min(rows_per, M - m0 - r_first);
+        float* cp = Cp + (long long)(m0 + r_first + lr0) * ldc + col;
+        const long long cstep = (long long)STEP * ldc;
+        uint32_t off = 0;
+#pragma unroll 4
+        for (int lr = lr0; lr < lim; lr += STEP, cp += cstep, off += STEP * LDS * 4) {
+          float4 acc = CS > 1 ? ld_cluster_v4(peer[0] + off)
+                              : *reinterpret_cast<const float4*>(reinterpret_cast<const char*>(stg + lr0 * LDS + col_t) + off);
+          if (CS > 1) {
+            float4 t[7];
+#pragma unroll
+            for (int s2 = 1; s2 < 8; ++s2) if (s2 < CS) t[s2 - 1] = ld_cluster_v4(peer[s2] + off);
+#pragma unroll
+            for (int s2 = 1; s2 < 8; ++s2)
+              if (s2 < CS) { acc.x += t[s2 - 1].x; acc.y += t[s2 - 1].y; acc.z += t[s2 - 1].z; acc.w += t[s2 - 1].w; }
           }
-        } else {
-          const float* arow = g.epi == EPI_RELU_BWD ? g.aux + orow * g.ldc + col0 : nullptr;
+          float4 o;
+          o.x = fmaxf(fmaf(alpha, acc.x, bias4.x), lo); o.y = fmaxf(fmaf(alpha, acc.y, bias4.y), lo);
+          o.z = fmaxf(fmaf(alpha, acc.z, bias4.z), lo); o.w = fmaxf(fmaf(alpha, acc.w, bias4.w), lo);
+          *reinterpret_cast<float4*>(cp) = o;
+        }
+      } else {
+#pragma unroll 1
+        for (int lr = lr0; lr < rows_per; lr += STEP) {
+          const int r_t = r_first + lr;
+          long long orow;
+          if (conv) {
+            const int f = cf0 + (r_t >> btl), t = ct0 + (r_t & btm);
+            orow = (f < cF && t < cT) ? ((long long)cb * cF + f) * cT + t : -1;
+          } else {
+            orow = (m0 + r_t < M) ? (long long)(m0 + r_t) : -1;
+          }
+          if (orow < 0) continue;
+          const uint32_t off = (uint32_t)((lr - lr0) * LDS * 4);
+          float4 acc = CS > 1 ? ld_cluster_v4(peer[0] + off) : *reinterpret_cast<const float4*>(stg + r_t * LDS + col_t);
 #pragma unroll
-          for (int j4 = 0; j4 < 32; j4 += 4) {
-            float v[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int col = col0 + j4 + j;
-              float t = g.alpha * __uint_as_float(r[j4 + j]);
-              if (g.bias && col < g.N) t += g.bias[col];
-              if (g.epi == EPI_RELU) t = fmaxf(t, 0.f);
-              v[j] = t;
+          for (int s2 = 1; s2 < 8; ++s2)
+            if (s2 < CS) { const float4 t = ld_cluster_v4(peer[s2] + off); acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w; }
+          float v[4] = {fmaxf(fmaf(alpha, acc.x, bias4.x), lo), fmaxf(fmaf(alpha, acc.y, bias4.y), lo),
+                        fmaxf(fmaf(alpha, acc.z, bias4.z), lo), fmaxf(fmaf(alpha, acc.w, bias4.w), lo)};
+          float* crow = Cp + orow * ldc + col;
+          if (atomic) {                             // atomic split-K (grid.z slabs without a cluster)
+            if (vec) red_add_v4(crow, v[0], v[1], v[2], v[3]);
+            else
+              for (int j = 0; j < 4; ++j) if (col + j < N) atomicAdd(crow + j, v[j]);
+            continue;
+          }
+          if (vec) {
+            if (epi == EPI_RELU_BWD) {
+              const float4 a = *reinterpret_cast<const float4*>(auxp + orow * ldc + col);
+              v[0] = a.x > 0.f ? v[0] : 0.f; v[1] = a.y > 0.f ? v[1] : 0.f;
+              v[2] = a.z > 0.f ? v[2] : 0.f; v[3] = a.w > 0.f ? v[3] : 0.f;
             }
-            if (P.vecC && col0 + j4 + 3 < g.N) {
-              if (arow) {
-                const float4 a = *reinterpret_cast<const float4*>(arow + j4);
-                v[0] = a.x > 0.f ? v[0] : 0.f; v[1] = a.y > 0.f ? v[1] : 0.f;
-                v[2] = a.z > 0.f ? v[2] : 0.f; v[3] = a.w > 0.f ? v[3] : 0.f;
-              }
-              if (g.beta != 0.f) {
-                const float4 o = *reinterpret_cast<const float4*>(crow + j4);
-                v[0] += g.beta * o.x; v[1] += g.beta * o.y; v[2] += g.beta * o.z; v[3] += g.beta * o.w;
-              }
-              *reinterpret_cast<float4*>(crow + j4) = make_float4(v[0], v[1], v[2], v[3]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                if (col0 + j4 + j < g.N) {
-                  float t = v[j];
-                  if (arow) t = arow[j4 + j] > 0.f ? t : 0.f;
-                  if (g.beta != 0.f) t += g.beta * crow[j4 + j];
-                  crow[j4 + j] = t;
-                }
+            if (beta != 0.f) {
+              const float4 o = *reinterpret_cast<const float4*>(crow);
+              v[0] += beta * o.x; v[1] += beta * o.y; v[2] += beta * o.z; v[3] += beta * o.w;
+            }
+            *reinterpret_cast<float4*>(crow) = make_float4(v[0], v[1], v[2], v[3]);
+          } else {
+            const float* arow = epi == EPI_RELU_BWD ? auxp + orow * ldc + col : nullptr;
+            for (int j = 0; j < 4; ++j) {
+              if (col + j < N) {
+                float t = v[j];
+                if (arow) t = arow[j] > 0.f ? t : 0.f;
+                if (beta != 0.f) t += beta * crow[j];
+                crow[j] = t;
               }
             }
           }
         }
       }
     }
+    if (threadIdx.x == 64) DBG_STAMP(6);
   }
+  if (CS > 1) cluster_sync_all();                   // nobody leaves while a peer may still read its staged rows
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) DBG_STAMP(7);
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN) : "memory");
@@ -473,6 +579,19 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& P, dim3
     MTL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     configured = true;
   }
+  static_assert(SMEM - 1280 >= BM * (BN + 4) * 4, "staging tile must fit in the operand stages");
+  if (P.cluster_k > 1) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = dim3(192, 1, 1); cfg.dynamicSmemBytes = SMEM; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = (unsigned)P.cluster_k;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    MTL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, P));
+    ++g_mtl_launches;
+    return MTL_OK;
+  }
   kern<<<grid, 192, SMEM, s>>>(ta, tb, P);
   MTL_CHECK_LAUNCH();
   return MTL_OK;
@@ -496,6 +615,12 @@ int dispatch(int bn, bool split3, bool a_mn, bool b_mn, const CUtensorMap& ta, c
 }
 
 inline bool al16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
+// MTL_CLUSTER_SPLITK=0 disables the cluster split (A/B measurements)
+bool cluster_split_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MTL_CLUSTER_SPLITK"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v != 0;
+}
 
 // Splits kb_total k-blocks over `want` CTAs (blockIdx.z); returns the grid depth and fills kb_per_split.
 int plan_split(TcParams& P, int want) {
@@ -552,8 +677,23 @@ int k_gemm_tc(const GemmArgs& g, int precision_mode, cudaStream_t s) {
   P.conv_mode = CONV_NONE;
   P.kb_total = mtl_cdiv(g.K, BK);
   if (g.split_k > 1) MTL_REQUIRE(g.beta == 1.f && g.epi == EPI_NONE && g.bias == nullptr, "split-K needs beta=1, no epilogue");
-  const int split = plan_split(P, g.split_k);
+  int split = plan_split(P, g.split_k);
+  P.cluster_k = 1;
+  if (g.split_k <= 1 && cluster_split_enabled()) {
+    // Few output tiles (M ~ 264 rows): one CTA per tile would stream its whole K extent through a single SM at
+    // one-TMA-latency per 3 stages.  Spread K over a cluster of up to 8 CTAs (deterministic DSMEM reduction).
+    const long long tiles = (long long)mtl_cdiv(g.M, BM) * mtl_cdiv(g.N, bn);
+    int cs = 1;
+    while (cs < 8 && tiles * (cs * 2) <= 160 && P.kb_total >= cs * 2) cs *= 2;
+    while (cs > 1 && (long long)(cs - 1) * mtl_cdiv(P.kb_total, cs) >= P.kb_total) cs /= 2;   // every CTA gets >= 1 k-block
+    if (cs > 1) {
+      P.cluster_k = cs;
+      P.kb_per_split = mtl_cdiv(P.kb_total, cs);
+      split = cs;
+    }
+  }
   P.vecC = al16(g.C) && (g.ldc % 4 == 0) && (g.epi != EPI_RELU_BWD || al16(g.aux));
+  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("MTL_GEMM_DBG"); dbg = e ? atoi(e) : 0; } P.dbg = dbg; }
   dim3 grid(mtl_cdiv(g.M, BM), mtl_cdiv(g.N, bn), split);
   MTL_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "gemm grid too large");
   return dispatch(bn, split3, a_mn, b_mn, ta, tb, P, grid, s);
@@ -569,6 +709,7 @@ int k_conv3x3_tc(const float* x, const float* wg, const float* bias, float* y, i
   TcParams P;
   memset(&P, 0, sizeof(P));
   P.conv_mode = CONV_FWD;
+  P.cluster_k = 1;
   P.cF = F; P.cT = T; P.cCin = Cin;
   P.bt_log2 = pick_bt_log2(BM, F, T, &P.tiles_t, &P.tiles_f);
   CUtensorMap ta, tb;
@@ -593,6 +734,7 @@ int k_conv3x3_wgrad_tc(const float* x, const float* dy, float* dwgT, int B, int 
   TcParams P;
   memset(&P, 0, sizeof(P));
   P.conv_mode = CONV_WGRAD;
+  P.cluster_k = 1;
   P.cF = F; P.cT = T; P.cCin = Cin;
   P.bt_log2 = pick_bt_log2(32, F, T, &P.tiles_t, &P.tiles_f);
   const int bt = 1 << P.bt_log2, bf = 32 >> P.bt_log2;
@@ -612,4 +754,10 @@ int k_conv3x3_wgrad_tc(const float* x, const float* dy, float* dwgT, int B, int 
   dim3 grid(mt, nt, split);
   MTL_REQUIRE(grid.z <= 65535, "conv wgrad grid too large");
   return dispatch(bn, split3, true, true, ta, tb, P, grid, s);
+}
+
+// debug: copies the 32 cycle stamps of the last instrumented GEMM launch to the host
+int k_gemm_tc_debug_stamps(long long* host32) {
+  MTL_CHECK_CUDA(cudaMemcpyFromSymbol(host32, g_dbg, sizeof(long long) * 32));
+  return MTL_OK;
 }

@@ -7,6 +7,8 @@
 #define LN_MAXV 32   // d <= 1024
 #define LN_EPS 1e-5f
 
+// One warp per row; each lane owns float4 column groups (4*(lane + 32 i) ..), so one Philox block
+// serves the 4 elements of a group.
 __global__ void __launch_bounds__(128) ln_fwd_kernel(
     const float* __restrict__ y, const float* __restrict__ res, const float* __restrict__ gamma,
     const float* __restrict__ beta, const float* __restrict__ rowmask, const float* __restrict__ pe,
@@ -15,41 +17,59 @@ __global__ void __launch_bounds__(128) ln_fwd_kernel(
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (row >= M) return;
-  float z[LN_MAXV];
+  constexpr int NV = LN_MAXV / 4;
+  const int d4 = d >> 2;
+  float4 z[NV];
   float sum = 0.f;
   const size_t base = (size_t)row * d;
+  const float4* y4 = reinterpret_cast<const float4*>(y + base);
+  const float4* r4 = res ? reinterpret_cast<const float4*>(res + base) : nullptr;
+  const unsigned long long seed = drop.p > 0.f ? mtl_eff_seed(drop) : 0ull;
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) {
-    int c = lane + i * 32;
-    float v = 0.f;
-    if (c < d) {
-      v = y[base + c];
-      if (drop.p > 0.f) v *= dropout_scale(mtl_eff_seed(drop), drop.site, base + c, drop.p, drop.inv_keep);
-      if (res) v += res[base + c];
+  for (int i = 0; i < NV; ++i) {
+    const int c = lane + i * 32;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < d4) {
+      v = y4[c];
+      if (drop.p > 0.f) {
+        const float4 sc = dropout_scale4(seed, drop.site, base + 4ull * c, drop.p, drop.inv_keep);
+        v.x *= sc.x; v.y *= sc.y; v.z *= sc.z; v.w *= sc.w;
+      }
+      if (r4) { const float4 r = r4[c]; v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w; }
     }
     z[i] = v;
-    sum += v;
+    sum += (v.x + v.y) + (v.z + v.w);
   }
   const float mean = warp_sum(sum) / (float)d;
   float var = 0.f;
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) {
-    int c = lane + i * 32;
-    if (c < d) { float t = z[i] - mean; var += t * t; }
+  for (int i = 0; i < NV; ++i) {
+    if (lane + i * 32 < d4) {
+      const float a = z[i].x - mean, b = z[i].y - mean, c = z[i].z - mean, e = z[i].w - mean;
+      var += (a * a + b * b) + (c * c + e * e);
+    }
   }
   var = warp_sum(var) / (float)d;
   const float rstd = rsqrtf(var + LN_EPS);
   const float rm = rowmask ? rowmask[row] : 1.f;
-  const float* per = pe ? pe + (size_t)(row % pe_period) * d : nullptr;
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+  const float4* p4 = pe ? reinterpret_cast<const float4*>(pe + (size_t)(row % pe_period) * d) : nullptr;
+  float4* xh4 = reinterpret_cast<float4*>(xhat + base);
+  float4* o4 = reinterpret_cast<float4*>(out + base);
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) {
-    int c = lane + i * 32;
-    if (c < d) {
-      float xh = (z[i] - mean) * rstd;
-      float o = xh * gamma[c] + beta[c];
-      if (per) o += per[c];
-      xhat[base + c] = xh;
-      out[base + c] = o * rm;
+  for (int i = 0; i < NV; ++i) {
+    const int c = lane + i * 32;
+    if (c < d4) {
+      const float4 g = g4[c], b = b4[c];
+      float4 xh, o;
+      xh.x = (z[i].x - mean) * rstd; xh.y = (z[i].y - mean) * rstd;
+      xh.z = (z[i].z - mean) * rstd; xh.w = (z[i].w - mean) * rstd;
+      o.x = xh.x * g.x + b.x; o.y = xh.y * g.y + b.y; o.z = xh.z * g.z + b.z; o.w = xh.w * g.w + b.w;
+      if (p4) { const float4 pp = p4[c]; o.x += pp.x; o.y += pp.y; o.z += pp.z; o.w += pp.w; }
+      o.x *= rm; o.y *= rm; o.z *= rm; o.w *= rm;
+      xh4[c] = xh;
+      o4[c] = o;
     }
   }
   if (lane == 0) rstd_out[row] = rstd;
@@ -58,7 +78,7 @@ __global__ void __launch_bounds__(128) ln_fwd_kernel(
 int k_ln_fwd(const float* y, const float* res, const float* gamma, const float* beta, const float* rowmask,
              const float* pe, int pe_period, MtlDrop drop, float* out, float* xhat, float* rstd, int M,
              int d, cudaStream_t s) {
-  MTL_REQUIRE(d <= 32 * LN_MAXV, "layer norm width > 1024");
+  MTL_REQUIRE(d <= 32 * LN_MAXV && d % 4 == 0, "layer norm width must be a multiple of 4, <= 1024");
   if (M == 0) return MTL_OK;
   ln_fwd_kernel<<<mtl_cdiv(M, 4), 128, 0, s>>>(y, res, gamma, beta, rowmask, pe, pe_period > 0 ? pe_period : 1,
                                               drop, out, xhat, rstd, M, d);
@@ -73,30 +93,53 @@ __global__ void __launch_bounds__(128) ln_bwd_kernel(
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (row >= M) return;
+  constexpr int NV = LN_MAXV / 4;
+  const int d4 = d >> 2;
   const size_t base = (size_t)row * d;
   const float rm = rowmask ? rowmask[row] : 1.f;
-  float dxh[LN_MAXV], xh[LN_MAXV];
+  const float4* do4 = reinterpret_cast<const float4*>(dout + base);
+  const float4* xh4 = reinterpret_cast<const float4*>(xhat + base);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  float4 dxh[NV], xh[NV];
   float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) {
-    int c = lane + i * 32;
-    float a = 0.f, b = 0.f;
-    if (c < d) { a = dout[base + c] * rm * gamma[c]; b = xhat[base + c]; }
+  for (int i = 0; i < NV; ++i) {
+    const int c = lane + i * 32;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (c < d4) {
+      const float4 g = g4[c];
+      a = do4[c]; b = xh4[c];
+      a.x *= rm * g.x; a.y *= rm * g.y; a.z *= rm * g.z; a.w *= rm * g.w;
+    }
     dxh[i] = a; xh[i] = b;
-    s1 += a; s2 += a * b;
+    s1 += (a.x + a.y) + (a.z + a.w);
+    s2 += (a.x * b.x + a.y * b.y) + (a.z * b.z + a.w * b.w);
   }
   s1 = warp_sum(s1) / (float)d;
   s2 = warp_sum(s2) / (float)d;
   const float r = rstd[row];
+  const unsigned long long seed = (dy && drop.p > 0.f) ? mtl_eff_seed(drop) : 0ull;
+  float4* dr4 = dres ? reinterpret_cast<float4*>(dres + base) : nullptr;
+  float4* dy4 = dy ? reinterpret_cast<float4*>(dy + base) : nullptr;
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) {
-    int c = lane + i * 32;
-    if (c < d) {
-      float dz = r * (dxh[i] - s1 - xh[i] * s2);
-      if (dres) dres[base + c] = dres_acc ? dres[base + c] + dz : dz;
-      if (dy) {
-        float sc = drop.p > 0.f ? dropout_scale(mtl_eff_seed(drop), drop.site, base + c, drop.p, drop.inv_keep) : 1.f;
-        dy[base + c] = dz * sc;
+  for (int i = 0; i < NV; ++i) {
+    const int c = lane + i * 32;
+    if (c < d4) {
+      float4 dz;
+      dz.x = r * (dxh[i].x - s1 - xh[i].x * s2); dz.y = r * (dxh[i].y - s1 - xh[i].y * s2);
+      dz.z = r * (dxh[i].z - s1 - xh[i].z * s2); dz.w = r * (dxh[i].w - s1 - xh[i].w * s2);
+      if (dr4) {
+        float4 o = dz;
+        if (dres_acc) { const float4 p = dr4[c]; o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
+        dr4[c] = o;
+      }
+      if (dy4) {
+        float4 o = dz;
+        if (drop.p > 0.f) {
+          const float4 sc = dropout_scale4(seed, drop.site, base + 4ull * c, drop.p, drop.inv_keep);
+          o.x *= sc.x; o.y *= sc.y; o.z *= sc.z; o.w *= sc.w;
+        }
+        dy4[c] = o;
       }
     }
   }
@@ -132,7 +175,7 @@ __global__ void __launch_bounds__(256) ln_param_grad_kernel(
 int k_ln_bwd(const float* dout, const float* xhat, const float* rstd, const float* gamma, const float* rowmask,
              MtlDrop drop, float* dy, float* dres, int dres_accumulate, float* dgamma, float* dbeta, int M,
              int d, cudaStream_t s) {
-  MTL_REQUIRE(d <= 32 * LN_MAXV, "layer norm width > 1024");
+  MTL_REQUIRE(d <= 32 * LN_MAXV && d % 4 == 0, "layer norm width must be a multiple of 4, <= 1024");
   if (M == 0) return MTL_OK;
   ln_bwd_kernel<<<mtl_cdiv(M, 4), 128, 0, s>>>(dout, xhat, rstd, gamma, rowmask, drop, dy, dres,
                                               dres_accumulate, M, d);

@@ -51,7 +51,8 @@ class _FusedLoss(torch.autograd.Function):
     fused softmax-minus-onehot gradient instead of materialising d(pred) on the host side."""
 
     @staticmethod
-    def forward(ctx, pred, model, ticket):
+    def forward(ctx, hook, model, ticket):
+        # hangs off the model's hook tensor, NOT off pred: nothing must flow back into _FusedForward.backward
         ctx.model, ctx.ticket = model, ticket
         return model._last["ce"][0].clone()
 
@@ -96,6 +97,7 @@ class Transformer(nn.Module):
         self._ticket = 0
         self._last = None
         self._seed = itertools.count(int(torch.initial_seed()) & 0x7FFFFFFF)
+        self._direct_grads = False           # True while a trainer writes the gradient arena directly (no autograd)
 
     # ------------------------------------------------------------------ engine binding
     def spec(self) -> mtl_b200.ModelSpec:
@@ -136,6 +138,11 @@ class Transformer(nn.Module):
         s.pe_dec = self.decoder.positional_encoding.pe[0]
         self._hook = torch.zeros(1, device=device, requires_grad=True)
 
+    def cuda(self, device=None):
+        if not torch.cuda.is_available():
+            raise mtl_b200.MtlError("model.cuda(): no CUDA device (sm_100a) is visible and libmtl_b200 has no CPU path")
+        return super().cuda(device)
+
     def _apply(self, fn, *a, **k):
         super()._apply(fn, *a, **k)
         p0 = next(self.parameters())
@@ -169,6 +176,18 @@ class Transformer(nn.Module):
             if p.grad is None:
                 p.grad = g
             elif p.grad.data_ptr() != g.data_ptr():
+                g.copy_(p.grad)
+                p.grad = g
+
+    def grads_pending(self) -> bool:
+        """True when the gradient arena holds gradients an optimizer step should consume."""
+        return self._direct_grads or any(p.grad is not None for p in self._params)
+
+    def _adopt_foreign_grads(self):
+        """Copies gradients that were assigned from outside (``p.grad = t``) into the arena views."""
+        for i, p in enumerate(self._params):
+            g = self._grad_views[i]
+            if p.grad is not None and p.grad.data_ptr() != g.data_ptr():
                 g.copy_(p.grad)
                 p.grad = g
 
@@ -230,7 +249,7 @@ class Transformer(nn.Module):
             return self._last["ce"][0].clone()
         if owner[1] != self._ticket:
             return None
-        return _FusedLoss.apply(pred, self, owner[1])
+        return _FusedLoss.apply(self._hook, self, owner[1])
 
     def encode(self, padded_input, input_lengths):
         raise NotImplementedError("encode/decode are fused in the engine: call the model (forward) instead")

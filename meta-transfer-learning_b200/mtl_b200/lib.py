@@ -77,6 +77,8 @@ SIGNATURES = {
     "mtl_arena_clip": (_I, [_P, _LL, _F, _P, _P]),
     "mtl_arena_adam": (_I, [_P, _P, _P, _P, _P, _D, _D, _D, _D, _LL, _P]),
     "mtl_gemm": (_I, [_I, _I, _I, _I, _I, _I, _F, _P, _I, _P, _I, _F, _P, _I, _P, _I, _P, _I, _P]),
+    "mtl_gemm_repeat": (_I, [_I, _I, _I, _I, _I, _I, _I, _P, _I, _P, _I, _F, _P, _I, _I, _P]),
+    "mtl_debug_gemm_stamps": (_I, [_P]),
     "mtl_ln_fwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _F, _ULL, _U, _P, _P, _P, _I, _I, _P]),
     "mtl_ln_bwd": (_I, [_P, _P, _P, _P, _P, _F, _ULL, _U, _P, _P, _I, _P, _P, _I, _I, _P]),
     "mtl_attn_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _ULL, _U, _P, _P, _P]),

@@ -25,7 +25,9 @@ class ArenaSGD(torch.optim.SGD):
     @torch.no_grad()
     def step(self, closure=None):
         s, theta, grad = _arena_model(self._model)
-        self._model._attach_grads()
+        if not self._model.grads_pending():          # torch semantics: parameters without a gradient are skipped
+            return
+        self._model._adopt_foreign_grads()
         s.sgd(theta, grad, float(self.param_groups[0]['lr']))
 
 
@@ -54,16 +56,25 @@ class ArenaAdam(torch.optim.Adam):
     @torch.no_grad()
     def step(self, closure=None):
         s, theta, grad = _arena_model(self._model)
-        self._model._attach_grads()
+        if not self._model.grads_pending():
+            return
+        self._model._adopt_foreign_grads()
         g = self.param_groups[0]
         s.adam(theta, grad, self.m, self.v, self.dev_state, float(g['lr']), g['betas'][0], g['betas'][1], g['eps'])
 
-    def state_dict(self):
+    def _refresh_steps(self):
         if hasattr(self, "dev_state"):               # (an unpickled copy only carries the base-class state)
             n = float(self.step_count)
             for st in self.state.values():
                 st["step"] = torch.tensor(n)
+
+    def state_dict(self):
+        self._refresh_steps()
         return super().state_dict()
+
+    def __getstate__(self):                          # checkpoints pickle the optimizer OBJECT (utils/functions.py:117-126)
+        self._refresh_steps()
+        return super().__getstate__()
 
     def load_state_dict(self, state_dict):
         super().load_state_dict(state_dict)          # casts / copies the loaded tensors

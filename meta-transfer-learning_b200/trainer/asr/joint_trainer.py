@@ -60,6 +60,7 @@ class JointTrainer(TransientTrainer):
         model.label_smoothing = float(smoothing)
         session = model.session
         theta, grad = model.arenas()
+        model._direct_grads = True                   # this trainer writes the gradient arena itself (no autograd)
         if opt_name == "adam":
             opt = ArenaAdam(model, args.lr)
         elif opt_name == "sgd":

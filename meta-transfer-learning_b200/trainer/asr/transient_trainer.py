@@ -121,6 +121,7 @@ class TransientTrainer():
         model.label_smoothing = float(smoothing)
         session = model.session
         theta, grad = model.arenas()
+        model._direct_grads = True                   # this trainer writes the gradient arena itself (no autograd)
 
         inner_opt = ArenaSGD(model, args.lr) if inner_opt is None else adopt(inner_opt, model, "sgd")
         outer_opt = ArenaAdam(model, args.meta_lr) if outer_opt is None else adopt(outer_opt, model, "adam")

@@ -1,0 +1,267 @@
+"""-m gpu: the reference-compatible Python surface on the B200 engine, checked against the CPU oracle.
+
+These tests read like what the reference's own tests would be if it had any: build the model with
+``init_transformer_model``, drive it through ``forward`` / ``calculate_metrics`` / ``loss.backward()`` /
+``torch.optim`` / the copy-grad API exactly as trainer/asr/transient_trainer.py:150-255 does, run the two
+trainers on K-shot samplers, and round-trip a checkpoint."""
+import contextlib
+import copy
+import io
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import api_util
+from gpu_util import rel_err
+from oracle import ref_asr, ref_meta
+
+pytestmark = pytest.mark.gpu
+
+TOL_OUT, TOL_GRAD, TOL_CONV = 1e-4, 1e-3, 5e-3          # default engine = 3xTF32 (see tests/test_gpu_parity.py)
+
+
+def _tol(name):
+    return TOL_CONV if name.startswith("conv.") else TOL_GRAD
+
+
+def _model(cfg, params=None, seed=0, **arg_over):
+    from utils.functions import init_transformer_model
+    torch.manual_seed(seed)
+    args = api_util.script_args(cfg, **arg_over)
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = init_transformer_model(args, api_util.make_vocab(cfg.vocab - 4), is_factorized=False, r=cfg.rank)
+    if params is not None:
+        missing = model.load_state_dict({k: v.clone() for k, v in params.items()}, strict=False)
+        assert not missing.unexpected_keys and all(k.endswith(".pe") for k in missing.missing_keys)
+    return model.cuda(), args
+
+
+def _sampler(batch):
+    x, lens, y = batch
+    return (x.clone(), lens.clone(), torch.ones(len(lens)), y.clone(), (y != 0).sum(1).to(torch.int32))
+
+
+class ListSampler:
+    """K-shot sampler honouring SpectrogramDataset.sample (utils/data_loader.py:245-321) from pre-built batches."""
+
+    def __init__(self, entries):
+        self.entries, self.i = list(entries), 0
+
+    def sample(self, k_train, k_valid, manifest_id):
+        e = self.entries[min(self.i, len(self.entries) - 1)]
+        self.i += 1
+        return e
+
+
+def test_forward_loss_backward_through_the_reference_api():
+    """model(src, lens, trg) -> calculate_metrics -> loss.backward() -> p.grad, as forward_one_batch does
+    (transient_trainer.py:25-46,198-199)."""
+    from utils.metrics import calculate_metrics
+    cfg = ref_asr.SMALL
+    p = ref_asr.init_params(cfg, 2)
+    batch = ref_meta.synth_batch(cfg, 4, 41, 7, 10, lengths=[41, 30, 9, 5], tgt_lengths=[7, 5, 3, 1])
+    loss_o, g_o, gold_o, hyp_o, pred_o = ref_meta.loss_and_grads(p, cfg, batch)
+    model, _ = _model(cfg, p)
+    model.eval()                                             # dropout off; gradients still flow
+    x, lens, y = batch
+    pred, gold, hyp = model(x.cuda(), lens, y.cuda())
+    assert pred.shape == pred_o.shape and pred.requires_grad and gold.dtype == torch.int64 and hyp.dtype == torch.int64
+    assert torch.equal(gold.cpu(), gold_o)
+    keep = gold_o != 0
+    assert torch.equal(hyp.cpu()[keep], hyp_o[keep])
+    assert rel_err(pred, pred_o) < TOL_OUT
+    loss, n_correct = calculate_metrics(pred, gold, model.vocab.PAD_ID, smoothing=0.0, loss_type="ce")
+    assert abs(loss.item() - loss_o) < TOL_OUT * loss_o
+    assert n_correct == ref_asr.num_correct(pred_o, gold_o)
+    torch.optim.SGD(model.parameters(), lr=0.1).zero_grad()
+    loss.backward()
+    for name, prm in model.named_parameters():
+        if float(g_o[name].abs().max()) > 1e-7:
+            assert rel_err(prm.grad, g_o[name]) < _tol(name), name
+    # the generic route: a loss the engine did not fuse (plain torch CE on pred) gives the same gradients
+    fused = {n: prm.grad.clone() for n, prm in model.named_parameters()}
+    model.zero_grad()
+    pred2, gold2, _ = model(x.cuda(), lens, y.cuda())
+    torch.nn.functional.cross_entropy(pred2.view(-1, pred2.size(2)), gold2.view(-1), ignore_index=0).backward()
+    for name, prm in model.named_parameters():
+        if float(fused[name].abs().max()) > 1e-7:
+            assert rel_err(prm.grad, fused[name]) < 2e-5, name
+
+
+def test_meta_step_written_against_the_model_api_like_the_reference_trainer():
+    """transient_trainer.py:155-255 restated with the public model API + torch.optim (deepcopy(state_dict), inner
+    SGD step in place, val backward WITHOUT zero_grad, add_copy_grad, load_state_dict, from_copy_grad, Adam)."""
+    from utils.metrics import calculate_metrics
+    cfg = ref_asr.SMALL
+    p = ref_asr.init_params(cfg, 3)
+    tasks = [ref_meta.synth_batch(cfg, 4, 41, 7, 100 + i) for i in range(3)]
+    val = ref_meta.synth_batch(cfg, 4, 37, 6, 150)
+    lr, meta_lr = 1e-2, 1e-3
+    po = {k: v.clone() for k, v in p.items()}
+    ref = ref_meta.meta_step(po, ref_meta.AdamState(), cfg, tasks, val, lr=lr, meta_lr=meta_lr)
+
+    model, _ = _model(cfg, p, dropout=0.0)
+    model.train()
+    inner_opt = torch.optim.SGD(model.parameters(), lr=lr)
+    outer_opt = torch.optim.Adam(model.parameters(), lr=meta_lr)
+    weights_original = copy.deepcopy(model.state_dict())
+    outer_opt.zero_grad()
+    model.zero_copy_grad()
+    val_losses = []
+    for x, lens, y in tasks:
+        pred, gold, _ = model(x.cuda(), lens, y.cuda())
+        tr_loss, _ = calculate_metrics(pred, gold, 0)
+        inner_opt.zero_grad()
+        tr_loss.backward()
+        inner_opt.step()
+        pred, gold, _ = model(val[0].cuda(), val[1], val[2].cuda())
+        val_loss, _ = calculate_metrics(pred, gold, 0)
+        val_losses.append(val_loss.item())
+        (val_loss / len(tasks)).backward()
+        model.add_copy_grad()
+        model.load_state_dict(weights_original)
+    cg = [c.clone() for c in model.copy_grad]
+    model.from_copy_grad()
+    outer_opt.step()
+    assert np.allclose(val_losses, ref["val_losses"], rtol=TOL_OUT)
+    for (name, prm), c in zip(model.named_parameters(), cg):
+        r = ref["copy_grad"][name]
+        if float(r.abs().max()) > 1e-7:
+            assert rel_err(c, r) < _tol(name), name
+        d = (prm.detach().cpu() - p[name]).abs()
+        assert float(d.max()) <= 2.1 * meta_lr, name
+        solid = r.abs() > 1e-2 * float(r.abs().max())
+        if solid.any():
+            assert float((prm.detach().cpu() - po[name]).abs()[solid].max()) <= 0.05 * meta_lr, name
+
+
+def _train_log(fn):
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        ret = fn()
+    out = buf.getvalue()
+    losses = [float(m) for m in re.findall(r"TRAIN LOSS:([0-9.]+)", out)]
+    cers = [float(m) for m in re.findall(r"CER:([0-9.]+)%", out)]
+    return ret, losses, cers, out
+
+
+def test_transient_trainer_two_iterations_match_the_oracle():
+    """TransientTrainer().train with the call signature of meta_transfer_train.py:204 on K-shot samplers."""
+    from trainer.asr.transient_trainer import TransientTrainer
+    cfg = ref_asr.SMALL
+    p = ref_asr.init_params(cfg, 3)
+    n_steps, lr, meta_lr = 2, 1e-2, 1e-3
+    steps = [([ref_meta.synth_batch(cfg, 4, 41, 7, 100 * s + i) for i in range(3)],
+              ref_meta.synth_batch(cfg, 4, 37 if s else 41, 6 if s else 7, 100 * s + 50)) for s in range(n_steps)]
+    po, adam = {k: v.clone() for k, v in p.items()}, ref_meta.AdamState()
+    refs = [ref_meta.meta_step(po, adam, cfg, t, v, lr=lr, meta_lr=meta_lr) for t, v in steps]
+
+    model, args = _model(cfg, p, dropout=0.0, lr=lr, meta_lr=meta_lr, k_train=4, k_valid=4)
+    samplers = [ListSampler([(_sampler(steps[s][0][i]), _sampler(steps[s][1])) for s in range(n_steps)]) for i in range(3)]
+    (inner, outer), losses, cers, out = _train_log(lambda: TransientTrainer().train(
+        model, model.vocab, samplers, [], "ce", 0, n_steps, args, inner_opt=None, outer_opt=None,
+        evaluate_every=10 ** 9, last_metrics=None, early_stop="loss,10", cpu_state_dict=False, is_copy_grad=True))
+    assert len(losses) == n_steps, out
+    assert abs(losses[0] - refs[0]["loss"]) < 2e-4 * refs[0]["loss"] + 5e-5      # printed with 4 decimals
+    assert abs(losses[1] - refs[1]["loss"]) < 2e-3 * refs[1]["loss"]             # after one Adam step (sign(g) noise)
+    assert all(0.0 <= c <= 1000.0 for c in cers)
+    assert outer.step_count == n_steps and inner.param_groups[0]['lr'] == lr
+    # parameters moved by at most ~2 Adam steps, and agree with the oracle where the gradient is solid
+    sd = model.state_dict()
+    for name in p:
+        assert float((sd[name].cpu() - p[name]).abs().max()) <= 2.1 * n_steps * meta_lr, name
+
+
+def test_joint_trainer_iteration_matches_the_oracle():
+    from trainer.asr.joint_trainer import JointTrainer
+    cfg = ref_asr.SMALL
+    p = ref_asr.init_params(cfg, 5)
+    tasks = [ref_meta.synth_batch(cfg, 2, 41, 7, 300 + i) for i in range(2)]
+    po = {k: v.clone() for k, v in p.items()}
+    ref = ref_meta.joint_step(po, ref_meta.AdamState(), cfg, tasks, lr=1e-3)
+    model, args = _model(cfg, p, dropout=0.0, lr=1e-3, k_train=2)
+    samplers = [ListSampler([(_sampler(t), _sampler(t))]) for t in tasks]
+    opt, losses, _, out = _train_log(lambda: JointTrainer().train(
+        model, model.vocab, samplers, [], "ce", 0, 1, args, evaluate_every=10 ** 9, last_metrics=None,
+        early_stop="loss,10", cpu_state_dict=False, is_copy_grad=True, discriminator=None))
+    assert len(losses) == 1 and abs(losses[0] - ref["loss"]) < 2e-4 * ref["loss"] + 5e-5, out
+    _, grad = model.arenas()
+    gv = model.session.views(grad)
+    for name, r in ref["grads"].items():
+        if float(r.abs().max()) > 1e-7:
+            assert rel_err(gv[name], r) < _tol(name), name
+    sd = model.state_dict()
+    for name, r in ref["grads"].items():
+        solid = r.abs() > 1e-2 * float(r.abs().max())
+        if solid.any():
+            assert float((sd[name].cpu() - po[name]).abs()[solid].max()) <= 0.05 * 1e-3, name
+
+
+def test_checkpoint_round_trip_and_resume(tmp_path):
+    """save_meta_model / load_meta_model keep the reference's file layout (utils/functions.py:101-126,158-188):
+    state_dict keys, pickled optimizer objects, args and vocab; resuming continues the Adam step count."""
+    from trainer.asr.transient_trainer import TransientTrainer
+    from utils.functions import load_meta_model, save_meta_model
+    cfg = ref_asr.SMALL
+    model, args = _model(cfg, None, seed=11, dropout=0.0, lr=1e-2, meta_lr=1e-3, k_train=2, k_valid=2,
+                         save_folder=str(tmp_path), name="ckpt", is_factorized=False)
+    batch = ref_meta.synth_batch(cfg, 2, 41, 7, 1)
+    samplers = [ListSampler([(_sampler(batch), _sampler(batch))]) for _ in range(2)]
+    (inner, outer), losses, _, _ = _train_log(lambda: TransientTrainer().train(
+        model, model.vocab, samplers, [], "ce", 0, 2, args, evaluate_every=10 ** 9, early_stop="loss,10", is_copy_grad=True))
+    with contextlib.redirect_stdout(io.StringIO()):
+        save_meta_model(model, model.vocab, 2, inner, outer, {"avg_valid_loss": 1.0}, args, best_model=False)
+    path = os.path.join(str(tmp_path), "ckpt", "epoch_2.th")
+    raw = torch.load(path, map_location="cpu", weights_only=False)
+    assert set(raw) == {"vocab", "args", "epoch", "model_state_dict", "inner_opt", "outer_opt", "metrics"}
+    assert list(raw["model_state_dict"].keys()) == list(model.state_dict().keys())
+    assert len(raw["model_state_dict"]) == len(ref_asr.param_specs(cfg)) + 2          # + the two PE buffers
+    with contextlib.redirect_stdout(io.StringIO()):
+        m2, vocab2, inner2, outer2, epoch, metrics, args2 = load_meta_model(path)
+    assert epoch == 2 and metrics["avg_valid_loss"] == 1.0 and vocab2.id2label == model.vocab.id2label
+    for (k, a), (_, b) in zip(model.state_dict().items(), m2.state_dict().items()):
+        assert torch.equal(a, b), k
+    assert outer2.step_count == 2 and torch.equal(outer2.m, outer.m) and torch.equal(outer2.v, outer.v)
+    samplers = [ListSampler([(_sampler(batch), _sampler(batch))]) for _ in range(2)]
+    (_, outer3), losses3, _, _ = _train_log(lambda: TransientTrainer().train(
+        m2, vocab2, samplers, [], "ce", epoch, epoch + 1, args2, inner_opt=inner2, outer_opt=outer2,
+        evaluate_every=10 ** 9, early_stop="loss,10", is_copy_grad=True))
+    assert outer3.step_count == 3 and len(losses3) == 1 and losses3[0] < losses[0]
+
+
+def test_script_flow_on_synthetic_wav_manifests_with_validation_and_checkpoint(tmp_path):
+    """What meta_transfer_train.py:141-204 does, on synthetic 16 kHz WAV manifests: Vocab from a label list,
+    one SpectrogramDataset per task over ALL manifests, validation loaders, init_transformer_model, .cuda(),
+    TransientTrainer.train with periodic validation + checkpointing."""
+    from trainer.asr.transient_trainer import TransientTrainer
+    from utils.data_loader import AudioDataLoader, SpectrogramDataset
+    from utils.functions import compute_num_params, init_transformer_model
+    labs = api_util.labels(40)
+    vocab = api_util.make_vocab(40)
+    args = api_util.script_args(num_enc_layers=1, num_dec_layers=1, num_heads=2, dim_model=64, dim_emb=64, dim_key=32,
+                                dim_value=32, dim_inner=64, r=12, k_train=3, k_valid=2, lr=1e-3, meta_lr=1e-3,
+                                save_folder=str(tmp_path), name="flow", save_every=2, dropout=0.1)
+    audio_conf = dict(sample_rate=16000, window_size=.02, window_stride=.01, window="hamming", noise_dir=None,
+                      noise_prob=0.4, noise_levels=(0.0, 0.5))
+    manifests = [api_util.write_manifest(str(tmp_path), f"train{i}", 6, seed=i, text_labels=labs[1:12]) for i in range(2)]
+    valid = api_util.write_manifest(str(tmp_path), "valid", 3, seed=9, text_labels=labs[1:12])
+    train_data_list = [SpectrogramDataset(vocab, args, audio_conf, manifest_filepath_list=manifests, normalize=True,
+                                          is_train=True) for _ in manifests]
+    valid_loader_list = [AudioDataLoader(pad_token_id=vocab.PAD_ID, num_workers=0,
+                                         dataset=SpectrogramDataset(vocab, args, audio_conf, manifest_filepath_list=[valid],
+                                                                    normalize=True))]
+    torch.manual_seed(123456)
+    np.random.seed(123456)
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = init_transformer_model(args, vocab, is_factorized=False, r=args.r).cuda()
+    assert compute_num_params(model)[0] > 0 and args.dim_input == 5120
+    _, losses, cers, out = _train_log(lambda: TransientTrainer().train(
+        model, vocab, train_data_list, valid_loader_list, "ce", 0, 6, args, evaluate_every=2, early_stop="loss,10",
+        is_copy_grad=True))
+    assert len(losses) == 6 and all(np.isfinite(losses)) and losses[-1] < losses[0], out[-1500:]
+    assert "VALID SET 0 LOSS" in out and "AVG VALID LOSS" in out
+    assert os.path.exists(os.path.join(str(tmp_path), "flow", "epoch_2.th"))
+    assert os.path.exists(os.path.join(str(tmp_path), "flow", "best_model.th"))
