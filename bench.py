@@ -35,6 +35,9 @@ T_FRAMES, L_TOKENS = 101, 32
 TASKS_PER_GPU = 3
 LR, META_LR, DROPOUT = 1e-4, 1e-4, 0.1
 METRIC = "meta-step utterances/sec (enc2/dec4/d512, k=8)"
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE conv.2-forward launch from the committed `ncu --set full`
+# capture (profiles/), per gemm mode; None until a capture of that mode exists
+ROOFLINE_TRAFFIC_BYTES = {}
 UNIT = "utterance-passes/s"
 
 
@@ -284,36 +287,51 @@ def run_ours(args, rank, world, local_rank):
 
 
 def roofline_conv_gemm(s, lib, dev, mode):
+    """Dominant (FLOP-wise) kernel of the step: the conv.2 forward implicit GEMM, 130088 pixels x 64 x 576
+    (models/asr/transformer.py:49), timed through the same entry point the engine launches
+    (mtl_conv3x3_relu_fwd -> gemm_tc_kernel<64,...> in CONV_FWD mode; mode 0 = im2col + fp32 GEMM).
+    Inputs are rotated over 5 buffers (5 x 67 MB read+write > 126 MB L2) so no launch re-reads a hot input.
+    Algorithmic FLOPs per launch = 2 * B*F*T * Cout * 9*Cin; algorithmic bytes = x + y + w."""
     import ctypes as C
     from mtl_b200 import lib as L
     B, F, T, Cin, Cout = K_TRAIN, 161, T_FRAMES, 64, 64
     M, N, Kd = B * F * T, Cout, 9 * Cin
-    col = torch.randn(M, Kd, device=dev)
-    w = torch.randn(N, Kd, device=dev) * 0.05
+    NB = 5
+    xs = [torch.randn(B, F, T, Cin, device=dev) for _ in range(NB)]
+    outs = [torch.empty(B, F, T, Cout, device=dev) for _ in range(NB)]
+    w = torch.randn(Cout, Cin, 3, 3, device=dev) * 0.05
     bias = torch.zeros(N, device=dev)
-    out = torch.empty(M, N, device=dev)
+    wg = torch.empty(N, Kd, device=dev)
+    col = torch.empty(M, Kd, device=dev) if mode == 0 else None
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    pv = lambda t: None if t is None else C.c_void_p(t.data_ptr())
 
-    def run():
-        L.check(lib.mtl_gemm(mode, 0, 1, M, N, Kd, 1.0, C.c_void_p(col.data_ptr()), Kd, C.c_void_p(w.data_ptr()), Kd,
-                             0.0, C.c_void_p(out.data_ptr()), N, C.c_void_p(bias.data_ptr()), 1, None, 1, st))
-    for _ in range(3):
-        run()
-    reps = 10
+    def run(i):
+        L.check(lib.mtl_conv3x3_relu_fwd(mode, pv(xs[i % NB]), pv(w), pv(bias), pv(col), pv(wg), pv(outs[i % NB]),
+                                         B, F, T, Cin, Cout, st))
+    for i in range(NB):
+        run(i)
+    reps = 20
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e0.record()
-    for _ in range(reps):
-        run()
+    for i in range(reps):
+        run(i)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     pk = _peaks()
-    ach = 2.0 * M * N * Kd / (ms * 1e-3) / 1e12
+    flops = 2.0 * M * N * Kd
+    ach = flops / (ms * 1e-3) / 1e12
     return {"bound": "tensor", "achieved": ach, "peak": pk["bf16"], "unit": "TFLOP/s", "frac": ach / pk["bf16"],
-            "traffic": None, "kernel": "conv.2 forward contraction as GEMM %dx%dx%d (%s)" % (
-                M, N, Kd, {0: "gemm_simt_kernel fp32 CUDA cores", 1: "tcgen05 tf32", 2: "tcgen05 3xtf32"}[mode]),
-            "ms_per_launch": ms, "peak_source": pk["src"] + " dense bf16 cuBLAS burst (tf32 nominal = half)"}
+            "traffic": ROOFLINE_TRAFFIC_BYTES.get(mode),
+            "algorithmic_bytes": 4 * (M * Cin + M * Cout + N * Kd), "flops_per_launch": flops,
+            "kernel": "conv.2 forward implicit GEMM %dx%dx%d (%s), incl. its weight re-layout launch" % (
+                M, N, Kd, {0: "im2col + gemm_simt_kernel fp32 CUDA cores", 1: "gemm_tc_kernel<64> tcgen05 tf32",
+                           2: "gemm_tc_kernel<64> tcgen05 3xtf32"}[mode]),
+            "ms_per_launch": ms,
+            "peak_source": pk["src"] + " dense bf16 cuBLAS burst (no fp32-input tensor peak is measured; tf32 nominal"
+                           " = 1/2 of bf16, 3xtf32 issues 3 MMAs per product => attainable <= 1/6 of this peak)"}
 
 
 def cpu_baseline():

@@ -27,6 +27,15 @@ def _tol(name):
     return TOL_CONV if name.startswith("conv.") else TOL_GRAD
 
 
+def _solid(r, gmax):
+    """Entries whose Adam update is decided by the gradient and not by rounding noise: Adam normalises every
+    gradient to ~+-lr, so a tensor whose gradient is analytically zero (key_linear_b.bias: softmax is invariant to
+    a shift of all keys, common_layers.py:321-329) moves by +-lr in a direction set purely by fp32 noise."""
+    if float(r.abs().max()) < 1e-4 * gmax:
+        return torch.zeros_like(r, dtype=torch.bool)
+    return r.abs() > 1e-2 * float(r.abs().max())
+
+
 def _model(cfg, params=None, seed=0, **arg_over):
     from utils.functions import init_transformer_model
     torch.manual_seed(seed)
@@ -127,13 +136,14 @@ def test_meta_step_written_against_the_model_api_like_the_reference_trainer():
     model.from_copy_grad()
     outer_opt.step()
     assert np.allclose(val_losses, ref["val_losses"], rtol=TOL_OUT)
+    gmax = max(float(r.abs().max()) for r in ref["copy_grad"].values())
     for (name, prm), c in zip(model.named_parameters(), cg):
         r = ref["copy_grad"][name]
         if float(r.abs().max()) > 1e-7:
             assert rel_err(c, r) < _tol(name), name
         d = (prm.detach().cpu() - p[name]).abs()
         assert float(d.max()) <= 2.1 * meta_lr, name
-        solid = r.abs() > 1e-2 * float(r.abs().max())
+        solid = _solid(r, gmax)
         if solid.any():
             assert float((prm.detach().cpu() - po[name]).abs()[solid].max()) <= 0.05 * meta_lr, name
 
@@ -194,8 +204,9 @@ def test_joint_trainer_iteration_matches_the_oracle():
         if float(r.abs().max()) > 1e-7:
             assert rel_err(gv[name], r) < _tol(name), name
     sd = model.state_dict()
+    gmax = max(float(r.abs().max()) for r in ref["grads"].values())
     for name, r in ref["grads"].items():
-        solid = r.abs() > 1e-2 * float(r.abs().max())
+        solid = _solid(r, gmax)
         if solid.any():
             assert float((sd[name].cpu() - po[name]).abs()[solid].max()) <= 0.05 * 1e-3, name
 

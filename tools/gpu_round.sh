@@ -1,0 +1,12 @@
+#!/bin/bash
+# One GPU-box visit: parity tests, both bench arms, ncu launch list + full capture of the conv kernel.
+set -u
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt 2>&1
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err
+timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
+timeout 600 python bench.py --steps 10 --warmup 3 --gemm-mode 1 --no-cpu-baseline > gpurun_out/bench_tf32.json 2> gpurun_out/bench_tf32.err
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tc_kernel -s 2 -c 1 -f -o gpurun_out/conv2_fwd_3xtf32 python tools/probes/one_conv.py 2 4 > gpurun_out/ncu_conv2.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tc_kernel -s 2 -c 1 -f -o gpurun_out/conv2_fwd_tf32 python tools/probes/one_conv.py 1 4 > gpurun_out/ncu_conv1.log 2>&1
+echo done
