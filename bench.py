@@ -37,7 +37,7 @@ LR, META_LR, DROPOUT = 1e-4, 1e-4, 0.1
 METRIC = "meta-step utterances/sec (enc2/dec4/d512, k=8)"
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE conv.2-forward launch from the committed `ncu --set full`
 # capture (profiles/), per gemm mode; None until a capture of that mode exists
-ROOFLINE_TRAFFIC_BYTES = {}
+ROOFLINE_TRAFFIC_BYTES = {1: 33483776 + 749568, 2: 33489408 + 824576}   # profiles/r01_c_ncu_full_conv2_fwd_*.txt
 UNIT = "utterance-passes/s"
 
 
