@@ -169,8 +169,9 @@ int mtl_gemm(int mode, int transA, int transB, int M, int N, int K, float alpha,
 /* measurement hook: `reps` back-to-back launches of the same GEMM (alpha = 1, no bias / epilogue) */
 int mtl_gemm_repeat(int reps, int mode, int transA, int transB, int M, int N, int K, const float* A, int lda,
                     const float* B, int ldb, float beta, float* C, int ldc, int split_k, void* stream);
-/* debug hook (MTL_GEMM_DBG=1): SM-cycle stamps of CTA (0,0,0) of the last tcgen05 GEMM launch */
-int mtl_debug_gemm_stamps(long long* host32);
+/* debug hook (MTL_GEMM_DBG=n): SM-cycle stamps of the last tcgen05 GEMM / conv launch into 160 host slots:
+ * [0,32) phase stamps of CTA (0,0,0); [32,160) per-k-block pipeline stamps (4 per k-block) of CTA (n-1,0,0) */
+int mtl_debug_gemm_stamps(long long* host160);
 /* LayerNorm(dropout(y)+res)*rowmask (+pe)  -- modules/common_layers.py:129-131,303-304 */
 int mtl_ln_fwd(const float* y, const float* res, const float* gamma, const float* beta,
                const float* rowmask, const float* pe, int pe_period, float drop_p,

@@ -12,6 +12,7 @@
 #include "kernels.h"
 #include "../../include/mtl_b200.h"
 #include <stdarg.h>
+#include <stdlib.h>
 #include <new>
 #include <utility>
 #include <vector>
@@ -110,7 +111,7 @@ struct FfnAct {
   MtlDrop drop;
   FfnP p;
 };
-struct ConvAct { const float* x; float* col; float* y; int B, F, T, Cin, Cout, widx; };
+struct ConvAct { const float* x; float* col; float* y; float* wg; float* wd; int B, F, T, Cin, Cout, widx; };
 struct Pass {
   bool valid = false;
   mtl_batch b;
@@ -135,11 +136,44 @@ struct Pass {
   size_t ws_cap;
 };
 
+// Side streams of one pass.  A forward/backward pass is a DAG, not a chain: the k / v projections run beside the
+// q projection, every parameter-gradient contraction (wgrad, bias column sums, embedding scatter) is off the
+// activation-gradient critical path, and the encoder-side gradients of the decoder's cross-attention only meet
+// the main chain where the encoder backward starts.  Branches are expressed with events between streams, so a
+// CUDA-graph capture of the step records the same DAG.  MTL_BRANCHES=0 serialises everything on the main stream.
+constexpr int kSides = 6;
+enum { S_K = 0, S_V = 1, S_W0 = 2, S_W1 = 3, S_X = 4, S_AUX = 5 };
+struct Branches {
+  cudaStream_t side[kSides] = {};
+  std::vector<cudaEvent_t> ev;        // round-robin pool: every event is waited on right after it is recorded
+  size_t next = 0;
+  bool dirty[kSides] = {};            // side stream holds work main has not joined yet
+};
+static bool branches_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MTL_BRANCHES"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v != 0;
+}
+static int branches_init(Branches& b) {
+  if (b.side[0]) return MTL_OK;
+  for (int i = 0; i < kSides; ++i) MTL_CHECK_CUDA(cudaStreamCreateWithFlags(&b.side[i], cudaStreamNonBlocking));
+  b.ev.resize(256);
+  for (auto& e : b.ev) MTL_CHECK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  return MTL_OK;
+}
+static void branches_destroy(Branches& b) {
+  for (auto e : b.ev) if (e) cudaEventDestroy(e);
+  for (int i = 0; i < kSides; ++i) if (b.side[i]) cudaStreamDestroy(b.side[i]);
+  b.ev.clear();
+  memset(b.side, 0, sizeof(b.side));
+}
+
 // One lane = one concurrently running task of a meta-step: its own stream and activation record.
 struct Lane {
   cudaStream_t st = nullptr;
   cudaEvent_t done = nullptr;
   Pass pass;
+  Branches br;
 };
 // A captured meta-step (all tasks, all lanes) keyed by every pointer / shape / hyper-parameter baked into it.
 struct GraphEntry {
@@ -156,6 +190,7 @@ struct mtl_session {
   Layout L;
   int mode = MTL_GEMM_SIMT_FP32;
   Pass pass;                          // record of the plain mtl_asr_forward / mtl_meta_task API
+  Branches br;                        // its side streams
   std::vector<Lane> lanes;
   cudaEvent_t ev_fork = nullptr;
   cudaStream_t cap_st = nullptr;      // capture origin (the caller's stream may be the legacy stream, which cannot capture)
@@ -183,7 +218,10 @@ struct Bump {
 struct Run {
   mtl_session* S;
   Pass* P;                                    // activation record this run fills / consumes
-  cudaStream_t st;
+  cudaStream_t st;                            // stream the launch wrappers enqueue on (main, or a side stream inside an On scope)
+  cudaStream_t main = nullptr;                // the pass's main stream
+  Branches* br = nullptr;                     // null: everything runs on main
+  int w_rr = 0;
   bool dry;
   Bump ws;
   const float* theta;
@@ -194,7 +232,47 @@ struct Run {
   unsigned long long seed_mul = 0;
   uint32_t site;
   MtlDrop next_drop() { return p_drop > 0.f ? mtl_drop(p_drop, seed, site++, seed_dev, seed_mul) : mtl_nodrop(); }
+  bool par() const { return br != nullptr && !dry; }
+  cudaStream_t side(int i) const { return par() ? br->side[i] : main; }
+  cudaStream_t wside() { w_rr ^= 1; return side(S_W0 + w_rr); }   // parameter-gradient work alternates over two streams
 };
+// Scope in which the launch wrappers enqueue on `s` instead of the main stream.
+struct On {
+  Run& R;
+  cudaStream_t saved;
+  On(Run& r, cudaStream_t s) : R(r), saved(r.st) { r.st = s; }
+  ~On() { R.st = saved; }
+};
+// Records "everything enqueued on s so far" (null event when the pass runs serially).
+static int ev_mark(Run& R, cudaStream_t s, cudaEvent_t* out) {
+  *out = nullptr;
+  if (!R.par()) return MTL_OK;
+  cudaEvent_t e = R.br->ev[R.br->next++ % R.br->ev.size()];
+  MTL_CHECK_CUDA(cudaEventRecord(e, s));
+  *out = e;
+  return MTL_OK;
+}
+// Work enqueued on s from now on starts after e.
+static int ev_wait(Run& R, cudaStream_t s, cudaEvent_t e) {
+  if (!e || !R.par()) return MTL_OK;
+  MTL_CHECK_CUDA(cudaStreamWaitEvent(s, e, 0));
+  for (int i = 0; i < kSides; ++i) if (s == R.br->side[i]) R.br->dirty[i] = true;
+  return MTL_OK;
+}
+// `to` continues from the current tail of `from`.
+static int chain(Run& R, cudaStream_t from, cudaStream_t to) {
+  if (from == to || !R.par()) return MTL_OK;
+  cudaEvent_t e;
+  MTL_TRY(ev_mark(R, from, &e));
+  return ev_wait(R, to, e);
+}
+// main waits for every side stream that holds un-joined work
+static int join_all(Run& R) {
+  if (!R.par()) return MTL_OK;
+  for (int i = 0; i < kSides; ++i)
+    if (R.br->dirty[i]) { MTL_TRY(chain(R, R.br->side[i], R.main)); R.br->dirty[i] = false; }
+  return MTL_OK;
+}
 
 #define K(call)                        \
   do {                                 \
@@ -247,31 +325,63 @@ static int lowrank_fwd(Run& R, LowRankAct& A, const float* x, int M, int Kd, int
   MTL_TRY(lin_fwd(R, A.a, r, R.theta + offBw, R.theta + offBb, A.y, N, M, N, r, EPI_NONE));
   return MTL_OK;
 }
-// dx (+)= d/dx ; parameter grads accumulated.  dx may be null.
-static int lowrank_bwd(Run& R, const LowRankAct& A, const float* dy, float* dx, float beta_dx) {
+// Backward of y = B(A x) + b in two parts so that callers can interleave several projections:
+//   head: da = dy . Bw on s_da (after e_dy when given), then the three parameter-gradient kernels on s_w;
+//   tail: dx (+)= da . A on s_x.
+// Scratch is never recycled inside a backward pass: side streams may still be reading it.
+struct LrBwd { float* da; cudaEvent_t e_da; };
+static int lowrank_bwd_head(Run& R, const LowRankAct& A, const float* dy, cudaEvent_t e_dy, cudaStream_t s_da,
+                            cudaStream_t s_w, LrBwd* h) {
   const int r = R.S->cfg.rank;
-  size_t mark = R.ws.off;
-  float* da = R.ws.f((size_t)A.M * r);
-  MTL_TRY(lin_dgrad(R, dy, A.N, R.theta + A.offBw, da, r, A.M, A.N, r, 0.f, EPI_NONE, nullptr));
-  MTL_TRY(lin_wgrad(R, dy, A.N, A.a, r, R.grad + A.offBw, A.M, A.N, r));
-  K(k_colsum_acc(dy, A.M, A.N, A.N, R.grad + A.offBb, R.st));
-  MTL_TRY(lin_wgrad(R, da, r, A.x, A.K, R.grad + A.offA, A.M, r, A.K));
-  if (dx) MTL_TRY(lin_dgrad(R, da, r, R.theta + A.offA, dx, A.K, A.M, r, A.K, beta_dx, EPI_NONE, nullptr));
-  R.ws.off = mark;
+  h->da = R.ws.f((size_t)A.M * r);
+  h->e_da = nullptr;
+  MTL_TRY(ev_wait(R, s_da, e_dy));
+  {
+    On on(R, s_da);
+    MTL_TRY(lin_dgrad(R, dy, A.N, R.theta + A.offBw, h->da, r, A.M, A.N, r, 0.f, EPI_NONE, nullptr));
+  }
+  MTL_TRY(ev_mark(R, s_da, &h->e_da));
+  if (s_w != s_da) MTL_TRY(ev_wait(R, s_w, h->e_da));
+  {
+    On on(R, s_w);
+    MTL_TRY(lin_wgrad(R, dy, A.N, A.a, r, R.grad + A.offBw, A.M, A.N, r));
+    K(k_colsum_acc(dy, A.M, A.N, A.N, R.grad + A.offBb, R.st));
+    MTL_TRY(lin_wgrad(R, h->da, r, A.x, A.K, R.grad + A.offA, A.M, r, A.K));
+  }
   return MTL_OK;
+}
+static int lowrank_bwd_tail(Run& R, const LowRankAct& A, const LrBwd& h, float* dx, float beta_dx, cudaStream_t s_x) {
+  const int r = R.S->cfg.rank;
+  MTL_TRY(ev_wait(R, s_x, h.e_da));
+  On on(R, s_x);
+  return lin_dgrad(R, h.da, r, R.theta + A.offA, dx, A.K, A.M, r, A.K, beta_dx, EPI_NONE, nullptr);
 }
 
 // ----------------------------------------------------------------------------- attention block
+// kv_pre: the k / v projections of this block were already enqueued on S_X / S_AUX (decoder cross-attention:
+// they depend on the encoder output only).
+static int attn_kv_fwd(Run& R, AttnAct& A, const AttnP& p, const float* xkv, int Mk, cudaStream_t sk, cudaStream_t sv) {
+  const mtl_model_cfg& c = R.S->cfg;
+  cudaEvent_t e;
+  MTL_TRY(ev_mark(R, R.main, &e));
+  MTL_TRY(ev_wait(R, sk, e));
+  { On on(R, sk); MTL_TRY(lowrank_fwd(R, A.k, xkv, Mk, c.d_model, c.n_heads * c.d_k, c.rank, p.ka, p.kb_w, p.kb_b)); }
+  MTL_TRY(ev_wait(R, sv, e));
+  { On on(R, sv); MTL_TRY(lowrank_fwd(R, A.v, xkv, Mk, c.d_model, c.n_heads * c.d_v, c.rank, p.va, p.vb_w, p.vb_b)); }
+  return MTL_OK;
+}
 static int attn_block_fwd(Run& R, AttnAct& A, const AttnP& p, const float* xq, const float* xkv, int B, int Tq,
-                          int Tk, const unsigned char* keypad, int causal, const float* rowmask) {
+                          int Tk, const unsigned char* keypad, int causal, const float* rowmask, bool kv_pre) {
   const mtl_model_cfg& c = R.S->cfg;
   const int d = c.d_model, H = c.n_heads, dk = c.d_k, dv = c.d_v, r = c.rank;
   const int Mq = B * Tq, Mk = B * Tk;
   A.p = p; A.xq = xq; A.xkv = xkv; A.B = B; A.Tq = Tq; A.Tk = Tk; A.causal = causal; A.keypad = keypad;
   A.rowmask = rowmask;
+  const cudaStream_t sk = R.side(kv_pre ? S_X : S_K), sv = R.side(kv_pre ? S_AUX : S_V);
+  if (!kv_pre) MTL_TRY(attn_kv_fwd(R, A, p, xkv, Mk, sk, sv));
   MTL_TRY(lowrank_fwd(R, A.q, xq, Mq, d, H * dk, r, p.qa, p.qb_w, p.qb_b));
-  MTL_TRY(lowrank_fwd(R, A.k, xkv, Mk, d, H * dk, r, p.ka, p.kb_w, p.kb_b));
-  MTL_TRY(lowrank_fwd(R, A.v, xkv, Mk, d, H * dv, r, p.va, p.vb_w, p.vb_b));
+  MTL_TRY(chain(R, sk, R.main));
+  MTL_TRY(chain(R, sv, R.main));
   A.oh = R.ws.f((size_t)Mq * H * dv);
   A.lse = R.ws.f((size_t)B * H * Tq);
   A.drop_attn = R.next_drop();
@@ -293,11 +403,11 @@ static int attn_block_fwd(Run& R, AttnAct& A, const AttnP& p, const float* xq, c
 }
 // dout -> dxq (overwritten: residual + query-side grads); key/value-side grads ACCUMULATE into dxkv
 // (dxkv may alias dxq for self-attention).
-static int attn_block_bwd(Run& R, const AttnAct& A, const float* dout, float* dxq, float* dxkv) {
+// cross: dxkv is the encoder-side gradient (decoder cross-attention); its whole k / v chain runs in order on S_X.
+static int attn_block_bwd(Run& R, const AttnAct& A, const float* dout, float* dxq, float* dxkv, bool cross) {
   const mtl_model_cfg& c = R.S->cfg;
   const int d = c.d_model, H = c.n_heads, dk = c.d_k, dv = c.d_v;
   const int Mq = A.B * A.Tq, Mk = A.B * A.Tk;
-  size_t mark = R.ws.off;
   float* do2 = R.ws.f((size_t)Mq * d);
   float* d_oh = R.ws.f((size_t)Mq * H * dv);
   float* dq = R.ws.f((size_t)Mq * H * dk);
@@ -306,7 +416,9 @@ static int attn_block_bwd(Run& R, const AttnAct& A, const float* dout, float* dx
   float* delta = R.ws.f((size_t)A.B * H * A.Tq);
   K(k_ln_bwd(dout, A.xhat, A.rstd, R.theta + A.p.ln_w, A.rowmask, A.drop_out, do2, dxq, 0, R.grad + A.p.ln_w,
              R.grad + A.p.ln_b, Mq, d, R.st));
-  MTL_TRY(lowrank_bwd(R, A.o, do2, d_oh, 0.f));
+  LrBwd ho, hq, hk, hv;
+  MTL_TRY(lowrank_bwd_head(R, A.o, do2, nullptr, R.main, R.wside(), &ho));
+  MTL_TRY(lowrank_bwd_tail(R, A.o, ho, d_oh, 0.f, R.main));
   AttnBwdArgs b;
   memset(&b, 0, sizeof(b));
   b.f.q = A.q.y; b.f.k = A.k.y; b.f.v = A.v.y; b.f.o = A.oh; b.f.lse = A.lse; b.f.keypad = A.keypad;
@@ -315,10 +427,25 @@ static int attn_block_bwd(Run& R, const AttnAct& A, const float* dout, float* dx
   b.f.causal = A.causal; b.f.inv_temp = 1.0f / sqrtf((float)dk); b.f.drop = A.drop_attn;
   b.d_o = d_oh; b.delta = delta; b.dq = dq; b.dk = dkk; b.dv = dvv;
   K(k_attn_bwd(b, R.st));
-  MTL_TRY(lowrank_bwd(R, A.q, dq, dxq, 1.f));
-  MTL_TRY(lowrank_bwd(R, A.k, dkk, dxkv, 1.f));
-  MTL_TRY(lowrank_bwd(R, A.v, dvv, dxkv, 1.f));
-  R.ws.off = mark;
+  cudaEvent_t e_qkv;
+  MTL_TRY(ev_mark(R, R.main, &e_qkv));
+  if (cross) {
+    // key / value side: dgrads accumulate into the shared encoder-side gradient, one stream keeps them ordered
+    const cudaStream_t sx = R.side(S_X);
+    MTL_TRY(lowrank_bwd_head(R, A.k, dkk, e_qkv, sx, R.wside(), &hk));
+    MTL_TRY(lowrank_bwd_tail(R, A.k, hk, dxkv, 1.f, sx));
+    MTL_TRY(lowrank_bwd_head(R, A.v, dvv, nullptr, sx, R.wside(), &hv));
+    MTL_TRY(lowrank_bwd_tail(R, A.v, hv, dxkv, 1.f, sx));
+    MTL_TRY(lowrank_bwd_head(R, A.q, dq, nullptr, R.main, R.wside(), &hq));
+    MTL_TRY(lowrank_bwd_tail(R, A.q, hq, dxq, 1.f, R.main));
+  } else {
+    MTL_TRY(lowrank_bwd_head(R, A.k, dkk, e_qkv, R.side(S_K), R.side(S_K), &hk));
+    MTL_TRY(lowrank_bwd_head(R, A.v, dvv, e_qkv, R.side(S_V), R.side(S_V), &hv));
+    MTL_TRY(lowrank_bwd_head(R, A.q, dq, nullptr, R.main, R.wside(), &hq));
+    MTL_TRY(lowrank_bwd_tail(R, A.q, hq, dxq, 1.f, R.main));
+    MTL_TRY(lowrank_bwd_tail(R, A.k, hk, dxkv, 1.f, R.main));
+    MTL_TRY(lowrank_bwd_tail(R, A.v, hv, dxkv, 1.f, R.main));
+  }
   return MTL_OK;
 }
 
@@ -342,22 +469,44 @@ static int ffn_block_fwd(Run& R, FfnAct& A, const FfnP& p, const float* x, int M
 static int ffn_block_bwd(Run& R, const FfnAct& A, const float* dout, float* dx) {
   const mtl_model_cfg& c = R.S->cfg;
   const int d = c.d_model, f = c.d_inner, M = A.M;
-  size_t mark = R.ws.off;
   float* df2 = R.ws.f((size_t)M * d);
   float* df1 = R.ws.f((size_t)M * f);
+  const cudaStream_t sw = R.wside();
   K(k_ln_bwd(dout, A.xhat, A.rstd, R.theta + A.p.ln_w, A.rowmask, A.drop, df2, dx, 0, R.grad + A.p.ln_w,
              R.grad + A.p.ln_b, M, d, R.st));
-  MTL_TRY(lin_wgrad(R, df2, d, A.f1, f, R.grad + A.p.w2, M, d, f));
-  K(k_colsum_acc(df2, M, d, d, R.grad + A.p.b2, R.st));
+  MTL_TRY(chain(R, R.main, sw));
+  {
+    On on(R, sw);
+    MTL_TRY(lin_wgrad(R, df2, d, A.f1, f, R.grad + A.p.w2, M, d, f));
+    K(k_colsum_acc(df2, M, d, d, R.grad + A.p.b2, R.st));
+  }
   MTL_TRY(lin_dgrad(R, df2, d, R.theta + A.p.w2, df1, f, M, d, f, 0.f, EPI_RELU_BWD, A.f1));
-  MTL_TRY(lin_wgrad(R, df1, f, A.x, d, R.grad + A.p.w1, M, f, d));
-  K(k_colsum_acc(df1, M, f, f, R.grad + A.p.b1, R.st));
+  MTL_TRY(chain(R, R.main, sw));
+  {
+    On on(R, sw);
+    MTL_TRY(lin_wgrad(R, df1, f, A.x, d, R.grad + A.p.w1, M, f, d));
+    K(k_colsum_acc(df1, M, f, f, R.grad + A.p.b1, R.st));
+  }
   MTL_TRY(lin_dgrad(R, df1, f, R.theta + A.p.w1, dx, d, M, f, d, 1.f, EPI_NONE, nullptr));
-  R.ws.off = mark;
   return MTL_OK;
 }
 
 // ----------------------------------------------------------------------------- 3x3 conv (+bias+ReLU) as GEMM
+// GEMM layouts of the three 3x3 weight tensors for this pass (forward Wg and flipped-tap dgrad Wd): they depend on
+// theta only, so they are produced on S_AUX while conv.0 runs.
+static int conv_weight_layouts(Run& R, Pass& P) {
+  const Layout& L = R.S->L;
+  MTL_TRY(chain(R, R.main, R.side(S_AUX)));
+  On on(R, R.side(S_AUX));
+  for (int i = 0; i < 3; ++i) {
+    const int widx = i + 1, Cin = kConvCin[widx], Cout = kConvCout[widx];
+    P.cv[i].wg = R.ws.f((size_t)Cout * 9 * Cin);
+    P.cv[i].wd = R.ws.f((size_t)Cin * 9 * Cout);
+    K(k_conv_w_fwd_layout(R.theta + L.conv_w[widx], P.cv[i].wg, Cout, Cin, R.st));
+    K(k_conv_w_dgrad_layout(R.theta + L.conv_w[widx], P.cv[i].wd, Cout, Cin, R.st));
+  }
+  return MTL_OK;
+}
 static int conv_fwd(Run& R, ConvAct& A, const float* x, int B, int F, int T, int widx) {
   const Layout& L = R.S->L;
   A.x = x; A.B = B; A.F = F; A.T = T; A.Cin = kConvCin[widx]; A.Cout = kConvCout[widx]; A.widx = widx;
@@ -365,41 +514,41 @@ static int conv_fwd(Run& R, ConvAct& A, const float* x, int B, int F, int T, int
   const int Kc = 9 * A.Cin;
   const bool implicit = R.S->mode != MTL_GEMM_SIMT_FP32;      // tcgen05 implicit GEMM: no patch matrix
   A.col = implicit ? nullptr : R.ws.f(P * Kc);
-  float* wg = R.ws.f((size_t)A.Cout * Kc);
   A.y = R.ws.f(P * A.Cout);
-  K(k_conv_w_fwd_layout(R.theta + L.conv_w[widx], wg, A.Cout, A.Cin, R.st));
   if (implicit) {
-    K(k_conv3x3_tc(x, wg, R.theta + L.conv_b[widx], A.y, B, F, T, A.Cin, A.Cout, EPI_RELU, nullptr, R.S->mode, R.st));
+    K(k_conv3x3_tc(x, A.wg, R.theta + L.conv_b[widx], A.y, B, F, T, A.Cin, A.Cout, EPI_RELU, nullptr, R.S->mode, R.st));
   } else {
     K(k_im2col3x3(x, A.col, B, F, T, A.Cin, R.st));
-    MTL_TRY(lin_fwd(R, A.col, Kc, wg, R.theta + L.conv_b[widx], A.y, A.Cout, (int)P, A.Cout, Kc, EPI_RELU));
+    MTL_TRY(lin_fwd(R, A.col, Kc, A.wg, R.theta + L.conv_b[widx], A.y, A.Cout, (int)P, A.Cout, Kc, EPI_RELU));
   }
   return MTL_OK;
 }
 // dy = gradient w.r.t. the pre-ReLU conv output.  dx (nullable) = gradient w.r.t. the conv input,
-// masked by relu_aux > 0 when relu_aux != null.
+// masked by relu_aux > 0 when relu_aux != null.  The weight / bias gradient runs on a side stream.
 static int conv_bwd(Run& R, const ConvAct& A, const float* dy, float* dx, const float* relu_aux) {
   const Layout& L = R.S->L;
   const size_t P = (size_t)A.B * A.F * A.T;
   const int Kc = 9 * A.Cin;
   const bool implicit = R.S->mode != MTL_GEMM_SIMT_FP32;
-  size_t mark = R.ws.off;
   float* dwg = R.ws.f((size_t)A.Cout * Kc);
-  K(k_zero(dwg, (size_t)A.Cout * Kc, R.st));
-  if (implicit) {
-    K(k_conv3x3_wgrad_tc(A.x, dy, dwg, A.B, A.F, A.T, A.Cin, A.Cout, R.S->mode, R.st));
-    K(k_conv_wgrad_scatter_t(dwg, R.grad + L.conv_w[A.widx], A.Cout, A.Cin, R.st));
-  } else {
-    MTL_TRY(lin_wgrad(R, dy, A.Cout, A.col, Kc, dwg, (int)P, A.Cout, Kc));
-    K(k_conv_wgrad_scatter(dwg, R.grad + L.conv_w[A.widx], A.Cout, A.Cin, R.st));
+  const cudaStream_t sw = R.wside();
+  MTL_TRY(chain(R, R.main, sw));
+  {
+    On on(R, sw);
+    K(k_zero(dwg, (size_t)A.Cout * Kc, R.st));
+    if (implicit) {
+      K(k_conv3x3_wgrad_tc(A.x, dy, dwg, A.B, A.F, A.T, A.Cin, A.Cout, R.S->mode, R.st));
+      K(k_conv_wgrad_scatter_t(dwg, R.grad + L.conv_w[A.widx], A.Cout, A.Cin, R.st));
+    } else {
+      MTL_TRY(lin_wgrad(R, dy, A.Cout, A.col, Kc, dwg, (int)P, A.Cout, Kc));
+      K(k_conv_wgrad_scatter(dwg, R.grad + L.conv_w[A.widx], A.Cout, A.Cin, R.st));
+    }
+    K(k_colsum_acc(dy, (int)P, A.Cout, A.Cout, R.grad + L.conv_b[A.widx], R.st));
   }
-  K(k_colsum_acc(dy, (int)P, A.Cout, A.Cout, R.grad + L.conv_b[A.widx], R.st));
   if (dx) {
     const int Kg = 9 * A.Cout;
-    float* wd = R.ws.f((size_t)A.Cin * Kg);
-    K(k_conv_w_dgrad_layout(R.theta + L.conv_w[A.widx], wd, A.Cout, A.Cin, R.st));
     if (implicit) {
-      K(k_conv3x3_tc(dy, wd, nullptr, dx, A.B, A.F, A.T, A.Cout, A.Cin, relu_aux ? EPI_RELU_BWD : EPI_NONE, relu_aux,
+      K(k_conv3x3_tc(dy, A.wd, nullptr, dx, A.B, A.F, A.T, A.Cout, A.Cin, relu_aux ? EPI_RELU_BWD : EPI_NONE, relu_aux,
                      R.S->mode, R.st));
     } else {
       float* colg = R.ws.f(P * Kg);
@@ -407,13 +556,12 @@ static int conv_bwd(Run& R, const ConvAct& A, const float* dy, float* dx, const 
       // dx[P,Cin] = colg[P,9Cout] . wd[Cin,9Cout]^T
       GemmArgs g;
       memset(&g, 0, sizeof(g));
-      g.A = colg; g.lda = Kg; g.transA = 0; g.B = wd; g.ldb = Kg; g.transB = 1; g.C = dx; g.ldc = A.Cin;
+      g.A = colg; g.lda = Kg; g.transA = 0; g.B = A.wd; g.ldb = Kg; g.transB = 1; g.C = dx; g.ldc = A.Cin;
       g.M = (int)P; g.N = A.Cin; g.K = Kg; g.alpha = 1.f; g.beta = 0.f;
       g.epi = relu_aux ? EPI_RELU_BWD : EPI_NONE; g.aux = relu_aux; g.split_k = 1;
       K(k_gemm(g, R.S->mode, R.st));
     }
   }
-  R.ws.off = mark;
   return MTL_OK;
 }
 
@@ -435,7 +583,9 @@ static int forward(Run& R, const mtl_batch& b, const float* pe_enc, const float*
 
   // ---- VGG front-end (transformer.py:47-59), NHWC
   P.c1 = R.ws.f((size_t)B * P.F * P.T * 64);
+  MTL_TRY(conv_weight_layouts(R, P));
   K(k_conv1_fwd(b.x, R.theta + L.conv_w[0], R.theta + L.conv_b[0], P.c1, B, P.F, P.T, 64, R.st));
+  MTL_TRY(chain(R, R.side(S_AUX), R.main));
   MTL_TRY(conv_fwd(R, P.cv[0], P.c1, B, P.F, P.T, 1));
   P.p2 = R.ws.f((size_t)B * P.F2 * P.T2 * 64);
   K(k_maxpool2_fwd(P.cv[0].y, P.p2, B, P.F, P.T, 64, R.st));
@@ -461,7 +611,7 @@ static int forward(Run& R, const mtl_batch& b, const float* pe_enc, const float*
   P.enc_sa.assign(c.n_enc, AttnAct());
   P.enc_ff.assign(c.n_enc, FfnAct());
   for (int l = 0; l < c.n_enc; ++l) {
-    MTL_TRY(attn_block_fwd(R, P.enc_sa[l], L.enc_sa[l], x, x, B, Tp, Tp, P.enc_keypad, 0, P.enc_rowmask));
+    MTL_TRY(attn_block_fwd(R, P.enc_sa[l], L.enc_sa[l], x, x, B, Tp, Tp, P.enc_keypad, 0, P.enc_rowmask, false));
     x = P.enc_sa[l].out;
     MTL_TRY(ffn_block_fwd(R, P.enc_ff[l], L.enc_ff[l], x, P.Me, P.enc_rowmask));
     x = P.enc_ff[l].out;
@@ -481,10 +631,13 @@ static int forward(Run& R, const mtl_batch& b, const float* pe_enc, const float*
   P.dec_sa.assign(c.n_dec, AttnAct());
   P.dec_ca.assign(c.n_dec, AttnAct());
   P.dec_ff.assign(c.n_dec, FfnAct());
+  // every cross-attention k / v projection depends on the encoder output only: start them all now on S_X / S_AUX
+  for (int l = 0; l < c.n_dec; ++l)
+    MTL_TRY(attn_kv_fwd(R, P.dec_ca[l], L.dec_ca[l], P.enc_out, P.Me, R.side(S_X), R.side(S_AUX)));
   for (int l = 0; l < c.n_dec; ++l) {
-    MTL_TRY(attn_block_fwd(R, P.dec_sa[l], L.dec_sa[l], x, x, B, n, n, P.dec_keypad, 1, P.dec_rowmask));
+    MTL_TRY(attn_block_fwd(R, P.dec_sa[l], L.dec_sa[l], x, x, B, n, n, P.dec_keypad, 1, P.dec_rowmask, false));
     x = P.dec_sa[l].out;
-    MTL_TRY(attn_block_fwd(R, P.dec_ca[l], L.dec_ca[l], x, P.enc_out, B, n, Tp, P.enc_keypad, 0, P.dec_rowmask));
+    MTL_TRY(attn_block_fwd(R, P.dec_ca[l], L.dec_ca[l], x, P.enc_out, B, n, Tp, P.enc_keypad, 0, P.dec_rowmask, true));
     x = P.dec_ca[l].out;
     MTL_TRY(ffn_block_fwd(R, P.dec_ff[l], L.dec_ff[l], x, P.Md, P.dec_rowmask));
     x = P.dec_ff[l].out;
@@ -504,6 +657,7 @@ static int forward(Run& R, const mtl_batch& b, const float* pe_enc, const float*
     if (b.gold_out) MTL_CHECK_CUDA(cudaMemcpyAsync(b.gold_out, P.seq_out, sizeof(int) * P.Md, cudaMemcpyDeviceToDevice, R.st));
     if (b.ce_out) MTL_CHECK_CUDA(cudaMemcpyAsync(b.ce_out, P.ce, sizeof(CeOut), cudaMemcpyDeviceToDevice, R.st));
   }
+  MTL_TRY(join_all(R));
   P.ws_after_fwd = R.ws.off;
   P.ws_base = R.ws.base;
   P.ws_cap = R.ws.cap;
@@ -528,36 +682,55 @@ static int backward(Run& R, float loss_scale, const float* dpred_ext, int ld_ext
   } else {
     K(k_ce_bwd(P.pred, P.ldp, P.seq_out, P.row_lse, P.ce, loss_scale, P.smoothing, 0, dpred, P.Md, V, R.st));
   }
-  // vocab projection
-  MTL_TRY(lin_wgrad(R, dpred, P.ldp, P.dec_last, d, R.grad + L.out_w, P.Md, V, d));
+  // vocab projection (its weight gradient, like every other, leaves the main chain)
+  {
+    const cudaStream_t sw = R.wside();
+    MTL_TRY(chain(R, R.main, sw));
+    On on(R, sw);
+    MTL_TRY(lin_wgrad(R, dpred, P.ldp, P.dec_last, d, R.grad + L.out_w, P.Md, V, d));
+  }
   float* gA = R.ws.f((size_t)P.Md * d);
   float* gB = R.ws.f((size_t)P.Md * d);
   MTL_TRY(lin_dgrad(R, dpred, P.ldp, R.theta + L.out_w, gA, d, P.Md, V, d, 0.f, EPI_NONE, nullptr));
   float* gE1 = R.ws.f((size_t)P.Me * d);
   float* gE2 = R.ws.f((size_t)P.Me * d);
   K(k_zero(gE1, (size_t)P.Me * d, R.st));
+  // The ping-pong buffers gA / gB are only ever read by main-chain kernels; everything a side stream reads is a
+  // forward activation or a scratch buffer that is written once per pass.
   for (int l = c.n_dec - 1; l >= 0; --l) {
     MTL_TRY(ffn_block_bwd(R, P.dec_ff[l], gA, gB));
     std::swap(gA, gB);
-    MTL_TRY(attn_block_bwd(R, P.dec_ca[l], gA, gB, gE1));
+    MTL_TRY(attn_block_bwd(R, P.dec_ca[l], gA, gB, gE1, true));
     std::swap(gA, gB);
-    MTL_TRY(attn_block_bwd(R, P.dec_sa[l], gA, gB, gB));
+    MTL_TRY(attn_block_bwd(R, P.dec_sa[l], gA, gB, gB, false));
     std::swap(gA, gB);
   }
-  K(k_embed_bwd(P.seq_in, gA, P.drop_emb, R.grad + L.emb, B, P.n, d, 0, R.st));
-  // encoder
+  {
+    // embedding gradient: gA is final here (the encoder backward below uses gE1 / gE2 only)
+    const cudaStream_t sw = R.wside();
+    MTL_TRY(chain(R, R.main, sw));
+    On on(R, sw);
+    K(k_embed_bwd(P.seq_in, gA, P.drop_emb, R.grad + L.emb, B, P.n, d, 0, R.st));
+  }
+  // encoder: gE1 has been accumulated on S_X
+  MTL_TRY(chain(R, R.side(S_X), R.main));
   for (int l = c.n_enc - 1; l >= 0; --l) {
     MTL_TRY(ffn_block_bwd(R, P.enc_ff[l], gE1, gE2));
     std::swap(gE1, gE2);
-    MTL_TRY(attn_block_bwd(R, P.enc_sa[l], gE1, gE2, gE2));
+    MTL_TRY(attn_block_bwd(R, P.enc_sa[l], gE1, gE2, gE2, false));
     std::swap(gE1, gE2);
   }
   // stem: e0 = LN(h) + PE
-  float* dh = gE2;
+  float* dh = R.ws.f((size_t)P.Me * d);
   K(k_ln_bwd(gE1, P.stem_xhat, P.stem_rstd, R.theta + L.lnin_w, nullptr, mtl_nodrop(), dh, nullptr, 0,
              R.grad + L.lnin_w, R.grad + L.lnin_b, P.Me, d, R.st));
-  MTL_TRY(lin_wgrad(R, dh, d, P.feat, P.d_in, R.grad + L.in_w, P.Me, d, P.d_in));
-  K(k_colsum_acc(dh, P.Me, d, d, R.grad + L.in_b, R.st));
+  {
+    const cudaStream_t sw = R.wside();
+    MTL_TRY(chain(R, R.main, sw));
+    On on(R, sw);
+    MTL_TRY(lin_wgrad(R, dh, d, P.feat, P.d_in, R.grad + L.in_w, P.Me, d, P.d_in));
+    K(k_colsum_acc(dh, P.Me, d, d, R.grad + L.in_b, R.st));
+  }
   float* dfeat = R.ws.f((size_t)P.Me * P.d_in);
   MTL_TRY(lin_dgrad(R, dh, d, R.theta + L.in_w, dfeat, P.d_in, P.Me, d, P.d_in, 0.f, EPI_NONE, nullptr));
   // VGG front-end
@@ -574,6 +747,7 @@ static int backward(Run& R, float loss_scale, const float* dpred_ext, int ld_ext
   float* dc1 = R.ws.f((size_t)B * P.F * P.T * 64);
   MTL_TRY(conv_bwd(R, P.cv[0], dc2, dc1, P.c1));
   K(k_conv1_wgrad(P.b.x, dc1, R.grad + L.conv_w[0], R.grad + L.conv_b[0], B, P.F, P.T, 64, R.st));
+  MTL_TRY(join_all(R));
   return MTL_OK;
 }
 
@@ -596,7 +770,8 @@ extern "C" int mtl_session_create(const mtl_model_cfg* cfg, mtl_session** out) {
 extern "C" void mtl_session_destroy(mtl_session* s) {
   if (!s) return;
   for (auto& g : s->graphs) { if (g.exec) cudaGraphExecDestroy(g.exec); if (g.graph) cudaGraphDestroy(g.graph); }
-  for (auto& l : s->lanes) { if (l.done) cudaEventDestroy(l.done); if (l.st) cudaStreamDestroy(l.st); }
+  for (auto& l : s->lanes) { branches_destroy(l.br); if (l.done) cudaEventDestroy(l.done); if (l.st) cudaStreamDestroy(l.st); }
+  branches_destroy(s->br);
   for (auto e : s->ev_axpy) cudaEventDestroy(e);
   if (s->ev_fork) cudaEventDestroy(s->ev_fork);
   if (s->cap_st) cudaStreamDestroy(s->cap_st);
@@ -650,24 +825,26 @@ static int check_ws(mtl_session* s, const mtl_batch* b, void* ws, long long ws_b
 
 // forward / backward of one batch on an explicit activation record
 struct SeedRef { unsigned long long seed; const unsigned long long* dev; unsigned long long mul; };
-static int run_forward(mtl_session* s, Pass* pass, const float* theta, const float* pe_enc, const float* pe_dec,
-                       void* workspace, long long workspace_bytes, const mtl_batch* batch, float dropout, SeedRef seed,
-                       float label_smoothing, cudaStream_t st) {
+static int run_forward(mtl_session* s, Pass* pass, Branches* br, const float* theta, const float* pe_enc,
+                       const float* pe_dec, void* workspace, long long workspace_bytes, const mtl_batch* batch,
+                       float dropout, SeedRef seed, float label_smoothing, cudaStream_t st) {
   MTL_REQUIRE(s && theta && pe_enc && pe_dec && batch && batch->x && batch->lens && batch->trg, "null argument");
   MTL_REQUIRE(dropout >= 0.f && dropout < 1.f, "dropout in [0,1)");
   MTL_TRY(check_ws(s, batch, workspace, workspace_bytes));
   Run R;
-  R.S = s; R.P = pass; R.st = st; R.dry = false; R.theta = theta; R.grad = nullptr;
+  R.S = s; R.P = pass; R.st = st; R.main = st; R.dry = false; R.theta = theta; R.grad = nullptr;
+  if (br && branches_enabled()) { MTL_TRY(branches_init(*br)); R.br = br; }
   R.p_drop = dropout; R.seed = seed.seed; R.seed_dev = seed.dev; R.seed_mul = seed.mul; R.site = 0;
   R.ws.base = (uintptr_t)workspace; R.ws.cap = (size_t)workspace_bytes;
   return forward(R, *batch, pe_enc, pe_dec, label_smoothing);
 }
-static int run_backward(mtl_session* s, Pass* pass, const float* theta, float* grad, float loss_scale,
+static int run_backward(mtl_session* s, Pass* pass, Branches* br, const float* theta, float* grad, float loss_scale,
                         const float* dpred_ext, int ld_ext, cudaStream_t st) {
   MTL_REQUIRE(s && theta && grad, "null argument");
   MTL_REQUIRE(pass->valid, "backward without a preceding forward");
   Run R;
-  R.S = s; R.P = pass; R.st = st; R.dry = false; R.theta = theta; R.grad = grad;
+  R.S = s; R.P = pass; R.st = st; R.main = st; R.dry = false; R.theta = theta; R.grad = grad;
+  if (br && branches_enabled()) { MTL_TRY(branches_init(*br)); R.br = br; }
   R.p_drop = 0.f; R.seed = 0; R.site = 0;
   R.ws.base = pass->ws_base; R.ws.cap = pass->ws_cap; R.ws.off = pass->ws_after_fwd;
   MTL_TRY(backward(R, loss_scale, dpred_ext, ld_ext));
@@ -681,7 +858,7 @@ extern "C" int mtl_asr_forward(mtl_session* s, const float* theta, const float* 
                                int* ldp_out) {
   MTL_REQUIRE(s, "null argument");
   SeedRef sr = {seed, nullptr, 0};
-  MTL_TRY(run_forward(s, &s->pass, theta, pe_enc, pe_dec, workspace, workspace_bytes, batch, dropout, sr,
+  MTL_TRY(run_forward(s, &s->pass, &s->br, theta, pe_enc, pe_dec, workspace, workspace_bytes, batch, dropout, sr,
                       label_smoothing, (cudaStream_t)stream));
   if (pred_out) *pred_out = s->pass.pred;
   if (ldp_out) *ldp_out = s->pass.ldp;
@@ -691,13 +868,13 @@ extern "C" int mtl_asr_forward(mtl_session* s, const float* theta, const float* 
 extern "C" int mtl_asr_backward(mtl_session* s, const float* theta, float* grad, float loss_scale,
                                 const float* dpred_ext, int ld_ext, void* stream) {
   MTL_REQUIRE(s, "null argument");
-  return run_backward(s, &s->pass, theta, grad, loss_scale, dpred_ext, ld_ext, (cudaStream_t)stream);
+  return run_backward(s, &s->pass, &s->br, theta, grad, loss_scale, dpred_ext, ld_ext, (cudaStream_t)stream);
 }
 
 // ----------------------------------------------------------------------------- C ABI: meta-step pieces
 // One task on one stream: trainer/asr/transient_trainer.py:188-229 at the weights in `theta`
 // (grad <- dCE_train; [clip]; theta -= lr*grad; grad += d(CE_val*val_scale)).
-static int task_body(mtl_session* s, Pass* pass, float* theta, float* grad, const float* pe_enc, const float* pe_dec,
+static int task_body(mtl_session* s, Pass* pass, Branches* br, float* theta, float* grad, const float* pe_enc, const float* pe_dec,
                      void* workspace, long long workspace_bytes, const mtl_batch* train, const mtl_batch* val,
                      const mtl_meta_hparams* hp, SeedRef seed_tr, SeedRef seed_va, float* results16, cudaStream_t st) {
   const size_t n = s->L.total;
@@ -709,17 +886,17 @@ static int task_body(mtl_session* s, Pass* pass, float* theta, float* grad, cons
   mtl_batch tr = *train, va = *val;
   if (results16) { tr.ce_out = results16; va.ce_out = results16 + 8; }
   MTL_TRY(k_zero(grad, n, st));                                                     // inner_opt.zero_grad()
-  MTL_TRY(run_forward(s, pass, theta, pe_enc, pe_dec, workspace, ws_main, &tr, hp->dropout, seed_tr,
+  MTL_TRY(run_forward(s, pass, br, theta, pe_enc, pe_dec, workspace, ws_main, &tr, hp->dropout, seed_tr,
                       hp->label_smoothing, st));
-  MTL_TRY(run_backward(s, pass, theta, grad, 1.f, nullptr, 0, st));                 // tr_loss.backward()
+  MTL_TRY(run_backward(s, pass, br, theta, grad, 1.f, nullptr, 0, st));             // tr_loss.backward()
   if (hp->clip) {
     MTL_TRY(k_clip_coef(grad, n, hp->max_norm, scratch, scratch + MTL_NORM_PARTIALS, st));
     MTL_TRY(k_scale_by_dev(grad, scratch + MTL_NORM_PARTIALS + 1, n, st));
   }
   MTL_TRY(k_sgd(theta, grad, hp->lr, n, st));                                       // inner_opt.step()
-  MTL_TRY(run_forward(s, pass, theta, pe_enc, pe_dec, workspace, ws_main, &va, hp->dropout, seed_va,
+  MTL_TRY(run_forward(s, pass, br, theta, pe_enc, pe_dec, workspace, ws_main, &va, hp->dropout, seed_va,
                       hp->label_smoothing, st));
-  MTL_TRY(run_backward(s, pass, theta, grad, hp->val_scale, nullptr, 0, st));       // (val_loss/N).backward(), no zero_grad
+  MTL_TRY(run_backward(s, pass, br, theta, grad, hp->val_scale, nullptr, 0, st));   // (val_loss/N).backward(), no zero_grad
   return MTL_OK;
 }
 
@@ -731,7 +908,7 @@ extern "C" int mtl_meta_task(mtl_session* s, float* theta, const float* theta0, 
   cudaStream_t st = (cudaStream_t)stream;
   const size_t n = s->L.total;
   SeedRef s0 = {hp->seed * 2ull + 0ull, nullptr, 0}, s1 = {hp->seed * 2ull + 1ull, nullptr, 0};
-  MTL_TRY(task_body(s, &s->pass, theta, grad, pe_enc, pe_dec, workspace, workspace_bytes, train, val, hp, s0, s1,
+  MTL_TRY(task_body(s, &s->pass, &s->br, theta, grad, pe_enc, pe_dec, workspace, workspace_bytes, train, val, hp, s0, s1,
                     results16, st));
   MTL_TRY(k_axpy(copy_grad, grad, 1.f, n, st));                                     // model.add_copy_grad()
   MTL_TRY(k_copy(theta, theta0, n, st));                                            // model.load_state_dict(weights_original)
@@ -782,7 +959,7 @@ static int meta_tasks_body(mtl_session* s, const mtl_meta_step_args* a, cudaStre
     const unsigned long long lo0 = (unsigned long long)t * 2ull, lo1 = lo0 + 1ull;
     if (dev_seed) { s0 = {lo0, a->seed_slot, 128ull}; s1 = {lo1, a->seed_slot, 128ull}; }
     else { s0 = {a->hp.seed * 128ull + lo0, nullptr, 0}; s1 = {a->hp.seed * 128ull + lo1, nullptr, 0}; }
-    MTL_TRY(task_body(s, &ln.pass, lb.theta, lb.grad, a->pe_enc, a->pe_dec, lb.workspace, lb.workspace_bytes,
+    MTL_TRY(task_body(s, &ln.pass, &ln.br, lb.theta, lb.grad, a->pe_enc, a->pe_dec, lb.workspace, lb.workspace_bytes,
                       &a->train[t], &va, &a->hp, s0, s1, a->results ? a->results + 16 * t : nullptr, ln.st));
     if (t > 0) MTL_CHECK_CUDA(cudaStreamWaitEvent(ln.st, s->ev_axpy[t - 1], 0));    // keep the reference's summation order
     MTL_TRY(k_axpy(a->copy_grad, lb.grad, 1.f, n, ln.st));                          // model.add_copy_grad()

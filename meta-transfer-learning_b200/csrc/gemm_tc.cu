@@ -57,8 +57,10 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 // Bounded wait: a pipeline bug must trap (error reported to the host), never hang the GPU.
 // debug stamps (MTL_GEMM_DBG=1): SM cycle counter at the main events of CTA (0,0,0)
-__device__ long long g_dbg[32];
+__device__ long long g_dbg[160];   // [0,32): phase stamps; [32,160): per-k-block pipeline stamps of CTA (0,0,0), 4 per k-block
 #define DBG_STAMP(i) do { if (P.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) g_dbg[i] = clock64(); } while (0)
+// role r (0 producer issued, 1 splitter saw full, 2 MMA saw ready/full, 3 MMA issued+committed) of k-block iteration it
+#define DBG_KB(it, r) do { if (P.dbg && (it) < 32 && blockIdx.x == P.dbg - 1 && blockIdx.y == 0 && blockIdx.z == 0) g_dbg[32 + (it) * 4 + (r)] = clock64(); } while (0)
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   const long long t0 = clock64();
@@ -87,6 +89,24 @@ __device__ __forceinline__ void tma_load_4d(uint32_t smem_dst, const CUtensorMap
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
       ::"r"(smem_dst), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
+}
+// TMA stores of a staged tile: plain, or reduce-add (C += tile, performed by the L2 -- replaces read-modify-write and atomics)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1, bool add) {
+  if (add)
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"((uint64_t)map), "r"(smem_src), "r"(c0), "r"(c1) : "memory");
+  else
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"((uint64_t)map), "r"(smem_src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1, int c2, int c3,
+                                             bool add) {
+  if (add)
+    asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"((uint64_t)map), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+  else
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"((uint64_t)map), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -121,6 +141,12 @@ __device__ __forceinline__ float tf32_rna(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
 }
+// Pins a loop-invariant value in a register (opaque to the optimiser, so it cannot be rematerialised from the
+// constant bank at every use).
+__device__ __forceinline__ int keep_reg(int v) { asm volatile("" : "+r"(v)); return v; }
+__device__ __forceinline__ float keep_reg(float v) { asm volatile("" : "+f"(v)); return v; }
+template <typename T>
+__device__ __forceinline__ T* keep_reg(T* p) { asm volatile("" : "+l"(p)); return p; }
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
@@ -175,12 +201,17 @@ struct TcParams {
   int bt_log2;       // pixel box: (1 << bt_log2) time steps wide
   int tiles_t, tiles_f;
   int dbg;
+  int aux_off;       // TMA epilogue: byte offset (from the aligned smem base) of the ReLU-mask tile
+  int tma_epi;       // epilogue through TMA: 1 = store, 2 = reduce-add (beta == 1 or split-K slabs)
+  int epi_test;      // measurement only (MTL_EPI_TEST): 1 = conv epilogue computes but does not store
   int cluster_k;     // > 1: grid.z CTAs form one cluster that splits K and reduces over distributed shared memory
 };
 
 template <int BN, int STAGES, bool A_MN, bool B_MN, bool SPLIT3>
 __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                      const __grid_constant__ CUtensorMap tmB, const TcParams P) {
+                                                      const __grid_constant__ CUtensorMap tmB,
+                                                      const __grid_constant__ CUtensorMap tmC,
+                                                      const __grid_constant__ CUtensorMap tmX, const TcParams P) {
   constexpr int B_STAGE_BYTES = BN * BK * 4;
   constexpr int HI_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   constexpr int STAGE_BYTES = HI_BYTES * (SPLIT3 ? 2 : 1);
@@ -191,7 +222,9 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
   uint64_t* empty = full + STAGES;
   uint64_t* ready = empty + STAGES;       // SPLIT3: splitter warps -> MMA issuer
   uint64_t* tmem_full = ready + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* aux_full = tmem_full + 1;     // TMA epilogue: the ReLU-mask tile has landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_full + 1);
+  float* bias_s = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);   // BN floats (TMA epilogue)
 
   const GemmArgs& g = P.g;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -214,6 +247,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&ready[s], 4); }
     mbar_init(tmem_full, 1);
+    mbar_init(aux_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {   // TMEM allocation: BN fp32 accumulator columns x 128 lanes
@@ -226,6 +260,12 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) DBG_STAMP(1);
+  if (P.tma_epi && warp >= 2) {
+    // bias slice of this tile -> shared memory now, so the epilogue never waits on a global load
+    const int t = threadIdx.x - 64, cn = blockIdx.y * BN + t;
+    if (t < BN) bias_s[t] = (P.g.bias && P.g.split_k <= 1 && cn < P.g.N) ? __ldg(P.g.bias + cn) : 0.f;
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+  }
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -258,6 +298,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
           const int kh = tap / 3, kw = tap - kh * 3;
           tma_load_4d(sa, &tmA, &full[s], c0, ct0 + kw - 1, cf0 + kh - 1, cb);
           tma_load_2d(sb, &tmB, &full[s], kb * BK, n0);
+          DBG_KB(it, 0);
         } else {                                             // CONV_WGRAD: k-block = 32-pixel box
           const int tt = kb % tiles_t, rem = kb / tiles_t;
           const int t0 = tt << btl, f0 = (rem % tiles_f) * (32 >> btl), b = rem / tiles_f;
@@ -286,17 +327,22 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
         const uint32_t ph = (it / STAGES) & 1;
         mbar_wait(SPLIT3 ? &ready[s] : &full[s], ph);
         if (it == 0) DBG_STAMP(3);
+        DBG_KB(it, 2);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + A_STAGE_BYTES;
+        // descriptors of this stage; a K=8 step advances the 16-byte-granular start-address field (bits [0,14)) by
+        // 32 B (K-major) or 1024 B (MN-major) -- no carry out of the field below 256 KB of shared memory
+        constexpr uint64_t STEP_A = A_MN ? 64 : 2, STEP_B = B_MN ? 64 : 2;
+        const uint64_t da0 = A_MN ? desc_mnmajor(sa) : desc_kmajor(sa);
+        const uint64_t db0 = B_MN ? desc_mnmajor(sb) : desc_kmajor(sb);
+        const uint64_t la0 = A_MN ? desc_mnmajor(sa + HI_BYTES) : desc_kmajor(sa + HI_BYTES);
+        const uint64_t lb0 = B_MN ? desc_mnmajor(sb + HI_BYTES) : desc_kmajor(sb + HI_BYTES);
 #pragma unroll
         for (int k = 0; k < BK / 8; ++k) {
-          const uint32_t oa = A_MN ? k * 1024 : k * 32, ob = B_MN ? k * 1024 : k * 32;
-          const uint64_t da = A_MN ? desc_mnmajor(sa + oa) : desc_kmajor(sa + oa);
-          const uint64_t db = B_MN ? desc_mnmajor(sb + ob) : desc_kmajor(sb + ob);
+          const uint64_t da = da0 + k * STEP_A, db = db0 + k * STEP_B;
           const uint32_t acc0 = (it > 0 || k > 0) ? 1u : 0u;
           if (SPLIT3) {
-            const uint64_t la = A_MN ? desc_mnmajor(sa + HI_BYTES + oa) : desc_kmajor(sa + HI_BYTES + oa);
-            const uint64_t lb = B_MN ? desc_mnmajor(sb + HI_BYTES + ob) : desc_kmajor(sb + HI_BYTES + ob);
+            const uint64_t la = la0 + k * STEP_A, lb = lb0 + k * STEP_B;
             tc_mma_tf32(tmem_base, la, db, idesc, acc0);     // small terms first
             tc_mma_tf32(tmem_base, da, lb, idesc, 1u);
             tc_mma_tf32(tmem_base, da, db, idesc, 1u);
@@ -305,6 +351,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
           }
         }
         tc_commit(&empty[s]);          // frees the smem slot once these MMAs have read it
+        DBG_KB(it, 3);
       }
       tc_commit(tmem_full);            // accumulator complete
       DBG_STAMP(4);
@@ -318,18 +365,25 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
         mbar_wait(&full[s], ph);
-        float4* hi = reinterpret_cast<float4*>(smem + s * STAGE_BYTES);
-        float4* lo = reinterpret_cast<float4*>(smem + s * STAGE_BYTES + HI_BYTES);
-#pragma unroll 4
-        for (int i = tid; i < HI_BYTES / 16; i += 128) {
-          const float4 a = hi[i];
+        if (threadIdx.x == 64) DBG_KB(it, 1);
+        float4* hi = reinterpret_cast<float4*>(smem + s * STAGE_BYTES) + tid;
+        float4* lo = reinterpret_cast<float4*>(smem + s * STAGE_BYTES + HI_BYTES) + tid;
+        // One warp per scheduler: a load -> convert -> store chain per element would expose the shared-memory latency
+        // PER times per k-block (measured 1400 cycles).  Issue every load first, then convert and store.
+        constexpr int PER = HI_BYTES / 16 / 128;
+        static_assert(HI_BYTES % (16 * 128) == 0, "splitter assumes whole float4 columns per thread");
+        float4 a[PER];
+#pragma unroll
+        for (int j = 0; j < PER; ++j) a[j] = hi[j * 128];
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
           float4 h, l;
-          h.x = tf32_rna(a.x); l.x = tf32_rna(a.x - h.x);
-          h.y = tf32_rna(a.y); l.y = tf32_rna(a.y - h.y);
-          h.z = tf32_rna(a.z); l.z = tf32_rna(a.z - h.z);
-          h.w = tf32_rna(a.w); l.w = tf32_rna(a.w - h.w);
-          hi[i] = h;
-          lo[i] = l;
+          h.x = tf32_rna(a[j].x); l.x = tf32_rna(a[j].x - h.x);
+          h.y = tf32_rna(a[j].y); l.y = tf32_rna(a[j].y - h.y);
+          h.z = tf32_rna(a[j].z); l.z = tf32_rna(a[j].z - h.z);
+          h.w = tf32_rna(a[j].w); l.w = tf32_rna(a[j].w - h.w);
+          hi[j * 128] = h;
+          lo[j * 128] = l;
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to the MMA (async proxy)
         __syncwarp();
@@ -351,6 +405,79 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
   const int rank = CS > 1 ? (int)cluster_ctarank() : 0;
   const int rows_per = BM / CS;
   const int q = warp & 3;                           // TMEM lane quarter this warp may access
+  if (P.tma_epi) {
+    // ---- TMA epilogue (no cluster split): each epilogue thread owns one accumulator row; per 32-column chunk it
+    // drains TMEM, applies alpha / bias / ReLU / ReLU-backward mask in registers and parks the row in a
+    // 128B-swizzled staging box; one thread then hands every box to the TMA unit (store, or reduce-add for
+    // beta == 1 and split-K slabs).  Row / column tails and the ragged edges of convolution pixel boxes are clipped
+    // by the TMA unit, so there is no per-row address arithmetic at all.
+    constexpr int CHUNKS = BN / 32, CHUNK_BYTES = BM * 128;
+    static_assert(CHUNKS * CHUNK_BYTES <= STAGES * STAGE_BYTES, "staging tile must fit in the operand stages");
+    if (warp >= 2) {
+      const bool conv = P.conv_mode == CONV_FWD;
+      const bool mask = g.epi == EPI_RELU_BWD;
+      const int nch = min(CHUNKS, (g.N - n0 + 31) / 32);          // chunks with at least one valid column
+      const uint32_t stg_u = base, aux_u = base + (uint32_t)P.aux_off;
+      mbar_wait(tmem_full, 0);                                     // accumulator complete => operand stages are dead
+      tc_fence_after();
+      if (threadIdx.x == 64) DBG_STAMP(5);
+      if (mask && threadIdx.x == 64) {
+        mbar_expect_tx(aux_full, (uint32_t)(nch * CHUNK_BYTES));
+        for (int c = 0; c < nch; ++c) {
+          if (conv) tma_load_4d(aux_u + c * CHUNK_BYTES, &tmX, aux_full, n0 + c * 32, ct0, cf0, cb);
+          else tma_load_2d(aux_u + c * CHUNK_BYTES, &tmX, aux_full, n0 + c * 32, m0);
+        }
+      }
+      const int row = q * 32 + lane;
+      const uint32_t row_u = (uint32_t)row * 128u, sw = (uint32_t)(row & 7);
+      const float alpha = g.alpha;
+      const float lo = g.epi == EPI_RELU ? 0.f : -INFINITY;        // branch-free ReLU
+      if (mask) mbar_wait(aux_full, 0);
+#pragma unroll 1
+      for (int c = 0; c < nch; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c * 32 + j * 4);
+          float4 o;
+          o.x = fmaxf(fmaf(alpha, __uint_as_float(v[4 * j + 0]), b4.x), lo);
+          o.y = fmaxf(fmaf(alpha, __uint_as_float(v[4 * j + 1]), b4.y), lo);
+          o.z = fmaxf(fmaf(alpha, __uint_as_float(v[4 * j + 2]), b4.z), lo);
+          o.w = fmaxf(fmaf(alpha, __uint_as_float(v[4 * j + 3]), b4.w), lo);
+          const uint32_t slot = (uint32_t)c * CHUNK_BYTES + row_u + ((((uint32_t)j) ^ sw) << 4);
+          if (mask) {
+            float4 a;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "r"(aux_u + slot));
+            o.x = a.x > 0.f ? o.x : 0.f; o.y = a.y > 0.f ? o.y : 0.f;
+            o.z = a.z > 0.f ? o.z : 0.f; o.w = a.w > 0.f ? o.w : 0.f;
+          }
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stg_u + slot), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staged rows -> visible to the TMA unit
+      if (threadIdx.x == 64) DBG_STAMP(9);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (threadIdx.x == 64) {
+        const bool add = P.tma_epi == 2;
+        for (int c = 0; c < nch; ++c) {
+          if (conv) tma_store_4d(&tmC, stg_u + c * CHUNK_BYTES, n0 + c * 32, ct0, cf0, cb, add);
+          else tma_store_2d(&tmC, stg_u + c * CHUNK_BYTES, n0 + c * 32, m0, add);
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the staging boxes must outlive the reads
+        DBG_STAMP(6);
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) DBG_STAMP(7);
+    if (warp == 1) {
+      tc_fence_after();
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN) : "memory");
+    }
+    return;
+  }
   if (warp >= 2) {
     mbar_wait(tmem_full, 0);
     tc_fence_after();
@@ -371,20 +498,24 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
   else if (warp >= 2) asm volatile("bar.sync 1, 128;" ::: "memory");
   if (threadIdx.x == 64) DBG_STAMP(10);
   if (warp >= 2) {
-    // Everything the loop needs lives in registers: re-reading kernel parameters from the constant bank inside the
-    // loop costs a dependent ~30-cycle load per field and, with one warp per scheduler, nothing hides it.
+    // Everything the row loop needs is pinned in registers (keep_reg): the compiler otherwise re-reads kernel
+    // parameters from the constant bank inside the loop, a dependent ~70-cycle load per field that nothing hides
+    // with one warp per scheduler (measured: 640 cycles per 2-row iteration, 11k cycles per conv tile).
     constexpr int LPR = BN / 4;                     // lanes per output row (float4 each)
     constexpr int RPI = 32 / LPR;                   // rows per warp iteration
     constexpr int STEP = 4 * RPI;                   // rows per iteration of the four epilogue warps
+    constexpr int UNR = 4;                          // rows in flight per thread
     const int col_t = (lane % LPR) * 4, col = n0 + col_t;
-    const int N = g.N, M = g.M, ldc = g.ldc, epi = g.epi;
-    const float alpha = g.alpha, beta = g.beta;
-    float* const Cp = g.C;
-    const float* const auxp = g.aux;
-    const bool atomic = g.split_k > 1;
+    const int N = keep_reg(g.N), M = keep_reg(g.M), ldc = keep_reg(g.ldc);
+    const float alpha = keep_reg(g.alpha), beta = keep_reg(g.beta);
+    float* const Cp = keep_reg(g.C);
+    const float* const auxp = keep_reg(g.aux);
+    const bool atomic = keep_reg((int)(g.split_k > 1)) != 0;
+    const bool mask = keep_reg((int)(g.epi == EPI_RELU_BWD)) != 0;
+    const bool has_beta = keep_reg((int)(beta != 0.f)) != 0;
     const bool vec = P.vecC && col + 3 < N;
-    const bool conv = P.conv_mode == CONV_FWD;
-    const int btl = P.bt_log2, btm = (1 << P.bt_log2) - 1, cF = P.cF, cT = P.cT;
+    const bool conv = keep_reg((int)(P.conv_mode == CONV_FWD)) != 0;
+    const int btl = keep_reg(P.bt_log2), btm = (1 << btl) - 1, cF = keep_reg(P.cF), cT = keep_reg(P.cT);
     float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (g.bias && !atomic) {
       if (col + 0 < N) bias4.x = g.bias[col + 0];
@@ -392,7 +523,8 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
       if (col + 2 < N) bias4.z = g.bias[col + 2];
       if (col + 3 < N) bias4.w = g.bias[col + 3];
     }
-    const float lo = epi == EPI_RELU ? 0.f : -INFINITY;   // branch-free ReLU
+    const float lo = g.epi == EPI_RELU ? 0.f : -INFINITY;   // branch-free ReLU
+    if (lane == 0) DBG_STAMP(11 + (warp - 2));      // per-warp: bias loaded, row loop starts
     const int lr0 = q * RPI + lane / LPR;
     const int r_first = rank * rows_per;            // first tile row this CTA finishes
     uint32_t peer[8];                               // staging address of (row r_first + lr0, col_t) in every peer CTA
@@ -401,8 +533,16 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
 #pragma unroll
       for (int s2 = 0; s2 < 8; ++s2) peer[s2] = (CS > 1 && s2 < CS) ? mapa_u32(a0, (uint32_t)s2) : a0;
     }
+    // element offset of tile row r_t in C / aux, or -1 when the row is outside the problem
+    auto row_off = [&](int r_t) -> long long {
+      if (conv) {
+        const int f = cf0 + (r_t >> btl), t = ct0 + (r_t & btm);
+        return (f < cF && t < cT) ? ((long long)(cb * cF + f) * cT + t) * ldc + col : -1;
+      }
+      return (m0 + r_t < M) ? (long long)(m0 + r_t) * ldc + col : -1;
+    };
     if (col < N) {
-      if (!conv && vec && !atomic && epi != EPI_RELU_BWD && beta == 0.f) {
+      if (!conv && vec && !atomic && !mask && !has_beta) {
         // hot path (every nn.Linear forward / dgrad): valid rows are a prefix of the tile
         const int lim = min(rows_per, M - m0 - r_first);
         float* cp = Cp + (long long)(m0 + r_first + lr0) * ldc + col;
@@ -425,58 +565,101 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
           o.z = fmaxf(fmaf(alpha, acc.z, bias4.z), lo); o.w = fmaxf(fmaf(alpha, acc.w, bias4.w), lo);
           *reinterpret_cast<float4*>(cp) = o;
         }
+      } else if (vec && CS == 1) {
+        // every other 16-byte-aligned case without a cluster (implicit conv rows, ReLU-backward mask, beta*C,
+        // split-K atomics): UNR rows per thread are in flight at once -- all loads first, then arithmetic and stores
+#pragma unroll 1
+        for (int lr = lr0; lr < BM; lr += STEP * UNR) {
+          long long o[UNR];
+          float4 acc[UNR], ax[UNR], cc[UNR];
+#pragma unroll
+          for (int u = 0; u < UNR; ++u) {
+            const int l2 = lr + u * STEP;
+            o[u] = l2 < BM ? row_off(l2) : -1;
+          }
+#pragma unroll
+          for (int u = 0; u < UNR; ++u) {
+            if (o[u] < 0) continue;
+            if (mask) ax[u] = *reinterpret_cast<const float4*>(auxp + o[u]);
+            if (has_beta) cc[u] = *reinterpret_cast<const float4*>(Cp + o[u]);
+            acc[u] = *reinterpret_cast<const float4*>(stg + (lr + u * STEP) * LDS + col_t);
+          }
+#pragma unroll
+          for (int u = 0; u < UNR; ++u) {
+            if (o[u] < 0) continue;
+            float4 v;
+            v.x = fmaxf(fmaf(alpha, acc[u].x, bias4.x), lo); v.y = fmaxf(fmaf(alpha, acc[u].y, bias4.y), lo);
+            v.z = fmaxf(fmaf(alpha, acc[u].z, bias4.z), lo); v.w = fmaxf(fmaf(alpha, acc[u].w, bias4.w), lo);
+            float* crow = Cp + o[u];
+            if (atomic) { red_add_v4(crow, v.x, v.y, v.z, v.w); continue; }   // split-K slabs without a cluster
+            if (mask) {
+              v.x = ax[u].x > 0.f ? v.x : 0.f; v.y = ax[u].y > 0.f ? v.y : 0.f;
+              v.z = ax[u].z > 0.f ? v.z : 0.f; v.w = ax[u].w > 0.f ? v.w : 0.f;
+            }
+            if (has_beta) {
+              v.x = fmaf(beta, cc[u].x, v.x); v.y = fmaf(beta, cc[u].y, v.y);
+              v.z = fmaf(beta, cc[u].z, v.z); v.w = fmaf(beta, cc[u].w, v.w);
+            }
+            if (P.epi_test != 1) *reinterpret_cast<float4*>(crow) = v;
+          }
+        }
+      } else if (vec) {
+        // the same with a cluster split-K: the CS partial tiles are summed over distributed shared memory first
+#pragma unroll 1
+        for (int lr = lr0; lr < rows_per; lr += STEP) {
+          const long long ro = row_off(r_first + lr);
+          if (ro < 0) continue;
+          float4 ax = make_float4(1.f, 1.f, 1.f, 1.f), cc = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (mask) ax = *reinterpret_cast<const float4*>(auxp + ro);
+          if (has_beta) cc = *reinterpret_cast<const float4*>(Cp + ro);
+          const uint32_t off = (uint32_t)((lr - lr0) * LDS * 4);
+          float4 t[8];
+#pragma unroll
+          for (int s2 = 0; s2 < 8; ++s2) if (s2 < CS) t[s2] = ld_cluster_v4(peer[s2] + off);
+          float4 acc = t[0];
+#pragma unroll
+          for (int s2 = 1; s2 < 8; ++s2)
+            if (s2 < CS) { acc.x += t[s2].x; acc.y += t[s2].y; acc.z += t[s2].z; acc.w += t[s2].w; }
+          float4 v;
+          v.x = fmaxf(fmaf(alpha, acc.x, bias4.x), lo); v.y = fmaxf(fmaf(alpha, acc.y, bias4.y), lo);
+          v.z = fmaxf(fmaf(alpha, acc.z, bias4.z), lo); v.w = fmaxf(fmaf(alpha, acc.w, bias4.w), lo);
+          if (mask) {
+            v.x = ax.x > 0.f ? v.x : 0.f; v.y = ax.y > 0.f ? v.y : 0.f;
+            v.z = ax.z > 0.f ? v.z : 0.f; v.w = ax.w > 0.f ? v.w : 0.f;
+          }
+          v.x = fmaf(beta, cc.x, v.x); v.y = fmaf(beta, cc.y, v.y);
+          v.z = fmaf(beta, cc.z, v.z); v.w = fmaf(beta, cc.w, v.w);
+          *reinterpret_cast<float4*>(Cp + ro) = v;
+        }
       } else {
+        // ragged / unaligned columns: scalar tail (rare: N % 4 != 0 or an unaligned C)
 #pragma unroll 1
         for (int lr = lr0; lr < rows_per; lr += STEP) {
           const int r_t = r_first + lr;
-          long long orow;
-          if (conv) {
-            const int f = cf0 + (r_t >> btl), t = ct0 + (r_t & btm);
-            orow = (f < cF && t < cT) ? ((long long)cb * cF + f) * cT + t : -1;
-          } else {
-            orow = (m0 + r_t < M) ? (long long)(m0 + r_t) : -1;
-          }
-          if (orow < 0) continue;
+          const long long ro = row_off(r_t);
+          if (ro < 0) continue;
           const uint32_t off = (uint32_t)((lr - lr0) * LDS * 4);
           float4 acc = CS > 1 ? ld_cluster_v4(peer[0] + off) : *reinterpret_cast<const float4*>(stg + r_t * LDS + col_t);
 #pragma unroll
           for (int s2 = 1; s2 < 8; ++s2)
             if (s2 < CS) { const float4 t = ld_cluster_v4(peer[s2] + off); acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w; }
-          float v[4] = {fmaxf(fmaf(alpha, acc.x, bias4.x), lo), fmaxf(fmaf(alpha, acc.y, bias4.y), lo),
-                        fmaxf(fmaf(alpha, acc.z, bias4.z), lo), fmaxf(fmaf(alpha, acc.w, bias4.w), lo)};
-          float* crow = Cp + orow * ldc + col;
-          if (atomic) {                             // atomic split-K (grid.z slabs without a cluster)
-            if (vec) red_add_v4(crow, v[0], v[1], v[2], v[3]);
-            else
-              for (int j = 0; j < 4; ++j) if (col + j < N) atomicAdd(crow + j, v[j]);
-            continue;
-          }
-          if (vec) {
-            if (epi == EPI_RELU_BWD) {
-              const float4 a = *reinterpret_cast<const float4*>(auxp + orow * ldc + col);
-              v[0] = a.x > 0.f ? v[0] : 0.f; v[1] = a.y > 0.f ? v[1] : 0.f;
-              v[2] = a.z > 0.f ? v[2] : 0.f; v[3] = a.w > 0.f ? v[3] : 0.f;
-            }
-            if (beta != 0.f) {
-              const float4 o = *reinterpret_cast<const float4*>(crow);
-              v[0] += beta * o.x; v[1] += beta * o.y; v[2] += beta * o.z; v[3] += beta * o.w;
-            }
-            *reinterpret_cast<float4*>(crow) = make_float4(v[0], v[1], v[2], v[3]);
-          } else {
-            const float* arow = epi == EPI_RELU_BWD ? auxp + orow * ldc + col : nullptr;
-            for (int j = 0; j < 4; ++j) {
-              if (col + j < N) {
-                float t = v[j];
-                if (arow) t = arow[j] > 0.f ? t : 0.f;
-                if (beta != 0.f) t += beta * crow[j];
-                crow[j] = t;
-              }
-            }
+          const float v[4] = {fmaxf(fmaf(alpha, acc.x, bias4.x), lo), fmaxf(fmaf(alpha, acc.y, bias4.y), lo),
+                              fmaxf(fmaf(alpha, acc.z, bias4.z), lo), fmaxf(fmaf(alpha, acc.w, bias4.w), lo)};
+          float* crow = Cp + ro;
+          const float* arow = mask ? auxp + ro : nullptr;
+          for (int j = 0; j < 4; ++j) {
+            if (col + j >= N) continue;
+            if (atomic) { atomicAdd(crow + j, v[j]); continue; }
+            float t = v[j];
+            if (arow) t = arow[j] > 0.f ? t : 0.f;
+            if (has_beta) t += beta * crow[j];
+            crow[j] = t;
           }
         }
       }
     }
     if (threadIdx.x == 64) DBG_STAMP(6);
+    if (lane == 0) DBG_STAMP(15 + (warp - 2));      // per-warp: row loop done
   }
   if (CS > 1) cluster_sync_all();                   // nobody leaves while a peer may still read its staged rows
   tc_fence_before();
@@ -569,49 +752,96 @@ int make_map_nhwc(const float* ptr, int B, int F, int T, int C, int bt, int bf, 
   return encode_cached(key, 4, dims, strides, box, tf32_type, mn_major, out);
 }
 
+struct Maps { CUtensorMap a, b, c, x; };
+
 template <int BN, int STAGES, bool A_MN, bool B_MN, bool SPLIT3>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& P, dim3 grid, cudaStream_t s) {
-  constexpr int SMEM = STAGES * (A_STAGE_BYTES + BN * BK * 4) * (SPLIT3 ? 2 : 1) + 1024 /*align slack*/ + 256 /*barriers*/;
-  static_assert(SMEM <= 227 * 1024, "shared memory budget");
+int launch(const Maps& tm, const TcParams& P_in, dim3 grid, cudaStream_t s) {
+  constexpr int STAGE_MEM = STAGES * (A_STAGE_BYTES + BN * BK * 4) * (SPLIT3 ? 2 : 1);
+  constexpr int TILE = BM * BN * 4;                       // one staged output / mask tile
+  constexpr int SMEM = STAGE_MEM + 1024 /*align slack*/ + 1024 /*barriers + bias slice*/;
+  constexpr bool AUX_INSIDE = 2 * TILE <= STAGE_MEM;
+  constexpr int SMEM_MAX = AUX_INSIDE ? SMEM : SMEM + TILE;
+  static_assert(SMEM_MAX <= 227 * 1024, "shared memory budget");
   static bool configured = false;
   auto kern = gemm_tc_kernel<BN, STAGES, A_MN, B_MN, SPLIT3>;
   if (!configured) {
-    MTL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    MTL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
     configured = true;
+  }
+  // ReLU-mask tile of the TMA epilogue: beside the staging tile inside the (dead) operand stages when they are
+  // large enough, else in extra dynamic shared memory behind the barrier block
+  TcParams P = P_in;
+  int smem = SMEM;
+  if (P.tma_epi && P.g.epi == EPI_RELU_BWD) {
+    if (AUX_INSIDE) P.aux_off = TILE;
+    else { P.aux_off = STAGE_MEM + 1024; smem = SMEM + TILE; }
   }
   static_assert(SMEM - 1280 >= BM * (BN + 4) * 4, "staging tile must fit in the operand stages");
   if (P.cluster_k > 1) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = grid; cfg.blockDim = dim3(192, 1, 1); cfg.dynamicSmemBytes = SMEM; cfg.stream = s;
+    cfg.gridDim = grid; cfg.blockDim = dim3(192, 1, 1); cfg.dynamicSmemBytes = smem; cfg.stream = s;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = (unsigned)P.cluster_k;
     cfg.attrs = at; cfg.numAttrs = 1;
-    MTL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, P));
+    MTL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tm.a, tm.b, tm.c, tm.x, P));
     ++g_mtl_launches;
     return MTL_OK;
   }
-  kern<<<grid, 192, SMEM, s>>>(ta, tb, P);
+  kern<<<grid, 192, smem, s>>>(tm.a, tm.b, tm.c, tm.x, P);
   MTL_CHECK_LAUNCH();
   return MTL_OK;
 }
 
-template <int BN, bool SPLIT3>
-int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& P, dim3 grid,
-                   cudaStream_t s) {
-  constexpr int STAGES = SPLIT3 ? (BN == 64 ? 4 : 3) : (BN == 64 ? 4 : 3);
-  if (!a_mn && !b_mn) return launch<BN, STAGES, false, false, SPLIT3>(ta, tb, P, grid, s);
-  if (!a_mn && b_mn) return launch<BN, STAGES, false, true, SPLIT3>(ta, tb, P, grid, s);
-  if (a_mn && !b_mn) return launch<BN, STAGES, true, false, SPLIT3>(ta, tb, P, grid, s);
-  return launch<BN, STAGES, true, true, SPLIT3>(ta, tb, P, grid, s);
+// 3xTF32 Cout=64 convolutions run with 2 pipeline stages (2 CTAs per SM: one tile's epilogue and prologue overlap the
+// other's main loop); MTL_CONV_STAGES=4 restores 4 stages / 1 CTA per SM (A/B measurements)
+bool conv_two_cta() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MTL_CONV_STAGES"); v = (e && e[0] == '4') ? 0 : 1; }
+  return v != 0;
 }
-int dispatch(int bn, bool split3, bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& P,
-             dim3 grid, cudaStream_t s) {
-  if (bn == 64) return split3 ? dispatch_major<64, true>(a_mn, b_mn, ta, tb, P, grid, s)
-                              : dispatch_major<64, false>(a_mn, b_mn, ta, tb, P, grid, s);
-  return split3 ? dispatch_major<128, true>(a_mn, b_mn, ta, tb, P, grid, s)
-                : dispatch_major<128, false>(a_mn, b_mn, ta, tb, P, grid, s);
+
+template <int BN, bool SPLIT3>
+int dispatch_major(bool a_mn, bool b_mn, const Maps& tm, const TcParams& P, dim3 grid, cudaStream_t s) {
+  constexpr int STAGES = SPLIT3 ? (BN == 64 ? 4 : 3) : (BN == 64 ? 4 : 3);
+  if (BN == 64 && SPLIT3 && !a_mn && !b_mn && P.conv_mode == CONV_FWD && conv_two_cta()) {
+    // 2 stages x 48 KB: two CTAs share an SM, so one tile's epilogue overlaps the other's main loop
+    return launch<BN, (BN == 64 && SPLIT3) ? 2 : STAGES, false, false, SPLIT3>(tm, P, grid, s);
+  }
+  if (!a_mn && !b_mn) return launch<BN, STAGES, false, false, SPLIT3>(tm, P, grid, s);
+  if (!a_mn && b_mn) return launch<BN, STAGES, false, true, SPLIT3>(tm, P, grid, s);
+  if (a_mn && !b_mn) return launch<BN, STAGES, true, false, SPLIT3>(tm, P, grid, s);
+  return launch<BN, STAGES, true, true, SPLIT3>(tm, P, grid, s);
+}
+int dispatch(int bn, bool split3, bool a_mn, bool b_mn, const Maps& tm, const TcParams& P, dim3 grid, cudaStream_t s) {
+  if (bn == 64) return split3 ? dispatch_major<64, true>(a_mn, b_mn, tm, P, grid, s)
+                              : dispatch_major<64, false>(a_mn, b_mn, tm, P, grid, s);
+  return split3 ? dispatch_major<128, true>(a_mn, b_mn, tm, P, grid, s)
+                : dispatch_major<128, false>(a_mn, b_mn, tm, P, grid, s);
+}
+
+// MTL_TMA_EPI=0 keeps the register/shared-memory epilogue everywhere (A/B measurements)
+bool tma_epi_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MTL_TMA_EPI"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v != 0;
+}
+// Picks the epilogue: TMA store / reduce-add when there is no cluster split, C (and the mask) are TMA-addressable
+// and beta is 0 or 1.  Fills tm.c / tm.x through `mk` (2-D matrices or NHWC pixel boxes).
+template <typename MakeMap>
+int plan_epilogue(TcParams& P, Maps& tm, MakeMap mk) {
+  const GemmArgs& g = P.g;
+  P.tma_epi = 0;
+  tm.c = tm.a; tm.x = tm.a;                                        // placeholders (never dereferenced)
+  const bool slab = g.split_k > 1;
+  // the TMA unit clips the innermost dimension at 16-byte granularity: N % 4 != 0 would spill into padding columns
+  if (!tma_epi_enabled() || P.cluster_k > 1 || !P.vecC || g.N % 4 != 0) return MTL_OK;
+  if (!(g.beta == 0.f || g.beta == 1.f)) return MTL_OK;
+  MTL_TRY(mk(g.C, &tm.c));
+  if (g.epi == EPI_RELU_BWD) MTL_TRY(mk(g.aux, &tm.x));
+  P.tma_epi = (slab || g.beta == 1.f) ? 2 : 1;
+  return MTL_OK;
 }
 
 inline bool al16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
@@ -668,7 +898,9 @@ int k_gemm_tc(const GemmArgs& g, int precision_mode, cudaStream_t s) {
   const bool a_mn = g.transA != 0;     // A stored [K,M]: M contiguous
   const bool b_mn = g.transB == 0;     // B stored [K,N]: N contiguous
   const int bn = g.N <= 64 ? 64 : 128;
-  CUtensorMap ta, tb;
+  Maps tm;
+  CUtensorMap& ta = tm.a;
+  CUtensorMap& tb = tm.b;
   if (!a_mn) MTL_TRY(make_map(g.A, g.K, g.M, g.lda, BM, false, tf, &ta)); else MTL_TRY(make_map(g.A, g.M, g.K, g.lda, 32, true, tf, &ta));
   if (!b_mn) MTL_TRY(make_map(g.B, g.K, g.N, g.ldb, bn, false, tf, &tb)); else MTL_TRY(make_map(g.B, g.N, g.K, g.ldb, 32, true, tf, &tb));
   TcParams P;
@@ -696,7 +928,9 @@ int k_gemm_tc(const GemmArgs& g, int precision_mode, cudaStream_t s) {
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("MTL_GEMM_DBG"); dbg = e ? atoi(e) : 0; } P.dbg = dbg; }
   dim3 grid(mtl_cdiv(g.M, BM), mtl_cdiv(g.N, bn), split);
   MTL_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "gemm grid too large");
-  return dispatch(bn, split3, a_mn, b_mn, ta, tb, P, grid, s);
+  const int M = g.M, N = g.N, ldc = g.ldc;
+  MTL_TRY(plan_epilogue(P, tm, [&](const float* ptr, CUtensorMap* out) { return make_map(ptr, N, M, ldc, BM, false, false, out); }));
+  return dispatch(bn, split3, a_mn, b_mn, tm, P, grid, s);
 }
 
 // y[pixel, co] = epi(sum_{tap,ci} x[pixel+tap, ci] * wg[co, tap*Cin+ci] + bias[co])   (x NHWC [B,F,T,Cin], y [B*F*T, Cout])
@@ -712,7 +946,9 @@ int k_conv3x3_tc(const float* x, const float* wg, const float* bias, float* y, i
   P.cluster_k = 1;
   P.cF = F; P.cT = T; P.cCin = Cin;
   P.bt_log2 = pick_bt_log2(BM, F, T, &P.tiles_t, &P.tiles_f);
-  CUtensorMap ta, tb;
+  Maps tm;
+  CUtensorMap& ta = tm.a;
+  CUtensorMap& tb = tm.b;
   MTL_TRY(make_map_nhwc(x, B, F, T, Cin, 1 << P.bt_log2, BM >> P.bt_log2, false, tf, &ta));
   MTL_TRY(make_map(wg, 9LL * Cin, Cout, 9LL * Cin, bn, false, tf, &tb));
   GemmArgs& g = P.g;
@@ -721,8 +957,12 @@ int k_conv3x3_tc(const float* x, const float* wg, const float* bias, float* y, i
   P.kb_total = 9 * (Cin / 32);
   P.kb_per_split = P.kb_total;
   P.vecC = 1;
+  { const char* e = getenv("MTL_GEMM_DBG"); P.dbg = e ? atoi(e) : 0; }
+  { const char* e = getenv("MTL_EPI_TEST"); P.epi_test = e ? atoi(e) : 0; }
   dim3 grid(B * P.tiles_f * P.tiles_t, mtl_cdiv(Cout, bn), 1);
-  return dispatch(bn, split3, false, false, ta, tb, P, grid, s);
+  const int bt = 1 << P.bt_log2, bf = BM >> P.bt_log2;
+  MTL_TRY(plan_epilogue(P, tm, [&](const float* ptr, CUtensorMap* out) { return make_map_nhwc(ptr, B, F, T, Cout, bt, bf, false, false, out); }));
+  return dispatch(bn, split3, false, false, tm, P, grid, s);
 }
 
 // dwgT[tap*Cin+ci, co] += sum_pixel x[pixel+tap, ci] * dy[pixel, co]   (vectorised atomics; dwgT must be pre-zeroed or hold a running sum)
@@ -738,7 +978,9 @@ int k_conv3x3_wgrad_tc(const float* x, const float* dy, float* dwgT, int B, int 
   P.cF = F; P.cT = T; P.cCin = Cin;
   P.bt_log2 = pick_bt_log2(32, F, T, &P.tiles_t, &P.tiles_f);
   const int bt = 1 << P.bt_log2, bf = 32 >> P.bt_log2;
-  CUtensorMap ta, tb;
+  Maps tm;
+  CUtensorMap& ta = tm.a;
+  CUtensorMap& tb = tm.b;
   MTL_TRY(make_map_nhwc(x, B, F, T, Cin, bt, bf, true, tf, &ta));
   MTL_TRY(make_map_nhwc(dy, B, F, T, Cout, bt, bf, true, tf, &tb));
   GemmArgs& g = P.g;
@@ -753,11 +995,12 @@ int k_conv3x3_wgrad_tc(const float* x, const float* dy, float* dwgT, int B, int 
   P.vecC = 1;
   dim3 grid(mt, nt, split);
   MTL_REQUIRE(grid.z <= 65535, "conv wgrad grid too large");
-  return dispatch(bn, split3, true, true, ta, tb, P, grid, s);
+  MTL_TRY(plan_epilogue(P, tm, [&](const float* ptr, CUtensorMap* out) { return make_map(ptr, Cout, 9LL * Cin, Cout, BM, false, false, out); }));
+  return dispatch(bn, split3, true, true, tm, P, grid, s);
 }
 
 // debug: copies the 32 cycle stamps of the last instrumented GEMM launch to the host
 int k_gemm_tc_debug_stamps(long long* host32) {
-  MTL_CHECK_CUDA(cudaMemcpyFromSymbol(host32, g_dbg, sizeof(long long) * 32));
+  MTL_CHECK_CUDA(cudaMemcpyFromSymbol(host32, g_dbg, sizeof(long long) * 160));
   return MTL_OK;
 }

@@ -15,7 +15,7 @@ torch.cuda.synchronize()
 print("ok", float(C.abs().sum()))
 if os.environ.get("MTL_GEMM_DBG", "0") != "0":
     import ctypes
-    buf = (ctypes.c_longlong * 32)()
+    buf = (ctypes.c_longlong * 160)()
     ok(lib().mtl_debug_gemm_stamps(buf))
     t = list(buf)[:16]
     names = ["entry", "setup done", "producer 1st issue", "mma sees full[0]", "mma committed all", "epilogue sees tmem_full",
