@@ -145,6 +145,7 @@ class ClockSampler:
 def run_ours(args, rank, world, local_rank):
     import mtl_b200
     from mtl_b200 import lib as L
+    from mtl_b200.shard import exchange_copy_grad
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     dist = None
@@ -197,8 +198,7 @@ def run_ours(args, rank, world, local_rank):
         stepper.load_val(*val, n=n_tok)
         res = stepper.run(theta, cg, LR, 1.0 / n_total, dropout=DROPOUT, seed=i * 64 + rank)
         all_results[i].copy_(res, non_blocking=True)
-        if dist is not None:
-            dist.all_reduce(cg, op=dist.ReduceOp.SUM)           # the one exchange step
+        exchange_copy_grad(cg, dist)                            # the one exchange step
         s.meta_finish(theta, grad, cg, m, v, adam_state, META_LR)
 
     def barrier():

@@ -73,9 +73,9 @@ class JointTrainer(TransientTrainer):
         last_sum_char = deque(maxlen=window_size)
         k_train = args.k_train
         n_tasks = len(train_data_list)
-        dist = torch.distributed if (torch.distributed.is_available() and torch.distributed.is_initialized()) else None
-        rank, world = (dist.get_rank(), dist.get_world_size()) if dist else (0, 1)
-        my_tasks = list(range(rank, n_tasks, world))
+        from mtl_b200.shard import dist_env, exchange_copy_grad, reduce_stats, task_shard
+        dist, rank, world = dist_env()
+        my_tasks = task_shard(n_tasks, rank, world)
         buffers = [[] for _ in range(n_tasks)]
 
         def fetch(buf):
@@ -101,8 +101,7 @@ class JointTrainer(TransientTrainer):
                     out = session.forward(theta, b, dropout=drop, seed=it * 64 + m, smoothing=float(smoothing))
                     session.backward(theta, grad, 1.0 / n_tasks)              # (tr_loss / N).backward()
                     outs.append(out)
-                if dist:
-                    dist.all_reduce(grad, op=dist.ReduceOp.SUM)
+                exchange_copy_grad(grad, dist)                                # one all-reduce of the flat gradient arena
                 if args.clip:
                     session.clip(grad, args.max_norm)
                 opt.step()
@@ -112,10 +111,7 @@ class JointTrainer(TransientTrainer):
                     total_loss += float(out["ce"][0])
                     c, n = _cer_counts(vocab, out["hyp"].cpu().tolist(), out["gold"].cpu().tolist())
                     total_cer, total_char = total_cer + c, total_char + n
-                if dist:
-                    t = torch.tensor([total_loss, total_cer, total_char], dtype=torch.float64, device=session.device)
-                    dist.all_reduce(t)
-                    total_loss, total_cer, total_char = float(t[0]), float(t[1]), float(t[2])
+                total_loss, total_cer, total_char = reduce_stats((total_loss, total_cer, total_char), session.device, dist)
                 last_sum_cer.append(total_cer)
                 last_sum_char.append(total_char)
                 last_sum_loss.append(total_loss)

@@ -100,6 +100,7 @@ class TransientTrainer():
         """
         from mtl_b200 import MetaStepper
         from mtl_b200.optim import ArenaAdam, ArenaSGD, adopt
+        from mtl_b200.shard import dist_env, exchange_copy_grad, reduce_stats, task_shard
         if loss_type != "ce":
             raise NotImplementedError("only the cross-entropy loss is on the B200 hot path")
         if not is_copy_grad:
@@ -132,9 +133,8 @@ class TransientTrainer():
 
         k_train, k_valid = args.k_train, args.k_valid
         n_tasks = len(train_data_list)
-        dist = torch.distributed if (torch.distributed.is_available() and torch.distributed.is_initialized()) else None
-        rank, world = (dist.get_rank(), dist.get_world_size()) if dist else (0, 1)
-        my_tasks = list(range(rank, n_tasks, world))
+        dist, rank, world = dist_env()
+        my_tasks = task_shard(n_tasks, rank, world)
         stepper = MetaStepper(session, max(1, len(my_tasks))) if my_tasks else None
         model.zero_copy_grad()
         copy_grad = model._cg
@@ -173,8 +173,7 @@ class TransientTrainer():
                     host_res.copy_(stepper.results, non_blocking=True)
                 else:
                     session.zero(copy_grad)
-                if dist:
-                    dist.all_reduce(copy_grad, op=dist.ReduceOp.SUM)          # the one exchange step of the meta-step
+                exchange_copy_grad(copy_grad, dist)                           # the one exchange step of the meta-step
                 g = outer_opt.param_groups[0]
                 session.meta_finish(theta, grad, copy_grad, outer_opt.m, outer_opt.v, outer_opt.dev_state, g['lr'],
                                     clip=args.clip, max_norm=args.max_norm)
@@ -188,10 +187,7 @@ class TransientTrainer():
                     for hyp, gold in ids:
                         c, n = _cer_counts(vocab, hyp.tolist(), gold.tolist())
                         total_cer, total_char = total_cer + c, total_char + n
-                if dist:
-                    t = torch.tensor([total_loss, total_cer, total_char], dtype=torch.float64, device=session.device)
-                    dist.all_reduce(t)
-                    total_loss, total_cer, total_char = float(t[0]), float(t[1]), float(t[2])
+                total_loss, total_cer, total_char = reduce_stats((total_loss, total_cer, total_char), session.device, dist)
 
                 last_sum_cer.append(total_cer)
                 last_sum_char.append(total_char)
