@@ -289,6 +289,15 @@ static int lin_fwd(Run& R, const float* x, int ldx, const float* W, const float*
   K(k_gemm(g, R.S->mode, R.st));
   return MTL_OK;
 }
+// K-slabs for an accumulating (beta == 1) contraction: about two CTAs per SM, at least one 32-deep k-block per slab.
+// Slabs merge through the TMA reduce-add epilogue (or vector atomics), so no cluster barrier is involved.
+static int slab_split(long long tiles, int k_extent) {
+  const int kb = mtl_cdiv(k_extent, 32);
+  long long split = (296 + tiles - 1) / tiles;
+  if (split > kb) split = kb;
+  if (split > 256) split = 256;
+  return split > 1 ? (int)split : 1;
+}
 // dx[M,K] = epi(dy[M,N] . W[N,K]) + beta*dx
 static int lin_dgrad(Run& R, const float* dy, int ldy, const float* W, float* dx, int ldx, int M, int N, int Kd,
                      float beta, int epi, const float* aux) {
@@ -296,6 +305,8 @@ static int lin_dgrad(Run& R, const float* dy, int ldy, const float* W, float* dx
   memset(&g, 0, sizeof(g));
   g.A = dy; g.lda = ldy; g.transA = 0; g.B = W; g.ldb = Kd; g.transB = 0; g.C = dx; g.ldc = ldx;
   g.M = M; g.N = Kd; g.K = N; g.alpha = 1.f; g.beta = beta; g.epi = epi; g.aux = aux; g.split_k = 1;
+  if (beta == 1.f && epi == EPI_NONE)
+    g.split_k = slab_split((long long)mtl_cdiv(M, 128) * mtl_cdiv(Kd, Kd <= 64 ? 64 : 128), N);
   K(k_gemm(g, R.S->mode, R.st));
   return MTL_OK;
 }
@@ -305,12 +316,7 @@ static int lin_wgrad(Run& R, const float* dy, int ldy, const float* x, int ldx, 
   memset(&g, 0, sizeof(g));
   g.A = dy; g.lda = ldy; g.transA = 1; g.B = x; g.ldb = ldx; g.transB = 0; g.C = dW; g.ldc = Kd;
   g.M = N; g.N = Kd; g.K = M; g.alpha = 1.f; g.beta = 1.f; g.epi = EPI_NONE;
-  long long tiles = (long long)mtl_cdiv(N, 128) * mtl_cdiv(Kd, 64);
-  int split = (int)((296 + tiles - 1) / tiles);
-  int max_split = M / 256;
-  if (split > max_split) split = max_split;
-  if (split > 256) split = 256;
-  g.split_k = split > 1 ? split : 1;
+  g.split_k = slab_split((long long)mtl_cdiv(N, 128) * mtl_cdiv(Kd, Kd <= 64 ? 64 : 128), M);
   K(k_gemm(g, R.S->mode, R.st));
   return MTL_OK;
 }

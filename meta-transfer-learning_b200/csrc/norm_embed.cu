@@ -148,13 +148,15 @@ __global__ void __launch_bounds__(128) ln_bwd_kernel(
 // dgamma[c] += sum_m dout*rm*xhat ; dbeta[c] += sum_m dout*rm.  Block = 32 columns x 8 row-lanes.
 __global__ void __launch_bounds__(256) ln_param_grad_kernel(
     const float* __restrict__ dout, const float* __restrict__ xhat, const float* __restrict__ rowmask,
-    float* __restrict__ dgamma, float* __restrict__ dbeta, int M, int d) {
+    float* __restrict__ dgamma, float* __restrict__ dbeta, int M, int d, int rows_per_slab) {
   __shared__ float sg[8][33], sb[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + tx;
+  const int m0 = blockIdx.y * rows_per_slab, m1 = min(M, m0 + rows_per_slab);
   float ag = 0.f, ab = 0.f;
   if (c < d) {
-    for (int m = ty; m < M; m += 8) {
+#pragma unroll 4
+    for (int m = m0 + ty; m < m1; m += 8) {
       float rm = rowmask ? rowmask[m] : 1.f;
       float g = dout[(size_t)m * d + c] * rm;
       ag += g * xhat[(size_t)m * d + c];
@@ -167,8 +169,8 @@ __global__ void __launch_bounds__(256) ln_param_grad_kernel(
     float g = 0.f, b = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) { g += sg[i][tx]; b += sb[i][tx]; }
-    dgamma[c] += g;
-    dbeta[c] += b;
+    if (gridDim.y == 1) { dgamma[c] += g; dbeta[c] += b; }
+    else { atomicAdd(dgamma + c, g); atomicAdd(dbeta + c, b); }
   }
 }
 
@@ -180,7 +182,11 @@ int k_ln_bwd(const float* dout, const float* xhat, const float* rstd, const floa
   ln_bwd_kernel<<<mtl_cdiv(M, 4), 128, 0, s>>>(dout, xhat, rstd, gamma, rowmask, drop, dy, dres,
                                               dres_accumulate, M, d);
   MTL_CHECK_LAUNCH();
-  ln_param_grad_kernel<<<mtl_cdiv(d, 32), 256, 0, s>>>(dout, xhat, rowmask, dgamma, dbeta, M, d);
+  // a (32 columns x 8 row-lanes) block walks its rows serially: slabs of 32 rows keep that walk 4 loads deep
+  // (M = 264: 16 x 9 blocks instead of 16 blocks doing 33 dependent-latency steps each)
+  const int slabs = M > 32 ? (mtl_cdiv(M, 32) < 512 ? mtl_cdiv(M, 32) : 512) : 1;
+  ln_param_grad_kernel<<<dim3(mtl_cdiv(d, 32), slabs), 256, 0, s>>>(dout, xhat, rowmask, dgamma, dbeta, M, d,
+                                                                   mtl_cdiv(M, slabs));
   MTL_CHECK_LAUNCH();
   return MTL_OK;
 }
@@ -207,9 +213,10 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x
 }
 int k_colsum_acc(const float* x, int M, int N, int ld, float* out, cudaStream_t s) {
   if (M == 0 || N == 0) return MTL_OK;
-  int slabs = 1;
-  if (M > 4096) slabs = mtl_cdiv(M, 2048);
-  if (slabs > 512) slabs = 512;
+  // slabs of ~32 rows (4 loads per thread) merged with atomics; large M keeps at most 512 slabs per column block
+  int slabs = M > 32 ? mtl_cdiv(M, 32) : 1;
+  const int max_slabs = N >= 2048 ? 64 : 512;
+  if (slabs > max_slabs) slabs = max_slabs;
   int rps = mtl_cdiv(M, slabs);
   colsum_kernel<<<dim3(mtl_cdiv(N, 32), slabs), 256, 0, s>>>(x, M, N, ld, out, rps);
   MTL_CHECK_LAUNCH();
