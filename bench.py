@@ -207,10 +207,12 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     # ---------------- device-resident throughput
+    # the clock sampler starts before the warm-up steps (nvidia-smi needs ~0.2 s to produce its first line and the
+    # timed region is only ~0.15 s long): its samples cover warm-up + timed region, all under load
+    clocks = ClockSampler(local_rank) if rank == 0 else None
     for i in range(args.warmup):
         meta_step(i, *resident[i])
     barrier()
-    clocks = ClockSampler(local_rank) if rank == 0 else None
     l0 = lib.mtl_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()

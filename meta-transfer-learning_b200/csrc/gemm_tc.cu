@@ -135,11 +135,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-// round-to-nearest fp32 -> tf32 (10 explicit mantissa bits, low 13 bits zero)
+// round-to-nearest (ties away from zero) fp32 -> tf32: 10 explicit mantissa bits, low 13 bits zero.  Same result as
+// cvt.rna.tf32.f32 for finite inputs, but two full-rate integer ops instead of a quarter-rate conversion-pipe
+// instruction: the splitter converts 12288 values per k-block, which at 16 conversions/clk/SM was ~770 cycles.
 __device__ __forceinline__ float tf32_rna(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 // Pins a loop-invariant value in a register (opaque to the optimiser, so it cannot be rematerialised from the
 // constant bank at every use).
@@ -215,6 +215,10 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
   constexpr int B_STAGE_BYTES = BN * BK * 4;
   constexpr int HI_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   constexpr int STAGE_BYTES = HI_BYTES * (SPLIT3 ? 2 : 1);
+  // stage layout: TF32 [A | B];  3xTF32 [A_hi | A_lo | B_hi | B_lo] -- B_hi and B_lo are adjacent so that ONE MMA with
+  // N = 2*BN multiplies A_hi by both (accumulator columns [0,BN) and [BN,2BN) are summed in the epilogue)
+  constexpr int B_OFF = SPLIT3 ? 2 * A_STAGE_BYTES : A_STAGE_BYTES;
+  constexpr int TMEM_COLS = SPLIT3 ? 2 * BN : BN;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // SWIZZLE_128B atoms need 1024 B alignment
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
@@ -251,7 +255,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {   // TMEM allocation: BN fp32 accumulator columns x 128 lanes
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(BN)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -278,7 +282,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
         mbar_wait(&empty[s], ph ^ 1);
         if (it == 0) DBG_STAMP(2);
         mbar_expect_tx(&full[s], HI_BYTES);
-        const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + A_STAGE_BYTES;
+        const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + B_OFF;
         if (conv_mode == CONV_NONE) {
           if (!A_MN) {
             tma_load_2d(sa, &tmA, &full[s], kb * BK, m0);
@@ -321,6 +325,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
       // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=tf32, majors, N>>3, M>>4
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                              ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      const uint32_t idesc2 = (idesc & ~(0x3Fu << 17)) | ((uint32_t)((2 * BN) >> 3) << 17);   // same, N = 2*BN
       int it = 0;
       for (int kb = kb0; kb < kb1; ++kb, ++it) {
         const int s = it % STAGES;
@@ -329,23 +334,22 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
         if (it == 0) DBG_STAMP(3);
         DBG_KB(it, 2);
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + A_STAGE_BYTES;
+        const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + B_OFF;
         // descriptors of this stage; a K=8 step advances the 16-byte-granular start-address field (bits [0,14)) by
         // 32 B (K-major) or 1024 B (MN-major) -- no carry out of the field below 256 KB of shared memory
         constexpr uint64_t STEP_A = A_MN ? 64 : 2, STEP_B = B_MN ? 64 : 2;
         const uint64_t da0 = A_MN ? desc_mnmajor(sa) : desc_kmajor(sa);
         const uint64_t db0 = B_MN ? desc_mnmajor(sb) : desc_kmajor(sb);
-        const uint64_t la0 = A_MN ? desc_mnmajor(sa + HI_BYTES) : desc_kmajor(sa + HI_BYTES);
-        const uint64_t lb0 = B_MN ? desc_mnmajor(sb + HI_BYTES) : desc_kmajor(sb + HI_BYTES);
+        const uint64_t la0 = A_MN ? desc_mnmajor(sa + A_STAGE_BYTES) : desc_kmajor(sa + A_STAGE_BYTES);
 #pragma unroll
         for (int k = 0; k < BK / 8; ++k) {
           const uint64_t da = da0 + k * STEP_A, db = db0 + k * STEP_B;
           const uint32_t acc0 = (it > 0 || k > 0) ? 1u : 0u;
           if (SPLIT3) {
-            const uint64_t la = la0 + k * STEP_A, lb = lb0 + k * STEP_B;
-            tc_mma_tf32(tmem_base, la, db, idesc, acc0);     // small terms first
-            tc_mma_tf32(tmem_base, da, lb, idesc, 1u);
-            tc_mma_tf32(tmem_base, da, db, idesc, 1u);
+            // a_hi * [b_hi ; b_lo] over all 2*BN accumulator columns (also initialises them), then a_lo * b_hi into the
+            // first BN: the three 3xTF32 products in two instructions, A_hi read from shared memory once
+            tc_mma_tf32(tmem_base, da, db, idesc2, acc0);
+            tc_mma_tf32(tmem_base, la0 + k * STEP_A, db, idesc, 1u);
           } else {
             tc_mma_tf32(tmem_base, da, db, idesc, acc0);
           }
@@ -366,24 +370,36 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
         const uint32_t ph = (it / STAGES) & 1;
         mbar_wait(&full[s], ph);
         if (threadIdx.x == 64) DBG_KB(it, 1);
-        float4* hi = reinterpret_cast<float4*>(smem + s * STAGE_BYTES) + tid;
-        float4* lo = reinterpret_cast<float4*>(smem + s * STAGE_BYTES + HI_BYTES) + tid;
         // One warp per scheduler: a load -> convert -> store chain per element would expose the shared-memory latency
-        // PER times per k-block (measured 1400 cycles).  Issue every load first, then convert and store.
-        constexpr int PER = HI_BYTES / 16 / 128;
-        static_assert(HI_BYTES % (16 * 128) == 0, "splitter assumes whole float4 columns per thread");
-        float4 a[PER];
+        // once per element.  Issue every load of an operand first, then convert and store (hi in place, lo beside it).
+        float4* a_hi = reinterpret_cast<float4*>(smem + s * STAGE_BYTES) + tid;
+        float4* b_hi = reinterpret_cast<float4*>(smem + s * STAGE_BYTES + B_OFF) + tid;
+        constexpr int PER_A = A_STAGE_BYTES / 16 / 128, PER_B = B_STAGE_BYTES / 16 / 128;
+        static_assert(A_STAGE_BYTES % (16 * 128) == 0 && B_STAGE_BYTES % (16 * 128) == 0, "whole float4 columns per thread");
+        float4 a[PER_A], b[PER_B];
 #pragma unroll
-        for (int j = 0; j < PER; ++j) a[j] = hi[j * 128];
+        for (int j = 0; j < PER_A; ++j) a[j] = a_hi[j * 128];
 #pragma unroll
-        for (int j = 0; j < PER; ++j) {
+        for (int j = 0; j < PER_B; ++j) b[j] = b_hi[j * 128];
+#pragma unroll
+        for (int j = 0; j < PER_A; ++j) {
           float4 h, l;
           h.x = tf32_rna(a[j].x); l.x = tf32_rna(a[j].x - h.x);
           h.y = tf32_rna(a[j].y); l.y = tf32_rna(a[j].y - h.y);
           h.z = tf32_rna(a[j].z); l.z = tf32_rna(a[j].z - h.z);
           h.w = tf32_rna(a[j].w); l.w = tf32_rna(a[j].w - h.w);
-          hi[j * 128] = h;
-          lo[j * 128] = l;
+          a_hi[j * 128] = h;
+          a_hi[j * 128 + A_STAGE_BYTES / 16] = l;
+        }
+#pragma unroll
+        for (int j = 0; j < PER_B; ++j) {
+          float4 h, l;
+          h.x = tf32_rna(b[j].x); l.x = tf32_rna(b[j].x - h.x);
+          h.y = tf32_rna(b[j].y); l.y = tf32_rna(b[j].y - h.y);
+          h.z = tf32_rna(b[j].z); l.z = tf32_rna(b[j].z - h.z);
+          h.w = tf32_rna(b[j].w); l.w = tf32_rna(b[j].w - h.w);
+          b_hi[j * 128] = h;
+          b_hi[j * 128 + B_STAGE_BYTES / 16] = l;
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to the MMA (async proxy)
         __syncwarp();
@@ -437,6 +453,12 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
       for (int c = 0; c < nch; ++c) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+        if (SPLIT3) {
+          uint32_t w[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + c * 32), w);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c * 32 + j * 4);
@@ -474,7 +496,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
     if (threadIdx.x == 0) DBG_STAMP(7);
     if (warp == 1) {
       tc_fence_after();
-      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN) : "memory");
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
     return;
   }
@@ -487,6 +509,12 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
     for (int c = 0; c < BN / 32; ++c) {
       uint32_t v[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+      if (SPLIT3) {
+        uint32_t w[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + c * 32), w);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
+      }
 #pragma unroll
       for (int j = 0; j < 32; j += 4)
         *reinterpret_cast<float4*>(dst + c * 32 + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
@@ -667,7 +695,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
   if (threadIdx.x == 0) DBG_STAMP(7);
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
