@@ -303,7 +303,7 @@ def roofline_conv_gemm(s, lib, dev, mode):
     outs = [torch.empty(B, F, T, Cout, device=dev) for _ in range(NB)]
     w = torch.randn(Cout, Cin, 3, 3, device=dev) * 0.05
     bias = torch.zeros(N, device=dev)
-    wg = torch.empty(N, Kd, device=dev)
+    wg = torch.empty(2, N, Kd, device=dev)                 # [hi | lo] tf32 halves of the weights in 3xTF32
     col = torch.empty(M, Kd, device=dev) if mode == 0 else None
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     pv = lambda t: None if t is None else C.c_void_p(t.data_ptr())

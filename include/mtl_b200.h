@@ -198,7 +198,8 @@ int mtl_ce_bwd(const float* logits, int ld, const int* gold, const float* row_ls
 int mtl_conv1_fwd(const float* x, const float* w, const float* b, float* out, int B, int F, int T,
                   int Cout, void* stream);
 /* relu(conv3x3(x) + b): mode 0 = im2col (col: B*F*T*9*Cin floats) + fp32 GEMM; modes 1/2 = tcgen05 implicit GEMM
- * through 4-D TMA boxes (col unused, may be NULL).  wg: Cout*9*Cin floats of scratch. */
+ * through 4-D TMA boxes (col unused, may be NULL).  wg: 2*Cout*9*Cin floats of scratch (GEMM-layout weights; in
+ * 3xTF32 their tf32 hi and lo halves). */
 int mtl_conv3x3_relu_fwd(int mode, const float* x, const float* w, const float* b, float* col,
                          float* wg, float* out, int B, int F, int T, int Cin, int Cout, void* stream);
 /* Backward of y = conv3x3(x) + b given dy (gradient w.r.t. the pre-ReLU output): dw += , db += ,

@@ -133,17 +133,25 @@ int k_im2col3x3(const float* x, float* col, int B, int F, int T, int C, cudaStre
 }
 
 // ------------------------------------------------------------------ weight layouts
-__global__ void conv_w_fwd_layout_kernel(const float* __restrict__ w, float* __restrict__ wg, int Cout, int Cin) {
+// 3xTF32 operand halves (same rounding as the in-kernel splitter of gemm_tc.cu): hi = rna_tf32(v), lo = rna_tf32(v - hi)
+__device__ __forceinline__ float tf32_rna_f(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
+__device__ __forceinline__ void store_w(float* __restrict__ dst, int i, int n, float v, int split) {
+  if (!split) { dst[i] = v; return; }
+  const float h = tf32_rna_f(v);
+  dst[i] = h;
+  dst[n + i] = tf32_rna_f(v - h);
+}
+__global__ void conv_w_fwd_layout_kernel(const float* __restrict__ w, float* __restrict__ wg, int Cout, int Cin, int split) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;          // over wg [Cout][9][Cin]
   if (i >= Cout * 9 * Cin) return;
   int ci = i % Cin, tap = (i / Cin) % 9, co = i / (9 * Cin);
-  wg[i] = w[((size_t)co * Cin + ci) * 9 + tap];
+  store_w(wg, i, Cout * 9 * Cin, w[((size_t)co * Cin + ci) * 9 + tap], split);
 }
-__global__ void conv_w_dgrad_layout_kernel(const float* __restrict__ w, float* __restrict__ wd, int Cout, int Cin) {
+__global__ void conv_w_dgrad_layout_kernel(const float* __restrict__ w, float* __restrict__ wd, int Cout, int Cin, int split) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;          // over wd [Cin][9][Cout]
   if (i >= Cout * 9 * Cin) return;
   int co = i % Cout, tap = (i / Cout) % 9, ci = i / (9 * Cout);
-  wd[i] = w[((size_t)co * Cin + ci) * 9 + (8 - tap)];       // flipped taps: (2-kh, 2-kw)
+  store_w(wd, i, Cout * 9 * Cin, w[((size_t)co * Cin + ci) * 9 + (8 - tap)], split);       // flipped taps: (2-kh, 2-kw)
 }
 __global__ void conv_wgrad_scatter_kernel(const float* __restrict__ dwg, float* __restrict__ dw, int Cout, int Cin) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;          // over dw [Cout][Cin][9]
@@ -161,12 +169,12 @@ int k_conv_wgrad_scatter_t(const float* dwgT, float* dw, int Cout, int Cin, cuda
   conv_wgrad_scatter_t_kernel<<<mtl_cdiv(Cout * 9 * Cin, 256), 256, 0, s>>>(dwgT, dw, Cout, Cin);
   MTL_CHECK_LAUNCH(); return MTL_OK;
 }
-int k_conv_w_fwd_layout(const float* w, float* wg, int Cout, int Cin, cudaStream_t s) {
-  conv_w_fwd_layout_kernel<<<mtl_cdiv(Cout * 9 * Cin, 256), 256, 0, s>>>(w, wg, Cout, Cin);
+int k_conv_w_fwd_layout(const float* w, float* wg, int Cout, int Cin, int split, cudaStream_t s) {
+  conv_w_fwd_layout_kernel<<<mtl_cdiv(Cout * 9 * Cin, 256), 256, 0, s>>>(w, wg, Cout, Cin, split);
   MTL_CHECK_LAUNCH(); return MTL_OK;
 }
-int k_conv_w_dgrad_layout(const float* w, float* wd, int Cout, int Cin, cudaStream_t s) {
-  conv_w_dgrad_layout_kernel<<<mtl_cdiv(Cout * 9 * Cin, 256), 256, 0, s>>>(w, wd, Cout, Cin);
+int k_conv_w_dgrad_layout(const float* w, float* wd, int Cout, int Cin, int split, cudaStream_t s) {
+  conv_w_dgrad_layout_kernel<<<mtl_cdiv(Cout * 9 * Cin, 256), 256, 0, s>>>(w, wd, Cout, Cin, split);
   MTL_CHECK_LAUNCH(); return MTL_OK;
 }
 int k_conv_wgrad_scatter(const float* dwg, float* dw, int Cout, int Cin, cudaStream_t s) {

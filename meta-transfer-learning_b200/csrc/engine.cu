@@ -506,10 +506,12 @@ static int conv_weight_layouts(Run& R, Pass& P) {
   On on(R, R.side(S_AUX));
   for (int i = 0; i < 3; ++i) {
     const int widx = i + 1, Cin = kConvCin[widx], Cout = kConvCout[widx];
-    P.cv[i].wg = R.ws.f((size_t)Cout * 9 * Cin);
-    P.cv[i].wd = R.ws.f((size_t)Cin * 9 * Cout);
-    K(k_conv_w_fwd_layout(R.theta + L.conv_w[widx], P.cv[i].wg, Cout, Cin, R.st));
-    K(k_conv_w_dgrad_layout(R.theta + L.conv_w[widx], P.cv[i].wd, Cout, Cin, R.st));
+    // 3xTF32 kw-box kernel: weights are split into tf32 hi / lo halves here, once per pass
+    const int sg = k_conv3x3_w_split(R.S->mode, Cout), sd = k_conv3x3_w_split(R.S->mode, Cin);
+    P.cv[i].wg = R.ws.f((size_t)Cout * 9 * Cin * (sg ? 2 : 1));
+    P.cv[i].wd = R.ws.f((size_t)Cin * 9 * Cout * (sd ? 2 : 1));
+    K(k_conv_w_fwd_layout(R.theta + L.conv_w[widx], P.cv[i].wg, Cout, Cin, sg, R.st));
+    K(k_conv_w_dgrad_layout(R.theta + L.conv_w[widx], P.cv[i].wd, Cout, Cin, sd, R.st));
   }
   return MTL_OK;
 }
@@ -522,7 +524,8 @@ static int conv_fwd(Run& R, ConvAct& A, const float* x, int B, int F, int T, int
   A.col = implicit ? nullptr : R.ws.f(P * Kc);
   A.y = R.ws.f(P * A.Cout);
   if (implicit) {
-    K(k_conv3x3_tc(x, A.wg, R.theta + L.conv_b[widx], A.y, B, F, T, A.Cin, A.Cout, EPI_RELU, nullptr, R.S->mode, R.st));
+    K(k_conv3x3_tc(x, A.wg, R.theta + L.conv_b[widx], A.y, B, F, T, A.Cin, A.Cout, EPI_RELU, nullptr, R.S->mode,
+                   k_conv3x3_w_split(R.S->mode, A.Cout), R.st));
   } else {
     K(k_im2col3x3(x, A.col, B, F, T, A.Cin, R.st));
     MTL_TRY(lin_fwd(R, A.col, Kc, A.wg, R.theta + L.conv_b[widx], A.y, A.Cout, (int)P, A.Cout, Kc, EPI_RELU));
@@ -555,7 +558,7 @@ static int conv_bwd(Run& R, const ConvAct& A, const float* dy, float* dx, const 
     const int Kg = 9 * A.Cout;
     if (implicit) {
       K(k_conv3x3_tc(dy, A.wd, nullptr, dx, A.B, A.F, A.T, A.Cout, A.Cin, relu_aux ? EPI_RELU_BWD : EPI_NONE, relu_aux,
-                     R.S->mode, R.st));
+                     R.S->mode, k_conv3x3_w_split(R.S->mode, A.Cin), R.st));
     } else {
       float* colg = R.ws.f(P * Kg);
       K(k_im2col3x3(dy, colg, A.B, A.F, A.T, A.Cout, R.st));
@@ -1203,8 +1206,9 @@ extern "C" int mtl_conv3x3_relu_fwd(int mode, const float* x, const float* w, co
                                     float* out, int B, int F, int T, int Cin, int Cout, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   MTL_REQUIRE(x && w && b && wg && out, "null argument");
-  MTL_TRY(k_conv_w_fwd_layout(w, wg, Cout, Cin, st));
-  if (mode != MTL_GEMM_SIMT_FP32) return k_conv3x3_tc(x, wg, b, out, B, F, T, Cin, Cout, EPI_RELU, nullptr, mode, st);
+  const int sg = mode != MTL_GEMM_SIMT_FP32 ? k_conv3x3_w_split(mode, Cout) : 0;
+  MTL_TRY(k_conv_w_fwd_layout(w, wg, Cout, Cin, sg, st));
+  if (mode != MTL_GEMM_SIMT_FP32) return k_conv3x3_tc(x, wg, b, out, B, F, T, Cin, Cout, EPI_RELU, nullptr, mode, sg, st);
   MTL_REQUIRE(col, "mode 0 needs the im2col buffer");
   MTL_TRY(k_im2col3x3(x, col, B, F, T, Cin, st));
   GemmArgs g;
@@ -1215,7 +1219,7 @@ extern "C" int mtl_conv3x3_relu_fwd(int mode, const float* x, const float* w, co
 }
 extern "C" long long mtl_conv3x3_bwd_scratch_floats(int mode, int B, int F, int T, int Cin, int Cout) {
   const long long P = (long long)B * F * T, wsz = (long long)Cout * 9 * Cin + 64;
-  return 2 * wsz + (mode == MTL_GEMM_SIMT_FP32 ? P * 9 * Cin + P * 9 * Cout + 128 : 0);
+  return 3 * wsz + (mode == MTL_GEMM_SIMT_FP32 ? P * 9 * Cin + P * 9 * Cout + 128 : 0);
 }
 extern "C" int mtl_conv3x3_bwd(int mode, const float* x, const float* w, const float* dy, const float* relu_aux,
                                float* dw, float* db, float* dx, float* scratch, int B, int F, int T, int Cin, int Cout,
@@ -1230,7 +1234,7 @@ extern "C" int mtl_conv3x3_bwd(int mode, const float* x, const float* w, const f
     MTL_TRY(k_conv3x3_wgrad_tc(x, dy, dwg, B, F, T, Cin, Cout, mode, st));
     MTL_TRY(k_conv_wgrad_scatter_t(dwg, dw, Cout, Cin, st));
   } else {
-    float* col = scratch + 2 * wsz;
+    float* col = scratch + 3 * wsz;
     MTL_TRY(k_im2col3x3(x, col, B, F, T, Cin, st));
     GemmArgs g;
     memset(&g, 0, sizeof(g));
@@ -1241,10 +1245,11 @@ extern "C" int mtl_conv3x3_bwd(int mode, const float* x, const float* w, const f
   }
   MTL_TRY(k_colsum_acc(dy, (int)P, Cout, Cout, db, st));
   if (!dx) return MTL_OK;
-  MTL_TRY(k_conv_w_dgrad_layout(w, wd, Cout, Cin, st));
+  const int sd = mode != MTL_GEMM_SIMT_FP32 ? k_conv3x3_w_split(mode, Cin) : 0;   // wd: 2 * wsz floats (hi | lo)
+  MTL_TRY(k_conv_w_dgrad_layout(w, wd, Cout, Cin, sd, st));
   const int epi = relu_aux ? EPI_RELU_BWD : EPI_NONE;
-  if (mode != MTL_GEMM_SIMT_FP32) return k_conv3x3_tc(dy, wd, nullptr, dx, B, F, T, Cout, Cin, epi, relu_aux, mode, st);
-  float* colg = scratch + 2 * wsz + ((P * 9 * Cin + 63) & ~(size_t)63);
+  if (mode != MTL_GEMM_SIMT_FP32) return k_conv3x3_tc(dy, wd, nullptr, dx, B, F, T, Cout, Cin, epi, relu_aux, mode, sd, st);
+  float* colg = scratch + 3 * wsz + ((P * 9 * Cin + 63) & ~(size_t)63);
   MTL_TRY(k_im2col3x3(dy, colg, B, F, T, Cout, st));
   GemmArgs g;
   memset(&g, 0, sizeof(g));

@@ -77,6 +77,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (clock64() - t0 > 4000000000LL) __trap();
   }
 }
+// Non-blocking probe of a phase (the kw-box producer polls two rings from one thread).
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return done != 0;
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -206,6 +218,81 @@ struct TcParams {
   int epi_test;      // measurement only (MTL_EPI_TEST): 1 = conv epilogue computes but does not store
   int cluster_k;     // > 1: grid.z CTAs form one cluster that splits K and reduces over distributed shared memory
 };
+
+// ---- TMA epilogue (shared by the GEMM / tap-box convolution kernel and the kw-box convolution kernel).
+// Runs in the four epilogue warps (threads 64..191): each thread owns one accumulator row (TMEM lane); per 32-column
+// chunk it drains TMEM, applies alpha / bias / ReLU / ReLU-backward mask in registers and parks the row in a
+// 128B-swizzled staging box; one thread then hands every box to the TMA unit (store, or reduce-add for beta == 1
+// and split-K slabs).  Row / column tails and the ragged edges of convolution pixel boxes are clipped by the TMA
+// unit, so there is no per-row address arithmetic at all.  stg_u / aux_u: 1024-aligned shared-memory addresses of
+// the staging tile and of the mask tile (both BN/32 boxes of 128 rows x 128 B); they alias dead operand buffers.
+template <int BN, bool SPLIT3>
+__device__ __forceinline__ void tma_epilogue_rows(const TcParams& P, const CUtensorMap* tmC, const CUtensorMap* tmX,
+                                                  uint32_t stg_u, uint32_t aux_u, uint64_t* tmem_full,
+                                                  uint64_t* aux_full, const float* bias_s, uint32_t tmem_base, int warp,
+                                                  int lane, int m0, int n0, bool conv, int ct0, int cf0, int cb) {
+  constexpr int CHUNKS = BN / 32, CHUNK_BYTES = BM * 128;
+  const GemmArgs& g = P.g;
+  const int q = warp & 3;                                        // TMEM lane quarter this warp may access
+  const bool mask = g.epi == EPI_RELU_BWD;
+  const int nch = min(CHUNKS, (g.N - n0 + 31) / 32);            // chunks with at least one valid column
+  mbar_wait(tmem_full, 0);                                       // accumulator complete => operand buffers are dead
+  tc_fence_after();
+  if (threadIdx.x == 64) DBG_STAMP(5);
+  if (mask && threadIdx.x == 64) {
+    mbar_expect_tx(aux_full, (uint32_t)(nch * CHUNK_BYTES));
+    for (int c = 0; c < nch; ++c) {
+      if (conv) tma_load_4d(aux_u + c * CHUNK_BYTES, tmX, aux_full, n0 + c * 32, ct0, cf0, cb);
+      else tma_load_2d(aux_u + c * CHUNK_BYTES, tmX, aux_full, n0 + c * 32, m0);
+    }
+  }
+  const int row = q * 32 + lane;
+  const uint32_t row_u = (uint32_t)row * 128u, sw = (uint32_t)(row & 7);
+  const float alpha = g.alpha;
+  const float lo = g.epi == EPI_RELU ? 0.f : -INFINITY;          // branch-free ReLU
+  if (mask) mbar_wait(aux_full, 0);
+#pragma unroll 1
+  for (int c = 0; c < nch; ++c) {
+    uint32_t v[32];
+    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+    if (SPLIT3) {                                                // 3xTF32: columns [BN, 2BN) hold the a_hi*b_lo products
+      uint32_t w[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + c * 32), w);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c * 32 + j * 4);
+      float4 o;
+      o.x = fmaxf(fmaf(alpha, __uint_as_float(v[4 * j + 0]), b4.x), lo);
+      o.y = fmaxf(fmaf(alpha, __uint_as_float(v[4 * j + 1]), b4.y), lo);
+      o.z = fmaxf(fmaf(alpha, __uint_as_float(v[4 * j + 2]), b4.z), lo);
+      o.w = fmaxf(fmaf(alpha, __uint_as_float(v[4 * j + 3]), b4.w), lo);
+      const uint32_t slot = (uint32_t)c * CHUNK_BYTES + row_u + ((((uint32_t)j) ^ sw) << 4);
+      if (mask) {
+        float4 a;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "r"(aux_u + slot));
+        o.x = a.x > 0.f ? o.x : 0.f; o.y = a.y > 0.f ? o.y : 0.f;
+        o.z = a.z > 0.f ? o.z : 0.f; o.w = a.w > 0.f ? o.w : 0.f;
+      }
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stg_u + slot), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
+    }
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staged rows -> visible to the TMA unit
+  if (threadIdx.x == 64) DBG_STAMP(9);
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  if (threadIdx.x == 64) {
+    const bool add = P.tma_epi == 2;
+    for (int c = 0; c < nch; ++c) {
+      if (conv) tma_store_4d(tmC, stg_u + c * CHUNK_BYTES, n0 + c * 32, ct0, cf0, cb, add);
+      else tma_store_2d(tmC, stg_u + c * CHUNK_BYTES, n0 + c * 32, m0, add);
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the staging boxes must outlive the reads
+    DBG_STAMP(6);
+  }
+}
 
 template <int BN, int STAGES, bool A_MN, bool B_MN, bool SPLIT3>
 __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
@@ -422,75 +509,11 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
   const int rows_per = BM / CS;
   const int q = warp & 3;                           // TMEM lane quarter this warp may access
   if (P.tma_epi) {
-    // ---- TMA epilogue (no cluster split): each epilogue thread owns one accumulator row; per 32-column chunk it
-    // drains TMEM, applies alpha / bias / ReLU / ReLU-backward mask in registers and parks the row in a
-    // 128B-swizzled staging box; one thread then hands every box to the TMA unit (store, or reduce-add for
-    // beta == 1 and split-K slabs).  Row / column tails and the ragged edges of convolution pixel boxes are clipped
-    // by the TMA unit, so there is no per-row address arithmetic at all.
-    constexpr int CHUNKS = BN / 32, CHUNK_BYTES = BM * 128;
-    static_assert(CHUNKS * CHUNK_BYTES <= STAGES * STAGE_BYTES, "staging tile must fit in the operand stages");
-    if (warp >= 2) {
-      const bool conv = P.conv_mode == CONV_FWD;
-      const bool mask = g.epi == EPI_RELU_BWD;
-      const int nch = min(CHUNKS, (g.N - n0 + 31) / 32);          // chunks with at least one valid column
-      const uint32_t stg_u = base, aux_u = base + (uint32_t)P.aux_off;
-      mbar_wait(tmem_full, 0);                                     // accumulator complete => operand stages are dead
-      tc_fence_after();
-      if (threadIdx.x == 64) DBG_STAMP(5);
-      if (mask && threadIdx.x == 64) {
-        mbar_expect_tx(aux_full, (uint32_t)(nch * CHUNK_BYTES));
-        for (int c = 0; c < nch; ++c) {
-          if (conv) tma_load_4d(aux_u + c * CHUNK_BYTES, &tmX, aux_full, n0 + c * 32, ct0, cf0, cb);
-          else tma_load_2d(aux_u + c * CHUNK_BYTES, &tmX, aux_full, n0 + c * 32, m0);
-        }
-      }
-      const int row = q * 32 + lane;
-      const uint32_t row_u = (uint32_t)row * 128u, sw = (uint32_t)(row & 7);
-      const float alpha = g.alpha;
-      const float lo = g.epi == EPI_RELU ? 0.f : -INFINITY;        // branch-free ReLU
-      if (mask) mbar_wait(aux_full, 0);
-#pragma unroll 1
-      for (int c = 0; c < nch; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
-        if (SPLIT3) {
-          uint32_t w[32];
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + c * 32), w);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c * 32 + j * 4);
-          float4 o;
-          o.x = fmaxf(fmaf(alpha, __uint_as_float(v[4 * j + 0]), b4.x), lo);
-          o.y = fmaxf(fmaf(alpha, __uint_as_float(v[4 * j + 1]), b4.y), lo);
-          o.z = fmaxf(fmaf(alpha, __uint_as_float(v[4 * j + 2]), b4.z), lo);
-          o.w = fmaxf(fmaf(alpha, __uint_as_float(v[4 * j + 3]), b4.w), lo);
-          const uint32_t slot = (uint32_t)c * CHUNK_BYTES + row_u + ((((uint32_t)j) ^ sw) << 4);
-          if (mask) {
-            float4 a;
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "r"(aux_u + slot));
-            o.x = a.x > 0.f ? o.x : 0.f; o.y = a.y > 0.f ? o.y : 0.f;
-            o.z = a.z > 0.f ? o.z : 0.f; o.w = a.w > 0.f ? o.w : 0.f;
-          }
-          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stg_u + slot), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
-        }
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staged rows -> visible to the TMA unit
-      if (threadIdx.x == 64) DBG_STAMP(9);
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (threadIdx.x == 64) {
-        const bool add = P.tma_epi == 2;
-        for (int c = 0; c < nch; ++c) {
-          if (conv) tma_store_4d(&tmC, stg_u + c * CHUNK_BYTES, n0 + c * 32, ct0, cf0, cb, add);
-          else tma_store_2d(&tmC, stg_u + c * CHUNK_BYTES, n0 + c * 32, m0, add);
-        }
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the staging boxes must outlive the reads
-        DBG_STAMP(6);
-      }
-    }
+    // ---- TMA epilogue (no cluster split); the staging tile aliases the (dead) operand stages
+    static_assert((BN / 32) * BM * 128 <= STAGES * STAGE_BYTES, "staging tile must fit in the operand stages");
+    if (warp >= 2)
+      tma_epilogue_rows<BN, SPLIT3>(P, &tmC, &tmX, base, base + (uint32_t)P.aux_off, tmem_full, aux_full, bias_s,
+                                    tmem_base, warp, lane, m0, n0, P.conv_mode == CONV_FWD, ct0, cf0, cb);
     tc_fence_before();
     __syncthreads();
     if (threadIdx.x == 0) DBG_STAMP(7);
@@ -699,6 +722,209 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
   }
 }
 
+// ----------------------------------------------------------------------------- kw-box 3x3 convolution
+// Second-generation implicit GEMM for the forward / dgrad convolutions.  The tap-box kernel above fetches (and, in
+// 3xTF32, re-splits) every input pixel nine times, once per tap.  Here a tile is a fixed 8 (t) x 16 (f) pixel box and
+// an A stage is the 8 x 18 box of ONE horizontal tap offset kw and one 32-channel chunk (144 rows of 128 B, rows in
+// (f, t) order): its three vertical taps kh = 0, 1, 2 are the row windows [8*kh, 8*kh + 128) of the same box, i.e.
+// UMMA descriptors that start kh * 1024 B further -- whole swizzle atoms, so no unaligned descriptor is needed.
+// Activations are therefore fetched and split 3x instead of 9x.  Weights arrive PRE-SPLIT (hi / lo matrices written
+// once per pass by the layout kernel) through their own ring, one (tap, chunk) 32-wide k-block per slot, so the
+// splitter warps only touch activations.
+//   warp 0: TMA producer (A ring + B ring); warp 1: TMEM allocator + MMA issuer; warps 2..5: A splitter (3xTF32),
+//   then the TMA epilogue.
+constexpr int KW_BT = 8, KW_BF = 16;                       // pixel box of a tile
+constexpr int KW_A_ROWS = (KW_BF + 2) * KW_BT;             // 144 rows per A box
+constexpr int KW_A_BYTES = KW_A_ROWS * 128;                // 18 KB
+constexpr int KW_NA = 2;                                   // A slots
+
+template <int BN, bool SPLIT3>
+struct KwCfg {
+  static constexpr int B_BYTES = BN * 128;                                 // one (tap, chunk) weight k-block
+  static constexpr int A_SLOT = KW_A_BYTES * (SPLIT3 ? 2 : 1);             // [A_hi | A_lo]
+  static constexpr int B_SLOT = B_BYTES * (SPLIT3 ? 2 : 1);                // [B_hi | B_lo]
+  // weight slots: 3xTF32 Cout<=64 keeps the CTA at ~106 KB so that two CTAs share an SM (one tile's epilogue
+  // overlaps the other's main loop)
+  static constexpr int NB = BN == 64 ? (SPLIT3 ? 2 : 4) : 3;
+  static constexpr int RING = KW_NA * A_SLOT + NB * B_SLOT;
+  static constexpr int TILE = BM * BN * 4;                                 // staged output tile (aliases the rings)
+  static constexpr int HEAD = 1024;                                        // barriers + bias slice, in front of the data
+  static constexpr int DATA = RING > TILE ? RING : TILE;
+  static constexpr int DATA_MASK = RING > 2 * TILE ? RING : 2 * TILE;      // + the ReLU-mask tile (EPI_RELU_BWD)
+  static constexpr int SMEM = HEAD + DATA + 1024 /*align slack*/;
+  static constexpr int SMEM_MASK = HEAD + DATA_MASK + 1024;
+  static constexpr int TMEM_COLS = SPLIT3 ? 2 * BN : BN;
+};
+
+template <int BN, bool SPLIT3>
+__global__ void __launch_bounds__(192) conv3x3_kw_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                         const __grid_constant__ CUtensorMap tmBh,
+                                                         const __grid_constant__ CUtensorMap tmBl,
+                                                         const __grid_constant__ CUtensorMap tmC,
+                                                         const __grid_constant__ CUtensorMap tmX, const TcParams P) {
+  using Cfg = KwCfg<BN, SPLIT3>;
+  constexpr int NB = Cfg::NB;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t head = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_head = smem_raw + (head - smem_u32(smem_raw));
+  const uint32_t base = head + Cfg::HEAD;                    // rings / staging tiles (1024 B aligned)
+  uint8_t* smem = smem_head + Cfg::HEAD;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_head);
+  uint64_t* a_empty = a_full + KW_NA;
+  uint64_t* a_ready = a_empty + KW_NA;
+  uint64_t* b_full = a_ready + KW_NA;
+  uint64_t* b_empty = b_full + NB;
+  uint64_t* tmem_full = b_empty + NB;
+  uint64_t* aux_full = tmem_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_full + 1);
+  float* bias_s = reinterpret_cast<float*>(smem_head + 256);   // BN floats
+  const uint32_t a_ring = base, b_ring = base + KW_NA * Cfg::A_SLOT;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.y * BN;
+  const int tt = blockIdx.x % P.tiles_t, rem = blockIdx.x / P.tiles_t;
+  const int ct0 = tt * KW_BT, cf0 = (rem % P.tiles_f) * KW_BF, cb = rem / P.tiles_f;
+  const int cpb = P.cCin >> 5;                               // 32-channel chunks
+  const int n_stage = 3 * cpb;                               // (chunk, kw) A boxes per tile
+
+  if (threadIdx.x == 0) DBG_STAMP(0);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < KW_NA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&a_ready[i], 4); }
+    for (int i = 0; i < NB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    mbar_init(tmem_full, 1);
+    mbar_init(aux_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(Cfg::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) DBG_STAMP(1);
+  if (warp >= 2) {
+    const int t = threadIdx.x - 64, cn = n0 + t;
+    if (t < BN) bias_s[t] = (P.g.bias && cn < P.g.N) ? __ldg(P.g.bias + cn) : 0.f;
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+  }
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    // One thread feeds both rings and must never block on one while the other has a free slot (an A box is needed
+    // one whole stage ahead of its weights), so it polls the two "empty" barriers instead of waiting on either.
+    if (lane == 0) {
+      const int n_b = 3 * n_stage;
+      int ia = 0, ib = 0;
+      const long long t0 = clock64();
+      while (ia < n_stage || ib < n_b) {
+        bool progress = false;
+        if (ia < n_stage) {
+          const int sa = ia % KW_NA;
+          if (mbar_test(&a_empty[sa], ((ia / KW_NA) & 1) ^ 1)) {
+            const int c = ia / 3, kw = ia - c * 3;
+            mbar_expect_tx(&a_full[sa], KW_A_BYTES);
+            tma_load_4d(a_ring + sa * Cfg::A_SLOT, &tmA, &a_full[sa], c << 5, ct0 + kw - 1, cf0 - 1, cb);
+            if (ia == 0) DBG_STAMP(2);
+            ++ia;
+            progress = true;
+          }
+        }
+        if (ib < n_b) {
+          const int sb = ib % NB;
+          if (mbar_test(&b_empty[sb], ((ib / NB) & 1) ^ 1)) {
+            const int st = ib / 3, kh = ib - st * 3;
+            const int c = st / 3, kw = st - c * 3;
+            const int kcol = ((kh * 3 + kw) * cpb + c) << 5;        // k-block (tap, chunk) of Wg[co, tap*Cin + ci]
+            const uint32_t dst = b_ring + sb * Cfg::B_SLOT;
+            mbar_expect_tx(&b_full[sb], Cfg::B_SLOT);
+            tma_load_2d(dst, &tmBh, &b_full[sb], kcol, n0);
+            if (SPLIT3) tma_load_2d(dst + Cfg::B_BYTES, &tmBl, &b_full[sb], kcol, n0);
+            ++ib;
+            progress = true;
+          }
+        }
+        if (!progress && clock64() - t0 > 4000000000LL) __trap();
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      const uint32_t idesc2 = (idesc & ~(0x3Fu << 17)) | ((uint32_t)((2 * BN) >> 3) << 17);
+      int ib = 0;
+      for (int st = 0; st < n_stage; ++st) {
+        const int sa = st % KW_NA;
+        mbar_wait(SPLIT3 ? &a_ready[sa] : &a_full[sa], (st / KW_NA) & 1);
+        tc_fence_after();
+        const uint32_t a_u = a_ring + sa * Cfg::A_SLOT;
+        for (int kh = 0; kh < 3; ++kh, ++ib) {
+          const int sb = ib % NB;
+          mbar_wait(&b_full[sb], (ib / NB) & 1);
+          tc_fence_after();
+          const uint64_t da0 = desc_kmajor(a_u + kh * 1024);                 // rows [8*kh, 8*kh + 128) of the box
+          const uint64_t la0 = desc_kmajor(a_u + KW_A_BYTES + kh * 1024);
+          const uint64_t db0 = desc_kmajor(b_ring + sb * Cfg::B_SLOT);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t acc0 = (st > 0 || kh > 0 || k > 0) ? 1u : 0u;
+            if (SPLIT3) {
+              tc_mma_tf32(tmem_base, da0 + 2 * k, db0 + 2 * k, idesc2, acc0);   // a_hi * [b_hi ; b_lo]
+              tc_mma_tf32(tmem_base, la0 + 2 * k, db0 + 2 * k, idesc, 1u);      // a_lo * b_hi
+            } else {
+              tc_mma_tf32(tmem_base, da0 + 2 * k, db0 + 2 * k, idesc, acc0);
+            }
+          }
+          tc_commit(&b_empty[sb]);
+        }
+        tc_commit(&a_empty[sa]);
+      }
+      tc_commit(tmem_full);
+      DBG_STAMP(4);
+    }
+  } else if (SPLIT3) {
+    // ===================== activation splitter: a -> (hi in place, lo beside it) =====================
+    const int tid = threadIdx.x - 64;
+    for (int st = 0; st < n_stage; ++st) {
+      const int sa = st % KW_NA;
+      mbar_wait(&a_full[sa], (st / KW_NA) & 1);
+      float4* hi = reinterpret_cast<float4*>(smem + sa * Cfg::A_SLOT) + tid;
+      constexpr int PER = KW_A_BYTES / 16 / 128;               // 9 float4 per thread
+      static_assert(KW_A_BYTES % (16 * 128) == 0, "whole float4 columns per thread");
+      float4 a[PER];
+#pragma unroll
+      for (int j = 0; j < PER; ++j) a[j] = hi[j * 128];
+#pragma unroll
+      for (int j = 0; j < PER; ++j) {
+        float4 h, l;
+        h.x = tf32_rna(a[j].x); l.x = tf32_rna(a[j].x - h.x);
+        h.y = tf32_rna(a[j].y); l.y = tf32_rna(a[j].y - h.y);
+        h.z = tf32_rna(a[j].z); l.z = tf32_rna(a[j].z - h.z);
+        h.w = tf32_rna(a[j].w); l.w = tf32_rna(a[j].w - h.w);
+        hi[j * 128] = h;
+        hi[j * 128 + KW_A_BYTES / 16] = l;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&a_ready[sa]);
+    }
+  }
+
+  // ===================== epilogue =====================
+  if (warp >= 2)
+    tma_epilogue_rows<BN, SPLIT3>(P, &tmC, &tmX, base, base + Cfg::TILE, tmem_full, aux_full, bias_s, tmem_base, warp, lane,
+                                  0, n0, true, ct0, cf0, cb);
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x == 0) DBG_STAMP(7);
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::TMEM_COLS) : "memory");
+  }
+}
+
 // ----------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -849,6 +1075,24 @@ int dispatch(int bn, bool split3, bool a_mn, bool b_mn, const Maps& tm, const Tc
                 : dispatch_major<128, false>(a_mn, b_mn, tm, P, grid, s);
 }
 
+struct KwMaps { CUtensorMap a, bh, bl, c, x; };
+template <int BN, bool SPLIT3>
+int launch_kw(const KwMaps& tm, const TcParams& P, dim3 grid, cudaStream_t s) {
+  using Cfg = KwCfg<BN, SPLIT3>;
+  static_assert(Cfg::SMEM_MASK <= 227 * 1024, "shared memory budget");
+  static_assert(256 + BN * 4 <= Cfg::HEAD, "bias slice must fit in the head block");
+  static bool configured = false;
+  auto kern = conv3x3_kw_kernel<BN, SPLIT3>;
+  if (!configured) {
+    MTL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_MASK));
+    configured = true;
+  }
+  const int smem = P.g.epi == EPI_RELU_BWD ? Cfg::SMEM_MASK : Cfg::SMEM;
+  kern<<<grid, 192, smem, s>>>(tm.a, tm.bh, tm.bl, tm.c, tm.x, P);
+  MTL_CHECK_LAUNCH();
+  return MTL_OK;
+}
+
 // MTL_TMA_EPI=0 keeps the register/shared-memory epilogue everywhere (A/B measurements)
 bool tma_epi_enabled() {
   static int v = -1;
@@ -961,9 +1205,26 @@ int k_gemm_tc(const GemmArgs& g, int precision_mode, cudaStream_t s) {
   return dispatch(bn, split3, a_mn, b_mn, tm, P, grid, s);
 }
 
+// MTL_CONV_KW=0 keeps the first-generation tap-box kernel for the forward / dgrad convolutions (A/B measurements)
+bool k_conv3x3_kw_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MTL_CONV_KW");
+    const char* t = getenv("MTL_TMA_EPI");
+    v = ((e && e[0] == '0') || (t && t[0] == '0')) ? 0 : 1;
+  }
+  return v != 0;
+}
+
+int k_conv3x3_w_split(int precision_mode, int Cout) {
+  return (precision_mode == 2 && k_conv3x3_kw_enabled() && Cout % 32 == 0) ? 1 : 0;
+}
+
 // y[pixel, co] = epi(sum_{tap,ci} x[pixel+tap, ci] * wg[co, tap*Cin+ci] + bias[co])   (x NHWC [B,F,T,Cin], y [B*F*T, Cout])
+// w_split != 0: wg holds TWO matrices, hi = tf32(w) followed by lo = tf32(w - hi) (k_conv_w_*_layout with lo != null);
+// required by the kw-box kernel in 3xTF32, ignored otherwise.
 int k_conv3x3_tc(const float* x, const float* wg, const float* bias, float* y, int B, int F, int T, int Cin, int Cout,
-                 int epi, const float* aux, int precision_mode, cudaStream_t s) {
+                 int epi, const float* aux, int precision_mode, int w_split, cudaStream_t s) {
   MTL_REQUIRE(Cin % 32 == 0 && Cout % 4 == 0 && al16(x) && al16(wg) && al16(y), "conv3x3_tc: Cin % 32, Cout % 4, 16 B alignment");
   MTL_REQUIRE(epi != EPI_RELU_BWD || (aux && al16(aux)), "conv3x3_tc: aux");
   const bool split3 = precision_mode == 2, tf = !split3;
@@ -973,12 +1234,6 @@ int k_conv3x3_tc(const float* x, const float* wg, const float* bias, float* y, i
   P.conv_mode = CONV_FWD;
   P.cluster_k = 1;
   P.cF = F; P.cT = T; P.cCin = Cin;
-  P.bt_log2 = pick_bt_log2(BM, F, T, &P.tiles_t, &P.tiles_f);
-  Maps tm;
-  CUtensorMap& ta = tm.a;
-  CUtensorMap& tb = tm.b;
-  MTL_TRY(make_map_nhwc(x, B, F, T, Cin, 1 << P.bt_log2, BM >> P.bt_log2, false, tf, &ta));
-  MTL_TRY(make_map(wg, 9LL * Cin, Cout, 9LL * Cin, bn, false, tf, &tb));
   GemmArgs& g = P.g;
   g.A = x; g.B = wg; g.C = y; g.M = B * F * T; g.N = Cout; g.K = 9 * Cin; g.lda = Cin; g.ldb = 9 * Cin; g.ldc = Cout;
   g.transA = 0; g.transB = 1; g.alpha = 1.f; g.beta = 0.f; g.bias = bias; g.epi = epi; g.aux = aux; g.split_k = 1;
@@ -987,6 +1242,31 @@ int k_conv3x3_tc(const float* x, const float* wg, const float* bias, float* y, i
   P.vecC = 1;
   { const char* e = getenv("MTL_GEMM_DBG"); P.dbg = e ? atoi(e) : 0; }
   { const char* e = getenv("MTL_EPI_TEST"); P.epi_test = e ? atoi(e) : 0; }
+  MTL_REQUIRE(!(split3 && w_split) || k_conv3x3_w_split(precision_mode, Cout), "conv3x3_tc: pre-split weights need the kw-box kernel");
+  if (k_conv3x3_kw_enabled() && Cout % 32 == 0 && (!split3 || w_split)) {
+    // kw-box kernel: fixed 8 (t) x 16 (f) pixel tiles, A boxes 8 x 18
+    P.bt_log2 = 3;
+    P.tiles_t = mtl_cdiv(T, KW_BT);
+    P.tiles_f = mtl_cdiv(F, KW_BF);
+    P.tma_epi = 1;
+    KwMaps km;
+    MTL_TRY(make_map_nhwc(x, B, F, T, Cin, KW_BT, KW_BF + 2, false, tf, &km.a));
+    MTL_TRY(make_map(wg, 9LL * Cin, Cout, 9LL * Cin, bn, false, tf, &km.bh));
+    km.bl = km.bh;
+    if (split3) MTL_TRY(make_map(wg + (size_t)Cout * 9 * Cin, 9LL * Cin, Cout, 9LL * Cin, bn, false, false, &km.bl));
+    MTL_TRY(make_map_nhwc(y, B, F, T, Cout, KW_BT, KW_BF, false, false, &km.c));
+    km.x = km.c;
+    if (epi == EPI_RELU_BWD) MTL_TRY(make_map_nhwc(aux, B, F, T, Cout, KW_BT, KW_BF, false, false, &km.x));
+    dim3 grid(B * P.tiles_f * P.tiles_t, mtl_cdiv(Cout, bn), 1);
+    if (bn == 64) return split3 ? launch_kw<64, true>(km, P, grid, s) : launch_kw<64, false>(km, P, grid, s);
+    return split3 ? launch_kw<128, true>(km, P, grid, s) : launch_kw<128, false>(km, P, grid, s);
+  }
+  P.bt_log2 = pick_bt_log2(BM, F, T, &P.tiles_t, &P.tiles_f);
+  Maps tm;
+  CUtensorMap& ta = tm.a;
+  CUtensorMap& tb = tm.b;
+  MTL_TRY(make_map_nhwc(x, B, F, T, Cin, 1 << P.bt_log2, BM >> P.bt_log2, false, tf, &ta));
+  MTL_TRY(make_map(wg, 9LL * Cin, Cout, 9LL * Cin, bn, false, tf, &tb));
   dim3 grid(B * P.tiles_f * P.tiles_t, mtl_cdiv(Cout, bn), 1);
   const int bt = 1 << P.bt_log2, bf = BM >> P.bt_log2;
   MTL_TRY(plan_epilogue(P, tm, [&](const float* ptr, CUtensorMap* out) { return make_map_nhwc(ptr, B, F, T, Cout, bt, bf, false, false, out); }));

@@ -47,8 +47,11 @@ int k_gemm(const GemmArgs& g, int mode, cudaStream_t s);
 // Implicit-GEMM 3x3 convolutions on NHWC activations (tcgen05; precision_mode 1 = TF32, 2 = 3xTF32):
 //   y[pixel,co] = epi(sum x[pixel+tap,ci] * wg[co, tap*Cin+ci] + bias[co])          (forward, and dgrad on dY with flipped taps)
 //   dwgT[tap*Cin+ci, co] += sum_pixel x[pixel+tap,ci] * dy[pixel,co]                  (weight gradient, atomics)
+// w_split: wg holds [hi | lo] tf32 halves (2 x Cout*9*Cin floats, written by k_conv_w_*_layout with split = 1); the
+// 3xTF32 kw-box kernel needs it -- k_conv3x3_w_split(mode, Cout) says whether this build / environment uses it.
 int k_conv3x3_tc(const float* x, const float* wg, const float* bias, float* y, int B, int F, int T, int Cin, int Cout,
-                 int epi, const float* aux, int precision_mode, cudaStream_t s);
+                 int epi, const float* aux, int precision_mode, int w_split, cudaStream_t s);
+int k_conv3x3_w_split(int precision_mode, int Cout);
 int k_conv3x3_wgrad_tc(const float* x, const float* dy, float* dwgT, int B, int F, int T, int Cin, int Cout,
                        int precision_mode, cudaStream_t s);
 
@@ -111,8 +114,9 @@ int k_conv1_fwd(const float* x, const float* w, const float* b, float* out, int 
 int k_conv1_wgrad(const float* x, const float* dout, float* dw, float* db, int B, int F, int T, int Cout, cudaStream_t s);
 int k_im2col3x3(const float* x, float* col, int B, int F, int T, int C, cudaStream_t s);   // col [B*F*T, 9*C], (tap,c) order
 // conv weight [Cout,Cin,3,3] -> GEMM layouts: fwd Wg[co,(tap,ci)], dgrad Wd[ci,(tap',co)] with flipped taps
-int k_conv_w_fwd_layout(const float* w, float* wg, int Cout, int Cin, cudaStream_t s);
-int k_conv_w_dgrad_layout(const float* w, float* wd, int Cout, int Cin, cudaStream_t s);
+// split != 0: the output holds two matrices, hi = tf32(w) and, Cout*9*Cin floats later, lo = tf32(w - hi)
+int k_conv_w_fwd_layout(const float* w, float* wg, int Cout, int Cin, int split, cudaStream_t s);
+int k_conv_w_dgrad_layout(const float* w, float* wd, int Cout, int Cin, int split, cudaStream_t s);
 int k_conv_wgrad_scatter(const float* dwg, float* dw, int Cout, int Cin, cudaStream_t s);  // dw[co,ci,kh,kw] += dwg[co,(tap,ci)]
 int k_conv_wgrad_scatter_t(const float* dwgT, float* dw, int Cout, int Cin, cudaStream_t s);  // dw[co,ci,kh,kw] += dwgT[(tap,ci),co]
 int k_maxpool2_fwd(const float* x, float* out, int B, int F, int T, int C, cudaStream_t s);

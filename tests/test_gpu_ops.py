@@ -243,7 +243,7 @@ def test_conv3x3_fwd_bwd(mode, B, Fq, T, cin, cout):
     # forward
     Pn = B * Fq * T
     col = torch.empty(Pn, 9 * cin, device=dev()) if mode == 0 else None
-    wg = torch.empty(cout, 9 * cin, device=dev())
+    wg = torch.empty(2, cout, 9 * cin, device=dev())              # [hi | lo] halves in 3xTF32
     o = torch.full((B, Fq, T, cout), 7.0, device=dev())
     xind, wd_, bd_ = _nhwc(xin).to(dev()), w.to(dev()), b.to(dev())
     ok(lib().mtl_conv3x3_relu_fwd(mode, P(xind), P(wd_), P(bd_), P(col), P(wg), P(o), B, Fq, T, cin, cout, stream()))

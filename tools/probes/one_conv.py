@@ -20,7 +20,7 @@ pv = lambda t: C.c_void_p(t.data_ptr())
 st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 w = torch.randn(Cout, Cin, 3, 3, device=dev) * 0.05
 bias = torch.zeros(Cout, device=dev)
-wg = torch.empty(Cout, 9 * Cin, device=dev)
+wg = torch.empty(2, Cout, 9 * Cin, device=dev)
 NB = 6
 xs = [torch.randn(B, F, T, Cin, device=dev) for _ in range(NB)]
 ys = [torch.empty(B, F, T, Cout, device=dev) for _ in range(NB)]
