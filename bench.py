@@ -255,6 +255,9 @@ def run_ours(args, rank, world, local_rank):
     ms_e2e = float(ms2)
     graph_caps, graph_reps = s.graph_stats()
 
+    if args.timeline and rank == 0:
+        dump_timeline(args.timeline, lambda: [meta_step(i, *resident[i]) for i in range(total_steps - 2, total_steps)])
+
     # ---------------- roofline of the dominant kernel: conv.2 forward contraction (130088 x 64 x 576)
     roof = None
     if rank == 0:
@@ -288,10 +291,31 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def dump_timeline(path, fn):
+    """Diagnostic (never part of a reported number): per-kernel start / duration / stream of the calls made by fn."""
+    import gzip
+    from torch.profiler import ProfilerActivity, profile
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        fn()
+        torch.cuda.synchronize()
+    tmp = path + ".trace.json"
+    prof.export_chrome_trace(tmp)
+    with open(tmp) as f:
+        ev = json.load(f)["traceEvents"]
+    os.remove(tmp)
+    with gzip.open(path, "wt") as f:
+        f.write("name,stream,start_us,dur_us\n")
+        for e in ev:
+            if e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset"):
+                name = e["name"].replace(",", ";")[:120]
+                f.write("%s,%s,%.3f,%.3f\n" % (name, e.get("args", {}).get("stream", e.get("tid")), e["ts"], e["dur"]))
+
+
 def roofline_conv_gemm(s, lib, dev, mode):
     """Dominant (FLOP-wise) kernel of the step: the conv.2 forward implicit GEMM, 130088 pixels x 64 x 576
     (models/asr/transformer.py:49), timed through the same entry point the engine launches
-    (mtl_conv3x3_relu_fwd -> gemm_tc_kernel<64,...> in CONV_FWD mode; mode 0 = im2col + fp32 GEMM).
+    (mtl_conv3x3_relu_fwd -> conv3x3_kw_kernel<64,...>; mode 0 = im2col + fp32 GEMM).
     Inputs are rotated over 5 buffers (5 x 67 MB read+write > 126 MB L2) so no launch re-reads a hot input.
     Algorithmic FLOPs per launch = 2 * B*F*T * Cout * 9*Cin; algorithmic bytes = x + y + w."""
     import ctypes as C
@@ -329,8 +353,8 @@ def roofline_conv_gemm(s, lib, dev, mode):
             "traffic": ROOFLINE_TRAFFIC_BYTES.get(mode),
             "algorithmic_bytes": 4 * (M * Cin + M * Cout + N * Kd), "flops_per_launch": flops,
             "kernel": "conv.2 forward implicit GEMM %dx%dx%d (%s), incl. its weight re-layout launch" % (
-                M, N, Kd, {0: "im2col + gemm_simt_kernel fp32 CUDA cores", 1: "gemm_tc_kernel<64> tcgen05 tf32",
-                           2: "gemm_tc_kernel<64> tcgen05 3xtf32"}[mode]),
+                M, N, Kd, {0: "im2col + gemm_simt_kernel fp32 CUDA cores", 1: "conv3x3_kw_kernel<64> tcgen05 tf32",
+                           2: "conv3x3_kw_kernel<64> tcgen05 3xtf32"}[mode]),
             "ms_per_launch": ms,
             "peak_source": pk["src"] + " dense bf16 cuBLAS burst (no fp32-input tensor peak is measured; tf32 nominal"
                            " = 1/2 of bf16, 3xtf32 issues 3 MMAs per product => attainable <= 1/6 of this peak)"}
@@ -370,6 +394,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="run the meta-step eagerly (no CUDA graph replay)")
     ap.add_argument("--lanes", type=int, default=0, help="concurrent task lanes (default: one per task)")
+    ap.add_argument("--timeline", default="", help="after the measurements, trace 2 more steps with torch.profiler "
+                    "(CUPTI kernel records) and write name/stream/start/duration rows to this .csv.gz (diagnostic)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

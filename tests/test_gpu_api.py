@@ -20,7 +20,7 @@ from oracle import ref_asr, ref_meta
 
 pytestmark = pytest.mark.gpu
 
-TOL_OUT, TOL_GRAD, TOL_CONV = 1e-4, 1e-3, 5e-3          # default engine = 3xTF32 (see tests/test_gpu_parity.py)
+TOL_OUT, TOL_GRAD, TOL_CONV = 1e-4, 1e-3, 3e-2          # default engine = 3xTF32; SMALL-config VGG bound: see TOL_CONV_SMALL in tests/test_gpu_parity.py
 
 
 def _tol(name):

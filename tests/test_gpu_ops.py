@@ -226,9 +226,11 @@ def test_conv1_fwd():
 
 
 @pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("masked", [True, False])
 @pytest.mark.parametrize("B,Fq,T,cin,cout", [(2, 21, 19, 64, 64), (2, 21, 19, 64, 128), (1, 9, 140, 128, 128),
-                                             (2, 161, 101, 64, 64), (2, 80, 50, 128, 128), (3, 5, 4, 64, 128)])
-def test_conv3x3_fwd_bwd(mode, B, Fq, T, cin, cout):
+                                             (2, 161, 101, 64, 64), (2, 80, 50, 128, 128), (3, 5, 4, 64, 128),
+                                             (4, 21, 41, 64, 64), (4, 10, 20, 64, 128), (4, 10, 20, 128, 128)])
+def test_conv3x3_fwd_bwd(mode, B, Fq, T, cin, cout, masked):
     """conv.2 / conv.5 / conv.7 (models/asr/transformer.py:51-57): forward with fused bias+ReLU, and the three
     backward contractions (weight grad, bias grad, input grad with the upstream ReLU mask) against autograd.
     Modes 1/2 are the tcgen05 implicit GEMMs (tap-shifted 4-D TMA boxes, zero padding = TMA OOB fill)."""
@@ -255,11 +257,11 @@ def test_conv3x3_fwd_bwd(mode, B, Fq, T, cin, cout):
     db = torch.ones(cout, device=dev())
     dx = torch.full((B, Fq, T, cin), 7.0, device=dev())
     dyd = _nhwc(dy).to(dev())
-    ok(lib().mtl_conv3x3_bwd(mode, P(xind), P(wd_), P(dyd), P(xind), P(dw), P(db), P(dx), P(scr), B, Fq, T, cin, cout,
-                             stream()))
+    ok(lib().mtl_conv3x3_bwd(mode, P(xind), P(wd_), P(dyd), P(xind) if masked else None, P(dw), P(db), P(dx), P(scr),
+                             B, Fq, T, cin, cout, stream()))
     assert rel_err(dw - 1.0, wr.grad) < tol
     assert rel_err(db - 1.0, br.grad) < max(tol, 2e-5)
-    assert rel_err(dx, _nhwc(xr.grad * (xin > 0))) < tol
+    assert rel_err(dx, _nhwc(xr.grad * (xin > 0) if masked else xr.grad)) < tol
 
 
 @pytest.mark.parametrize("Fq,T", [(21, 19), (20, 18), (161, 101)])

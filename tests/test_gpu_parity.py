@@ -25,10 +25,18 @@ TOL_GRAD = {0: 2e-4, 1: 5e-3, 2: 1e-3}[GEMM_MODE]
 # The VGG gradients (conv.0 above all: a sum over every pixel of relu-masked terms with heavy cancellation)
 # amplify the engine's per-element error: ~1e-7 (fp32 FMA) / ~1e-6 (3xTF32) / ~3e-4 (TF32) of activations.
 TOL_CONV = {0: 1e-3, 1: 5e-2, 2: 5e-3}[GEMM_MODE]
+# SMALL-config VGG gradients: the batch has only 3444 conv pixels and ~28 target tokens, so ONE relu / max-pool decision
+# taken the other way moves a conv gradient by percent of the tensor max.  Measured (seed 5 / batch seed 1): the pool
+# window (b 3, ch 17, f 16-17, t 24-25) of conv.2 holds 0.20169985 and 0.20169957 (gap 1.4e-6 relative, inside any
+# non-bit-exact engine's rounding); routed to the other pixel it changes exactly two elements of d(conv.2 output) and
+# moves conv.2.weight by 2.0e-2 and conv.0.weight by 1.0e-2 of their maxima (workspace diff between two correct
+# kernels, tools/probes/ws_dump.py).  The kernels' own precision is pinned at the op level (tests/test_gpu_ops.py:
+# 5e-5) and the full-size gradients by the cfg-2 golden tests below (TOL_CONV); here the bound only has to catch wiring errors.
+TOL_CONV_SMALL = {0: 1e-3, 1: 5e-2, 2: 3e-2}[GEMM_MODE]
 
 
-def _tol(name):
-    return TOL_CONV if name.startswith("conv.") else TOL_GRAD
+def _tol(name, small=True):
+    return (TOL_CONV_SMALL if small else TOL_CONV) if name.startswith("conv.") else TOL_GRAD
 
 
 def _session(cfg):
