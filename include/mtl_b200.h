@@ -172,6 +172,8 @@ int mtl_gemm_repeat(int reps, int mode, int transA, int transB, int M, int N, in
 /* debug hook (MTL_GEMM_DBG=n): SM-cycle stamps of the last tcgen05 GEMM / conv launch into 160 host slots:
  * [0,32) phase stamps of CTA (0,0,0); [32,160) per-k-block pipeline stamps (4 per k-block) of CTA (n-1,0,0) */
 int mtl_debug_gemm_stamps(long long* host160);
+/* MTL_GEMM_DBG=99: %globaltimer (ns) at entry / exit of the first 256 CTAs of the last tcgen05 GEMM launch */
+int mtl_debug_gemm_span(unsigned long long* host512);
 /* LayerNorm(dropout(y)+res)*rowmask (+pe)  -- modules/common_layers.py:129-131,303-304 */
 int mtl_ln_fwd(const float* y, const float* res, const float* gamma, const float* beta,
                const float* rowmask, const float* pe, int pe_period, float drop_p,

@@ -1149,6 +1149,8 @@ extern "C" int mtl_gemm_repeat(int reps, int mode, int transA, int transB, int M
   for (int i = 0; i < reps; ++i) MTL_TRY(k_gemm(g, mode, (cudaStream_t)stream));
   return MTL_OK;
 }
+int k_gemm_tc_debug_span(unsigned long long* host512);
+extern "C" int mtl_debug_gemm_span(unsigned long long* host512) { return k_gemm_tc_debug_span(host512); }
 int k_gemm_tc_debug_stamps(long long* host32);
 extern "C" int mtl_debug_gemm_stamps(long long* host32) { return k_gemm_tc_debug_stamps(host32); }
 extern "C" int mtl_ln_fwd(const float* y, const float* res, const float* gamma, const float* beta,

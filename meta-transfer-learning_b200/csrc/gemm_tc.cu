@@ -58,6 +58,9 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // Bounded wait: a pipeline bug must trap (error reported to the host), never hang the GPU.
 // debug stamps (MTL_GEMM_DBG=1): SM cycle counter at the main events of CTA (0,0,0)
 __device__ long long g_dbg[160];   // [0,32): phase stamps; [32,160): per-k-block pipeline stamps of CTA (0,0,0), 4 per k-block
+__device__ unsigned long long g_cta_span[512];   // MTL_GEMM_DBG=99: globaltimer at entry / exit of the first 256 CTAs of the last launch
+__device__ __forceinline__ unsigned long long globaltimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define DBG_SPAN(slot) do { if (P.dbg == 99 && threadIdx.x == 0) { const unsigned id = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z); if (id < 256) g_cta_span[2 * id + (slot)] = globaltimer_ns(); } } while (0)
 #define DBG_STAMP(i) do { if (P.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) g_dbg[i] = clock64(); } while (0)
 // role r (0 producer issued, 1 splitter saw full, 2 MMA saw ready/full, 3 MMA issued+committed) of k-block iteration it
 #define DBG_KB(it, r) do { if (P.dbg && (it) < 32 && blockIdx.x == P.dbg - 1 && blockIdx.y == 0 && blockIdx.z == 0) g_dbg[32 + (it) * 4 + (r)] = clock64(); } while (0)
@@ -334,6 +337,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
     cb = rem / P.tiles_f;
   }
 
+  DBG_SPAN(0);
   if (threadIdx.x == 0) DBG_STAMP(0);
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&ready[s], 4); }
@@ -521,6 +525,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
       tc_fence_after();
       asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
+    DBG_SPAN(1);
     return;
   }
   if (warp >= 2) {
@@ -720,6 +725,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
+  DBG_SPAN(1);
 }
 
 // ----------------------------------------------------------------------------- kw-box 3x3 convolution
@@ -1307,6 +1313,11 @@ int k_conv3x3_wgrad_tc(const float* x, const float* dy, float* dwgT, int B, int 
   return dispatch(bn, split3, true, true, tm, P, grid, s);
 }
 
+// debug (MTL_GEMM_DBG=99): per-CTA globaltimer entry / exit pairs of the last GEMM launch
+int k_gemm_tc_debug_span(unsigned long long* host512) {
+  MTL_CHECK_CUDA(cudaMemcpyFromSymbol(host512, g_cta_span, sizeof(unsigned long long) * 512));
+  return MTL_OK;
+}
 // debug: copies the 32 cycle stamps of the last instrumented GEMM launch to the host
 int k_gemm_tc_debug_stamps(long long* host32) {
   MTL_CHECK_CUDA(cudaMemcpyFromSymbol(host32, g_dbg, sizeof(long long) * 160));
