@@ -9,6 +9,10 @@
 #include "kernels.h"
 #include <math.h>
 
+int k_attn_small_fwd(const AttnArgs& a, cudaStream_t s);
+int k_attn_small_bwd(const AttnBwdArgs& a, cudaStream_t s);
+bool k_attn_small_eligible(const AttnArgs& a);
+
 #define ATT_TILE 32      // keys (fwd/dQ) or queries (dKV) per smem tile == warp width
 #define ATT_ROWS 16      // rows per CTA (4 warps x 4 rows)
 #define ATT_RPW 4
@@ -93,6 +97,7 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(AttnArgs a) {
 int k_attn_fwd(const AttnArgs& a, cudaStream_t s) {
   MTL_REQUIRE(a.dk == 32 || a.dk == 64, "attention head dim must be 32 or 64");
   if (a.B * a.H * a.Tq == 0) return MTL_OK;
+  if (k_attn_small_eligible(a)) return k_attn_small_fwd(a, s);
   dim3 grid(mtl_cdiv(a.Tq, ATT_ROWS), a.H, a.B);
   if (a.dk == 64) attn_fwd_kernel<64><<<grid, 128, 0, s>>>(a);
   else attn_fwd_kernel<32><<<grid, 128, 0, s>>>(a);
@@ -291,5 +296,260 @@ static int attn_bwd_launch(const AttnBwdArgs& a, cudaStream_t s) {
 int k_attn_bwd(const AttnBwdArgs& a, cudaStream_t s) {
   MTL_REQUIRE(a.f.dk == 32 || a.f.dk == 64, "attention head dim must be 32 or 64");
   if (a.f.B * a.f.H * a.f.Tq == 0) return MTL_OK;
+  if (k_attn_small_eligible(a.f) && (((uintptr_t)a.d_o | (uintptr_t)a.dq | (uintptr_t)a.dk | (uintptr_t)a.dv) & 15u) == 0)
+    return k_attn_small_bwd(a, s);
   return a.f.dk == 64 ? attn_bwd_launch<64>(a, s) : attn_bwd_launch<32>(a, s);
 }
+
+// ----------------------------------------------------------------------------- short sequences (Tq, Tk <= 64)
+// BASELINE cfg 2 runs attention over T' = 25 encoder frames and n = 33 decoder tokens: one (b, h) pair is a 33 x 33 x 64
+// problem.  The tiled kernels above pay a whole 32-wide tile for the 33rd key / query and split the backward over three
+// launches on the critical path; here ONE CTA owns one (b, h): Q, K, V (and dO) sit in shared memory once, the scores
+// never leave it, and the backward (delta, dQ, dK, dV) is a single kernel.  Every product runs on a 16 x 16 thread grid
+// with 4 x 4 register blocks and float4 shared-memory operands.  Same masks, same Philox dropout indices and the same
+// fully-masked-row semantics (NaN, like softmax over a row of -inf) as the tiled kernels.
+constexpr int SA_T = 64;           // rows (queries / keys) a CTA can hold
+constexpr int SA_LD = 68;          // row stride in floats: 16 B aligned rows, 16 consecutive rows hit distinct bank quads
+
+struct SaSmem {
+  float q[SA_T][SA_LD], k[SA_T][SA_LD], v[SA_T][SA_LD], g[SA_T][SA_LD];   // g = dO (backward only)
+  float p[SA_T][SA_LD], ds[SA_T][SA_LD];                                   // probabilities (after dropout) / dS
+  float lse[SA_T], delta[SA_T];
+};
+static_assert(sizeof(SaSmem) <= 227 * 1024, "shared memory budget");
+
+// rows [0, T) of a (B*T, ld) matrix's head-h column block -> shared memory, rows [T, SA_T) zero
+template <int DK>
+__device__ __forceinline__ void sa_load(float (*dst)[SA_LD], const float* src, int b, int T, int ld, int h) {
+  constexpr int C4 = DK / 4;
+  for (int i = threadIdx.x; i < SA_T * C4; i += 256) {
+    const int r = i / C4, c4 = i % C4;
+    float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < T) val = *reinterpret_cast<const float4*>(src + (size_t)(b * T + r) * ld + h * DK + c4 * 4);
+    *reinterpret_cast<float4*>(&dst[r][c4 * 4]) = val;
+  }
+}
+__device__ __forceinline__ float dot4(const float4& a, const float4& b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
+// acc[r][c] = sum_d X[ty + 16 r][d] * Y[tx + 16 c][d]   (r < nr, c < nc)
+template <int DK>
+__device__ __forceinline__ void sa_nt(float (&acc)[4][4], const float (*X)[SA_LD], const float (*Y)[SA_LD], int ty, int tx,
+                                      int nr, int nc) {
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+#pragma unroll 4
+  for (int d = 0; d < DK; d += 4) {
+    float4 x[4], y[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) if (r < nr) x[r] = *reinterpret_cast<const float4*>(&X[ty + 16 * r][d]);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) if (c < nc) y[c] = *reinterpret_cast<const float4*>(&Y[tx + 16 * c][d]);
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) if (r < nr && c < nc) acc[r][c] += dot4(x[r], y[c]);
+  }
+}
+// out[ty + 16 r][4 tx .. 4 tx + 3] = scale * sum_{j < J} W[ty + 16 r][j] * Y[j][4 tx ..]   (r < nr; J padded to 4 with zeros)
+template <int DK>
+__device__ __forceinline__ void sa_nn(float* out, int ld, const float (*W)[SA_LD], const float (*Y)[SA_LD], int ty, int tx,
+                                      int nr, int rows, int J, float scale) {
+  if (tx * 4 >= DK) return;
+  float4 acc[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int j = 0; j < J; j += 4) {
+    float4 y[4], w[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) y[u] = *reinterpret_cast<const float4*>(&Y[j + u][tx * 4]);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) if (r < nr) w[r] = *reinterpret_cast<const float4*>(&W[ty + 16 * r][j]);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      if (r >= nr) continue;
+      acc[r].x += w[r].x * y[0].x + w[r].y * y[1].x + w[r].z * y[2].x + w[r].w * y[3].x;
+      acc[r].y += w[r].x * y[0].y + w[r].y * y[1].y + w[r].z * y[2].y + w[r].w * y[3].y;
+      acc[r].z += w[r].x * y[0].z + w[r].y * y[1].z + w[r].z * y[2].z + w[r].w * y[3].z;
+      acc[r].w += w[r].x * y[0].w + w[r].y * y[1].w + w[r].z * y[2].w + w[r].w * y[3].w;
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int i = ty + 16 * r;
+    if (r < nr && i < rows)
+      *reinterpret_cast<float4*>(out + (size_t)i * ld + tx * 4) =
+          make_float4(acc[r].x * scale, acc[r].y * scale, acc[r].z * scale, acc[r].w * scale);
+  }
+}
+// out[ty + 16 r][4 tx ..] = scale * sum_{i < I} W[i][ty + 16 r] * Y[i][4 tx ..]   (contraction over ROWS of W)
+template <int DK>
+__device__ __forceinline__ void sa_tn(float* out, int ld, const float (*W)[SA_LD], const float (*Y)[SA_LD], int ty, int tx,
+                                      int nr, int rows, int I, float scale) {
+  if (tx * 4 >= DK) return;
+  float4 acc[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 2
+  for (int i = 0; i < I; ++i) {
+    const float4 y = *reinterpret_cast<const float4*>(&Y[i][tx * 4]);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      if (r >= nr) continue;
+      const float w = W[i][ty + 16 * r];
+      acc[r].x += w * y.x; acc[r].y += w * y.y; acc[r].z += w * y.z; acc[r].w += w * y.w;
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int j = ty + 16 * r;
+    if (r < nr && j < rows)
+      *reinterpret_cast<float4*>(out + (size_t)j * ld + tx * 4) =
+          make_float4(acc[r].x * scale, acc[r].y * scale, acc[r].z * scale, acc[r].w * scale);
+  }
+}
+
+template <int DK>
+__global__ void __launch_bounds__(256) attn_small_fwd_kernel(AttnArgs a) {
+  extern __shared__ __align__(16) unsigned char sa_raw[];
+  SaSmem& S = *reinterpret_cast<SaSmem*>(sa_raw);
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int nrq = (a.Tq + 15) >> 4, nck = (a.Tk + 15) >> 4;
+  sa_load<DK>(S.q, a.q, b, a.Tq, a.ldq, h);
+  sa_load<DK>(S.k, a.k, b, a.Tk, a.ldk, h);
+  sa_load<DK>(S.v, a.v, b, a.Tk, a.ldv, h);
+  __syncthreads();
+  {  // masked, scaled scores -> S.p
+    float acc[4][4];
+    sa_nt<DK>(acc, S.q, S.k, ty, tx, nrq, nck);
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (r >= nrq || c >= nck) continue;
+        const int i = ty + 16 * r, j = tx + 16 * c;
+        const bool ok = i < a.Tq && j < a.Tk && !(a.keypad && a.keypad[(size_t)b * a.Tk + j]) && !(a.causal && j > i);
+        S.p[i][j] = ok ? acc[r][c] * a.inv_temp : -INFINITY;
+      }
+  }
+  __syncthreads();
+  const unsigned long long seed = a.drop.p > 0.f ? mtl_eff_seed(a.drop) : 0ull;
+  for (int i = w; i < a.Tq; i += 8) {  // softmax over keys, one warp per query row
+    const float s0 = lane < a.Tk ? S.p[i][lane] : -INFINITY, s1 = lane + 32 < a.Tk ? S.p[i][lane + 32] : -INFINITY;
+    const float m = warp_max(fmaxf(s0, s1));
+    float p0 = 0.f, p1 = 0.f;
+    if (m != -INFINITY) { p0 = __expf(s0 - m); p1 = __expf(s1 - m); }   // exp(-inf) = 0 for masked keys
+    const float l = warp_sum(p0 + p1);
+    const float inv = 1.f / l;                                          // fully masked row -> 0 * inf = NaN, like the reference
+    p0 *= inv; p1 *= inv;
+    if (a.drop.p > 0.f) {
+      const unsigned long long base = ((unsigned long long)(b * a.H + h) * a.Tq + i) * a.Tk;
+      if (s0 != -INFINITY) p0 *= dropout_scale(seed, a.drop.site, base + lane, a.drop.p, a.drop.inv_keep);
+      if (s1 != -INFINITY) p1 *= dropout_scale(seed, a.drop.site, base + lane + 32, a.drop.p, a.drop.inv_keep);
+    }
+    S.p[i][lane] = p0; S.p[i][lane + 32] = p1;
+    if (lane == 0) a.lse[((size_t)b * a.H + h) * a.Tq + i] = m + logf(l);
+  }
+  __syncthreads();
+  sa_nn<DK>(a.o + (size_t)b * a.Tq * a.ldo + h * DK, a.ldo, S.p, S.v, ty, tx, nrq, a.Tq, (a.Tk + 3) & ~3, 1.f);
+}
+
+template <int DK>
+__global__ void __launch_bounds__(256) attn_small_bwd_kernel(AttnBwdArgs a) {
+  extern __shared__ __align__(16) unsigned char sa_raw[];
+  SaSmem& S = *reinterpret_cast<SaSmem*>(sa_raw);
+  const AttnArgs& f = a.f;
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int nrq = (f.Tq + 15) >> 4, nck = (f.Tk + 15) >> 4;
+  sa_load<DK>(S.q, f.q, b, f.Tq, f.ldq, h);
+  sa_load<DK>(S.k, f.k, b, f.Tk, f.ldk, h);
+  sa_load<DK>(S.v, f.v, b, f.Tk, f.ldv, h);
+  sa_load<DK>(S.g, a.d_o, b, f.Tq, f.ldo, h);
+  for (int i = w; i < SA_T; i += 8) {          // delta_i = dO_i . O_i (== sum_j P_ij dP_ij, also with dropout); lse
+    float s = 0.f;
+    if (i < f.Tq) {
+#pragma unroll
+      for (int v = 0; v < DK / 32; ++v) {
+        const size_t off = (size_t)(b * f.Tq + i) * f.ldo + h * DK + lane + 32 * v;
+        s += a.d_o[off] * f.o[off];
+      }
+      s = warp_sum(s);
+    }
+    if (lane == 0) {
+      S.delta[i] = s;
+      S.lse[i] = i < f.Tq ? f.lse[((size_t)b * f.H + h) * f.Tq + i] : 0.f;
+    }
+  }
+  __syncthreads();
+  {
+    float sc[4][4], dp[4][4];
+    sa_nt<DK>(sc, S.q, S.k, ty, tx, nrq, nck);
+    sa_nt<DK>(dp, S.g, S.v, ty, tx, nrq, nck);
+    const unsigned long long seed = f.drop.p > 0.f ? mtl_eff_seed(f.drop) : 0ull;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (r >= nrq || c >= nck) continue;
+        const int i = ty + 16 * r, j = tx + 16 * c;
+        const bool ok = i < f.Tq && j < f.Tk && !(f.keypad && f.keypad[(size_t)b * f.Tk + j]) && !(f.causal && j > i);
+        const float p = ok ? __expf(sc[r][c] * f.inv_temp - S.lse[i]) : 0.f;
+        float pd = p, d = dp[r][c];
+        if (f.drop.p > 0.f && ok) {
+          const unsigned long long idx = (((unsigned long long)(b * f.H + h) * f.Tq + i) * f.Tk + j);
+          const float s = dropout_scale(seed, f.drop.site, idx, f.drop.p, f.drop.inv_keep);
+          pd = p * s; d *= s;
+        }
+        S.p[i][j] = pd;
+        S.ds[i][j] = p * (d - S.delta[i]);
+      }
+  }
+  __syncthreads();
+  const int j4 = (f.Tk + 3) & ~3;
+  sa_nn<DK>(a.dq + (size_t)b * f.Tq * f.ldq + h * DK, f.ldq, S.ds, S.k, ty, tx, nrq, f.Tq, j4, f.inv_temp);
+  sa_tn<DK>(a.dk + (size_t)b * f.Tk * f.ldk + h * DK, f.ldk, S.ds, S.q, ty, tx, nck, f.Tk, f.Tq, f.inv_temp);
+  sa_tn<DK>(a.dv + (size_t)b * f.Tk * f.ldv + h * DK, f.ldv, S.p, S.g, ty, tx, nck, f.Tk, f.Tq, 1.f);
+}
+
+// MTL_ATTN_SMALL=0 keeps the tiled kernels for short sequences too (A/B measurements)
+static bool attn_small_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MTL_ATTN_SMALL"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v != 0;
+}
+static bool attn_small_ok(const AttnArgs& a) {
+  auto al = [](const void* p) { return (((uintptr_t)p) & 15u) == 0; };
+  return attn_small_enabled() && a.Tq <= SA_T && a.Tk <= SA_T && a.ldq % 4 == 0 && a.ldk % 4 == 0 && a.ldv % 4 == 0 &&
+         a.ldo % 4 == 0 && al(a.q) && al(a.k) && al(a.v) && al(a.o);
+}
+template <int DK>
+static int attn_small_fwd_launch(const AttnArgs& a, cudaStream_t s) {
+  static bool configured = false;
+  if (!configured) {
+    MTL_CHECK_CUDA(cudaFuncSetAttribute(attn_small_fwd_kernel<DK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SaSmem)));
+    configured = true;
+  }
+  attn_small_fwd_kernel<DK><<<dim3(a.H, a.B), 256, sizeof(SaSmem), s>>>(a);
+  MTL_CHECK_LAUNCH();
+  return MTL_OK;
+}
+template <int DK>
+static int attn_small_bwd_launch(const AttnBwdArgs& a, cudaStream_t s) {
+  static bool configured = false;
+  if (!configured) {
+    MTL_CHECK_CUDA(cudaFuncSetAttribute(attn_small_bwd_kernel<DK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SaSmem)));
+    configured = true;
+  }
+  attn_small_bwd_kernel<DK><<<dim3(a.f.H, a.f.B), 256, sizeof(SaSmem), s>>>(a);
+  MTL_CHECK_LAUNCH();
+  return MTL_OK;
+}
+int k_attn_small_fwd(const AttnArgs& a, cudaStream_t s) {
+  return a.dk == 64 ? attn_small_fwd_launch<64>(a, s) : attn_small_fwd_launch<32>(a, s);
+}
+int k_attn_small_bwd(const AttnBwdArgs& a, cudaStream_t s) {
+  return a.f.dk == 64 ? attn_small_bwd_launch<64>(a, s) : attn_small_bwd_launch<32>(a, s);
+}
+bool k_attn_small_eligible(const AttnArgs& a) { return attn_small_ok(a); }
