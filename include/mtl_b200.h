@@ -172,6 +172,8 @@ int mtl_gemm_repeat(int reps, int mode, int transA, int transB, int M, int N, in
 /* debug hook (MTL_GEMM_DBG=n): SM-cycle stamps of the last tcgen05 GEMM / conv launch into 160 host slots:
  * [0,32) phase stamps of CTA (0,0,0); [32,160) per-k-block pipeline stamps (4 per k-block) of CTA (n-1,0,0) */
 int mtl_debug_gemm_stamps(long long* host160);
+/* clock64 stamps of CTA (0,0) of the last short-sequence attention launches: [0,8) forward phases, [16,24) backward */
+int mtl_debug_attn_stamps(long long* host32);
 /* MTL_GEMM_DBG=99: %globaltimer (ns) at entry / exit of the first 256 CTAs of the last tcgen05 GEMM launch */
 int mtl_debug_gemm_span(unsigned long long* host512);
 /* LayerNorm(dropout(y)+res)*rowmask (+pe)  -- modules/common_layers.py:129-131,303-304 */

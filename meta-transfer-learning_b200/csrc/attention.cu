@@ -308,6 +308,12 @@ int k_attn_bwd(const AttnBwdArgs& a, cudaStream_t s) {
 // never leave it, and the backward (delta, dQ, dK, dV) is a single kernel.  Every product runs on a 16 x 16 thread grid
 // with 4 x 4 register blocks and float4 shared-memory operands.  Same masks, same Philox dropout indices and the same
 // fully-masked-row semantics (NaN, like softmax over a row of -inf) as the tiled kernels.
+__device__ long long g_attn_dbg[32];   // cycle stamps of CTA (0,0): [0,8) forward phases, [16,24) backward phases
+#define SA_STAMP(i) do { if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) g_attn_dbg[i] = clock64(); } while (0)
+int k_attn_debug_stamps(long long* host32) {
+  MTL_CHECK_CUDA(cudaMemcpyFromSymbol(host32, g_attn_dbg, sizeof(long long) * 32));
+  return MTL_OK;
+}
 constexpr int SA_T = 64;           // rows (queries / keys) a CTA can hold
 constexpr int SA_LD = 68;          // row stride in floats: 16 B aligned rows, 16 consecutive rows hit distinct bank quads
 
@@ -315,59 +321,90 @@ struct SaSmem {
   float q[SA_T][SA_LD], k[SA_T][SA_LD], v[SA_T][SA_LD], g[SA_T][SA_LD];   // g = dO (backward only)
   float p[SA_T][SA_LD], ds[SA_T][SA_LD];                                   // probabilities (after dropout) / dS
   float lse[SA_T], delta[SA_T];
+  int kmask[SA_T];                                                         // 1 = key masked (padding) or beyond Tk
 };
-static_assert(sizeof(SaSmem) <= 227 * 1024, "shared memory budget");
-
-// rows [0, T) of a (B*T, ld) matrix's head-h column block -> shared memory, rows [T, SA_T) zero
-template <int DK>
-__device__ __forceinline__ void sa_load(float (*dst)[SA_LD], const float* src, int b, int T, int ld, int h) {
-  constexpr int C4 = DK / 4;
-  for (int i = threadIdx.x; i < SA_T * C4; i += 256) {
-    const int r = i / C4, c4 = i % C4;
-    float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (r < T) val = *reinterpret_cast<const float4*>(src + (size_t)(b * T + r) * ld + h * DK + c4 * 4);
-    *reinterpret_cast<float4*>(&dst[r][c4 * 4]) = val;
+// key-pad flags of batch row b -> shared memory (one global round trip for the whole CTA, not one per score)
+__device__ __forceinline__ void sa_load_kmask(int* dst, const unsigned char* keypad, int b, int Tk) {
+  if (threadIdx.x < SA_T) {
+    const int j = threadIdx.x;
+    dst[j] = (j >= Tk || (keypad && keypad[(size_t)b * Tk + j])) ? 1 : 0;
   }
 }
-__device__ __forceinline__ float dot4(const float4& a, const float4& b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
-// acc[r][c] = sum_d X[ty + 16 r][d] * Y[tx + 16 c][d]   (r < nr, c < nc)
-template <int DK>
-__device__ __forceinline__ void sa_nt(float (&acc)[4][4], const float (*X)[SA_LD], const float (*Y)[SA_LD], int ty, int tx,
-                                      int nr, int nc) {
+static_assert(sizeof(SaSmem) <= 227 * 1024, "shared memory budget");
+
+// rows [0, T) of a (B*T, ld) matrix's head-h column block -> shared memory, rows [T, SA_T) zero.  Two phases (every
+// global load of the CTA is in flight before the first shared-memory store) so that a kernel pays ONE global round
+// trip for all of its operands: sa_fetch into registers for each matrix, then sa_store for each.
+template <int DK, int NT>
+struct SaTile { float4 v[SA_T * (DK / 4) / NT]; };
+template <int DK, int NT>
+__device__ __forceinline__ void sa_fetch(SaTile<DK, NT>& t, const float* src, int b, int T, int ld, int h) {
+  constexpr int C4 = DK / 4, N = SA_T * C4 / NT;
 #pragma unroll
-  for (int r = 0; r < 4; ++r)
+  for (int u = 0; u < N; ++u) {
+    const int i = threadIdx.x + u * NT, r = i / C4, c4 = i % C4;
+    t.v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < T) t.v[u] = __ldg(reinterpret_cast<const float4*>(src + (size_t)(b * T + r) * ld + h * DK + c4 * 4));
+  }
+}
+template <int DK, int NT>
+__device__ __forceinline__ void sa_store(float (*dst)[SA_LD], const SaTile<DK, NT>& t) {
+  constexpr int C4 = DK / 4, N = SA_T * C4 / NT;
+#pragma unroll
+  for (int u = 0; u < N; ++u) {
+    const int i = threadIdx.x + u * NT, r = i / C4, c4 = i % C4;
+    *reinterpret_cast<float4*>(&dst[r][c4 * 4]) = t.v[u];
+  }
+}
+__device__ __forceinline__ void fma4(float& acc, const float4& a, const float4& b) {
+  acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
+}
+// Thread grid of the products: tx = thread % 16 walks columns, ty = thread / 16 walks rows with stride RS = NT / 16;
+// a thread owns R = SA_T / RS register rows.
+// acc[r][c] = sum_d X[ty + RS r][d] * Y[tx + 16 c][d]   (rows ty + RS r < rows, c < nc).  The row test is per thread: with
+// 16 warps and T = 33 only the warp that owns row 32 runs the second register row at all.
+template <int DK, int RS>
+__device__ __forceinline__ void sa_nt(float (&acc)[SA_T / RS][4], const float (*X)[SA_LD], const float (*Y)[SA_LD], int ty,
+                                      int tx, int rows, int nc) {
+  constexpr int R = SA_T / RS;
+  bool rv[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    rv[r] = ty + RS * r < rows;
 #pragma unroll
     for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+  }
 #pragma unroll 4
   for (int d = 0; d < DK; d += 4) {
-    float4 x[4], y[4];
+    float4 x[R], y[4];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) if (r < nr) x[r] = *reinterpret_cast<const float4*>(&X[ty + 16 * r][d]);
+    for (int r = 0; r < R; ++r) if (rv[r]) x[r] = *reinterpret_cast<const float4*>(&X[ty + RS * r][d]);
 #pragma unroll
     for (int c = 0; c < 4; ++c) if (c < nc) y[c] = *reinterpret_cast<const float4*>(&Y[tx + 16 * c][d]);
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
+    for (int r = 0; r < R; ++r)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) if (r < nr && c < nc) acc[r][c] += dot4(x[r], y[c]);
+      for (int c = 0; c < 4; ++c) if (rv[r] && c < nc) fma4(acc[r][c], x[r], y[c]);
   }
 }
-// out[ty + 16 r][4 tx .. 4 tx + 3] = scale * sum_{j < J} W[ty + 16 r][j] * Y[j][4 tx ..]   (r < nr; J padded to 4 with zeros)
-template <int DK>
+// out[ty + RS r][4 tx .. 4 tx + 3] = scale * sum_{j < J} W[ty + RS r][j] * Y[j][4 tx ..]   (r < nr; J padded to 4 with zeros)
+template <int DK, int RS>
 __device__ __forceinline__ void sa_nn(float* out, int ld, const float (*W)[SA_LD], const float (*Y)[SA_LD], int ty, int tx,
                                       int nr, int rows, int J, float scale) {
   if (tx * 4 >= DK) return;
-  float4 acc[4];
+  constexpr int R = SA_T / RS;
+  float4 acc[R];
 #pragma unroll
-  for (int r = 0; r < 4; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int r = 0; r < R; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int j = 0; j < J; j += 4) {
-    float4 y[4], w[4];
+    float4 y[4], w[R];
 #pragma unroll
     for (int u = 0; u < 4; ++u) y[u] = *reinterpret_cast<const float4*>(&Y[j + u][tx * 4]);
 #pragma unroll
-    for (int r = 0; r < 4; ++r) if (r < nr) w[r] = *reinterpret_cast<const float4*>(&W[ty + 16 * r][j]);
+    for (int r = 0; r < R; ++r) if (ty + RS * r < rows) w[r] = *reinterpret_cast<const float4*>(&W[ty + RS * r][j]);
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      if (r >= nr) continue;
+    for (int r = 0; r < R; ++r) {
+      if (ty + RS * r >= rows) continue;
       acc[r].x += w[r].x * y[0].x + w[r].y * y[1].x + w[r].z * y[2].x + w[r].w * y[3].x;
       acc[r].y += w[r].x * y[0].y + w[r].y * y[1].y + w[r].z * y[2].y + w[r].w * y[3].y;
       acc[r].z += w[r].x * y[0].z + w[r].y * y[1].z + w[r].z * y[2].z + w[r].w * y[3].z;
@@ -375,126 +412,157 @@ __device__ __forceinline__ void sa_nn(float* out, int ld, const float (*W)[SA_LD
     }
   }
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const int i = ty + 16 * r;
-    if (r < nr && i < rows)
+  for (int r = 0; r < R; ++r) {
+    const int i = ty + RS * r;
+    if (i < rows)
       *reinterpret_cast<float4*>(out + (size_t)i * ld + tx * 4) =
           make_float4(acc[r].x * scale, acc[r].y * scale, acc[r].z * scale, acc[r].w * scale);
   }
 }
-// out[ty + 16 r][4 tx ..] = scale * sum_{i < I} W[i][ty + 16 r] * Y[i][4 tx ..]   (contraction over ROWS of W)
-template <int DK>
+// out[ty + RS r][4 tx ..] = scale * sum_{i < I} W[i][ty + RS r] * Y[i][4 tx ..]   (contraction over ROWS of W)
+template <int DK, int RS>
 __device__ __forceinline__ void sa_tn(float* out, int ld, const float (*W)[SA_LD], const float (*Y)[SA_LD], int ty, int tx,
                                       int nr, int rows, int I, float scale) {
   if (tx * 4 >= DK) return;
-  float4 acc[4];
+  constexpr int R = SA_T / RS;
+  float4 acc[R];
 #pragma unroll
-  for (int r = 0; r < 4; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int r = 0; r < R; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 2
   for (int i = 0; i < I; ++i) {
     const float4 y = *reinterpret_cast<const float4*>(&Y[i][tx * 4]);
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      if (r >= nr) continue;
-      const float w = W[i][ty + 16 * r];
+    for (int r = 0; r < R; ++r) {
+      if (ty + RS * r >= rows) continue;
+      const float w = W[i][ty + RS * r];
       acc[r].x += w * y.x; acc[r].y += w * y.y; acc[r].z += w * y.z; acc[r].w += w * y.w;
     }
   }
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const int j = ty + 16 * r;
-    if (r < nr && j < rows)
+  for (int r = 0; r < R; ++r) {
+    const int j = ty + RS * r;
+    if (j < rows)
       *reinterpret_cast<float4*>(out + (size_t)j * ld + tx * 4) =
           make_float4(acc[r].x * scale, acc[r].y * scale, acc[r].z * scale, acc[r].w * scale);
   }
 }
 
-template <int DK>
-__global__ void __launch_bounds__(256) attn_small_fwd_kernel(AttnArgs a) {
+template <int DK, int NT>
+__global__ void __launch_bounds__(NT) attn_small_fwd_kernel(AttnArgs a) {
+  constexpr int RS = NT / 16, R = SA_T / RS, NW = NT / 32;
   extern __shared__ __align__(16) unsigned char sa_raw[];
   SaSmem& S = *reinterpret_cast<SaSmem*>(sa_raw);
   const int h = blockIdx.x, b = blockIdx.y;
   const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int nrq = (a.Tq + 15) >> 4, nck = (a.Tk + 15) >> 4;
-  sa_load<DK>(S.q, a.q, b, a.Tq, a.ldq, h);
-  sa_load<DK>(S.k, a.k, b, a.Tk, a.ldk, h);
-  sa_load<DK>(S.v, a.v, b, a.Tk, a.ldv, h);
+  const int nrq = (a.Tq + RS - 1) / RS, nck = (a.Tk + 15) >> 4;
+  pdl_wait();
+  pdl_trigger();
+  SA_STAMP(0);
+  {
+    SaTile<DK, NT> tq, tk, tv;
+    sa_fetch<DK, NT>(tq, a.q, b, a.Tq, a.ldq, h);
+    sa_fetch<DK, NT>(tk, a.k, b, a.Tk, a.ldk, h);
+    sa_fetch<DK, NT>(tv, a.v, b, a.Tk, a.ldv, h);
+    sa_load_kmask(S.kmask, a.keypad, b, a.Tk);
+    sa_store<DK, NT>(S.q, tq); sa_store<DK, NT>(S.k, tk); sa_store<DK, NT>(S.v, tv);
+  }
   __syncthreads();
+  SA_STAMP(1);
   {  // masked, scaled scores -> S.p
-    float acc[4][4];
-    sa_nt<DK>(acc, S.q, S.k, ty, tx, nrq, nck);
+    float acc[R][4];
+    sa_nt<DK, RS>(acc, S.q, S.k, ty, tx, a.Tq, nck);
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
+    for (int r = 0; r < R; ++r)
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         if (r >= nrq || c >= nck) continue;
-        const int i = ty + 16 * r, j = tx + 16 * c;
-        const bool ok = i < a.Tq && j < a.Tk && !(a.keypad && a.keypad[(size_t)b * a.Tk + j]) && !(a.causal && j > i);
+        const int i = ty + RS * r, j = tx + 16 * c;
+        const bool ok = i < a.Tq && !S.kmask[j] && !(a.causal && j > i);
         S.p[i][j] = ok ? acc[r][c] * a.inv_temp : -INFINITY;
       }
   }
   __syncthreads();
+  SA_STAMP(2);
   const unsigned long long seed = a.drop.p > 0.f ? mtl_eff_seed(a.drop) : 0ull;
-  for (int i = w; i < a.Tq; i += 8) {  // softmax over keys, one warp per query row
-    const float s0 = lane < a.Tk ? S.p[i][lane] : -INFINITY, s1 = lane + 32 < a.Tk ? S.p[i][lane + 32] : -INFINITY;
+  // softmax over keys, one warp per query row; the rows of a warp are independent dependency chains (shuffles, exp,
+  // Philox): unrolled so that they overlap instead of running back to back
+  const int Tk = a.Tk, Tq = a.Tq;
+  const float drop_p = a.drop.p, inv_keep = a.drop.inv_keep;
+  const uint32_t site = a.drop.site;
+#pragma unroll
+  for (int u = 0; u < SA_T / NW; ++u) {
+    const int i = w + NW * u;
+    if (i >= Tq) continue;                                              // warp-uniform
+    const float s0 = lane < Tk ? S.p[i][lane] : -INFINITY, s1 = lane + 32 < Tk ? S.p[i][lane + 32] : -INFINITY;
     const float m = warp_max(fmaxf(s0, s1));
     float p0 = 0.f, p1 = 0.f;
     if (m != -INFINITY) { p0 = __expf(s0 - m); p1 = __expf(s1 - m); }   // exp(-inf) = 0 for masked keys
     const float l = warp_sum(p0 + p1);
     const float inv = 1.f / l;                                          // fully masked row -> 0 * inf = NaN, like the reference
     p0 *= inv; p1 *= inv;
-    if (a.drop.p > 0.f) {
-      const unsigned long long base = ((unsigned long long)(b * a.H + h) * a.Tq + i) * a.Tk;
-      if (s0 != -INFINITY) p0 *= dropout_scale(seed, a.drop.site, base + lane, a.drop.p, a.drop.inv_keep);
-      if (s1 != -INFINITY) p1 *= dropout_scale(seed, a.drop.site, base + lane + 32, a.drop.p, a.drop.inv_keep);
+    if (drop_p > 0.f) {
+      const unsigned long long base = ((unsigned long long)(b * a.H + h) * Tq + i) * Tk;
+      if (s0 != -INFINITY) p0 *= dropout_scale(seed, site, base + lane, drop_p, inv_keep);
+      if (s1 != -INFINITY) p1 *= dropout_scale(seed, site, base + lane + 32, drop_p, inv_keep);
     }
     S.p[i][lane] = p0; S.p[i][lane + 32] = p1;
-    if (lane == 0) a.lse[((size_t)b * a.H + h) * a.Tq + i] = m + logf(l);
+    if (lane == 0) a.lse[((size_t)b * a.H + h) * Tq + i] = m + logf(l);
   }
   __syncthreads();
-  sa_nn<DK>(a.o + (size_t)b * a.Tq * a.ldo + h * DK, a.ldo, S.p, S.v, ty, tx, nrq, a.Tq, (a.Tk + 3) & ~3, 1.f);
+  SA_STAMP(3);
+  sa_nn<DK, RS>(a.o + (size_t)b * a.Tq * a.ldo + h * DK, a.ldo, S.p, S.v, ty, tx, nrq, a.Tq, (a.Tk + 3) & ~3, 1.f);
+  SA_STAMP(4);
 }
 
-template <int DK>
-__global__ void __launch_bounds__(256) attn_small_bwd_kernel(AttnBwdArgs a) {
+template <int DK, int NT>
+__global__ void __launch_bounds__(NT) attn_small_bwd_kernel(AttnBwdArgs a) {
+  constexpr int RS = NT / 16, R = SA_T / RS, NW = NT / 32;
   extern __shared__ __align__(16) unsigned char sa_raw[];
   SaSmem& S = *reinterpret_cast<SaSmem*>(sa_raw);
   const AttnArgs& f = a.f;
   const int h = blockIdx.x, b = blockIdx.y;
   const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int nrq = (f.Tq + 15) >> 4, nck = (f.Tk + 15) >> 4;
-  sa_load<DK>(S.q, f.q, b, f.Tq, f.ldq, h);
-  sa_load<DK>(S.k, f.k, b, f.Tk, f.ldk, h);
-  sa_load<DK>(S.v, f.v, b, f.Tk, f.ldv, h);
-  sa_load<DK>(S.g, a.d_o, b, f.Tq, f.ldo, h);
-  for (int i = w; i < SA_T; i += 8) {          // delta_i = dO_i . O_i (== sum_j P_ij dP_ij, also with dropout); lse
-    float s = 0.f;
-    if (i < f.Tq) {
-#pragma unroll
-      for (int v = 0; v < DK / 32; ++v) {
-        const size_t off = (size_t)(b * f.Tq + i) * f.ldo + h * DK + lane + 32 * v;
-        s += a.d_o[off] * f.o[off];
-      }
-      s = warp_sum(s);
-    }
-    if (lane == 0) {
-      S.delta[i] = s;
+  const int nrq = (f.Tq + RS - 1) / RS, nck = (f.Tk + 15) >> 4, nrk = (f.Tk + RS - 1) / RS;
+  pdl_wait();
+  pdl_trigger();
+  SA_STAMP(16);
+  {
+    SaTile<DK, NT> tq, tk, tv, tg, to;
+    sa_fetch<DK, NT>(tq, f.q, b, f.Tq, f.ldq, h);
+    sa_fetch<DK, NT>(tk, f.k, b, f.Tk, f.ldk, h);
+    sa_fetch<DK, NT>(tv, f.v, b, f.Tk, f.ldv, h);
+    sa_fetch<DK, NT>(tg, a.d_o, b, f.Tq, f.ldo, h);
+    sa_fetch<DK, NT>(to, f.o, b, f.Tq, f.ldo, h);      // O rows, only for delta (S.p is rewritten below)
+    sa_load_kmask(S.kmask, f.keypad, b, f.Tk);
+    if (threadIdx.x >= 64 && threadIdx.x < 64 + SA_T) {
+      const int i = threadIdx.x - 64;
       S.lse[i] = i < f.Tq ? f.lse[((size_t)b * f.H + h) * f.Tq + i] : 0.f;
     }
+    sa_store<DK, NT>(S.q, tq); sa_store<DK, NT>(S.k, tk); sa_store<DK, NT>(S.v, tv); sa_store<DK, NT>(S.g, tg); sa_store<DK, NT>(S.p, to);
   }
   __syncthreads();
+  SA_STAMP(17);
+  for (int i = w; i < SA_T; i += NW) {         // delta_i = dO_i . O_i (== sum_j P_ij dP_ij, also with dropout)
+    float s = 0.f;
+#pragma unroll
+    for (int v = 0; v < DK / 32; ++v) s += S.g[i][lane + 32 * v] * S.p[i][lane + 32 * v];
+    s = warp_sum(s);
+    if (lane == 0) S.delta[i] = s;
+  }
+  __syncthreads();
+  SA_STAMP(18);
   {
-    float sc[4][4], dp[4][4];
-    sa_nt<DK>(sc, S.q, S.k, ty, tx, nrq, nck);
-    sa_nt<DK>(dp, S.g, S.v, ty, tx, nrq, nck);
+    float sc[R][4], dp[R][4];
+    sa_nt<DK, RS>(sc, S.q, S.k, ty, tx, f.Tq, nck);
+    sa_nt<DK, RS>(dp, S.g, S.v, ty, tx, f.Tq, nck);
     const unsigned long long seed = f.drop.p > 0.f ? mtl_eff_seed(f.drop) : 0ull;
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
+    for (int r = 0; r < R; ++r)
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         if (r >= nrq || c >= nck) continue;
-        const int i = ty + 16 * r, j = tx + 16 * c;
-        const bool ok = i < f.Tq && j < f.Tk && !(f.keypad && f.keypad[(size_t)b * f.Tk + j]) && !(f.causal && j > i);
+        const int i = ty + RS * r, j = tx + 16 * c;
+        const bool ok = i < f.Tq && !S.kmask[j] && !(f.causal && j > i);
         const float p = ok ? __expf(sc[r][c] * f.inv_temp - S.lse[i]) : 0.f;
         float pd = p, d = dp[r][c];
         if (f.drop.p > 0.f && ok) {
@@ -507,10 +575,12 @@ __global__ void __launch_bounds__(256) attn_small_bwd_kernel(AttnBwdArgs a) {
       }
   }
   __syncthreads();
+  SA_STAMP(19);
   const int j4 = (f.Tk + 3) & ~3;
-  sa_nn<DK>(a.dq + (size_t)b * f.Tq * f.ldq + h * DK, f.ldq, S.ds, S.k, ty, tx, nrq, f.Tq, j4, f.inv_temp);
-  sa_tn<DK>(a.dk + (size_t)b * f.Tk * f.ldk + h * DK, f.ldk, S.ds, S.q, ty, tx, nck, f.Tk, f.Tq, f.inv_temp);
-  sa_tn<DK>(a.dv + (size_t)b * f.Tk * f.ldv + h * DK, f.ldv, S.p, S.g, ty, tx, nck, f.Tk, f.Tq, 1.f);
+  sa_nn<DK, RS>(a.dq + (size_t)b * f.Tq * f.ldq + h * DK, f.ldq, S.ds, S.k, ty, tx, nrq, f.Tq, j4, f.inv_temp);
+  sa_tn<DK, RS>(a.dk + (size_t)b * f.Tk * f.ldk + h * DK, f.ldk, S.ds, S.q, ty, tx, nrk, f.Tk, f.Tq, f.inv_temp);
+  sa_tn<DK, RS>(a.dv + (size_t)b * f.Tk * f.ldv + h * DK, f.ldv, S.p, S.g, ty, tx, nrk, f.Tk, f.Tq, 1.f);
+  SA_STAMP(20);
 }
 
 // MTL_ATTN_SMALL=0 keeps the tiled kernels for short sequences too (A/B measurements)
@@ -524,32 +594,40 @@ static bool attn_small_ok(const AttnArgs& a) {
   return attn_small_enabled() && a.Tq <= SA_T && a.Tk <= SA_T && a.ldq % 4 == 0 && a.ldk % 4 == 0 && a.ldv % 4 == 0 &&
          a.ldo % 4 == 0 && al(a.q) && al(a.k) && al(a.v) && al(a.o);
 }
-template <int DK>
+// MTL_ATTN_THREADS=256 runs the short-sequence kernels with 8 warps per CTA instead of 16 (A/B measurements)
+static int attn_small_threads() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MTL_ATTN_THREADS"); v = (e && atoi(e) == 256) ? 256 : 512; }
+  return v;
+}
+template <int DK, int NT>
 static int attn_small_fwd_launch(const AttnArgs& a, cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
-    MTL_CHECK_CUDA(cudaFuncSetAttribute(attn_small_fwd_kernel<DK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SaSmem)));
+    MTL_CHECK_CUDA(cudaFuncSetAttribute(attn_small_fwd_kernel<DK, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SaSmem)));
     configured = true;
   }
-  attn_small_fwd_kernel<DK><<<dim3(a.H, a.B), 256, sizeof(SaSmem), s>>>(a);
-  MTL_CHECK_LAUNCH();
+  MTL_CHECK_CUDA(mtl_launch_pdl(attn_small_fwd_kernel<DK, NT>, dim3(a.H, a.B), dim3(NT), sizeof(SaSmem), s, a));
+  ++g_mtl_launches;
   return MTL_OK;
 }
-template <int DK>
+template <int DK, int NT>
 static int attn_small_bwd_launch(const AttnBwdArgs& a, cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
-    MTL_CHECK_CUDA(cudaFuncSetAttribute(attn_small_bwd_kernel<DK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SaSmem)));
+    MTL_CHECK_CUDA(cudaFuncSetAttribute(attn_small_bwd_kernel<DK, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SaSmem)));
     configured = true;
   }
-  attn_small_bwd_kernel<DK><<<dim3(a.f.H, a.f.B), 256, sizeof(SaSmem), s>>>(a);
-  MTL_CHECK_LAUNCH();
+  MTL_CHECK_CUDA(mtl_launch_pdl(attn_small_bwd_kernel<DK, NT>, dim3(a.f.H, a.f.B), dim3(NT), sizeof(SaSmem), s, a));
+  ++g_mtl_launches;
   return MTL_OK;
 }
 int k_attn_small_fwd(const AttnArgs& a, cudaStream_t s) {
-  return a.dk == 64 ? attn_small_fwd_launch<64>(a, s) : attn_small_fwd_launch<32>(a, s);
+  if (attn_small_threads() == 256) return a.dk == 64 ? attn_small_fwd_launch<64, 256>(a, s) : attn_small_fwd_launch<32, 256>(a, s);
+  return a.dk == 64 ? attn_small_fwd_launch<64, 512>(a, s) : attn_small_fwd_launch<32, 512>(a, s);
 }
 int k_attn_small_bwd(const AttnBwdArgs& a, cudaStream_t s) {
-  return a.f.dk == 64 ? attn_small_bwd_launch<64>(a, s) : attn_small_bwd_launch<32>(a, s);
+  if (attn_small_threads() == 256) return a.f.dk == 64 ? attn_small_bwd_launch<64, 256>(a, s) : attn_small_bwd_launch<32, 256>(a, s);
+  return a.f.dk == 64 ? attn_small_bwd_launch<64, 512>(a, s) : attn_small_bwd_launch<32, 512>(a, s);
 }
 bool k_attn_small_eligible(const AttnArgs& a) { return attn_small_ok(a); }

@@ -43,9 +43,31 @@ extern unsigned long long g_mtl_launches;   // kernels enqueued by this library 
     if (_r != MTL_OK) return _r; \
   } while (0)
 
+// MTL_PDL=0 disables programmatic dependent launch (A/B measurements); defined in engine.cu
+bool mtl_pdl_enabled();
+
 static inline int mtl_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 #ifdef __CUDACC__
+// Programmatic dependent launch (kernels launched through mtl_launch_pdl; both are no-ops otherwise).
+// pdl_wait: everything the previous kernel in the stream wrote is visible after it -- nothing before it may touch
+// global memory.  pdl_trigger: the next kernel's CTAs may become resident and run their prologue (barrier init, TMEM
+// allocation, descriptor fetch, index math) while this one finishes.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// <<<grid, block, smem, s>>> with the programmatic-stream-serialization attribute (the kernel MUST call pdl_wait)
+template <typename... KArgs, typename... Args>
+static inline cudaError_t mtl_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                                         Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = mtl_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -26,6 +26,11 @@ void mtl_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 unsigned long long g_mtl_launches = 0;
+bool mtl_pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MTL_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v != 0;
+}
 extern "C" const char* mtl_last_error(void) { return g_err; }
 extern "C" unsigned long long mtl_launch_count(void) { return g_mtl_launches; }
 extern "C" int mtl_abi_version(void) { return MTL_ABI_VERSION; }
@@ -1151,6 +1156,8 @@ extern "C" int mtl_gemm_repeat(int reps, int mode, int transA, int transB, int M
 }
 int k_gemm_tc_debug_span(unsigned long long* host512);
 extern "C" int mtl_debug_gemm_span(unsigned long long* host512) { return k_gemm_tc_debug_span(host512); }
+int k_attn_debug_stamps(long long* host32);
+extern "C" int mtl_debug_attn_stamps(long long* host32) { return k_attn_debug_stamps(host32); }
 int k_gemm_tc_debug_stamps(long long* host32);
 extern "C" int mtl_debug_gemm_stamps(long long* host32) { return k_gemm_tc_debug_stamps(host32); }
 extern "C" int mtl_ln_fwd(const float* y, const float* res, const float* gamma, const float* beta,

@@ -354,6 +354,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                          // prologue above overlapped the previous kernel's tail; global memory from here on
   if (threadIdx.x == 0) DBG_STAMP(1);
   if (P.tma_epi && warp >= 2) {
     // bias slice of this tile -> shared memory now, so the epilogue never waits on a global load
@@ -449,6 +450,9 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
         DBG_KB(it, 3);
       }
       tc_commit(tmem_full);            // accumulator complete
+      // main loop issued: the next kernel may start its prologue.  Not earlier -- a waiting grid holds shared memory
+      // and TMEM, so at most one per stream, and only once this grid owns its own TMEM.
+      pdl_trigger();
       DBG_STAMP(4);
     }
   } else {
@@ -810,6 +814,7 @@ __global__ void __launch_bounds__(192) conv3x3_kw_kernel(const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
   if (threadIdx.x == 0) DBG_STAMP(1);
   if (warp >= 2) {
     const int t = threadIdx.x - 64, cn = n0 + t;
@@ -888,6 +893,7 @@ __global__ void __launch_bounds__(192) conv3x3_kw_kernel(const __grid_constant__
         tc_commit(&a_empty[sa]);
       }
       tc_commit(tmem_full);
+      pdl_trigger();
       DBG_STAMP(4);
     }
   } else if (SPLIT3) {
@@ -1037,20 +1043,24 @@ int launch(const Maps& tm, const TcParams& P_in, dim3 grid, cudaStream_t s) {
     else { P.aux_off = STAGE_MEM + 1024; smem = SMEM + TILE; }
   }
   static_assert(SMEM - 1280 >= BM * (BN + 4) * 4, "staging tile must fit in the operand stages");
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = dim3(192, 1, 1); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[2];
+  int na = 0;
   if (P.cluster_k > 1) {
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = grid; cfg.blockDim = dim3(192, 1, 1); cfg.dynamicSmemBytes = smem; cfg.stream = s;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = (unsigned)P.cluster_k;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    MTL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tm.a, tm.b, tm.c, tm.x, P));
-    ++g_mtl_launches;
-    return MTL_OK;
+    at[na].id = cudaLaunchAttributeClusterDimension;
+    at[na].val.clusterDim.x = 1; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = (unsigned)P.cluster_k;
+    ++na;
   }
-  kern<<<grid, 192, smem, s>>>(tm.a, tm.b, tm.c, tm.x, P);
-  MTL_CHECK_LAUNCH();
+  if (mtl_pdl_enabled()) {
+    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = at; cfg.numAttrs = na;
+  MTL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tm.a, tm.b, tm.c, tm.x, P));
+  ++g_mtl_launches;
   return MTL_OK;
 }
 
@@ -1094,8 +1104,8 @@ int launch_kw(const KwMaps& tm, const TcParams& P, dim3 grid, cudaStream_t s) {
     configured = true;
   }
   const int smem = P.g.epi == EPI_RELU_BWD ? Cfg::SMEM_MASK : Cfg::SMEM;
-  kern<<<grid, 192, smem, s>>>(tm.a, tm.bh, tm.bl, tm.c, tm.x, P);
-  MTL_CHECK_LAUNCH();
+  MTL_CHECK_CUDA(mtl_launch_pdl(kern, grid, dim3(192, 1, 1), (size_t)smem, s, tm.a, tm.bh, tm.bl, tm.c, tm.x, P));
+  ++g_mtl_launches;
   return MTL_OK;
 }
 

@@ -14,6 +14,8 @@ __global__ void __launch_bounds__(128) ln_fwd_kernel(
     const float* __restrict__ beta, const float* __restrict__ rowmask, const float* __restrict__ pe,
     int pe_period, MtlDrop drop, float* __restrict__ out, float* __restrict__ xhat,
     float* __restrict__ rstd_out, int M, int d) {
+  pdl_wait();
+  pdl_trigger();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (row >= M) return;
@@ -80,9 +82,9 @@ int k_ln_fwd(const float* y, const float* res, const float* gamma, const float* 
              int d, cudaStream_t s) {
   MTL_REQUIRE(d <= 32 * LN_MAXV && d % 4 == 0, "layer norm width must be a multiple of 4, <= 1024");
   if (M == 0) return MTL_OK;
-  ln_fwd_kernel<<<mtl_cdiv(M, 4), 128, 0, s>>>(y, res, gamma, beta, rowmask, pe, pe_period > 0 ? pe_period : 1,
-                                              drop, out, xhat, rstd, M, d);
-  MTL_CHECK_LAUNCH();
+  MTL_CHECK_CUDA(mtl_launch_pdl(ln_fwd_kernel, dim3(mtl_cdiv(M, 4)), dim3(128), 0, s, y, res, gamma, beta, rowmask, pe,
+                                pe_period > 0 ? pe_period : 1, drop, out, xhat, rstd, M, d));
+  ++g_mtl_launches;
   return MTL_OK;
 }
 
@@ -90,6 +92,8 @@ __global__ void __launch_bounds__(128) ln_bwd_kernel(
     const float* __restrict__ dout, const float* __restrict__ xhat, const float* __restrict__ rstd,
     const float* __restrict__ gamma, const float* __restrict__ rowmask, MtlDrop drop,
     float* __restrict__ dy, float* __restrict__ dres, int dres_acc, int M, int d) {
+  pdl_wait();
+  pdl_trigger();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (row >= M) return;
@@ -179,9 +183,9 @@ int k_ln_bwd(const float* dout, const float* xhat, const float* rstd, const floa
              int d, cudaStream_t s) {
   MTL_REQUIRE(d <= 32 * LN_MAXV && d % 4 == 0, "layer norm width must be a multiple of 4, <= 1024");
   if (M == 0) return MTL_OK;
-  ln_bwd_kernel<<<mtl_cdiv(M, 4), 128, 0, s>>>(dout, xhat, rstd, gamma, rowmask, drop, dy, dres,
-                                              dres_accumulate, M, d);
-  MTL_CHECK_LAUNCH();
+  MTL_CHECK_CUDA(mtl_launch_pdl(ln_bwd_kernel, dim3(mtl_cdiv(M, 4)), dim3(128), 0, s, dout, xhat, rstd, gamma, rowmask, drop,
+                                dy, dres, dres_accumulate, M, d));
+  ++g_mtl_launches;
   // a (32 columns x 8 row-lanes) block walks its rows serially: slabs of 32 rows keep that walk 4 loads deep
   // (M = 264: 16 x 9 blocks instead of 16 blocks doing 33 dependent-latency steps each)
   const int slabs = M > 32 ? (mtl_cdiv(M, 32) < 512 ? mtl_cdiv(M, 32) : 512) : 1;

@@ -79,6 +79,7 @@ SIGNATURES = {
     "mtl_gemm": (_I, [_I, _I, _I, _I, _I, _I, _F, _P, _I, _P, _I, _F, _P, _I, _P, _I, _P, _I, _P]),
     "mtl_gemm_repeat": (_I, [_I, _I, _I, _I, _I, _I, _I, _P, _I, _P, _I, _F, _P, _I, _I, _P]),
     "mtl_debug_gemm_stamps": (_I, [_P]),
+    "mtl_debug_attn_stamps": (_I, [_P]),
     "mtl_debug_gemm_span": (_I, [_P]),
     "mtl_ln_fwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _F, _ULL, _U, _P, _P, _P, _I, _I, _P]),
     "mtl_ln_bwd": (_I, [_P, _P, _P, _P, _P, _F, _ULL, _U, _P, _P, _I, _P, _P, _I, _I, _P]),
