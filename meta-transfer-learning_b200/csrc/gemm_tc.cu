@@ -1204,7 +1204,9 @@ int k_gemm_tc(const GemmArgs& g, int precision_mode, cudaStream_t s) {
     // one-TMA-latency per 3 stages.  Spread K over a cluster of up to 8 CTAs (deterministic DSMEM reduction).
     const long long tiles = (long long)mtl_cdiv(g.M, BM) * mtl_cdiv(g.N, bn);
     int cs = 1;
-    while (cs < 8 && tiles * (cs * 2) <= 160 && P.kb_total >= cs * 2) cs *= 2;
+    // K <= 128 (e.g. the rank-100 side of the low-rank projections: 4 k-blocks) is not worth a cluster: measured as a
+    // graph node, 264 x 512 x 100 runs 9.2 us alone vs 10.9 us split 4 ways (the reduction costs more than it saves)
+    while (P.kb_total > 4 && cs < 8 && tiles * (cs * 2) <= 160 && P.kb_total >= cs * 2) cs *= 2;
     while (cs > 1 && (long long)(cs - 1) * mtl_cdiv(P.kb_total, cs) >= P.kb_total) cs /= 2;   // every CTA gets >= 1 k-block
     if (cs > 1) {
       P.cluster_k = cs;
