@@ -35,9 +35,12 @@ T_FRAMES, L_TOKENS = 101, 32
 TASKS_PER_GPU = 3
 LR, META_LR, DROPOUT = 1e-4, 1e-4, 0.1
 METRIC = "meta-step utterances/sec (enc2/dec4/d512, k=8)"
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE conv.2-forward launch from the committed `ncu --set full`
-# capture (profiles/), per gemm mode; None until a capture of that mode exists
-ROOFLINE_TRAFFIC_BYTES = {1: 33483776 + 749568, 2: 33489408 + 824576}   # profiles/r01_c_ncu_full_conv2_fwd_*.txt
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE conv.2-forward launch (conv3x3_kw_kernel<64>) from the committed
+# `ncu --set full` captures, per gemm mode; None until a capture of that mode exists
+ROOFLINE_TRAFFIC_BYTES = {1: 33474816 + 765184, 2: 33627648 + 661760}   # profiles/r01_f_ncu_full_conv2_kw_{tf32,3xtf32}.txt
+# sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active of the same captures: how busy the tcgen05 pipe is with
+# the instruction mix the mode issues (3xTF32 issues 3 MMA-products per useful product)
+ROOFLINE_TENSOR_PIPE_PCT = {1: 30.7, 2: 50.4}
 UNIT = "utterance-passes/s"
 
 
@@ -351,6 +354,7 @@ def roofline_conv_gemm(s, lib, dev, mode):
     ach = flops / (ms * 1e-3) / 1e12
     return {"bound": "tensor", "achieved": ach, "peak": pk["bf16"], "unit": "TFLOP/s", "frac": ach / pk["bf16"],
             "traffic": ROOFLINE_TRAFFIC_BYTES.get(mode),
+            "tensor_pipe_active_pct_ncu": ROOFLINE_TENSOR_PIPE_PCT.get(mode),
             "algorithmic_bytes": 4 * (M * Cin + M * Cout + N * Kd), "flops_per_launch": flops,
             "kernel": "conv.2 forward implicit GEMM %dx%dx%d (%s), incl. its weight re-layout launch" % (
                 M, N, Kd, {0: "im2col + gemm_simt_kernel fp32 CUDA cores", 1: "conv3x3_kw_kernel<64> tcgen05 tf32",
