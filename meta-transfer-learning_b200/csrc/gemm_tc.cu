@@ -156,6 +156,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 __device__ __forceinline__ float tf32_rna(float x) {
   return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
+// Truncating split: hi = the top 19 bits of the fp32 word -- exactly what the tensor core reads from a raw fp32 tile under
+// kind::tf32 (it ignores the low 13 mantissa bits), so the hi operand needs NO rewrite; lo = rna_tf32(a - hi) carries the
+// next 11 bits.  a - hi is exact, so the only rounding is lo's (<= 2^-21 |a|, unbiased); the dropped lo*lo term is
+// <= 2^-20 |a||b|.  The splitter then moves 1 load + 1 store per element instead of 1 + 2 (shared-memory traffic is
+// what bounds it).
+__device__ __forceinline__ float tf32_lo_trunc(float x) {
+  return tf32_rna(x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u));
+}
 // Pins a loop-invariant value in a register (opaque to the optimiser, so it cannot be rematerialised from the
 // constant bank at every use).
 __device__ __forceinline__ int keep_reg(int v) { asm volatile("" : "+r"(v)); return v; }
@@ -220,6 +228,7 @@ struct TcParams {
   int tma_epi;       // epilogue through TMA: 1 = store, 2 = reduce-add (beta == 1 or split-K slabs)
   int epi_test;      // measurement only (MTL_EPI_TEST): 1 = conv epilogue computes but does not store
   int cluster_k;     // > 1: grid.z CTAs form one cluster that splits K and reduces over distributed shared memory
+  int split_trunc;   // 3xTF32 splitter: 1 = truncating split (hi stays the raw tile), 0 = round-to-nearest hi written in place
 };
 
 // ---- TMA epilogue (shared by the GEMM / tap-box convolution kernel and the kw-box convolution kernel).
@@ -479,21 +488,29 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
 #pragma unroll
         for (int j = 0; j < PER_A; ++j) {
           float4 h, l;
-          h.x = tf32_rna(a[j].x); l.x = tf32_rna(a[j].x - h.x);
-          h.y = tf32_rna(a[j].y); l.y = tf32_rna(a[j].y - h.y);
-          h.z = tf32_rna(a[j].z); l.z = tf32_rna(a[j].z - h.z);
-          h.w = tf32_rna(a[j].w); l.w = tf32_rna(a[j].w - h.w);
-          a_hi[j * 128] = h;
+          if (P.split_trunc) {
+            l.x = tf32_lo_trunc(a[j].x); l.y = tf32_lo_trunc(a[j].y); l.z = tf32_lo_trunc(a[j].z); l.w = tf32_lo_trunc(a[j].w);
+          } else {
+            h.x = tf32_rna(a[j].x); l.x = tf32_rna(a[j].x - h.x);
+            h.y = tf32_rna(a[j].y); l.y = tf32_rna(a[j].y - h.y);
+            h.z = tf32_rna(a[j].z); l.z = tf32_rna(a[j].z - h.z);
+            h.w = tf32_rna(a[j].w); l.w = tf32_rna(a[j].w - h.w);
+            a_hi[j * 128] = h;
+          }
           a_hi[j * 128 + A_STAGE_BYTES / 16] = l;
         }
 #pragma unroll
         for (int j = 0; j < PER_B; ++j) {
           float4 h, l;
-          h.x = tf32_rna(b[j].x); l.x = tf32_rna(b[j].x - h.x);
-          h.y = tf32_rna(b[j].y); l.y = tf32_rna(b[j].y - h.y);
-          h.z = tf32_rna(b[j].z); l.z = tf32_rna(b[j].z - h.z);
-          h.w = tf32_rna(b[j].w); l.w = tf32_rna(b[j].w - h.w);
-          b_hi[j * 128] = h;
+          if (P.split_trunc) {
+            l.x = tf32_lo_trunc(b[j].x); l.y = tf32_lo_trunc(b[j].y); l.z = tf32_lo_trunc(b[j].z); l.w = tf32_lo_trunc(b[j].w);
+          } else {
+            h.x = tf32_rna(b[j].x); l.x = tf32_rna(b[j].x - h.x);
+            h.y = tf32_rna(b[j].y); l.y = tf32_rna(b[j].y - h.y);
+            h.z = tf32_rna(b[j].z); l.z = tf32_rna(b[j].z - h.z);
+            h.w = tf32_rna(b[j].w); l.w = tf32_rna(b[j].w - h.w);
+            b_hi[j * 128] = h;
+          }
           b_hi[j * 128 + B_STAGE_BYTES / 16] = l;
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to the MMA (async proxy)
@@ -911,11 +928,15 @@ __global__ void __launch_bounds__(192) conv3x3_kw_kernel(const __grid_constant__
 #pragma unroll
       for (int j = 0; j < PER; ++j) {
         float4 h, l;
-        h.x = tf32_rna(a[j].x); l.x = tf32_rna(a[j].x - h.x);
-        h.y = tf32_rna(a[j].y); l.y = tf32_rna(a[j].y - h.y);
-        h.z = tf32_rna(a[j].z); l.z = tf32_rna(a[j].z - h.z);
-        h.w = tf32_rna(a[j].w); l.w = tf32_rna(a[j].w - h.w);
-        hi[j * 128] = h;
+        if (P.split_trunc) {
+          l.x = tf32_lo_trunc(a[j].x); l.y = tf32_lo_trunc(a[j].y); l.z = tf32_lo_trunc(a[j].z); l.w = tf32_lo_trunc(a[j].w);
+        } else {
+          h.x = tf32_rna(a[j].x); l.x = tf32_rna(a[j].x - h.x);
+          h.y = tf32_rna(a[j].y); l.y = tf32_rna(a[j].y - h.y);
+          h.z = tf32_rna(a[j].z); l.z = tf32_rna(a[j].z - h.z);
+          h.w = tf32_rna(a[j].w); l.w = tf32_rna(a[j].w - h.w);
+          hi[j * 128] = h;
+        }
         hi[j * 128 + KW_A_BYTES / 16] = l;
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -1133,6 +1154,12 @@ int plan_epilogue(TcParams& P, Maps& tm, MakeMap mk) {
 }
 
 inline bool al16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
+// MTL_SPLIT_TRUNC=0 restores the round-to-nearest in-place split (A/B measurements)
+int split_trunc_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MTL_SPLIT_TRUNC"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v;
+}
 // MTL_CLUSTER_SPLITK=0 disables the cluster split (A/B measurements)
 bool cluster_split_enabled() {
   static int v = -1;
@@ -1193,6 +1220,7 @@ int k_gemm_tc(const GemmArgs& g, int precision_mode, cudaStream_t s) {
   if (!b_mn) MTL_TRY(make_map(g.B, g.K, g.N, g.ldb, bn, false, tf, &tb)); else MTL_TRY(make_map(g.B, g.N, g.K, g.ldb, 32, true, tf, &tb));
   TcParams P;
   memset(&P, 0, sizeof(P));
+  P.split_trunc = split_trunc_enabled();
   P.g = g;
   P.conv_mode = CONV_NONE;
   P.kb_total = mtl_cdiv(g.K, BK);
@@ -1249,6 +1277,7 @@ int k_conv3x3_tc(const float* x, const float* wg, const float* bias, float* y, i
   const int bn = Cout <= 64 ? 64 : 128;
   TcParams P;
   memset(&P, 0, sizeof(P));
+  P.split_trunc = split_trunc_enabled();
   P.conv_mode = CONV_FWD;
   P.cluster_k = 1;
   P.cF = F; P.cT = T; P.cCin = Cin;
@@ -1299,6 +1328,7 @@ int k_conv3x3_wgrad_tc(const float* x, const float* dy, float* dwgT, int B, int 
   const int bn = Cout <= 64 ? 64 : 128;
   TcParams P;
   memset(&P, 0, sizeof(P));
+  P.split_trunc = split_trunc_enabled();
   P.conv_mode = CONV_WGRAD;
   P.cluster_k = 1;
   P.cF = F; P.cT = T; P.cCin = Cin;

@@ -153,6 +153,8 @@ __global__ void __launch_bounds__(128) ln_bwd_kernel(
 __global__ void __launch_bounds__(256) ln_param_grad_kernel(
     const float* __restrict__ dout, const float* __restrict__ xhat, const float* __restrict__ rowmask,
     float* __restrict__ dgamma, float* __restrict__ dbeta, int M, int d, int rows_per_slab) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float sg[8][33], sb[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + tx;
@@ -189,9 +191,9 @@ int k_ln_bwd(const float* dout, const float* xhat, const float* rstd, const floa
   // a (32 columns x 8 row-lanes) block walks its rows serially: slabs of 32 rows keep that walk 4 loads deep
   // (M = 264: 16 x 9 blocks instead of 16 blocks doing 33 dependent-latency steps each)
   const int slabs = M > 32 ? (mtl_cdiv(M, 32) < 512 ? mtl_cdiv(M, 32) : 512) : 1;
-  ln_param_grad_kernel<<<dim3(mtl_cdiv(d, 32), slabs), 256, 0, s>>>(dout, xhat, rowmask, dgamma, dbeta, M, d,
-                                                                   mtl_cdiv(M, slabs));
-  MTL_CHECK_LAUNCH();
+  MTL_CHECK_CUDA(mtl_launch_pdl(ln_param_grad_kernel, dim3(mtl_cdiv(d, 32), slabs), dim3(256), 0, s, dout, xhat, rowmask, dgamma,
+                                dbeta, M, d, mtl_cdiv(M, slabs)));
+  ++g_mtl_launches;
   return MTL_OK;
 }
 
