@@ -131,7 +131,9 @@ def _attn_ref(q, k, v, keypad, B, H, Tq, Tk, dk, causal):
 
 
 @pytest.mark.parametrize("B,H,Tq,Tk,dk,causal", [(8, 8, 25, 25, 64, 0), (8, 8, 33, 33, 64, 1), (8, 8, 33, 25, 64, 0),
-                                                 (2, 2, 70, 70, 32, 1), (2, 3, 45, 100, 64, 0), (1, 2, 130, 130, 64, 1)])
+                                                 (2, 2, 70, 70, 32, 1), (2, 3, 45, 100, 64, 0), (1, 2, 130, 130, 64, 1),
+                                                 (2, 2, 64, 64, 32, 1), (3, 2, 1, 7, 64, 0), (2, 4, 48, 17, 64, 0),
+                                                 (2, 2, 17, 64, 32, 0)])
 def test_attention_fwd_bwd(B, H, Tq, Tk, dk, causal):
     q, k, v = _r(B * Tq, H * dk, seed=1), _r(B * Tk, H * dk, seed=2), _r(B * Tk, H * dk, seed=3)
     keypad = torch.zeros(B, Tk, dtype=torch.uint8)

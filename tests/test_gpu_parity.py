@@ -333,6 +333,31 @@ def test_cfg2_meta_step_golden_from_live_reference():
     assert n_bad <= 0.002 * n_tot, (n_bad, n_tot)
 
 
+@pytest.mark.timeout(900)
+def test_cfg4_dims_fwd_bwd_vs_oracle():
+    """BASELINE configs[3] dimensions (enc4/dec6, d_model 768, 12 heads; fp32-grade arithmetic instead of its bf16) on a
+    batch the CPU oracle finishes in seconds: B = 2, 403 frames (T' = 100 > 64: the tiled attention kernels, ragged
+    lengths), 20 target tokens.  Outputs / loss / decode indices at the cfg-2 bounds.  Gradients at 3e-3: with only
+    200 encoder rows ONE relu decision of a position-wise FFN taken the other way (pre-activation within rounding of
+    zero) moves that layer's linear_1.weight / bias by ~1e-3 of the tensor max -- measured with all three engines,
+    including the exact fp32 CUDA-core one (7.4e-4 on encoder.layers.2, a different unit than 3xTF32's 1.1e-3 on
+    encoder.layers.1), so it is a property of the tiny batch, not of the arithmetic."""
+    cfg = ref_asr.ModelConfig(n_enc=4, n_dec=6, d_model=768, n_heads=12, d_k=64, d_v=64, d_inner=768)
+    p = ref_asr.init_params(cfg, 41)
+    batch = ref_meta.synth_batch(cfg, 2, 403, 20, 4100, lengths=[403, 288], tgt_lengths=[20, 13])
+    loss_o, g_o, gold_o, hyp_o, pred_o = ref_meta.loss_and_grads(p, cfg, batch)
+    out, pred, grads = _fwd_bwd(_session(cfg), p, batch)
+    assert torch.equal(out["gold"].cpu().long(), gold_o)
+    keep = gold_o != 0
+    assert torch.equal(out["hyp"].cpu().long()[keep], hyp_o[keep])
+    assert rel_err(pred, pred_o) < TOL_OUT
+    assert abs(float(out["ce"][0]) - loss_o) < TOL_OUT * abs(loss_o)
+    bad = {k: rel_err(grads[k], g_o[k]) for k in g_o if float(g_o[k].abs().max()) > 1e-7}
+    top = sorted(bad.items(), key=lambda kv: -kv[1])[:5]
+    print("cfg4 worst gradient errors:", top)
+    assert all(v < max(_tol(k), 3e-3) for k, v in bad.items()), top
+
+
 @pytest.mark.parametrize("lanes", [1, 2, 3])
 def test_meta_tasks_lanes_match_sequential_meta_task(lanes):
     """mtl_meta_tasks (tasks on concurrent lanes, per-lane weight copies) == the sequential
