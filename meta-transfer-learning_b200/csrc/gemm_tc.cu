@@ -1344,7 +1344,9 @@ int k_conv3x3_wgrad_tc(const float* x, const float* dy, float* dwgT, int B, int 
   g.transA = 1; g.transB = 0; g.alpha = 1.f; g.beta = 1.f; g.bias = nullptr; g.epi = EPI_NONE; g.aux = nullptr;
   P.kb_total = B * P.tiles_f * P.tiles_t;
   const int mt = mtl_cdiv(g.M, BM), nt = mtl_cdiv(Cout, bn);
-  int want = mtl_cdiv(2 * 148, (long long)mt * nt);        // about two waves of CTAs
+  // two FULL waves of CTAs at one CTA per SM (192 KB of operand stages): rounding the slab count UP used to leave a third,
+  // nearly empty wave behind (conv.2: 5 x 60 = 300 CTAs, conv.4: 9 x 33 = 297 on 148 SMs)
+  int want = (2 * 148) / (mt * nt);
   if (want > P.kb_total / 8) want = P.kb_total / 8 > 0 ? P.kb_total / 8 : 1;
   const int split = plan_split(P, want > 1 ? want : 2);
   P.g.split_k = 2;
