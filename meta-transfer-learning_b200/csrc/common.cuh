@@ -22,6 +22,7 @@ void mtl_set_error(const char* fmt, ...);
     }                                                                                         \
   } while (0)
 
+extern int g_mtl_concurrency;                 // task lanes being enqueued together (1 outside mtl_meta_tasks)
 extern unsigned long long g_mtl_launches;   // kernels enqueued by this library (bench.py reports it)
 #define MTL_CHECK_LAUNCH()               \
   do {                                   \

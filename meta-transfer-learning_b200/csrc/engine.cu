@@ -26,6 +26,7 @@ void mtl_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 unsigned long long g_mtl_launches = 0;
+int g_mtl_concurrency = 1;   // task lanes whose kernels are being enqueued together (set by mtl_meta_tasks; GEMM CTA budgets read it)
 bool mtl_pdl_enabled() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("MTL_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
@@ -296,12 +297,19 @@ static int lin_fwd(Run& R, const float* x, int ldx, const float* W, const float*
 }
 // K-slabs for an accumulating (beta == 1) contraction: about two CTAs per SM, at least one 32-deep k-block per slab.
 // Slabs merge through the TMA reduce-add epilogue (or vector atomics), so no cluster barrier is involved.
-static int slab_split(long long tiles, int k_extent) {
+static int slab_split(long long tiles, int k_extent, int ctas = 296) {
   const int kb = mtl_cdiv(k_extent, 32);
-  long long split = (296 + tiles - 1) / tiles;
+  long long split = (ctas + tiles - 1) / tiles;
   if (split > kb) split = kb;
   if (split > 256) split = 256;
   return split > 1 ? (int)split : 1;
+}
+// CTA budget of a weight-gradient contraction.  Nothing waits for a wgrad until the end of the pass, but every CTA of a
+// tcgen05 GEMM owns a whole SM while it lives: off the critical path the slab count is sized for SM-time, not latency.
+static int wgrad_ctas() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MTL_WGRAD_CTAS"); v = e ? atoi(e) : 24; }   // 296 -> 24: 9.47 -> 8.96 ms/step (3 lanes)
+  return v;
 }
 // dx[M,K] = epi(dy[M,N] . W[N,K]) + beta*dx
 static int lin_dgrad(Run& R, const float* dy, int ldy, const float* W, float* dx, int ldx, int M, int N, int Kd,
@@ -321,7 +329,7 @@ static int lin_wgrad(Run& R, const float* dy, int ldy, const float* x, int ldx, 
   memset(&g, 0, sizeof(g));
   g.A = dy; g.lda = ldy; g.transA = 1; g.B = x; g.ldb = ldx; g.transB = 0; g.C = dW; g.ldc = Kd;
   g.M = N; g.N = Kd; g.K = M; g.alpha = 1.f; g.beta = 1.f; g.epi = EPI_NONE;
-  g.split_k = slab_split((long long)mtl_cdiv(N, 128) * mtl_cdiv(Kd, Kd <= 64 ? 64 : 128), M);
+  g.split_k = slab_split((long long)mtl_cdiv(N, 128) * mtl_cdiv(Kd, Kd <= 64 ? 64 : 128), M, wgrad_ctas());
   K(k_gemm(g, R.S->mode, R.st));
   return MTL_OK;
 }
@@ -1003,6 +1011,7 @@ extern "C" int mtl_meta_tasks(mtl_session* s, const mtl_meta_step_args* a, void*
     MTL_REQUIRE(a->lanes[l].theta && a->lanes[l].grad && a->lanes[l].workspace, "lane buffers");
   cudaStream_t st = (cudaStream_t)stream;
   MTL_TRY(ensure_lanes(s, a->n_lanes, a->n_tasks));
+  struct Hint { Hint(int n) { g_mtl_concurrency = n; } ~Hint() { g_mtl_concurrency = 1; } } hint(a->n_lanes < a->n_tasks ? a->n_lanes : a->n_tasks);
   if (!a->use_graph || !a->seed_slot) return meta_tasks_body(s, a, st);
 
   std::vector<unsigned long long> key;

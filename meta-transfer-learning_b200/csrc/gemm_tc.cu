@@ -1234,12 +1234,15 @@ int k_gemm_tc(const GemmArgs& g, int precision_mode, cudaStream_t s) {
     int cs = 1;
     // K <= 128 (e.g. the rank-100 side of the low-rank projections: 4 k-blocks) is not worth a cluster: measured as a
     // graph node, 264 x 512 x 100 runs 9.2 us alone vs 10.9 us split 4 ways (the reduction costs more than it saves)
-    static int cs_max = -1, cta_max = -1;
-    // a cluster CTA owns a whole SM (192 KB of stages) for its ~8 us life: with three task lanes in flight SM-time is the
-    // scarce resource, so clusters stay at <= 4 CTAs and <= 64 CTAs per GEMM (measured 9.80 -> 9.48 ms/step; 8 / 160
-    // is ~0.3 us faster for a GEMM running alone).  MTL_CLUSTER_MAX / MTL_CLUSTER_CTAS override.
-    if (cs_max < 0) { const char* e = getenv("MTL_CLUSTER_MAX"); cs_max = e ? atoi(e) : 4; }
-    if (cta_max < 0) { const char* e = getenv("MTL_CLUSTER_CTAS"); cta_max = e ? atoi(e) : 64; }
+    // a cluster CTA owns a whole SM (192 KB of stages) for its ~8 us life: with several task lanes in flight SM-time is
+    // the scarce resource, so clusters stay at <= 4 CTAs and <= 64 CTAs per GEMM there (measured 9.80 -> 9.48 ms/step
+    // with three lanes); a pass running alone takes 8 / 160 (14.7 vs 15.9 ms/step with one lane).
+    // MTL_CLUSTER_MAX / MTL_CLUSTER_CTAS override both.
+    static int env_cs = -1, env_cta = -1;
+    if (env_cs < 0) { const char* e = getenv("MTL_CLUSTER_MAX"); env_cs = e ? atoi(e) : 0; }
+    if (env_cta < 0) { const char* e = getenv("MTL_CLUSTER_CTAS"); env_cta = e ? atoi(e) : 0; }
+    const int cs_max = env_cs > 0 ? env_cs : (g_mtl_concurrency >= 2 ? 4 : 8);
+    const int cta_max = env_cta > 0 ? env_cta : (g_mtl_concurrency >= 2 ? 64 : 160);
     while (P.kb_total > 4 && cs < cs_max && tiles * (cs * 2) <= cta_max && P.kb_total >= cs * 2) cs *= 2;
     while (cs > 1 && (long long)(cs - 1) * mtl_cdiv(P.kb_total, cs) >= P.kb_total) cs /= 2;   // every CTA gets >= 1 k-block
     if (cs > 1) {
