@@ -1353,9 +1353,12 @@ int k_conv3x3_wgrad_tc(const float* x, const float* dy, float* dwgT, int B, int 
   g.transA = 1; g.transB = 0; g.alpha = 1.f; g.beta = 1.f; g.bias = nullptr; g.epi = EPI_NONE; g.aux = nullptr;
   P.kb_total = B * P.tiles_f * P.tiles_t;
   const int mt = mtl_cdiv(g.M, BM), nt = mtl_cdiv(Cout, bn);
-  // two FULL waves of CTAs at one CTA per SM (192 KB of operand stages): rounding the slab count UP used to leave a third,
-  // nearly empty wave behind (conv.2: 5 x 60 = 300 CTAs, conv.4: 9 x 33 = 297 on 148 SMs)
-  int want = (2 * 148) / (mt * nt);
+  // ONE full wave of CTAs at one CTA per SM (192 KB of operand stages).  History: rounding the slab count UP to ~2 waves
+  // left a third, nearly empty wave behind (conv.2: 5 x 60 = 300 CTAs on 148 SMs); two exact waves: 9.91 -> 9.80 ms/step;
+  // one wave (longer K per CTA, half the reduce-add epilogues): 8.67 -> 8.49 ms/step.  MTL_CONV_WGRAD_WAVES overrides.
+  static int waves = -1;
+  if (waves < 0) { const char* e = getenv("MTL_CONV_WGRAD_WAVES"); waves = e && atoi(e) > 0 ? atoi(e) : 1; }
+  int want = (waves * 148) / (mt * nt);
   if (want > P.kb_total / 8) want = P.kb_total / 8 > 0 ? P.kb_total / 8 : 1;
   const int split = plan_split(P, want > 1 ? want : 2);
   P.g.split_k = 2;
