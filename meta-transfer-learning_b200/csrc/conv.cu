@@ -14,13 +14,14 @@ __global__ void __launch_bounds__(256) conv1_fwd_kernel(const float* __restrict_
   for (int i = threadIdx.x; i < 9 * Cout; i += blockDim.x) { int co = i / 9, tap = i % 9; sw[tap * Cout + co] = w[i]; }
   for (int i = threadIdx.x; i < Cout; i += blockDim.x) sw[9 * Cout + i] = bias[i];
   __syncthreads();
-  const int cg = Cout >> 2;
-  const size_t total = (size_t)B * F * T * cg;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+  const unsigned cg = (unsigned)Cout >> 2;
+  const unsigned total = (unsigned)B * F * T * cg;      // < 2^31 (checked by the launcher): 32-bit divisions only
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int c4 = (int)(i % cg) * 4;
-    const size_t p = i / cg;
-    const int t = (int)(p % T), f = (int)((p / T) % F);
-    const size_t img = (p / ((size_t)F * T)) * (size_t)F * T;
+    const unsigned p = i / cg;
+    const unsigned row = p / (unsigned)T;
+    const int t = (int)(p - row * (unsigned)T), f = (int)(row % (unsigned)F);
+    const size_t img = (size_t)(row / (unsigned)F) * (size_t)F * T;
     float4 acc = *reinterpret_cast<const float4*>(sw + 9 * Cout + c4);
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh) {
@@ -36,7 +37,7 @@ __global__ void __launch_bounds__(256) conv1_fwd_kernel(const float* __restrict_
       }
     }
     acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f);
-    *reinterpret_cast<float4*>(out + p * Cout + c4) = acc;
+    *reinterpret_cast<float4*>(out + (size_t)p * Cout + c4) = acc;
   }
 }
 int k_conv1_fwd(const float* x, const float* w, const float* b, float* out, int B, int F, int T, int Cout,
@@ -44,6 +45,7 @@ int k_conv1_fwd(const float* x, const float* w, const float* b, float* out, int 
   MTL_REQUIRE(Cout % 4 == 0, "conv1 Cout % 4");
   size_t total = (size_t)B * F * T * (Cout / 4);
   if (!total) return MTL_OK;
+  MTL_REQUIRE(total < (1ull << 31), "conv1: B*F*T*Cout/4 must stay below 2^31");
   int grid = (int)((total + 255) / 256); if (grid > 148 * 16) grid = 148 * 16;
   conv1_fwd_kernel<<<grid, 256, (size_t)10 * Cout * sizeof(float), s>>>(x, w, b, out, B, F, T, Cout);
   MTL_CHECK_LAUNCH();
@@ -93,8 +95,68 @@ __global__ void __launch_bounds__(256) conv1_wgrad_kernel(const float* __restric
     if (k < 9) atomicAdd(dw + c * 9 + k, t); else atomicAdd(db + c, t);
   }
 }
+// Cout == 64 (the model's conv.0): one warp per (b, f) row, the two half-warps take alternate time steps, a lane owns 4
+// channels -- every dout load is one coalesced float4 (a whole pixel per half-warp), the nine x taps are L1 broadcasts,
+// no division in the loop.  33 MB of dout are read once; the block's 640 partial sums leave through atomics.
+__global__ void __launch_bounds__(128) conv1_wgrad64_kernel(const float* __restrict__ x, const float* __restrict__ dout,
+                                                            float* __restrict__ dw, float* __restrict__ db, int B, int F,
+                                                            int T) {
+  __shared__ float red[4][640];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int row = blockIdx.x * 4 + warp;                    // (b, f)
+  const int half = lane >> 4, c4 = (lane & 15) * 4;
+  float acc[10][4];
+#pragma unroll
+  for (int i = 0; i < 10; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  if (row < B * F) {
+    const int f = row % F, b = row / F;
+    const float* xr[3];
+    bool rv[3];
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int ff = f + kh - 1;
+      rv[kh] = ff >= 0 && ff < F;
+      xr[kh] = x + ((size_t)b * F + (rv[kh] ? ff : f)) * T;
+    }
+    const float* g = dout + (size_t)row * T * 64 + c4;
+#pragma unroll 4
+    for (int t = half; t < T; t += 2) {
+      const float4 gv = __ldg(reinterpret_cast<const float4*>(g + (size_t)t * 64));
+      acc[9][0] += gv.x; acc[9][1] += gv.y; acc[9][2] += gv.z; acc[9][3] += gv.w;
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const int tt = t + kw - 1;
+          const float xv = (rv[kh] && tt >= 0 && tt < T) ? __ldg(xr[kh] + tt) : 0.f;
+          acc[kh * 3 + kw][0] += xv * gv.x; acc[kh * 3 + kw][1] += xv * gv.y;
+          acc[kh * 3 + kw][2] += xv * gv.z; acc[kh * 3 + kw][3] += xv * gv.w;
+        }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 10; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      acc[i][j] += __shfl_xor_sync(0xffffffffu, acc[i][j], 16);
+      if (lane < 16) red[warp][(c4 + j) * 10 + i] = acc[i][j];
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 640; i += 128) {
+    const float t = red[0][i] + red[1][i] + red[2][i] + red[3][i];
+    const int c = i / 10, k = i % 10;
+    if (k < 9) atomicAdd(dw + c * 9 + k, t); else atomicAdd(db + c, t);
+  }
+}
 int k_conv1_wgrad(const float* x, const float* dout, float* dw, float* db, int B, int F, int T, int Cout,
                   cudaStream_t s) {
+  if (Cout == 64 && B * F > 0 && T > 0 && (((uintptr_t)dout) & 15u) == 0) {
+    conv1_wgrad64_kernel<<<mtl_cdiv(B * F, 4), 128, 0, s>>>(x, dout, dw, db, B, F, T);
+    MTL_CHECK_LAUNCH();
+    return MTL_OK;
+  }
   MTL_REQUIRE(Cout <= 256 && 256 % Cout == 0, "conv1 Cout must divide 256");
   size_t P = (size_t)B * F * T;
   if (!P) return MTL_OK;
@@ -224,12 +286,13 @@ __global__ void __launch_bounds__(256) maxpool2_relu_bwd_kernel(const float4* __
                                                                 const float4* __restrict__ dpool,
                                                                 float4* __restrict__ dx, int B, int F, int T, int C4) {
   const int F2 = F / 2, T2 = T / 2;
-  const size_t total = (size_t)B * F * T * C4;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C4);
-    const size_t p = i / C4;
-    const int t = (int)(p % T), f = (int)((p / T) % F);
-    const size_t b = p / ((size_t)F * T);
+  const unsigned total = (unsigned)B * F * T * C4;       // < 2^31 (checked by the launcher): 32-bit divisions only
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c = (int)(i % (unsigned)C4);
+    const unsigned p = i / (unsigned)C4;
+    const unsigned prow = p / (unsigned)T;
+    const int t = (int)(p - prow * (unsigned)T), f = (int)(prow % (unsigned)F);
+    const size_t b = prow / (unsigned)F;
     float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
     const int f2 = f >> 1, t2 = t >> 1;
     if (f2 < F2 && t2 < T2) {
@@ -247,6 +310,7 @@ int k_maxpool2_relu_bwd(const float* x, const float* dpool, float* dx, int B, in
   MTL_REQUIRE(C % 4 == 0, "pool C % 4");
   size_t total = (size_t)B * F * T * (C / 4);
   if (!total) return MTL_OK;
+  MTL_REQUIRE(total < (1ull << 31), "maxpool bwd: B*F*T*C/4 must stay below 2^31");
   size_t g = (total + 255) / 256; if (g > 148 * 16) g = 148 * 16;
   maxpool2_relu_bwd_kernel<<<(int)g, 256, 0, s>>>((const float4*)x, (const float4*)dpool, (float4*)dx, B, F, T, C / 4);
   MTL_CHECK_LAUNCH();
