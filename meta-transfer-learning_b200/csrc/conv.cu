@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(256) conv1_wgrad_kernel(const float* __restric
     if (k < 9) atomicAdd(dw + c * 9 + k, t); else atomicAdd(db + c, t);
   }
 }
-// Cout == 64 (the model's conv.0): one warp per (b, f) row, the two half-warps take alternate time steps, a lane owns 4
+// Cout == 64 (the model's conv.0): one warp per quarter of a (b, f) row, the two half-warps take alternate time steps, a lane owns 4
 // channels -- every dout load is one coalesced float4 (a whole pixel per half-warp), the nine x taps are L1 broadcasts,
 // no division in the loop.  33 MB of dout are read once; the block's 640 partial sums leave through atomics.
 __global__ void __launch_bounds__(128) conv1_wgrad64_kernel(const float* __restrict__ x, const float* __restrict__ dout,
@@ -103,7 +103,10 @@ __global__ void __launch_bounds__(128) conv1_wgrad64_kernel(const float* __restr
                                                             int T) {
   __shared__ float red[4][640];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int row = blockIdx.x * 4 + warp;                    // (b, f)
+  constexpr int TS = 4;                                     // time segments per row: enough warps in flight to cover HBM latency
+  const int unit = blockIdx.x * 4 + warp;
+  const int row = unit / TS, seg = unit % TS;               // (b, f) row, quarter of its time axis
+  const int tlen = (T + TS - 1) / TS, t0 = seg * tlen, t1 = min(T, t0 + tlen);
   const int half = lane >> 4, c4 = (lane & 15) * 4;
   float acc[10][4];
 #pragma unroll
@@ -122,7 +125,7 @@ __global__ void __launch_bounds__(128) conv1_wgrad64_kernel(const float* __restr
     }
     const float* g = dout + (size_t)row * T * 64 + c4;
 #pragma unroll 4
-    for (int t = half; t < T; t += 2) {
+    for (int t = t0 + half; t < t1; t += 2) {
       const float4 gv = __ldg(reinterpret_cast<const float4*>(g + (size_t)t * 64));
       acc[9][0] += gv.x; acc[9][1] += gv.y; acc[9][2] += gv.z; acc[9][3] += gv.w;
 #pragma unroll
@@ -153,7 +156,7 @@ __global__ void __launch_bounds__(128) conv1_wgrad64_kernel(const float* __restr
 int k_conv1_wgrad(const float* x, const float* dout, float* dw, float* db, int B, int F, int T, int Cout,
                   cudaStream_t s) {
   if (Cout == 64 && B * F > 0 && T > 0 && (((uintptr_t)dout) & 15u) == 0) {
-    conv1_wgrad64_kernel<<<mtl_cdiv(B * F, 4), 128, 0, s>>>(x, dout, dw, db, B, F, T);
+    conv1_wgrad64_kernel<<<B * F, 128, 0, s>>>(x, dout, dw, db, B, F, T);      // 4 warps = the 4 time segments of one row
     MTL_CHECK_LAUNCH();
     return MTL_OK;
   }
