@@ -138,6 +138,8 @@ struct Pass {
   CeOut* ce;
   float smoothing;
   size_t ws_after_fwd;
+  uintptr_t wz_base = 0;              // zero pool of the pass (see Run::wz)
+  size_t wz_off = 0, wz_cap = 0;
   uintptr_t ws_base;
   size_t ws_cap;
 };
@@ -230,6 +232,12 @@ struct Run {
   int w_rr = 0;
   bool dry;
   Bump ws;
+  // Zero pool: a block at the head of the workspace, cleared once per pass on a side stream while the VGG front-end
+  // runs.  The output of a beta == 0 GEMM with few tiles and a long K is allocated here so that the GEMM can run as
+  // K slabs merged by TMA reduce-add (bias added by slab 0) instead of a cluster with a DSMEM reduction: slab CTAs live
+  // ~5 us instead of ~8 us and need no cluster barrier.  Sized by the dry plan (zbytes).
+  Bump wz;
+  size_t zbytes = 0;
   const float* theta;
   float* grad;
   float p_drop;
@@ -286,18 +294,25 @@ static int join_all(Run& R) {
   } while (0)
 
 // ----------------------------------------------------------------------------- GEMM wrappers
+static int slab_split(long long tiles, int k_extent, int ctas);
+static int zslab_ctas();
+// y_zeroed: y was allocated from the zero pool (use_zslab) -- the GEMM may accumulate K slabs into it
 static int lin_fwd(Run& R, const float* x, int ldx, const float* W, const float* bias, float* y, int ldy, int M,
-                   int N, int Kd, int epi) {
+                   int N, int Kd, int epi, bool y_zeroed = false) {
   GemmArgs g;
   memset(&g, 0, sizeof(g));
   g.A = x; g.lda = ldx; g.transA = 0; g.B = W; g.ldb = Kd; g.transB = 1; g.C = y; g.ldc = ldy;
   g.M = M; g.N = N; g.K = Kd; g.alpha = 1.f; g.beta = 0.f; g.bias = bias; g.epi = epi; g.split_k = 1;
+  if (y_zeroed && epi == EPI_NONE) {
+    const int sp = slab_split((long long)mtl_cdiv(M, 128) * mtl_cdiv(N, N <= 64 ? 64 : 128), Kd, zslab_ctas());
+    if (sp > 1) { g.beta = 1.f; g.split_k = sp; }
+  }
   K(k_gemm(g, R.S->mode, R.st));
   return MTL_OK;
 }
 // K-slabs for an accumulating (beta == 1) contraction: about two CTAs per SM, at least one 32-deep k-block per slab.
 // Slabs merge through the TMA reduce-add epilogue (or vector atomics), so no cluster barrier is involved.
-static int slab_split(long long tiles, int k_extent, int ctas = 296) {
+static int slab_split(long long tiles, int k_extent, int ctas) {
   const int kb = mtl_cdiv(k_extent, 32);
   long long split = (ctas + tiles - 1) / tiles;
   if (split > kb) split = kb;
@@ -313,6 +328,25 @@ static int dgrad_ctas() {
   if (v < 0) { const char* e = getenv("MTL_DGRAD_CTAS"); v = e ? atoi(e) : 0; }
   return v > 0 ? v : (g_mtl_concurrency >= 2 ? 24 : 296);
 }
+// Slab budget of a zero-pool GEMM (on the critical path).  A pass running alone is latency-bound and takes the slabs
+// (14.1 -> 13.4 ms/step with one lane); with several lanes in flight the step is SM-time-bound, slabs and clusters
+// measure the same (8.18 vs 8.21 ms/step) and the cluster path keeps the forward bit-reproducible: 1 = no slabs.
+static int zslab_ctas() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MTL_ZSLAB_CTAS"); v = e ? atoi(e) : 0; }
+  return v > 0 ? v : (g_mtl_concurrency >= 2 ? 1 : 160);
+}
+// MTL_ZSLAB=0 keeps the cluster split-K path for every beta == 0 GEMM (A/B measurements)
+static bool zslab_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MTL_ZSLAB"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v != 0;
+}
+// Should the [M, N] output of a K-deep beta == 0 GEMM live in the zero pool?
+static bool use_zslab(const Run& R, int M, int N, int Kd) {
+  if (!zslab_enabled() || R.S->mode == MTL_GEMM_SIMT_FP32 || N % 4 != 0 || Kd < 256) return false;
+  return (long long)mtl_cdiv(M, 128) * mtl_cdiv(N, N <= 64 ? 64 : 128) <= 16;
+}
 static int wgrad_ctas() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("MTL_WGRAD_CTAS"); v = e ? atoi(e) : 24; }   // 296 -> 24: 9.47 -> 8.96 ms/step (3 lanes)
@@ -320,13 +354,17 @@ static int wgrad_ctas() {
 }
 // dx[M,K] = epi(dy[M,N] . W[N,K]) + beta*dx
 static int lin_dgrad(Run& R, const float* dy, int ldy, const float* W, float* dx, int ldx, int M, int N, int Kd,
-                     float beta, int epi, const float* aux) {
+                     float beta, int epi, const float* aux, bool dx_zeroed = false) {
   GemmArgs g;
   memset(&g, 0, sizeof(g));
   g.A = dy; g.lda = ldy; g.transA = 0; g.B = W; g.ldb = Kd; g.transB = 0; g.C = dx; g.ldc = ldx;
   g.M = M; g.N = Kd; g.K = N; g.alpha = 1.f; g.beta = beta; g.epi = epi; g.aux = aux; g.split_k = 1;
   if (beta == 1.f && epi == EPI_NONE)
     g.split_k = slab_split((long long)mtl_cdiv(M, 128) * mtl_cdiv(Kd, Kd <= 64 ? 64 : 128), N, dgrad_ctas());
+  else if (dx_zeroed && beta == 0.f && epi == EPI_NONE) {
+    const int sp = slab_split((long long)mtl_cdiv(M, 128) * mtl_cdiv(Kd, Kd <= 64 ? 64 : 128), N, zslab_ctas());
+    if (sp > 1) { g.beta = 1.f; g.split_k = sp; }
+  }
   K(k_gemm(g, R.S->mode, R.st));
   return MTL_OK;
 }
@@ -345,9 +383,10 @@ static int lin_wgrad(Run& R, const float* dy, int ldy, const float* x, int ldx, 
 static int lowrank_fwd(Run& R, LowRankAct& A, const float* x, int M, int Kd, int N, int r, size_t offA,
                        size_t offBw, size_t offBb) {
   A.x = x; A.M = M; A.K = Kd; A.N = N; A.offA = offA; A.offBw = offBw; A.offBb = offBb;
-  A.a = R.ws.f((size_t)M * r);
+  const bool za = use_zslab(R, M, r, Kd);
+  A.a = za ? R.wz.f((size_t)M * r) : R.ws.f((size_t)M * r);
   A.y = R.ws.f((size_t)M * N);
-  MTL_TRY(lin_fwd(R, x, Kd, R.theta + offA, nullptr, A.a, r, M, r, Kd, EPI_NONE));
+  MTL_TRY(lin_fwd(R, x, Kd, R.theta + offA, nullptr, A.a, r, M, r, Kd, EPI_NONE, za));
   MTL_TRY(lin_fwd(R, A.a, r, R.theta + offBw, R.theta + offBb, A.y, N, M, N, r, EPI_NONE));
   return MTL_OK;
 }
@@ -359,12 +398,13 @@ struct LrBwd { float* da; cudaEvent_t e_da; };
 static int lowrank_bwd_head(Run& R, const LowRankAct& A, const float* dy, cudaEvent_t e_dy, cudaStream_t s_da,
                             cudaStream_t s_w, LrBwd* h) {
   const int r = R.S->cfg.rank;
-  h->da = R.ws.f((size_t)A.M * r);
+  const bool zd = use_zslab(R, A.M, r, A.N);
+  h->da = zd ? R.wz.f((size_t)A.M * r) : R.ws.f((size_t)A.M * r);
   h->e_da = nullptr;
   MTL_TRY(ev_wait(R, s_da, e_dy));
   {
     On on(R, s_da);
-    MTL_TRY(lin_dgrad(R, dy, A.N, R.theta + A.offBw, h->da, r, A.M, A.N, r, 0.f, EPI_NONE, nullptr));
+    MTL_TRY(lin_dgrad(R, dy, A.N, R.theta + A.offBw, h->da, r, A.M, A.N, r, 0.f, EPI_NONE, nullptr, zd));
   }
   MTL_TRY(ev_mark(R, s_da, &h->e_da));
   if (s_w != s_da) MTL_TRY(ev_wait(R, s_w, h->e_da));
@@ -481,12 +521,13 @@ static int ffn_block_fwd(Run& R, FfnAct& A, const FfnP& p, const float* x, int M
   const int d = c.d_model, f = c.d_inner;
   A.p = p; A.x = x; A.M = M; A.rowmask = rowmask;
   A.f1 = R.ws.f((size_t)M * f);
-  A.f2 = R.ws.f((size_t)M * d);
+  const bool z2 = use_zslab(R, M, d, f);
+  A.f2 = z2 ? R.wz.f((size_t)M * d) : R.ws.f((size_t)M * d);
   A.xhat = R.ws.f((size_t)M * d);
   A.rstd = R.ws.f(M);
   A.out = R.ws.f((size_t)M * d);
   MTL_TRY(lin_fwd(R, x, d, R.theta + p.w1, R.theta + p.b1, A.f1, f, M, f, d, EPI_RELU));
-  MTL_TRY(lin_fwd(R, A.f1, f, R.theta + p.w2, R.theta + p.b2, A.f2, d, M, d, f, EPI_NONE));
+  MTL_TRY(lin_fwd(R, A.f1, f, R.theta + p.w2, R.theta + p.b2, A.f2, d, M, d, f, EPI_NONE, z2));
   A.drop = R.next_drop();
   K(k_ln_fwd(A.f2, x, R.theta + p.ln_w, R.theta + p.ln_b, rowmask, nullptr, 1, A.drop, A.out, A.xhat, A.rstd, M, d,
              R.st));
@@ -610,6 +651,18 @@ static int forward(Run& R, const mtl_batch& b, const float* pe_enc, const float*
   const int B = P.B, d = c.d_model, Tp = P.T4, n = P.n;
   R.site = 0;
 
+  // ---- zero pool (head of the workspace), cleared beside the VGG front-end
+  if (R.dry) { R.wz.base = 0; R.wz.off = 0; R.wz.cap = ~(size_t)0; R.wz.peak = 0; }
+  else {
+    void* zb = R.ws.raw(R.zbytes);
+    R.wz.base = (uintptr_t)zb; R.wz.off = 0; R.wz.cap = R.zbytes; R.wz.peak = 0;
+    if (R.zbytes) {
+      MTL_TRY(chain(R, R.main, R.side(S_AUX)));
+      MTL_CHECK_CUDA(cudaMemsetAsync(zb, 0, R.zbytes, R.side(S_AUX)));
+      if (R.par()) R.br->dirty[S_AUX] = true;
+    }
+  }
+
   // ---- VGG front-end (transformer.py:47-59), NHWC
   P.c1 = R.ws.f((size_t)B * P.F * P.T * 64);
   MTL_TRY(conv_weight_layouts(R, P));
@@ -629,11 +682,12 @@ static int forward(Run& R, const mtl_batch& b, const float* pe_enc, const float*
   P.enc_rowmask = R.ws.f(P.Me);
   P.enc_keypad = R.ws.u8(P.Me);
   K(k_enc_masks(b.lens, B, Tp, P.enc_rowmask, P.enc_keypad, R.st));
-  P.h = R.ws.f((size_t)P.Me * d);
+  const bool zh = use_zslab(R, P.Me, d, P.d_in);
+  P.h = zh ? R.wz.f((size_t)P.Me * d) : R.ws.f((size_t)P.Me * d);
   P.e0 = R.ws.f((size_t)P.Me * d);
   P.stem_xhat = R.ws.f((size_t)P.Me * d);
   P.stem_rstd = R.ws.f(P.Me);
-  MTL_TRY(lin_fwd(R, P.feat, P.d_in, R.theta + L.in_w, R.theta + L.in_b, P.h, d, P.Me, d, P.d_in, EPI_NONE));
+  MTL_TRY(lin_fwd(R, P.feat, P.d_in, R.theta + L.in_w, R.theta + L.in_b, P.h, d, P.Me, d, P.d_in, EPI_NONE, zh));
   K(k_ln_fwd(P.h, nullptr, R.theta + L.lnin_w, R.theta + L.lnin_b, nullptr, pe_enc, Tp, mtl_nodrop(), P.e0,
              P.stem_xhat, P.stem_rstd, P.Me, d, R.st));
   const float* x = P.e0;
@@ -688,6 +742,7 @@ static int forward(Run& R, const mtl_batch& b, const float* pe_enc, const float*
   }
   MTL_TRY(join_all(R));
   P.ws_after_fwd = R.ws.off;
+  P.wz_base = R.wz.base; P.wz_off = R.wz.off; P.wz_cap = R.wz.cap;
   P.ws_base = R.ws.base;
   P.ws_cap = R.ws.cap;
   P.valid = !R.dry;
@@ -718,9 +773,10 @@ static int backward(Run& R, float loss_scale, const float* dpred_ext, int ld_ext
     On on(R, sw);
     MTL_TRY(lin_wgrad(R, dpred, P.ldp, P.dec_last, d, R.grad + L.out_w, P.Md, V, d));
   }
-  float* gA = R.ws.f((size_t)P.Md * d);
+  const bool zg = use_zslab(R, P.Md, d, V);
+  float* gA = zg ? R.wz.f((size_t)P.Md * d) : R.ws.f((size_t)P.Md * d);   // only its FIRST use needs the zeros
   float* gB = R.ws.f((size_t)P.Md * d);
-  MTL_TRY(lin_dgrad(R, dpred, P.ldp, R.theta + L.out_w, gA, d, P.Md, V, d, 0.f, EPI_NONE, nullptr));
+  MTL_TRY(lin_dgrad(R, dpred, P.ldp, R.theta + L.out_w, gA, d, P.Md, V, d, 0.f, EPI_NONE, nullptr, zg));
   float* gE1 = R.ws.f((size_t)P.Me * d);
   float* gE2 = R.ws.f((size_t)P.Me * d);
   K(k_zero(gE1, (size_t)P.Me * d, R.st));
@@ -820,7 +876,7 @@ extern "C" int mtl_param_info(const mtl_session* s, int idx, long long* off, lon
   return MTL_OK;
 }
 
-static int dry_plan(mtl_session* s, int B, int T, int n, size_t* bytes) {
+static int dry_plan(mtl_session* s, int B, int T, int n, size_t* bytes, size_t* zbytes = nullptr) {
   Pass scratch;
   Run R;
   R.S = s; R.P = &scratch; R.st = 0; R.dry = true; R.theta = nullptr; R.grad = nullptr; R.p_drop = 0.f; R.seed = 0;
@@ -831,7 +887,9 @@ static int dry_plan(mtl_session* s, int B, int T, int n, size_t* bytes) {
   b.B = B; b.T = T; b.L = n > 1 ? n - 1 : 1; b.n = n;
   int rc = forward(R, b, nullptr, nullptr, 0.f);
   if (rc == MTL_OK) rc = backward(R, 1.f, nullptr, 0);
-  *bytes = R.ws.peak + 256;
+  const size_t zb = (R.wz.peak + 255) & ~(size_t)255;
+  *bytes = R.ws.peak + zb + 512;
+  if (zbytes) *zbytes = zb;
   return rc;
 }
 extern "C" long long mtl_workspace_bytes(mtl_session* s, int B, int T, int n) {
@@ -841,10 +899,10 @@ extern "C" long long mtl_workspace_bytes(mtl_session* s, int B, int T, int n) {
   return (long long)bytes;
 }
 
-static int check_ws(mtl_session* s, const mtl_batch* b, void* ws, long long ws_bytes) {
+static int check_ws(mtl_session* s, const mtl_batch* b, void* ws, long long ws_bytes, size_t* zbytes) {
   MTL_REQUIRE(ws && (((uintptr_t)ws) & 255u) == 0, "workspace must be 256B aligned");
   size_t need = 0;
-  MTL_TRY(dry_plan(s, b->B, b->T, b->n, &need));
+  MTL_TRY(dry_plan(s, b->B, b->T, b->n, &need, zbytes));
   if ((long long)need > ws_bytes) {
     mtl_set_error("workspace too small: need %zu bytes, have %lld", need, ws_bytes);
     return MTL_ERR_WORKSPACE;
@@ -859,8 +917,10 @@ static int run_forward(mtl_session* s, Pass* pass, Branches* br, const float* th
                        float dropout, SeedRef seed, float label_smoothing, cudaStream_t st) {
   MTL_REQUIRE(s && theta && pe_enc && pe_dec && batch && batch->x && batch->lens && batch->trg, "null argument");
   MTL_REQUIRE(dropout >= 0.f && dropout < 1.f, "dropout in [0,1)");
-  MTL_TRY(check_ws(s, batch, workspace, workspace_bytes));
+  size_t zbytes = 0;
+  MTL_TRY(check_ws(s, batch, workspace, workspace_bytes, &zbytes));
   Run R;
+  R.zbytes = zbytes;
   R.S = s; R.P = pass; R.st = st; R.main = st; R.dry = false; R.theta = theta; R.grad = nullptr;
   if (br && branches_enabled()) { MTL_TRY(branches_init(*br)); R.br = br; }
   R.p_drop = dropout; R.seed = seed.seed; R.seed_dev = seed.dev; R.seed_mul = seed.mul; R.site = 0;
@@ -876,6 +936,7 @@ static int run_backward(mtl_session* s, Pass* pass, Branches* br, const float* t
   if (br && branches_enabled()) { MTL_TRY(branches_init(*br)); R.br = br; }
   R.p_drop = 0.f; R.seed = 0; R.site = 0;
   R.ws.base = pass->ws_base; R.ws.cap = pass->ws_cap; R.ws.off = pass->ws_after_fwd;
+  R.wz.base = pass->wz_base; R.wz.cap = pass->wz_cap; R.wz.off = pass->wz_off;
   MTL_TRY(backward(R, loss_scale, dpred_ext, ld_ext));
   pass->valid = false;
   return MTL_OK;

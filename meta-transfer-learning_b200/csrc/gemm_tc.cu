@@ -368,7 +368,8 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
   if (P.tma_epi && warp >= 2) {
     // bias slice of this tile -> shared memory now, so the epilogue never waits on a global load
     const int t = threadIdx.x - 64, cn = blockIdx.y * BN + t;
-    if (t < BN) bias_s[t] = (P.g.bias && P.g.split_k <= 1 && cn < P.g.N) ? __ldg(P.g.bias + cn) : 0.f;
+    // K slabs (split_k > 1) accumulate into a zeroed / running C: slab 0 alone adds the bias
+    if (t < BN) bias_s[t] = (P.g.bias && (P.g.split_k <= 1 || blockIdx.z == 0) && cn < P.g.N) ? __ldg(P.g.bias + cn) : 0.f;
     asm volatile("bar.sync 1, 128;" ::: "memory");
   }
 
@@ -1224,7 +1225,7 @@ int k_gemm_tc(const GemmArgs& g, int precision_mode, cudaStream_t s) {
   P.g = g;
   P.conv_mode = CONV_NONE;
   P.kb_total = mtl_cdiv(g.K, BK);
-  if (g.split_k > 1) MTL_REQUIRE(g.beta == 1.f && g.epi == EPI_NONE && g.bias == nullptr, "split-K needs beta=1, no epilogue");
+  if (g.split_k > 1) MTL_REQUIRE(g.beta == 1.f && g.epi == EPI_NONE, "split-K needs beta=1, no activation epilogue");
   int split = plan_split(P, g.split_k);
   P.cluster_k = 1;
   if (g.split_k <= 1 && cluster_split_enabled()) {
@@ -1257,6 +1258,7 @@ int k_gemm_tc(const GemmArgs& g, int precision_mode, cudaStream_t s) {
   MTL_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "gemm grid too large");
   const int M = g.M, N = g.N, ldc = g.ldc;
   MTL_TRY(plan_epilogue(P, tm, [&](const float* ptr, CUtensorMap* out) { return make_map(ptr, N, M, ldc, BM, false, false, out); }));
+  MTL_REQUIRE(!(g.split_k > 1 && g.bias) || P.tma_epi, "split-K with bias needs the TMA epilogue (16 B aligned C, N % 4 == 0)");
   return dispatch(bn, split3, a_mn, b_mn, tm, P, grid, s);
 }
 

@@ -432,8 +432,10 @@ def test_dropout_pass_is_deterministic_given_seed_and_unbiased():
     o1, pred1, g1 = _fwd_bwd(s, p, b, dropout=0.1, seed=42)
     g1 = {k: v.clone() for k, v in g1.items()}
     o2, pred2, g2 = _fwd_bwd(s, p, b, dropout=0.1, seed=42)
-    assert torch.equal(pred1, pred2)
+    # same seed -> same Philox masks.  Not bit-identical: K-slab GEMMs (stem projection here) merge their partial sums
+    # through TMA reduce-add, whose order is not fixed -- fp32 round-off only (a different mask moves pred by ~1e-1)
+    assert rel_err(pred1, pred2) < 1e-5
     o3, pred3, _ = _fwd_bwd(s, p, b, dropout=0.1, seed=43)
-    assert not torch.equal(pred1, pred3)
+    assert rel_err(pred1, pred3) > 1e-3
     o0, pred0, _ = _fwd_bwd(s, p, b, dropout=0.0)
     assert 0.0 < rel_err(pred1, pred0) < 1.0
