@@ -285,35 +285,50 @@ __device__ __forceinline__ float pool_route(float v00, float v01, float v10, flo
   float mine = me == 0 ? v00 : (me == 1 ? v01 : (me == 2 ? v10 : v11));
   return (am == me && mine > 0.f) ? g : 0.f;
 }
+// One thread per 2x2 window and channel quad: the four x values are read once, the four dx values written once (the
+// element-per-thread version read every window four times).  Windows that floor pooling drops (odd last row / column)
+// get zeros.
 __global__ void __launch_bounds__(256) maxpool2_relu_bwd_kernel(const float4* __restrict__ x,
                                                                 const float4* __restrict__ dpool,
                                                                 float4* __restrict__ dx, int B, int F, int T, int C4) {
-  const int F2 = F / 2, T2 = T / 2;
-  const unsigned total = (unsigned)B * F * T * C4;       // < 2^31 (checked by the launcher): 32-bit divisions only
+  const int F2 = F / 2, T2 = T / 2, Fw = (F + 1) / 2, Tw = (T + 1) / 2;
+  const unsigned total = (unsigned)B * Fw * Tw * C4;      // < 2^31 (checked by the launcher): 32-bit divisions only
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int c = (int)(i % (unsigned)C4);
     const unsigned p = i / (unsigned)C4;
-    const unsigned prow = p / (unsigned)T;
-    const int t = (int)(p - prow * (unsigned)T), f = (int)(prow % (unsigned)F);
-    const size_t b = prow / (unsigned)F;
-    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int f2 = f >> 1, t2 = t >> 1;
+    const unsigned prow = p / (unsigned)Tw;
+    const int t2 = (int)(p - prow * (unsigned)Tw), f2 = (int)(prow % (unsigned)Fw);
+    const size_t b = prow / (unsigned)Fw;
+    const int f = 2 * f2, t = 2 * t2;
+    const bool hf = f + 1 < F, ht = t + 1 < T;            // second row / column of the window exists
+    const size_t base = ((b * F + f) * T + t) * C4 + c, down = (size_t)T * C4;
     if (f2 < F2 && t2 < T2) {
-      const size_t base = ((b * F + 2 * f2) * T + 2 * t2) * C4 + c;
-      float4 a = x[base], bb = x[base + C4], cc = x[base + (size_t)T * C4], d = x[base + (size_t)T * C4 + C4];
-      float4 g = dpool[((b * F2 + f2) * T2 + t2) * C4 + c];
-      const int me = (f & 1) * 2 + (t & 1);
-      r.x = pool_route(a.x, bb.x, cc.x, d.x, me, g.x); r.y = pool_route(a.y, bb.y, cc.y, d.y, me, g.y);
-      r.z = pool_route(a.z, bb.z, cc.z, d.z, me, g.z); r.w = pool_route(a.w, bb.w, cc.w, d.w, me, g.w);
+      const float4 a = x[base], bb = x[base + C4], cc = x[base + down], d = x[base + down + C4];
+      const float4 g = dpool[((b * F2 + f2) * T2 + t2) * C4 + c];
+      float4 r0, r1, r2, r3;
+      r0.x = pool_route(a.x, bb.x, cc.x, d.x, 0, g.x); r0.y = pool_route(a.y, bb.y, cc.y, d.y, 0, g.y);
+      r0.z = pool_route(a.z, bb.z, cc.z, d.z, 0, g.z); r0.w = pool_route(a.w, bb.w, cc.w, d.w, 0, g.w);
+      r1.x = pool_route(a.x, bb.x, cc.x, d.x, 1, g.x); r1.y = pool_route(a.y, bb.y, cc.y, d.y, 1, g.y);
+      r1.z = pool_route(a.z, bb.z, cc.z, d.z, 1, g.z); r1.w = pool_route(a.w, bb.w, cc.w, d.w, 1, g.w);
+      r2.x = pool_route(a.x, bb.x, cc.x, d.x, 2, g.x); r2.y = pool_route(a.y, bb.y, cc.y, d.y, 2, g.y);
+      r2.z = pool_route(a.z, bb.z, cc.z, d.z, 2, g.z); r2.w = pool_route(a.w, bb.w, cc.w, d.w, 2, g.w);
+      r3.x = pool_route(a.x, bb.x, cc.x, d.x, 3, g.x); r3.y = pool_route(a.y, bb.y, cc.y, d.y, 3, g.y);
+      r3.z = pool_route(a.z, bb.z, cc.z, d.z, 3, g.z); r3.w = pool_route(a.w, bb.w, cc.w, d.w, 3, g.w);
+      dx[base] = r0; dx[base + C4] = r1; dx[base + down] = r2; dx[base + down + C4] = r3;
+    } else {
+      dx[base] = zero;
+      if (ht) dx[base + C4] = zero;
+      if (hf) dx[base + down] = zero;
+      if (hf && ht) dx[base + down + C4] = zero;
     }
-    dx[i] = r;
   }
 }
 int k_maxpool2_relu_bwd(const float* x, const float* dpool, float* dx, int B, int F, int T, int C, cudaStream_t s) {
   MTL_REQUIRE(C % 4 == 0, "pool C % 4");
-  size_t total = (size_t)B * F * T * (C / 4);
+  size_t total = (size_t)B * ((F + 1) / 2) * ((T + 1) / 2) * (C / 4);
   if (!total) return MTL_OK;
-  MTL_REQUIRE(total < (1ull << 31), "maxpool bwd: B*F*T*C/4 must stay below 2^31");
+  MTL_REQUIRE((size_t)B * F * T * (C / 4) < (1ull << 31), "maxpool bwd: B*F*T*C/4 must stay below 2^31");
   size_t g = (total + 255) / 256; if (g > 148 * 16) g = 148 * 16;
   maxpool2_relu_bwd_kernel<<<(int)g, 256, 0, s>>>((const float4*)x, (const float4*)dpool, (float4*)dx, B, F, T, C / 4);
   MTL_CHECK_LAUNCH();
