@@ -1094,12 +1094,23 @@ bool conv_two_cta() {
   return v != 0;
 }
 
+// Cout = 64-wide conv weight-gradient tiles run with 2 pipeline stages / 2 CTAs per SM; MTL_CONV_WGRAD_2CTA=0 restores 4 / 1
+bool conv_wgrad_two_cta() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MTL_CONV_WGRAD_2CTA"); v = (e && e[0] == '0') ? 0 : 1; }   // 8.16 -> 7.99 ms/step
+  return v != 0;
+}
+
 template <int BN, bool SPLIT3>
 int dispatch_major(bool a_mn, bool b_mn, const Maps& tm, const TcParams& P, dim3 grid, cudaStream_t s) {
   constexpr int STAGES = SPLIT3 ? (BN == 64 ? 4 : 3) : (BN == 64 ? 4 : 3);
   if (BN == 64 && SPLIT3 && !a_mn && !b_mn && P.conv_mode == CONV_FWD && conv_two_cta()) {
     // 2 stages x 48 KB: two CTAs share an SM, so one tile's epilogue overlaps the other's main loop
     return launch<BN, (BN == 64 && SPLIT3) ? 2 : STAGES, false, false, SPLIT3>(tm, P, grid, s);
+  }
+  if (BN == 64 && SPLIT3 && a_mn && b_mn && P.conv_mode == CONV_WGRAD && conv_wgrad_two_cta()) {
+    // conv.2 weight gradient: 2 stages x 48 KB so that two CTAs share an SM (their TMA / split / MMA phases interleave)
+    return launch<BN, (BN == 64 && SPLIT3) ? 2 : STAGES, true, true, SPLIT3>(tm, P, grid, s);
   }
   if (!a_mn && !b_mn) return launch<BN, STAGES, false, false, SPLIT3>(tm, P, grid, s);
   if (!a_mn && b_mn) return launch<BN, STAGES, false, true, SPLIT3>(tm, P, grid, s);
@@ -1285,7 +1296,7 @@ int k_conv3x3_tc(const float* x, const float* wg, const float* bias, float* y, i
   MTL_REQUIRE(Cin % 32 == 0 && Cout % 4 == 0 && al16(x) && al16(wg) && al16(y), "conv3x3_tc: Cin % 32, Cout % 4, 16 B alignment");
   MTL_REQUIRE(epi != EPI_RELU_BWD || (aux && al16(aux)), "conv3x3_tc: aux");
   const bool split3 = precision_mode == 2, tf = !split3;
-  const int bn = Cout <= 64 ? 64 : 128;
+  const int bn = Cout <= 64 ? 64 : 128;   // (64-wide tiles / 2 CTAs per SM for Cout = 128 measured no better: 8.03 vs 7.99 ms/step)
   TcParams P;
   memset(&P, 0, sizeof(P));
   P.split_trunc = split_trunc_enabled();
@@ -1360,7 +1371,8 @@ int k_conv3x3_wgrad_tc(const float* x, const float* dy, float* dwgT, int B, int 
   // one wave (longer K per CTA, half the reduce-add epilogues): 8.67 -> 8.49 ms/step.  MTL_CONV_WGRAD_WAVES overrides.
   static int waves = -1;
   if (waves < 0) { const char* e = getenv("MTL_CONV_WGRAD_WAVES"); waves = e && atoi(e) > 0 ? atoi(e) : 1; }
-  int want = (waves * 148) / (mt * nt);
+  const int w_eff = (bn == 64 && split3 && conv_wgrad_two_cta()) ? 2 * waves : waves;     // two co-resident CTAs per SM
+  int want = (w_eff * 148) / (mt * nt);
   if (want > P.kb_total / 8) want = P.kb_total / 8 > 0 ? P.kb_total / 8 : 1;
   const int split = plan_split(P, want > 1 ? want : 2);
   P.g.split_k = 2;
