@@ -10,6 +10,8 @@
 __global__ void __launch_bounds__(256) conv1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                         const float* __restrict__ bias, float* __restrict__ out,
                                                         int B, int F, int T, int Cout) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float sw[];               // [9][Cout] + bias[Cout]
   for (int i = threadIdx.x; i < 9 * Cout; i += blockDim.x) { int co = i / 9, tap = i % 9; sw[tap * Cout + co] = w[i]; }
   for (int i = threadIdx.x; i < Cout; i += blockDim.x) sw[9 * Cout + i] = bias[i];
@@ -47,8 +49,8 @@ int k_conv1_fwd(const float* x, const float* w, const float* b, float* out, int 
   if (!total) return MTL_OK;
   MTL_REQUIRE(total < (1ull << 31), "conv1: B*F*T*Cout/4 must stay below 2^31");
   int grid = (int)((total + 255) / 256); if (grid > 148 * 16) grid = 148 * 16;
-  conv1_fwd_kernel<<<grid, 256, (size_t)10 * Cout * sizeof(float), s>>>(x, w, b, out, B, F, T, Cout);
-  MTL_CHECK_LAUNCH();
+  MTL_CHECK_CUDA(mtl_launch_pdl(conv1_fwd_kernel, dim3(grid), dim3(256), (size_t)10 * Cout * sizeof(float), s, x, w, b, out, B, F, T, Cout));
+  ++g_mtl_launches;
   return MTL_OK;
 }
 
@@ -101,6 +103,8 @@ __global__ void __launch_bounds__(256) conv1_wgrad_kernel(const float* __restric
 __global__ void __launch_bounds__(128) conv1_wgrad64_kernel(const float* __restrict__ x, const float* __restrict__ dout,
                                                             float* __restrict__ dw, float* __restrict__ db, int B, int F,
                                                             int T) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float red[4][640];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int TS = 4;                                     // time segments per row: enough warps in flight to cover HBM latency
@@ -156,8 +160,8 @@ __global__ void __launch_bounds__(128) conv1_wgrad64_kernel(const float* __restr
 int k_conv1_wgrad(const float* x, const float* dout, float* dw, float* db, int B, int F, int T, int Cout,
                   cudaStream_t s) {
   if (Cout == 64 && B * F > 0 && T > 0 && (((uintptr_t)dout) & 15u) == 0) {
-    conv1_wgrad64_kernel<<<B * F, 128, 0, s>>>(x, dout, dw, db, B, F, T);      // 4 warps = the 4 time segments of one row
-    MTL_CHECK_LAUNCH();
+    MTL_CHECK_CUDA(mtl_launch_pdl(conv1_wgrad64_kernel, dim3(B * F), dim3(128), 0, s, x, dout, dw, db, B, F, T));   // 4 warps = the 4 time segments of one row
+    ++g_mtl_launches;
     return MTL_OK;
   }
   MTL_REQUIRE(Cout <= 256 && 256 % Cout == 0, "conv1 Cout must divide 256");
@@ -250,6 +254,8 @@ int k_conv_wgrad_scatter(const float* dwg, float* dw, int Cout, int Cin, cudaStr
 // ------------------------------------------------------------------ 2x2 max-pool (floor) on NHWC
 __global__ void __launch_bounds__(256) maxpool2_fwd_kernel(const float4* __restrict__ x, float4* __restrict__ out,
                                                            int B, int F, int T, int C4) {
+  pdl_wait();
+  pdl_trigger();
   const int F2 = F / 2, T2 = T / 2;
   const size_t total = (size_t)B * F2 * T2 * C4;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -270,8 +276,8 @@ int k_maxpool2_fwd(const float* x, float* out, int B, int F, int T, int C, cudaS
   size_t total = (size_t)B * (F / 2) * (T / 2) * (C / 4);
   if (!total) return MTL_OK;
   size_t g = (total + 255) / 256; if (g > 148 * 16) g = 148 * 16;
-  maxpool2_fwd_kernel<<<(int)g, 256, 0, s>>>((const float4*)x, (float4*)out, B, F, T, C / 4);
-  MTL_CHECK_LAUNCH();
+  MTL_CHECK_CUDA(mtl_launch_pdl(maxpool2_fwd_kernel, dim3((unsigned)g), dim3(256), 0, s, (const float4*)x, (float4*)out, B, F, T, C / 4));
+  ++g_mtl_launches;
   return MTL_OK;
 }
 // Gradient of relu -> maxpool w.r.t. the pre-ReLU conv output, given x = post-ReLU activation.
@@ -291,6 +297,8 @@ __device__ __forceinline__ float pool_route(float v00, float v01, float v10, flo
 __global__ void __launch_bounds__(256) maxpool2_relu_bwd_kernel(const float4* __restrict__ x,
                                                                 const float4* __restrict__ dpool,
                                                                 float4* __restrict__ dx, int B, int F, int T, int C4) {
+  pdl_wait();
+  pdl_trigger();
   const int F2 = F / 2, T2 = T / 2, Fw = (F + 1) / 2, Tw = (T + 1) / 2;
   const unsigned total = (unsigned)B * Fw * Tw * C4;      // < 2^31 (checked by the launcher): 32-bit divisions only
   const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -330,14 +338,16 @@ int k_maxpool2_relu_bwd(const float* x, const float* dpool, float* dx, int B, in
   if (!total) return MTL_OK;
   MTL_REQUIRE((size_t)B * F * T * (C / 4) < (1ull << 31), "maxpool bwd: B*F*T*C/4 must stay below 2^31");
   size_t g = (total + 255) / 256; if (g > 148 * 16) g = 148 * 16;
-  maxpool2_relu_bwd_kernel<<<(int)g, 256, 0, s>>>((const float4*)x, (const float4*)dpool, (float4*)dx, B, F, T, C / 4);
-  MTL_CHECK_LAUNCH();
+  MTL_CHECK_CUDA(mtl_launch_pdl(maxpool2_relu_bwd_kernel, dim3((unsigned)g), dim3(256), 0, s, (const float4*)x, (const float4*)dpool, (float4*)dx, B, F, T, C / 4));
+  ++g_mtl_launches;
   return MTL_OK;
 }
 
 // ------------------------------------------------------------------ (B,F4,T4,C) <-> (B,T4,C*F4)
 __global__ void __launch_bounds__(256) feat_transpose_kernel(const float* __restrict__ p4, float* __restrict__ feat,
                                                              int B, int F4, int T4, int C) {
+  pdl_wait();
+  pdl_trigger();
   const size_t total = (size_t)B * T4 * C * F4;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int f = (int)(i % F4), c = (int)((i / F4) % C);
@@ -349,6 +359,8 @@ __global__ void __launch_bounds__(256) feat_transpose_kernel(const float* __rest
 }
 __global__ void __launch_bounds__(256) feat_transpose_bwd_kernel(const float* __restrict__ dfeat,
                                                                  float* __restrict__ dp4, int B, int F4, int T4, int C) {
+  pdl_wait();
+  pdl_trigger();
   const size_t total = (size_t)B * T4 * C * F4;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % C), t = (int)((i / C) % T4);
@@ -362,15 +374,15 @@ int k_feat_transpose(const float* p4, float* feat, int B, int F4, int T4, int C,
   size_t total = (size_t)B * T4 * C * F4;
   if (!total) return MTL_OK;
   size_t g = (total + 255) / 256; if (g > 148 * 16) g = 148 * 16;
-  feat_transpose_kernel<<<(int)g, 256, 0, s>>>(p4, feat, B, F4, T4, C);
-  MTL_CHECK_LAUNCH();
+  MTL_CHECK_CUDA(mtl_launch_pdl(feat_transpose_kernel, dim3((unsigned)g), dim3(256), 0, s, p4, feat, B, F4, T4, C));
+  ++g_mtl_launches;
   return MTL_OK;
 }
 int k_feat_transpose_bwd(const float* dfeat, float* dp4, int B, int F4, int T4, int C, cudaStream_t s) {
   size_t total = (size_t)B * T4 * C * F4;
   if (!total) return MTL_OK;
   size_t g = (total + 255) / 256; if (g > 148 * 16) g = 148 * 16;
-  feat_transpose_bwd_kernel<<<(int)g, 256, 0, s>>>(dfeat, dp4, B, F4, T4, C);
-  MTL_CHECK_LAUNCH();
+  MTL_CHECK_CUDA(mtl_launch_pdl(feat_transpose_bwd_kernel, dim3((unsigned)g), dim3(256), 0, s, dfeat, dp4, B, F4, T4, C));
+  ++g_mtl_launches;
   return MTL_OK;
 }

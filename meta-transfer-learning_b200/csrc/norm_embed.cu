@@ -200,6 +200,8 @@ int k_ln_bwd(const float* dout, const float* xhat, const float* rstd, const floa
 // out[n] += sum_m x[m*ld + n].  Rows are split over gridDim.y slabs when M is large (atomic merge).
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, int M, int N, int ld,
                                                      float* __restrict__ out, int rows_per_slab) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float sm[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + tx;
@@ -224,8 +226,8 @@ int k_colsum_acc(const float* x, int M, int N, int ld, float* out, cudaStream_t 
   const int max_slabs = N >= 2048 ? 64 : 512;
   if (slabs > max_slabs) slabs = max_slabs;
   int rps = mtl_cdiv(M, slabs);
-  colsum_kernel<<<dim3(mtl_cdiv(N, 32), slabs), 256, 0, s>>>(x, M, N, ld, out, rps);
-  MTL_CHECK_LAUNCH();
+  MTL_CHECK_CUDA(mtl_launch_pdl(colsum_kernel, dim3(mtl_cdiv(N, 32), slabs), dim3(256), 0, s, x, M, N, ld, out, rps));
+  ++g_mtl_launches;
   return MTL_OK;
 }
 
@@ -233,6 +235,8 @@ int k_colsum_acc(const float* x, int M, int N, int ld, float* out, cudaStream_t 
 __global__ void __launch_bounds__(256) embed_fwd_kernel(const int* __restrict__ tok, const float* __restrict__ E,
                                                         const float* __restrict__ pe, MtlDrop drop,
                                                         float* __restrict__ out, int rows, int n, int d) {
+  pdl_wait();
+  pdl_trigger();
   size_t total = (size_t)rows * d;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     int row = (int)(i / d), c = (int)(i % d);
@@ -247,13 +251,15 @@ int k_embed_fwd(const int* tok, const float* E, const float* pe, MtlDrop drop, f
   size_t total = (size_t)B * n * d;
   if (!total) return MTL_OK;
   int grid = (int)((total + 255) / 256); if (grid > 148 * 16) grid = 148 * 16;
-  embed_fwd_kernel<<<grid, 256, 0, s>>>(tok, E, pe, drop, out, B * n, n, d);
-  MTL_CHECK_LAUNCH();
+  MTL_CHECK_CUDA(mtl_launch_pdl(embed_fwd_kernel, dim3(grid), dim3(256), 0, s, tok, E, pe, drop, out, B * n, n, d));
+  ++g_mtl_launches;
   return MTL_OK;
 }
 __global__ void __launch_bounds__(256) embed_bwd_kernel(const int* __restrict__ tok, const float* __restrict__ dout,
                                                         MtlDrop drop, float* __restrict__ dE, int rows, int d,
                                                         int pad_id) {
+  pdl_wait();
+  pdl_trigger();
   size_t total = (size_t)rows * d;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     int row = (int)(i / d), c = (int)(i % d);
@@ -269,8 +275,8 @@ int k_embed_bwd(const int* tok, const float* dout, MtlDrop drop, float* dE, int 
   size_t total = (size_t)B * n * d;
   if (!total) return MTL_OK;
   int grid = (int)((total + 255) / 256); if (grid > 148 * 16) grid = 148 * 16;
-  embed_bwd_kernel<<<grid, 256, 0, s>>>(tok, dout, drop, dE, B * n, d, pad_id);
-  MTL_CHECK_LAUNCH();
+  MTL_CHECK_CUDA(mtl_launch_pdl(embed_bwd_kernel, dim3(grid), dim3(256), 0, s, tok, dout, drop, dE, B * n, d, pad_id));
+  ++g_mtl_launches;
   return MTL_OK;
 }
 
