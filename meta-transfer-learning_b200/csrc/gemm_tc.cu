@@ -959,32 +959,39 @@ __global__ void __launch_bounds__(192) conv3x3_kw_kernel(const __grid_constant__
   }
 }
 
-// ----------------------------------------------------------------------------- kw-box 3x3 weight gradient (Cin = 128)
-// dWgT[(kh, kw, ci), co] += sum_pixels x[pixel + (kh - 1, kw - 1), ci] * dy[pixel, co] for ONE horizontal tap kw per CTA and a
-// slab of 32-pixel k-blocks (8 t x 4 f).  K runs over pixels (MN-major operands, SWIZZLE_128B_BASE32B): an A stage is four
-// boxes {32 ci, 8 t, 4 + 2 f} = 48 K-rows each (LBO = 6144 between the 32-channel groups of the M = 128 tile), and the
-// vertical tap kh is the K window that starts 8 rows = 1024 B = one K-step later -- so the x boxes are fetched (and, in
-// 3xTF32, split) once for three taps instead of once per tap, and the dY boxes once for three taps instead of once per
-// M tile.  Three accumulators (kh) of 128 columns live in TMEM (512 allocated); 3xTF32 issues a_hi*b_hi + a_lo*b_hi +
-// a_hi*b_lo into the same columns (no N-concatenated operand: 384 columns are already taken).  Epilogue: one tap after
-// the other through the TMA reduce-add staging path.
+// ----------------------------------------------------------------------------- kw-box 3x3 weight gradient
+// dWgT[(kh, kw, ci), co] += sum_pixels x[pixel + (kh - 1, kw - 1), ci] * dy[pixel, co] for a slab of 32-pixel k-blocks
+// (8 t x 4 f).  K runs over pixels (MN-major operands, SWIZZLE_128B_BASE32B): an A stage is four boxes {32 ci, 8 t,
+// 4 + 2 f} = 48 K-rows each (LBO = 6144 between the 32-channel groups of the M = 128 tile), and the vertical tap kh is the
+// K window that starts 8 rows = 1024 B = one K-step later -- so the x boxes are fetched (and, in 3xTF32, split) once for
+// three taps instead of once per tap, and the dY boxes once for three taps instead of once per M tile.
+//   Cin = 128: the four groups are the channel chunks of ONE horizontal tap kw = blockIdx.x (grid.x = 3).
+//   Cin =  64: the four groups are two horizontal taps x two chunks; blockIdx.x = 0 -> taps kw 0, 1 (128 rows of dWgT per
+//              kh), blockIdx.x = 1 -> tap kw 2 loaded twice (rows 64..127 of the tile are duplicates: a 64-row store box).
+// Three accumulators (kh) of BN columns live in TMEM; 3xTF32 issues a_hi*b_hi + a_lo*b_hi + a_hi*b_lo into the same
+// columns (no N-concatenated operand: 3 * BN columns are already taken).  Epilogue: one tap row after the other through
+// the TMA reduce-add staging path.
 //   warp 0: TMA producer; warp 1: TMEM allocator + MMA issuer; warps 2..5: splitter (3xTF32, truncating), then epilogue.
 constexpr int WK_ROWS_A = 48, WK_A_BOX = WK_ROWS_A * 128, WK_B_BOX = 32 * 128;      // 6144 B / 4096 B per 32-column box
-constexpr int WK_A_BYTES = 4 * WK_A_BOX, WK_B_BYTES = 4 * WK_B_BOX;                  // Cin = 128, Cout = 128
+constexpr int WK_A_BYTES = 4 * WK_A_BOX;
 constexpr int WK_STAGES = 2, WK_HEAD = 1024;
-template <bool SPLIT3>
+template <int BN, bool SPLIT3>
 struct WkCfg {
-  static constexpr int STAGE = (WK_A_BYTES + WK_B_BYTES) * (SPLIT3 ? 2 : 1);         // [A | A_lo | B | B_lo]
+  static constexpr int B_BYTES = (BN / 32) * WK_B_BOX;
+  static constexpr int STAGE = (WK_A_BYTES + B_BYTES) * (SPLIT3 ? 2 : 1);            // [A | A_lo | B | B_lo]
   static constexpr int B_OFF = WK_A_BYTES * (SPLIT3 ? 2 : 1);
-  static constexpr int DATA = WK_STAGES * STAGE > BM * 128 * 4 ? WK_STAGES * STAGE : BM * 128 * 4;
+  static constexpr int DATA = WK_STAGES * STAGE > BM * BN * 4 ? WK_STAGES * STAGE : BM * BN * 4;
   static constexpr int SMEM = WK_HEAD + DATA + 1024;
+  static constexpr int TMEM_COLS = BN == 128 ? 512 : 256;                            // 3 * BN rounded up to a power of two
 };
-template <bool SPLIT3>
+template <int CIN, int BN, bool SPLIT3>
 __global__ void __launch_bounds__(192) conv3x3_wgrad_kw_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                const __grid_constant__ CUtensorMap tmB,
-                                                               const __grid_constant__ CUtensorMap tmC, const TcParams P) {
-  using Cfg = WkCfg<SPLIT3>;
-  constexpr int BN = 128;
+                                                               const __grid_constant__ CUtensorMap tmC,
+                                                               const __grid_constant__ CUtensorMap tmC64, const TcParams P) {
+  using Cfg = WkCfg<BN, SPLIT3>;
+  constexpr int NCH = CIN / 32;                                  // 32-channel chunks per tap: 4 or 2
+  static_assert(NCH == 4 || NCH == 2, "Cin must be 64 or 128");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t head = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_head = smem_raw + (head - smem_u32(smem_raw));
@@ -999,7 +1006,6 @@ __global__ void __launch_bounds__(192) conv3x3_wgrad_kw_kernel(const __grid_cons
   float* bias_s = reinterpret_cast<float*>(smem_head + 256);    // zeros (the shared epilogue adds a bias slice)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kw = blockIdx.x;
   const int kb0 = blockIdx.y * P.kb_per_split, kb1 = min(P.kb_total, kb0 + P.kb_per_split);
 
   if (threadIdx.x == 0) {
@@ -1009,7 +1015,7 @@ __global__ void __launch_bounds__(192) conv3x3_wgrad_kw_kernel(const __grid_cons
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(Cfg::TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -1019,7 +1025,7 @@ __global__ void __launch_bounds__(192) conv3x3_wgrad_kw_kernel(const __grid_cons
   pdl_wait();
   if (warp >= 2) {
     const int t = threadIdx.x - 64;
-    bias_s[t] = 0.f;
+    if (t < BN) bias_s[t] = 0.f;
     asm volatile("bar.sync 1, 128;" ::: "memory");
   }
 
@@ -1030,14 +1036,19 @@ __global__ void __launch_bounds__(192) conv3x3_wgrad_kw_kernel(const __grid_cons
       for (int kb = kb0; kb < kb1; ++kb, ++it) {
         const int s2 = it % WK_STAGES;
         mbar_wait(&empty[s2], ((it / WK_STAGES) & 1) ^ 1);
-        mbar_expect_tx(&full[s2], WK_A_BYTES + WK_B_BYTES);
+        mbar_expect_tx(&full[s2], WK_A_BYTES + Cfg::B_BYTES);
         const int tt = kb % P.tiles_t, rem = kb / P.tiles_t;
         const int t0 = tt * 8, f0 = (rem % P.tiles_f) * 4, b = rem / P.tiles_f;
         const uint32_t sa = base + s2 * Cfg::STAGE, sb = sa + Cfg::B_OFF;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) tma_load_4d(sa + c * WK_A_BOX, &tmA, &full[s2], c * 32, t0 + kw - 1, f0 - 1, b);
+        for (int g = 0; g < 4; ++g) {
+          // group g of the M tile = (horizontal tap, 32-channel chunk)
+          const int kw = NCH == 4 ? (int)blockIdx.x : (blockIdx.x == 0 ? g / 2 : 2);
+          const int c = NCH == 4 ? g : g % 2;
+          tma_load_4d(sa + g * WK_A_BOX, &tmA, &full[s2], c * 32, t0 + kw - 1, f0 - 1, b);
+        }
 #pragma unroll
-        for (int c = 0; c < 4; ++c) tma_load_4d(sb + c * WK_B_BOX, &tmB, &full[s2], c * 32, t0, f0, b);
+        for (int c = 0; c < BN / 32; ++c) tma_load_4d(sb + c * WK_B_BOX, &tmB, &full[s2], c * 32, t0, f0, b);
       }
     }
   } else if (warp == 1) {
@@ -1052,7 +1063,7 @@ __global__ void __launch_bounds__(192) conv3x3_wgrad_kw_kernel(const __grid_cons
         tc_fence_after();
         const uint32_t sa = base + s2 * Cfg::STAGE, sb = sa + Cfg::B_OFF;
         const uint64_t da0 = umma_desc(sa, WK_A_BOX, 512, 1), la0 = umma_desc(sa + WK_A_BYTES, WK_A_BOX, 512, 1);
-        const uint64_t db0 = desc_mnmajor(sb), lb0 = desc_mnmajor(sb + WK_B_BYTES);
+        const uint64_t db0 = desc_mnmajor(sb), lb0 = desc_mnmajor(sb + Cfg::B_BYTES);
 #pragma unroll
         for (int kh = 0; kh < 3; ++kh) {
           const uint32_t d = tmem_base + (uint32_t)(kh * BN);
@@ -1080,7 +1091,7 @@ __global__ void __launch_bounds__(192) conv3x3_wgrad_kw_kernel(const __grid_cons
       mbar_wait(&full[s2], (it / WK_STAGES) & 1);
       float4* a4 = reinterpret_cast<float4*>(smem + s2 * Cfg::STAGE) + tid;
       float4* b4 = reinterpret_cast<float4*>(smem + s2 * Cfg::STAGE + Cfg::B_OFF) + tid;
-      constexpr int PA = WK_A_BYTES / 16 / 128, PB = WK_B_BYTES / 16 / 128;
+      constexpr int PA = WK_A_BYTES / 16 / 128, PB = Cfg::B_BYTES / 16 / 128;
       float4 a[PA], bq[PB];
 #pragma unroll
       for (int j = 0; j < PA; ++j) a[j] = a4[j * 128];
@@ -1096,7 +1107,7 @@ __global__ void __launch_bounds__(192) conv3x3_wgrad_kw_kernel(const __grid_cons
       for (int j = 0; j < PB; ++j) {
         float4 l;
         l.x = tf32_lo_trunc(bq[j].x); l.y = tf32_lo_trunc(bq[j].y); l.z = tf32_lo_trunc(bq[j].z); l.w = tf32_lo_trunc(bq[j].w);
-        b4[j * 128 + WK_B_BYTES / 16] = l;
+        b4[j * 128 + Cfg::B_BYTES / 16] = l;
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
@@ -1104,12 +1115,16 @@ __global__ void __launch_bounds__(192) conv3x3_wgrad_kw_kernel(const __grid_cons
     }
   }
 
-  // ===================== epilogue: tap kh -> rows [(kh * 3 + kw) * 128, +128) of dWgT, reduce-add =====================
+  // ===================== epilogue: tap row kh -> rows of dWgT, reduce-add =====================
   if (warp >= 2) {
+    // Cin = 128: tile = tap (kh, kw = blockIdx.x), 128 rows.  Cin = 64: blockIdx.x = 0 -> taps (kh, 0), (kh, 1) = 128 rows
+    // from (kh * 3) * 64; blockIdx.x = 1 -> tap (kh, 2), 64 rows (the tile's upper half repeats them: 64-row store box).
+    const CUtensorMap* mapC = (NCH == 2 && blockIdx.x == 1) ? &tmC64 : &tmC;
 #pragma unroll 1
     for (int kh = 0; kh < 3; ++kh) {
-      tma_epilogue_rows<BN, false>(P, &tmC, &tmC, base, base, tmem_full, aux_full, bias_s, tmem_base + (uint32_t)(kh * BN), warp,
-                                   lane, (kh * 3 + kw) * 128, 0, false, 0, 0, 0);
+      const int m0 = NCH == 4 ? (kh * 3 + (int)blockIdx.x) * 128 : (kh * 3 + (blockIdx.x == 0 ? 0 : 2)) * 64;
+      tma_epilogue_rows<BN, false>(P, mapC, mapC, base, base, tmem_full, aux_full, bias_s, tmem_base + (uint32_t)(kh * BN), warp,
+                                   lane, m0, 0, false, 0, 0, 0);
       asm volatile("bar.sync 1, 128;" ::: "memory");            // the staging tile is free again (its TMA reads are done)
     }
   }
@@ -1117,7 +1132,7 @@ __global__ void __launch_bounds__(192) conv3x3_wgrad_kw_kernel(const __grid_cons
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::TMEM_COLS) : "memory");
   }
 }
 
@@ -1311,18 +1326,24 @@ bool conv_wgrad_kw_enabled() {
   if (v < 0) { const char* e = getenv("MTL_CONV_WGRAD_KW"); v = (e && e[0] == '0') ? 0 : 1; }
   return v != 0;
 }
-template <bool SPLIT3>
-int launch_wgrad_kw(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const TcParams& P, dim3 grid,
-                    cudaStream_t s) {
-  using Cfg = WkCfg<SPLIT3>;
+// the Cin = 64 variants (conv.2, conv.3) of the kw-box weight gradient: MTL_CONV_WGRAD_KW64=1 until validated on the GPU
+bool conv_wgrad_kw64_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MTL_CONV_WGRAD_KW64"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v != 0;
+}
+template <int CIN, int BN, bool SPLIT3>
+int launch_wgrad_kw(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tc64,
+                    const TcParams& P, dim3 grid, cudaStream_t s) {
+  using Cfg = WkCfg<BN, SPLIT3>;
   static_assert(Cfg::SMEM <= 227 * 1024, "shared memory budget");
   static bool configured = false;
-  auto kern = conv3x3_wgrad_kw_kernel<SPLIT3>;
+  auto kern = conv3x3_wgrad_kw_kernel<CIN, BN, SPLIT3>;
   if (!configured) {
     MTL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     configured = true;
   }
-  MTL_CHECK_CUDA(mtl_launch_pdl(kern, grid, dim3(192, 1, 1), (size_t)Cfg::SMEM, s, ta, tb, tc, P));
+  MTL_CHECK_CUDA(mtl_launch_pdl(kern, grid, dim3(192, 1, 1), (size_t)Cfg::SMEM, s, ta, tb, tc, tc64, P));
   ++g_mtl_launches;
   return MTL_OK;
 }
@@ -1549,25 +1570,32 @@ int k_conv3x3_wgrad_tc(const float* x, const float* dy, float* dwgT, int B, int 
   GemmArgs& g = P.g;
   g.A = x; g.B = dy; g.C = dwgT; g.M = 9 * Cin; g.N = Cout; g.K = B * F * T; g.lda = Cin; g.ldb = Cout; g.ldc = Cout;
   g.transA = 1; g.transB = 0; g.alpha = 1.f; g.beta = 1.f; g.bias = nullptr; g.epi = EPI_NONE; g.aux = nullptr;
-  if (conv_wgrad_kw_enabled() && Cin == 128 && Cout == 128 && (!split3 || P.split_trunc)) {
-    // kw-box weight gradient: one CTA per horizontal tap and pixel slab, k-blocks of 8 (t) x 4 (f) pixels
+  const bool kw_shape = (Cin == 128 && Cout == 128) || (conv_wgrad_kw64_enabled() && Cin == 64 && (Cout == 64 || Cout == 128));
+  if (conv_wgrad_kw_enabled() && kw_shape && (!split3 || P.split_trunc)) {
+    // kw-box weight gradient: k-blocks of 8 (t) x 4 (f) pixels, one wave of CTAs
+    const int gx = Cin == 128 ? 3 : 2;
     P.bt_log2 = 3;
     P.tiles_t = mtl_cdiv(T, 8); P.tiles_f = mtl_cdiv(F, 4);
     P.kb_total = B * P.tiles_f * P.tiles_t;
-    int want = 148 / 3;
+    int want = 148 / gx;
     if (want > P.kb_total) want = P.kb_total;
     P.kb_per_split = mtl_cdiv(P.kb_total, want);
     const int split = mtl_cdiv(P.kb_total, P.kb_per_split);
     P.g.split_k = 2;
     P.tma_epi = 2;
     P.vecC = 1;
-    CUtensorMap ka, kb, kc;
+    CUtensorMap ka, kb, kc, kc64;
     MTL_TRY(make_map_nhwc(x, B, F, T, Cin, 8, 6, true, tf, &ka));
     MTL_TRY(make_map_nhwc(dy, B, F, T, Cout, 8, 4, true, tf, &kb));
     MTL_TRY(make_map(dwgT, Cout, 9LL * Cin, Cout, BM, false, false, &kc));
-    dim3 grid(3, split, 1);
-    if (split3) return launch_wgrad_kw<true>(ka, kb, kc, P, grid, s);
-    return launch_wgrad_kw<false>(ka, kb, kc, P, grid, s);
+    MTL_TRY(make_map(dwgT, Cout, 9LL * Cin, Cout, 64, false, false, &kc64));
+    dim3 grid(gx, split, 1);
+    if (Cin == 128) return split3 ? launch_wgrad_kw<128, 128, true>(ka, kb, kc, kc64, P, grid, s)
+                                  : launch_wgrad_kw<128, 128, false>(ka, kb, kc, kc64, P, grid, s);
+    if (Cout == 128) return split3 ? launch_wgrad_kw<64, 128, true>(ka, kb, kc, kc64, P, grid, s)
+                                   : launch_wgrad_kw<64, 128, false>(ka, kb, kc, kc64, P, grid, s);
+    return split3 ? launch_wgrad_kw<64, 64, true>(ka, kb, kc, kc64, P, grid, s)
+                  : launch_wgrad_kw<64, 64, false>(ka, kb, kc, kc64, P, grid, s);
   }
   P.kb_total = B * P.tiles_f * P.tiles_t;
   const int mt = mtl_cdiv(g.M, BM), nt = mtl_cdiv(Cout, bn);
