@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define MTL_ABI_VERSION 1
+#define MTL_ABI_VERSION 2
 
 /* GEMM engines (mtl_session_set_gemm_mode / mtl_gemm `mode`) */
 #define MTL_GEMM_SIMT_FP32 0 /* CUDA-core fp32, exact                        */
@@ -49,6 +49,23 @@ typedef struct mtl_session mtl_session;
 int mtl_session_create(const mtl_model_cfg* cfg, mtl_session** out);
 void mtl_session_destroy(mtl_session* s);
 int mtl_session_set_gemm_mode(mtl_session* s, int mode);
+/* Per-operation-class precision policy (tensor-core engines only; the fp32 CUDA-core engine is all-or-nothing).
+ * Every contraction of the pass belongs to one class; its engine is op_mode[class] if set, else the session mode.
+ * mode: MTL_GEMM_TC_TF32, MTL_GEMM_TC_3XTF32, or -1 = follow the session mode.  The classes name the
+ * reference's nn.Conv2d / nn.Linear call sites: VGG convs (models/asr/transformer.py:47-59) forward, input
+ * gradient and weight gradient; the nn.Linear layers of the attention / FFN blocks
+ * (modules/common_layers.py:117-118,250-257); the encoder input Linear (modules/encoder.py:44) and the
+ * vocabulary projection (modules/decoder.py:50) in all three directions. */
+#define MTL_OP_CONV_FWD 0
+#define MTL_OP_CONV_DGRAD 1
+#define MTL_OP_CONV_WGRAD 2
+#define MTL_OP_LIN_FWD 3
+#define MTL_OP_LIN_DGRAD 4
+#define MTL_OP_LIN_WGRAD 5
+#define MTL_OP_STEM 6
+#define MTL_OP_VOCAB 7
+#define MTL_OP_CLASSES 8
+int mtl_session_set_op_mode(mtl_session* s, int op_class, int mode);
 long long mtl_param_arena_floats(const mtl_session* s);
 int mtl_param_count(const mtl_session* s);
 int mtl_param_info(const mtl_session* s, int idx, long long* offset_floats, long long* numel);
@@ -143,11 +160,12 @@ typedef struct mtl_meta_step_args {
 } mtl_meta_step_args;
 int mtl_meta_tasks(mtl_session* s, const mtl_meta_step_args* args, void* stream);
 int mtl_graph_stats(const mtl_session* s, unsigned long long* captures, unsigned long long* replays);
-/* transient_trainer.py:248-255: grad <- copy_grad; [clip]; theta <- Adam(theta, grad).
+/* transient_trainer.py:248-255: grad <- copy_grad; [clip]; theta <- Adam(theta, grad) with the outer optimizer's
+ * betas / eps (torch.optim.Adam defaults 0.9, 0.999, 1e-8 at :109; a resumed optimizer keeps its own).
  * adam_state (device): int step, float step_size, float bc2_sqrt, pad (16 bytes). */
 int mtl_meta_finish(float* theta, float* grad, const float* copy_grad, float* adam_m, float* adam_v,
-                    void* adam_state, double meta_lr, int clip, float max_norm, float* scratch1032,
-                    long long n, void* stream);
+                    void* adam_state, double meta_lr, double beta1, double beta2, double eps, int clip,
+                    float max_norm, float* scratch1032, long long n, void* stream);
 
 /* ------------------------------------------------------------------ flat-arena ops
  * models/asr/transformer.py:204-240 (zero/add/from_copy_grad), deepcopy(state_dict) /

@@ -197,6 +197,7 @@ struct mtl_session {
   mtl_model_cfg cfg;
   Layout L;
   int mode = MTL_GEMM_SIMT_FP32;
+  int op_mode[MTL_OP_CLASSES];        // per-operation-class engine (see mtl_session_set_op_mode); -1 = follow `mode`
   Pass pass;                          // record of the plain mtl_asr_forward / mtl_meta_task API
   Branches br;                        // its side streams
   std::vector<Lane> lanes;
@@ -250,6 +251,13 @@ struct Run {
   cudaStream_t side(int i) const { return par() ? br->side[i] : main; }
   cudaStream_t wside() { w_rr ^= 1; return side(S_W0 + w_rr); }   // parameter-gradient work alternates over two streams
 };
+// Engine of one operation class: the fp32 CUDA-core engine (mode 0) is all-or-nothing; otherwise the per-class policy
+// (mtl_session_set_op_mode, default = the session mode) picks TF32 or 3xTF32 for this contraction.
+static inline int op_mode(const mtl_session* S, int cls) {
+  if (S->mode == MTL_GEMM_SIMT_FP32) return MTL_GEMM_SIMT_FP32;
+  const int m = S->op_mode[cls];
+  return m > 0 ? m : S->mode;
+}
 // Scope in which the launch wrappers enqueue on `s` instead of the main stream.
 struct On {
   Run& R;
@@ -298,7 +306,7 @@ static int slab_split(long long tiles, int k_extent, int ctas);
 static int zslab_ctas();
 // y_zeroed: y was allocated from the zero pool (use_zslab) -- the GEMM may accumulate K slabs into it
 static int lin_fwd(Run& R, const float* x, int ldx, const float* W, const float* bias, float* y, int ldy, int M,
-                   int N, int Kd, int epi, bool y_zeroed = false) {
+                   int N, int Kd, int epi, bool y_zeroed = false, int cls = MTL_OP_LIN_FWD) {
   GemmArgs g;
   memset(&g, 0, sizeof(g));
   g.A = x; g.lda = ldx; g.transA = 0; g.B = W; g.ldb = Kd; g.transB = 1; g.C = y; g.ldc = ldy;
@@ -307,7 +315,7 @@ static int lin_fwd(Run& R, const float* x, int ldx, const float* W, const float*
     const int sp = slab_split((long long)mtl_cdiv(M, 128) * mtl_cdiv(N, N <= 64 ? 64 : 128), Kd, zslab_ctas());
     if (sp > 1) { g.beta = 1.f; g.split_k = sp; }
   }
-  K(k_gemm(g, R.S->mode, R.st));
+  K(k_gemm(g, op_mode(R.S, cls), R.st));
   return MTL_OK;
 }
 // K-slabs for an accumulating (beta == 1) contraction: about two CTAs per SM, at least one 32-deep k-block per slab.
@@ -354,7 +362,7 @@ static int wgrad_ctas() {
 }
 // dx[M,K] = epi(dy[M,N] . W[N,K]) + beta*dx
 static int lin_dgrad(Run& R, const float* dy, int ldy, const float* W, float* dx, int ldx, int M, int N, int Kd,
-                     float beta, int epi, const float* aux, bool dx_zeroed = false) {
+                     float beta, int epi, const float* aux, bool dx_zeroed = false, int cls = MTL_OP_LIN_DGRAD) {
   GemmArgs g;
   memset(&g, 0, sizeof(g));
   g.A = dy; g.lda = ldy; g.transA = 0; g.B = W; g.ldb = Kd; g.transB = 0; g.C = dx; g.ldc = ldx;
@@ -365,17 +373,18 @@ static int lin_dgrad(Run& R, const float* dy, int ldy, const float* W, float* dx
     const int sp = slab_split((long long)mtl_cdiv(M, 128) * mtl_cdiv(Kd, Kd <= 64 ? 64 : 128), N, zslab_ctas());
     if (sp > 1) { g.beta = 1.f; g.split_k = sp; }
   }
-  K(k_gemm(g, R.S->mode, R.st));
+  K(k_gemm(g, op_mode(R.S, cls), R.st));
   return MTL_OK;
 }
 // dW[N,K] += dy[M,N]^T . x[M,K]
-static int lin_wgrad(Run& R, const float* dy, int ldy, const float* x, int ldx, float* dW, int M, int N, int Kd) {
+static int lin_wgrad(Run& R, const float* dy, int ldy, const float* x, int ldx, float* dW, int M, int N, int Kd,
+                     int cls = MTL_OP_LIN_WGRAD) {
   GemmArgs g;
   memset(&g, 0, sizeof(g));
   g.A = dy; g.lda = ldy; g.transA = 1; g.B = x; g.ldb = ldx; g.transB = 0; g.C = dW; g.ldc = Kd;
   g.M = N; g.N = Kd; g.K = M; g.alpha = 1.f; g.beta = 1.f; g.epi = EPI_NONE;
   g.split_k = slab_split((long long)mtl_cdiv(N, 128) * mtl_cdiv(Kd, Kd <= 64 ? 64 : 128), M, wgrad_ctas());
-  K(k_gemm(g, R.S->mode, R.st));
+  K(k_gemm(g, op_mode(R.S, cls), R.st));
   return MTL_OK;
 }
 
@@ -568,7 +577,7 @@ static int conv_weight_layouts(Run& R, Pass& P) {
   for (int i = 0; i < 3; ++i) {
     const int widx = i + 1, Cin = kConvCin[widx], Cout = kConvCout[widx];
     // 3xTF32 kw-box kernel: weights are split into tf32 hi / lo halves here, once per pass
-    const int sg = k_conv3x3_w_split(R.S->mode, Cout), sd = k_conv3x3_w_split(R.S->mode, Cin);
+    const int sg = k_conv3x3_w_split(op_mode(R.S, MTL_OP_CONV_FWD), Cout), sd = k_conv3x3_w_split(op_mode(R.S, MTL_OP_CONV_DGRAD), Cin);
     P.cv[i].wg = R.ws.f((size_t)Cout * 9 * Cin * (sg ? 2 : 1));
     P.cv[i].wd = R.ws.f((size_t)Cin * 9 * Cout * (sd ? 2 : 1));
     K(k_conv_w_fwd_layout(R.theta + L.conv_w[widx], P.cv[i].wg, Cout, Cin, sg, R.st));
@@ -585,8 +594,8 @@ static int conv_fwd(Run& R, ConvAct& A, const float* x, int B, int F, int T, int
   A.col = implicit ? nullptr : R.ws.f(P * Kc);
   A.y = R.ws.f(P * A.Cout);
   if (implicit) {
-    K(k_conv3x3_tc(x, A.wg, R.theta + L.conv_b[widx], A.y, B, F, T, A.Cin, A.Cout, EPI_RELU, nullptr, R.S->mode,
-                   k_conv3x3_w_split(R.S->mode, A.Cout), R.st));
+    K(k_conv3x3_tc(x, A.wg, R.theta + L.conv_b[widx], A.y, B, F, T, A.Cin, A.Cout, EPI_RELU, nullptr, op_mode(R.S, MTL_OP_CONV_FWD),
+                   k_conv3x3_w_split(op_mode(R.S, MTL_OP_CONV_FWD), A.Cout), R.st));
   } else {
     K(k_im2col3x3(x, A.col, B, F, T, A.Cin, R.st));
     MTL_TRY(lin_fwd(R, A.col, Kc, A.wg, R.theta + L.conv_b[widx], A.y, A.Cout, (int)P, A.Cout, Kc, EPI_RELU));
@@ -607,7 +616,7 @@ static int conv_bwd(Run& R, const ConvAct& A, const float* dy, float* dx, const 
     On on(R, sw);
     K(k_zero(dwg, (size_t)A.Cout * Kc, R.st));
     if (implicit) {
-      K(k_conv3x3_wgrad_tc(A.x, dy, dwg, A.B, A.F, A.T, A.Cin, A.Cout, R.S->mode, R.st));
+      K(k_conv3x3_wgrad_tc(A.x, dy, dwg, A.B, A.F, A.T, A.Cin, A.Cout, op_mode(R.S, MTL_OP_CONV_WGRAD), R.st));
       K(k_conv_wgrad_scatter_t(dwg, R.grad + L.conv_w[A.widx], A.Cout, A.Cin, R.st));
     } else {
       MTL_TRY(lin_wgrad(R, dy, A.Cout, A.col, Kc, dwg, (int)P, A.Cout, Kc));
@@ -619,7 +628,7 @@ static int conv_bwd(Run& R, const ConvAct& A, const float* dy, float* dx, const 
     const int Kg = 9 * A.Cout;
     if (implicit) {
       K(k_conv3x3_tc(dy, A.wd, nullptr, dx, A.B, A.F, A.T, A.Cout, A.Cin, relu_aux ? EPI_RELU_BWD : EPI_NONE, relu_aux,
-                     R.S->mode, k_conv3x3_w_split(R.S->mode, A.Cin), R.st));
+                     op_mode(R.S, MTL_OP_CONV_DGRAD), k_conv3x3_w_split(op_mode(R.S, MTL_OP_CONV_DGRAD), A.Cin), R.st));
     } else {
       float* colg = R.ws.f(P * Kg);
       K(k_im2col3x3(dy, colg, A.B, A.F, A.T, A.Cout, R.st));
@@ -642,7 +651,7 @@ static int forward(Run& R, const mtl_batch& b, const float* pe_enc, const float*
   const Layout& L = S->L;
   Pass& P = *R.P;
   P.valid = false;
-  MTL_REQUIRE(b.B > 0 && b.T > 0 && b.L > 0 && b.n >= 2, "empty batch");
+  MTL_REQUIRE(b.B > 0 && b.T > 0 && b.L >= 0 && b.n >= 1, "empty batch");   // n == 1: every transcript empty (SOS -> EOS only)
   P.b = b;
   P.B = b.B; P.T = b.T; P.F = c.n_freq; P.F2 = P.F / 2; P.T2 = P.T / 2; P.F4 = P.F2 / 2; P.T4 = P.T2 / 2;
   MTL_REQUIRE(P.T4 >= 1 && P.F4 >= 1, "input shorter than 4 frames / 4 bins");
@@ -687,7 +696,7 @@ static int forward(Run& R, const mtl_batch& b, const float* pe_enc, const float*
   P.e0 = R.ws.f((size_t)P.Me * d);
   P.stem_xhat = R.ws.f((size_t)P.Me * d);
   P.stem_rstd = R.ws.f(P.Me);
-  MTL_TRY(lin_fwd(R, P.feat, P.d_in, R.theta + L.in_w, R.theta + L.in_b, P.h, d, P.Me, d, P.d_in, EPI_NONE, zh));
+  MTL_TRY(lin_fwd(R, P.feat, P.d_in, R.theta + L.in_w, R.theta + L.in_b, P.h, d, P.Me, d, P.d_in, EPI_NONE, zh, MTL_OP_STEM));
   K(k_ln_fwd(P.h, nullptr, R.theta + L.lnin_w, R.theta + L.lnin_b, nullptr, pe_enc, Tp, mtl_nodrop(), P.e0,
              P.stem_xhat, P.stem_rstd, P.Me, d, R.st));
   const float* x = P.e0;
@@ -727,7 +736,7 @@ static int forward(Run& R, const mtl_batch& b, const float* pe_enc, const float*
   }
   P.dec_last = x;
   P.pred = R.ws.f((size_t)P.Md * P.ldp);
-  MTL_TRY(lin_fwd(R, x, d, R.theta + L.out_w, nullptr, P.pred, P.ldp, P.Md, c.vocab, d, EPI_NONE));
+  MTL_TRY(lin_fwd(R, x, d, R.theta + L.out_w, nullptr, P.pred, P.ldp, P.Md, c.vocab, d, EPI_NONE, false, MTL_OP_VOCAB));
 
   // ---- CE + top-1 (metrics.py:126, transformer.py:146)
   P.row_lse = R.ws.f(P.Md);
@@ -771,12 +780,12 @@ static int backward(Run& R, float loss_scale, const float* dpred_ext, int ld_ext
     const cudaStream_t sw = R.wside();
     MTL_TRY(chain(R, R.main, sw));
     On on(R, sw);
-    MTL_TRY(lin_wgrad(R, dpred, P.ldp, P.dec_last, d, R.grad + L.out_w, P.Md, V, d));
+    MTL_TRY(lin_wgrad(R, dpred, P.ldp, P.dec_last, d, R.grad + L.out_w, P.Md, V, d, MTL_OP_VOCAB));
   }
   const bool zg = use_zslab(R, P.Md, d, V);
   float* gA = zg ? R.wz.f((size_t)P.Md * d) : R.ws.f((size_t)P.Md * d);   // only its FIRST use needs the zeros
   float* gB = R.ws.f((size_t)P.Md * d);
-  MTL_TRY(lin_dgrad(R, dpred, P.ldp, R.theta + L.out_w, gA, d, P.Md, V, d, 0.f, EPI_NONE, nullptr, zg));
+  MTL_TRY(lin_dgrad(R, dpred, P.ldp, R.theta + L.out_w, gA, d, P.Md, V, d, 0.f, EPI_NONE, nullptr, zg, MTL_OP_VOCAB));
   float* gE1 = R.ws.f((size_t)P.Me * d);
   float* gE2 = R.ws.f((size_t)P.Me * d);
   K(k_zero(gE1, (size_t)P.Me * d, R.st));
@@ -813,11 +822,11 @@ static int backward(Run& R, float loss_scale, const float* dpred_ext, int ld_ext
     const cudaStream_t sw = R.wside();
     MTL_TRY(chain(R, R.main, sw));
     On on(R, sw);
-    MTL_TRY(lin_wgrad(R, dh, d, P.feat, P.d_in, R.grad + L.in_w, P.Me, d, P.d_in));
+    MTL_TRY(lin_wgrad(R, dh, d, P.feat, P.d_in, R.grad + L.in_w, P.Me, d, P.d_in, MTL_OP_STEM));
     K(k_colsum_acc(dh, P.Me, d, d, R.grad + L.in_b, R.st));
   }
   float* dfeat = R.ws.f((size_t)P.Me * P.d_in);
-  MTL_TRY(lin_dgrad(R, dh, d, R.theta + L.in_w, dfeat, P.d_in, P.Me, d, P.d_in, 0.f, EPI_NONE, nullptr));
+  MTL_TRY(lin_dgrad(R, dh, d, R.theta + L.in_w, dfeat, P.d_in, P.Me, d, P.d_in, 0.f, EPI_NONE, nullptr, false, MTL_OP_STEM));
   // VGG front-end
   float* dp4 = R.ws.f((size_t)B * P.F4 * P.T4 * 128);
   K(k_feat_transpose_bwd(dfeat, dp4, B, P.F4, P.T4, 128, R.st));
@@ -849,6 +858,15 @@ extern "C" int mtl_session_create(const mtl_model_cfg* cfg, mtl_session** out) {
   MTL_REQUIRE(s, "out of host memory");
   s->cfg = *cfg;
   build_layout(s->L, s->cfg);
+  for (int i = 0; i < MTL_OP_CLASSES; ++i) s->op_mode[i] = -1;
+  if (const char* e = getenv("MTL_OP_MODES")) {                 // A/B: comma-separated engine per class, e.g. "1,1,2,1,1,2,2,2"
+    for (int i = 0; i < MTL_OP_CLASSES && *e; ++i) {
+      const int v = atoi(e);
+      if (v == MTL_GEMM_TC_TF32 || v == MTL_GEMM_TC_3XTF32) s->op_mode[i] = v;
+      while (*e && *e != ',') ++e;
+      if (*e == ',') ++e;
+    }
+  }
   *out = s;
   return MTL_OK;
 }
@@ -865,6 +883,12 @@ extern "C" void mtl_session_destroy(mtl_session* s) {
 extern "C" int mtl_session_set_gemm_mode(mtl_session* s, int mode) {
   MTL_REQUIRE(s && mode >= 0 && mode <= 2, "gemm mode");
   s->mode = mode;
+  return MTL_OK;
+}
+extern "C" int mtl_session_set_op_mode(mtl_session* s, int op_class, int mode) {
+  MTL_REQUIRE(s && op_class >= 0 && op_class < MTL_OP_CLASSES, "operation class");
+  MTL_REQUIRE(mode == -1 || mode == MTL_GEMM_TC_TF32 || mode == MTL_GEMM_TC_3XTF32, "op mode: -1 (session mode), 1 (TF32) or 2 (3xTF32)");
+  s->op_mode[op_class] = mode;
   return MTL_OK;
 }
 extern "C" long long mtl_param_arena_floats(const mtl_session* s) { return s ? (long long)s->L.total : -1; }
@@ -884,7 +908,7 @@ static int dry_plan(mtl_session* s, int B, int T, int n, size_t* bytes, size_t* 
   R.ws.base = 0; R.ws.cap = ~(size_t)0;
   mtl_batch b;
   memset(&b, 0, sizeof(b));
-  b.B = B; b.T = T; b.L = n > 1 ? n - 1 : 1; b.n = n;
+  b.B = B; b.T = T; b.L = n > 1 ? n - 1 : 0; b.n = n;
   int rc = forward(R, b, nullptr, nullptr, 0.f);
   if (rc == MTL_OK) rc = backward(R, 1.f, nullptr, 0);
   const size_t zb = (R.wz.peak + 255) & ~(size_t)255;
@@ -915,7 +939,7 @@ struct SeedRef { unsigned long long seed; const unsigned long long* dev; unsigne
 static int run_forward(mtl_session* s, Pass* pass, Branches* br, const float* theta, const float* pe_enc,
                        const float* pe_dec, void* workspace, long long workspace_bytes, const mtl_batch* batch,
                        float dropout, SeedRef seed, float label_smoothing, cudaStream_t st) {
-  MTL_REQUIRE(s && theta && pe_enc && pe_dec && batch && batch->x && batch->lens && batch->trg, "null argument");
+  MTL_REQUIRE(s && theta && pe_enc && pe_dec && batch && batch->x && batch->lens && (batch->trg || batch->L == 0), "null argument");
   MTL_REQUIRE(dropout >= 0.f && dropout < 1.f, "dropout in [0,1)");
   size_t zbytes = 0;
   MTL_TRY(check_ws(s, batch, workspace, workspace_bytes, &zbytes));
@@ -1096,6 +1120,7 @@ extern "C" int mtl_meta_tasks(mtl_session* s, const mtl_meta_step_args* a, void*
   key.push_back(fbits(a->hp.max_norm)); key.push_back(fbits(a->hp.dropout)); key.push_back(fbits(a->hp.label_smoothing));
   key.push_back((unsigned long long)(uintptr_t)a->results); key.push_back((unsigned long long)(uintptr_t)a->seed_slot);
   key.push_back((unsigned long long)s->mode);
+  for (int i = 0; i < MTL_OP_CLASSES; ++i) key.push_back((unsigned long long)(unsigned)s->op_mode[i]);
 
   GraphEntry* e = nullptr;
   for (auto& g : s->graphs) if (g.key == key) { e = &g; break; }
@@ -1190,13 +1215,13 @@ extern "C" int mtl_arena_clip(float* g, long long n, float max_norm, float* scra
   return MTL_OK;
 }
 extern "C" int mtl_meta_finish(float* theta, float* grad, const float* copy_grad, float* adam_m, float* adam_v,
-                               void* adam_state, double meta_lr, int clip, float max_norm, float* scratch1032,
-                               long long n, void* stream) {
+                               void* adam_state, double meta_lr, double beta1, double beta2, double eps, int clip,
+                               float max_norm, float* scratch1032, long long n, void* stream) {
   MTL_REQUIRE(theta && grad && copy_grad && adam_m && adam_v && adam_state, "null argument");
   cudaStream_t st = (cudaStream_t)stream;
   MTL_TRY(k_copy(grad, copy_grad, (size_t)n, st));                                  // model.from_copy_grad()
   if (clip) MTL_TRY(mtl_arena_clip(grad, n, max_norm, scratch1032, stream));
-  MTL_TRY(mtl_arena_adam(theta, grad, adam_m, adam_v, adam_state, meta_lr, 0.9, 0.999, 1e-8, n, stream));
+  MTL_TRY(mtl_arena_adam(theta, grad, adam_m, adam_v, adam_state, meta_lr, beta1, beta2, eps, n, stream));
   return MTL_OK;
 }
 extern "C" int mtl_arena_zero(float* p, long long n, void* stream) { return k_zero(p, (size_t)n, (cudaStream_t)stream); }

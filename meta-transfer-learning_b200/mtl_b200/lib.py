@@ -58,6 +58,7 @@ SIGNATURES = {
     "mtl_session_create": (_I, [C.POINTER(ModelCfg), C.POINTER(_P)]),
     "mtl_session_destroy": (None, [_P]),
     "mtl_session_set_gemm_mode": (_I, [_P, _I]),
+    "mtl_session_set_op_mode": (_I, [_P, _I, _I]),
     "mtl_param_arena_floats": (_LL, [_P]),
     "mtl_param_count": (_I, [_P]),
     "mtl_param_info": (_I, [_P, _I, C.POINTER(_LL), C.POINTER(_LL)]),
@@ -69,7 +70,7 @@ SIGNATURES = {
                            C.POINTER(MetaHParams), _P, _P]),
     "mtl_meta_tasks": (_I, [_P, C.POINTER(MetaStepArgs), _P]),
     "mtl_graph_stats": (_I, [_P, C.POINTER(_ULL), C.POINTER(_ULL)]),
-    "mtl_meta_finish": (_I, [_P, _P, _P, _P, _P, _P, _D, _I, _F, _P, _LL, _P]),
+    "mtl_meta_finish": (_I, [_P, _P, _P, _P, _P, _P, _D, _D, _D, _D, _I, _F, _P, _LL, _P]),
     "mtl_arena_zero": (_I, [_P, _LL, _P]),
     "mtl_arena_copy": (_I, [_P, _P, _LL, _P]),
     "mtl_arena_axpy": (_I, [_P, _P, _F, _LL, _P]),

@@ -89,13 +89,60 @@ class ArenaAdam(torch.optim.Adam):
         self._bind_state()
 
 
+def _cpu(obj):
+    if torch.is_tensor(obj):
+        return obj.detach().cpu().clone()
+    if isinstance(obj, dict):
+        return {k: _cpu(v) for k, v in obj.items()}
+    if isinstance(obj, (list, tuple)):
+        return type(obj)(_cpu(v) for v in obj)
+    return obj
+
+
+def to_torch(opt, host_params=None):
+    """A plain ``torch.optim.SGD`` / ``Adam`` on the host carrying ``opt``'s hyper-parameters and state: what goes
+    into a checkpoint, so that the reference's ``load_meta_model`` (utils/functions.py:183-186: it only calls
+    ``.state_dict()`` on the pickled object) can read files written here without this package being importable.
+    ``host_params``: host tensors in ``model.parameters()`` order to build the optimizer over (shared storage with
+    the checkpoint's model_state_dict, so the pickle stores them once)."""
+    if not isinstance(opt, (ArenaSGD, ArenaAdam)):
+        return opt
+    if host_params is None:
+        host_params = [p.detach().cpu().clone() for p in opt._model._params]
+    params = [torch.nn.Parameter(t, requires_grad=True) for t in host_params]
+    g = opt.param_groups[0]
+    if isinstance(opt, ArenaSGD):
+        new = torch.optim.SGD(params, lr=g['lr'])
+    else:
+        new = torch.optim.Adam(params, lr=g['lr'], betas=tuple(g['betas']), eps=g['eps'])
+    sd = _cpu(opt.state_dict())
+    if len(sd["state"]):
+        new.load_state_dict(sd)
+    else:
+        new.param_groups[0]['lr'] = g['lr']
+    return new
+
+
 def adopt(opt, model, kind):
     """Returns an arena optimizer equivalent to ``opt`` (a torch.optim.SGD / Adam over model.parameters(), e.g.
-    one restored by a reference-style ``load_meta_model``); arena optimizers pass through."""
+    one restored by a reference-style ``load_meta_model``); arena optimizers pass through.  Options the arena
+    kernels do not implement are refused instead of being dropped silently."""
     if isinstance(opt, (ArenaSGD, ArenaAdam)):
         return opt
-    lr = opt.param_groups[0]['lr']
-    new = ArenaSGD(model, lr) if kind == "sgd" else ArenaAdam(model, lr)
-    if kind == "adam" and len(opt.state):
+    if len(opt.param_groups) != 1:
+        raise NotImplementedError("arena optimizers take one parameter group")
+    g = opt.param_groups[0]
+    if g.get('weight_decay', 0) != 0:
+        raise NotImplementedError("weight_decay is not implemented by the arena optimizers")
+    if kind == "sgd":
+        if g.get('momentum', 0) != 0 or g.get('nesterov', False) or g.get('dampening', 0) != 0:
+            raise NotImplementedError("ArenaSGD is plain SGD (transient_trainer.py:106): no momentum / nesterov")
+        return ArenaSGD(model, g['lr'])
+    if g.get('amsgrad', False) or g.get('maximize', False):
+        raise NotImplementedError("ArenaAdam implements torch.optim.Adam without amsgrad / maximize")
+    new = ArenaAdam(model, g['lr'])
+    new.param_groups[0]['betas'] = tuple(g['betas'])
+    new.param_groups[0]['eps'] = g['eps']
+    if len(opt.state):
         new.load_state_dict(opt.state_dict())
     return new

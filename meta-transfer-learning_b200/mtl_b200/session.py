@@ -96,6 +96,13 @@ class Session:
         _l.check(self.lib.mtl_session_set_gemm_mode(self._h, int(mode)))
         self.gemm_mode = int(mode)
 
+    OP_CLASSES = ("conv_fwd", "conv_dgrad", "conv_wgrad", "lin_fwd", "lin_dgrad", "lin_wgrad", "stem", "vocab")
+
+    def set_op_mode(self, op_class, mode: int):
+        """Per-operation-class engine (include/mtl_b200.h: mtl_session_set_op_mode); mode -1 = follow gemm_mode."""
+        idx = self.OP_CLASSES.index(op_class) if isinstance(op_class, str) else int(op_class)
+        _l.check(self.lib.mtl_session_set_op_mode(self._h, idx, int(mode)))
+
     def new_arena(self) -> torch.Tensor:
         return torch.zeros(self.n_floats, dtype=torch.float32, device=self.device)
 
@@ -123,7 +130,7 @@ class Session:
         B, _, F, T = b.x.shape
         assert F == self.spec.n_freq, "input frequency bins != model n_freq"
         cb = _l.CBatch()
-        cb.x, cb.lens, cb.trg = b.x.data_ptr(), b.lens.data_ptr(), b.trg.data_ptr()
+        cb.x, cb.lens, cb.trg = b.x.data_ptr(), b.lens.data_ptr(), (b.trg.data_ptr() if b.trg.numel() else None)
         cb.B, cb.T, cb.L, cb.n = B, T, b.trg.shape[1], b.n
         cb.hyp_out = hyp.data_ptr() if hyp is not None else None
         cb.gold_out = gold.data_ptr() if gold is not None else None
@@ -182,9 +189,10 @@ class Session:
         return int(cap.value), int(rep.value)
 
     def meta_finish(self, theta, grad, copy_grad, adam_m, adam_v, adam_state, meta_lr: float, clip: bool = False,
-                    max_norm: float = 400.0):
+                    max_norm: float = 400.0, betas=(0.9, 0.999), eps: float = 1e-8):
         _l.check(self.lib.mtl_meta_finish(_ptr(theta), _ptr(grad), _ptr(copy_grad), _ptr(adam_m), _ptr(adam_v),
-                                          _ptr(adam_state), float(meta_lr), int(bool(clip)), float(max_norm),
+                                          _ptr(adam_state), float(meta_lr), float(betas[0]), float(betas[1]),
+                                          float(eps), int(bool(clip)), float(max_norm),
                                           _ptr(self._scratch), self.n_floats, _stream()))
 
     def new_adam_state(self) -> torch.Tensor:
@@ -238,15 +246,28 @@ class MetaStepper:
 
     # ------------------------------------------------------------------ static input slots
     def _slot(self, who, B, F, T, L):
-        key = (who, B, F, T, L)
-        if key not in self._slots:
+        """ONE set of static device buffers per input role (`who`), sized by capacity: SpectrogramDataset.sample pads to
+        the batch's own longest utterance / transcript, so (T, L) change almost every iteration of a real run.  The
+        batch of this step is a contiguous PREFIX view of the capacity buffers (the engine takes the logical (B, T, L)
+        from mtl_batch), so the base pointers stay put while shapes vary; capacities grow geometrically (rounded up to
+        64 frames / 16 tokens) and the outgrown buffers are released."""
+        need_x, need_t = B * F * T, max(1, B * L)
+        cur = self._slots.get(who)
+        if cur is None or cur[0].numel() < need_x or cur[2].numel() < need_t or cur[1].numel() < B:
             dev = self.s.device
-            self._slots[key] = (torch.zeros(B, 1, F, T, dtype=torch.float32, device=dev),
-                                torch.zeros(B, dtype=torch.int32, device=dev),
-                                torch.zeros(B, L, dtype=torch.int64, device=dev),
-                                torch.zeros(B * (L + 1), dtype=torch.int32, device=dev),     # hyp
-                                torch.zeros(B * (L + 1), dtype=torch.int32, device=dev))     # gold
-        return self._slots[key]
+            cap_x = B * F * ((T + 63) // 64 * 64)
+            cap_t = B * ((L + 15) // 16 * 16 + 1)
+            if cur is not None:
+                cap_x = max(cap_x, min(2 * cur[0].numel(), 2 * need_x))
+                cap_t = max(cap_t, min(2 * cur[2].numel(), 2 * need_t))
+                self._slots[who] = cur = None
+            self._slots[who] = cur = (torch.zeros(cap_x, dtype=torch.float32, device=dev),
+                                      torch.zeros(B, dtype=torch.int32, device=dev),
+                                      torch.zeros(cap_t, dtype=torch.int64, device=dev),
+                                      torch.zeros(cap_t + B, dtype=torch.int32, device=dev),     # hyp
+                                      torch.zeros(cap_t + B, dtype=torch.int32, device=dev))     # gold
+        bx, bl, bt, hyp, gold = cur
+        return bx[:need_x].view(B, 1, F, T), bl[:B], bt[:B * L].view(B, L), hyp, gold
 
     def _stage(self, who, x, lens, trg, n):
         B, _, F, T = x.shape
@@ -254,7 +275,8 @@ class MetaStepper:
         sx, sl, st, hyp, gold = self._slot(who, B, F, T, L)
         sx.copy_(x, non_blocking=True)
         sl.copy_(lens, non_blocking=True)
-        st.copy_(trg, non_blocking=True)
+        if L:
+            st.copy_(trg, non_blocking=True)
         if n is None:
             n = int((trg != 0).sum(dim=1).max().item()) + 1      # host tensors: no device sync
         return Batch(sx, sl, st, n), hyp, gold

@@ -73,7 +73,7 @@ class JointTrainer(TransientTrainer):
         last_sum_char = deque(maxlen=window_size)
         k_train = args.k_train
         n_tasks = len(train_data_list)
-        from mtl_b200.shard import dist_env, exchange_copy_grad, reduce_stats, task_shard
+        from mtl_b200.shard import dist_env, exchange_copy_grad, reduce_stats, step_seed, task_shard
         dist, rank, world = dist_env()
         my_tasks = task_shard(n_tasks, rank, world)
         buffers = [[] for _ in range(n_tasks)]
@@ -98,7 +98,7 @@ class JointTrainer(TransientTrainer):
                 for m in my_tasks:
                     (tr_inputs, tr_input_sizes, _, tr_targets, _), _ = batches[m]
                     b = Batch.from_host(tr_inputs, tr_input_sizes, tr_targets, session.device)
-                    out = session.forward(theta, b, dropout=drop, seed=it * 64 + m, smoothing=float(smoothing))
+                    out = session.forward(theta, b, dropout=drop, seed=step_seed(it * 64 + m), smoothing=float(smoothing))
                     session.backward(theta, grad, 1.0 / n_tasks)              # (tr_loss / N).backward()
                     outs.append(out)
                 exchange_copy_grad(grad, dist)                                # one all-reduce of the flat gradient arena

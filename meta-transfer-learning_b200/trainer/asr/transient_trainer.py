@@ -100,7 +100,7 @@ class TransientTrainer():
         """
         from mtl_b200 import MetaStepper
         from mtl_b200.optim import ArenaAdam, ArenaSGD, adopt
-        from mtl_b200.shard import dist_env, exchange_copy_grad, reduce_stats, task_shard
+        from mtl_b200.shard import MetaExchange, dist_env, reduce_stats, step_seed, task_shard
         if loss_type != "ce":
             raise NotImplementedError("only the cross-entropy loss is on the B200 hot path")
         if not is_copy_grad:
@@ -136,6 +136,7 @@ class TransientTrainer():
         dist, rank, world = dist_env()
         my_tasks = task_shard(n_tasks, rank, world)
         stepper = MetaStepper(session, max(1, len(my_tasks))) if my_tasks else None
+        exchange = MetaExchange(session, dist)                        # the one exchange step of the meta-step + Adam
         model.zero_copy_grad()
         copy_grad = model._cg
 
@@ -169,14 +170,13 @@ class TransientTrainer():
                     stepper.load_val(val_inputs, val_input_sizes, val_targets)
                     stepper.run(theta, copy_grad, self.get_lr(inner_opt), 1.0 / n_tasks, clip=args.clip,
                                 max_norm=args.max_norm, dropout=float(model.encoder.dropout_rate),
-                                smoothing=float(smoothing), seed=it)
+                                smoothing=float(smoothing), seed=step_seed(it, rank, world))
                     host_res.copy_(stepper.results, non_blocking=True)
                 else:
                     session.zero(copy_grad)
-                exchange_copy_grad(copy_grad, dist)                           # the one exchange step of the meta-step
                 g = outer_opt.param_groups[0]
-                session.meta_finish(theta, grad, copy_grad, outer_opt.m, outer_opt.v, outer_opt.dev_state, g['lr'],
-                                    clip=args.clip, max_norm=args.max_norm)
+                exchange.finish(theta, grad, copy_grad, outer_opt.m, outer_opt.v, outer_opt.dev_state, g['lr'],
+                                clip=args.clip, max_norm=args.max_norm, betas=g['betas'], eps=g['eps'])
 
                 # the only host read-back of the iteration: losses + train indices for the CER strings
                 total_loss, total_cer, total_char = 0.0, 0, 0

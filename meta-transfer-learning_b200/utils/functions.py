@@ -99,8 +99,14 @@ def save_meta_model(model, vocab, epoch, inner_opt, outer_opt, metrics, args, be
     path = _ckpt_path(args, epoch, best_model)
     print("SAVE MODEL to", path)
     logging.info("SAVE MODEL to " + path)
-    torch.save({'vocab': vocab, 'args': args, 'epoch': epoch, 'model_state_dict': _host_state_dict(model),
-                'inner_opt': inner_opt, 'outer_opt': outer_opt, 'metrics': metrics}, path)
+    from mtl_b200.optim import to_torch
+    sd = _host_state_dict(model)
+    host_params = [sd[name] for name, _ in model.named_parameters()]
+    # the optimizers go in as plain torch.optim objects over the same host tensors: the reference's
+    # load_meta_model (functions.py:183-186) reads such a file without this package
+    torch.save({'vocab': vocab, 'args': args, 'epoch': epoch, 'model_state_dict': sd,
+                'inner_opt': to_torch(inner_opt, host_params), 'outer_opt': to_torch(outer_opt, host_params),
+                'metrics': metrics}, path)
 
 
 def save_joint_model(model, vocab, epoch, opt, metrics, args, best_model=False):
@@ -110,8 +116,10 @@ def save_joint_model(model, vocab, epoch, opt, metrics, args, best_model=False):
     path = _ckpt_path(args, epoch, best_model)
     print("SAVE MODEL to", path)
     logging.info("SAVE MODEL to " + path)
-    torch.save({'vocab': vocab, 'args': args, 'epoch': epoch, 'model_state_dict': _host_state_dict(model),
-                'opt': opt, 'metrics': metrics}, path)
+    from mtl_b200.optim import to_torch
+    sd = _host_state_dict(model)
+    torch.save({'vocab': vocab, 'args': args, 'epoch': epoch, 'model_state_dict': sd,
+                'opt': to_torch(opt, [sd[name] for name, _ in model.named_parameters()]), 'metrics': metrics}, path)
 
 
 save_model = save_joint_model

@@ -9,6 +9,7 @@ import copy
 import io
 import os
 import re
+import sys
 
 import numpy as np
 import pytest
@@ -19,6 +20,7 @@ from gpu_util import rel_err
 from oracle import ref_asr, ref_meta
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 TOL_OUT, TOL_GRAD, TOL_CONV = 1e-4, 1e-3, 3e-2          # default engine = 3xTF32; SMALL-config VGG bound: see TOL_CONV_SMALL in tests/test_gpu_parity.py
 
@@ -276,3 +278,42 @@ def test_script_flow_on_synthetic_wav_manifests_with_validation_and_checkpoint(t
     assert "VALID SET 0 LOSS" in out and "AVG VALID LOSS" in out
     assert os.path.exists(os.path.join(str(tmp_path), "flow", "epoch_2.th"))
     assert os.path.exists(os.path.join(str(tmp_path), "flow", "best_model.th"))
+
+
+REF_STAGE = os.path.join(ROOT, "baseline", "_ref")
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("script", ["meta_transfer_train.py", "joint_train.py"])
+def test_unchanged_reference_script_trains_on_the_gpu(tmp_path, script):
+    """The reference's CLI script, byte for byte (staged under baseline/_ref/ by __graft_entry__.build(), never committed),
+    executed by tools/run_reference_script.py against this package: argparse, Vocab, datasets, loaders,
+    init_transformer_model, .cuda() and three training iterations on synthetic WAV manifests
+    (meta_transfer_train.py:116-204 / joint_train.py:120-226)."""
+    import json
+    import subprocess
+    path = os.path.join(REF_STAGE, script)
+    if not os.path.exists(path):
+        pytest.skip("reference scripts not staged (run __graft_entry__.build() in the build container)")
+    labs = api_util.labels(40)
+    labels_path = tmp_path / "labels.json"
+    labels_path.write_text(json.dumps(labs), encoding="utf8")
+    trs = [api_util.write_manifest(str(tmp_path), f"train{i}", 5, seed=i, text_labels=labs[1:12]) for i in range(2)]
+    va = api_util.write_manifest(str(tmp_path), "valid0", 3, seed=9, text_labels=labs[1:12])
+    cmd = [sys.executable, os.path.join(ROOT, "tools", "run_reference_script.py"), path,
+           "--train-manifest-list", *trs, "--valid-manifest-list", va, "--test-manifest-list", va,
+           "--labels-path", str(labels_path), "--sample-rate", "16000", "--k-train", "3",
+           "--num-workers", "1", "--num-enc-layers", "1", "--num-dec-layers", "1", "--num-heads", "2",
+           "--dim-model", "64", "--dim-key", "32", "--dim-value", "32", "--dim-inner", "64", "--dim-emb", "64",
+           "--r", "12", "--cuda", "--copy-grad", "--epochs", "3", "--evaluate-every", "2", "--save-every", "2",
+           "--lr", "1e-3", "--name", "gpu_script", "--save-folder", str(tmp_path)]
+    if script == "meta_transfer_train.py":
+        cmd += ["--k-valid", "2", "--meta-lr", "1e-3"]
+    p = subprocess.run(cmd, cwd=str(tmp_path), capture_output=True, text=True, timeout=800)
+    out = p.stdout + p.stderr
+    assert p.returncode == 0, out[-3000:]
+    import re
+    losses = [float(x) for x in re.findall(r"TRAIN LOSS:([0-9.]+)", out)]
+    assert len(losses) >= 3 and all(np.isfinite(losses)), out[-3000:]
+    assert "VALID SET 0 LOSS" in out, out[-3000:]
+    assert os.path.exists(os.path.join(str(tmp_path), "gpu_script", "epoch_2.th")), out[-3000:]

@@ -3,7 +3,7 @@ on the same seeded inputs, and against the golden vectors the live reference pro
 
 Tolerances.  north_star: "within 1e-3 relative fp32 tolerance (bit-exact for argmax decode indices)".
 Per-tensor relative error = max|a-b| / max|b|.  The default engine is the tcgen05 3xTF32 one (MTL_GEMM_MODE=2):
-logits / loss within 1e-4, gradients within 1e-3 (5e-3 for the cancellation-heavy VGG gradients).
+logits / loss within 1e-4, gradients within 1e-3 (VGG gradients included at cfg-2 size).
 MTL_GEMM_MODE=0 runs the same suite on the exact fp32 CUDA-core engine (1e-4 / 2e-4), MTL_GEMM_MODE=1 on
 plain TF32 (1e-3 on outputs / loss, 5e-3 on gradients)."""
 import os
@@ -24,7 +24,7 @@ TOL_OUT = {0: 1e-4, 1: 1e-3, 2: 1e-4}[GEMM_MODE]
 TOL_GRAD = {0: 2e-4, 1: 5e-3, 2: 1e-3}[GEMM_MODE]
 # The VGG gradients (conv.0 above all: a sum over every pixel of relu-masked terms with heavy cancellation)
 # amplify the engine's per-element error: ~1e-7 (fp32 FMA) / ~1e-6 (3xTF32) / ~3e-4 (TF32) of activations.
-TOL_CONV = {0: 1e-3, 1: 5e-2, 2: 5e-3}[GEMM_MODE]
+TOL_CONV = {0: 1e-3, 1: 5e-2, 2: 1e-3}[GEMM_MODE]
 # SMALL-config VGG gradients: the batch has only 3444 conv pixels and ~28 target tokens, so ONE relu / max-pool decision
 # taken the other way moves a conv gradient by percent of the tensor max.  Measured (seed 5 / batch seed 1): the pool
 # window (b 3, ch 17, f 16-17, t 24-25) of conv.2 holds 0.20169985 and 0.20169957 (gap 1.4e-6 relative, inside any
@@ -439,3 +439,53 @@ def test_dropout_pass_is_deterministic_given_seed_and_unbiased():
     assert rel_err(pred1, pred3) > 1e-3
     o0, pred0, _ = _fwd_bwd(s, p, b, dropout=0.0)
     assert 0.0 < rel_err(pred1, pred0) < 1.0
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# BASELINE cfg 2, EVERY element of every tensor, against the oracle run on this box's CPU cores (north_star: 1e-3
+# relative fp32; rel_err = max|a-b| / max|b| per tensor).  The golden-fixture tests above sample 32 elements per tensor
+# because the fixtures have to stay small; these do not sample.
+TOL_FULL = {0: 5e-4, 1: 1e-2, 2: 1e-3}[GEMM_MODE]
+
+
+@pytest.mark.timeout(900)
+def test_cfg2_full_tensor_fwd_bwd_vs_oracle():
+    cfg = ref_asr.CFG2
+    p = ref_asr.init_params(cfg, 31)
+    batch = mg.cfg2_batch(3100, ragged=True)
+    torch.set_num_threads(os.cpu_count() or 1)
+    loss_o, g_o, gold_o, hyp_o, pred_o = ref_meta.loss_and_grads(p, cfg, batch)
+    out, pred, grads = _fwd_bwd(_session(cfg), p, batch)
+    assert torch.equal(out["gold"].cpu().long(), gold_o)
+    keep = gold_o != 0
+    assert torch.equal(out["hyp"].cpu().long()[keep], hyp_o[keep])          # bit-exact decode indices
+    assert rel_err(pred, pred_o) < TOL_OUT
+    assert abs(float(out["ce"][0]) - loss_o) < TOL_OUT * abs(loss_o)
+    errs = {k: rel_err(grads[k], g_o[k]) for k in g_o if float(g_o[k].abs().max()) > 1e-7}
+    top = sorted(errs.items(), key=lambda kv: -kv[1])[:5]
+    print("cfg2 full-tensor worst gradient errors:", top)
+    assert len(errs) >= 180
+    assert all(v < TOL_FULL for v in errs.values()), top
+
+
+@pytest.mark.timeout(900)
+def test_cfg2_full_tensor_meta_step_copy_grad_vs_oracle():
+    """One full cfg-2 meta-step (trainer/asr/transient_trainer.py:178-237: 3 tasks x (train at theta0, SGD step, shared
+    val batch at the adapted weights, train-gradient leak)): every element of the 190 copy_grad tensors and the val
+    losses against oracle/ref_meta.meta_step on the CPU."""
+    cfg, m = ref_asr.CFG2, mg.CFG2_META
+    p = ref_asr.init_params(cfg, m["seed"])
+    tasks, val = mg.cfg2_tasks()
+    torch.set_num_threads(os.cpu_count() or 1)
+    po = {k: v.clone() for k, v in p.items()}
+    r = ref_meta.meta_step(po, ref_meta.AdamState(), cfg, tasks, val, lr=m["lr"], meta_lr=m["meta_lr"])
+    losses, cg, theta, _ = _meta_run_lanes(_session(cfg), p, [(tasks, val)], m["lr"], m["meta_lr"])
+    assert abs(losses[0] - r["loss"]) < TOL_OUT * abs(r["loss"])
+    errs = {k: rel_err(cg[k], r["copy_grad"][k]) for k in r["copy_grad"] if float(r["copy_grad"][k].abs().max()) > 1e-7}
+    top = sorted(errs.items(), key=lambda kv: -kv[1])[:5]
+    print("cfg2 full-tensor worst copy_grad errors:", top)
+    assert all(v < TOL_FULL for v in errs.values()), top
+    # first Adam step from zero moments: |delta| = meta_lr * |g| / (|g| + eps) -> exactly meta_lr wherever |g| >> eps
+    for k in po:
+        d = (theta[k].cpu() - po[k]).abs()
+        assert float(d.max()) <= 2.1 * m["meta_lr"], k

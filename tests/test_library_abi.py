@@ -29,7 +29,7 @@ def test_every_declared_symbol_is_exported(lib):
     for name in declared:
         assert hasattr(lib, name), name
     assert declared == set(L.SIGNATURES), declared ^ set(L.SIGNATURES)
-    assert lib.mtl_abi_version() == 1
+    assert lib.mtl_abi_version() == 2
 
 
 @pytest.mark.parametrize("cfg", [ref_asr.SMALL, ref_asr.CFG2])

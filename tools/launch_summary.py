@@ -8,7 +8,31 @@ import csv
 import sys
 
 
+def main_timeline(path):
+    """bench.py --timeline rows (name,stream,start_us,dur_us; CUPTI through torch.profiler): real concurrent durations."""
+    import gzip
+    agg = collections.defaultdict(lambda: [0, 0.0])
+    t0, t1 = None, None
+    with gzip.open(path, "rt") as f:
+        next(f)
+        for line in f:
+            name, _, start, dur = line.rstrip("\n").rsplit(",", 3)
+            start, dur = float(start), float(dur)
+            t0 = start if t0 is None else min(t0, start)
+            t1 = start + dur if t1 is None else max(t1, start + dur)
+            k = name.split("(")[0][-90:]
+            agg[k][0] += 1
+            agg[k][1] += dur
+    tot = sum(v[1] for v in agg.values())
+    print(f"# {path}: {sum(v[0] for v in agg.values())} launches, {tot:.1f} us summed kernel time over a {t1 - t0:.1f} us span")
+    print(f"{'us':>11} {'share':>6} {'n':>6} {'avg us':>8}  kernel")
+    for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print(f"{v[1]:11.1f} {100 * v[1] / tot:5.1f}% {v[0]:6d} {v[1] / v[0]:8.1f}  {k}")
+
+
 def main(path):
+    if path.endswith(".gz"):
+        return main_timeline(path)
     rows = list(csv.reader(open(path, errors="replace")))
     hi = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
     hdr, data = rows[hi], rows[hi + 1:]
