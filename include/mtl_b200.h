@@ -194,6 +194,9 @@ int mtl_debug_gemm_stamps(long long* host160);
 int mtl_debug_attn_stamps(long long* host32);
 /* MTL_GEMM_DBG=99: %globaltimer (ns) at entry / exit of the first 256 CTAs of the last tcgen05 GEMM launch */
 int mtl_debug_gemm_span(unsigned long long* host512);
+/* debug: device pointers (inside the caller's workspace) of the VGG front-end intermediates of the last
+ * mtl_asr_forward + mtl_asr_backward: c1, c2, p2, c3, c4, p4, feat, dfeat, dp4, dc4, dc3, dp2, dc2, dc1, dh, NULL */
+int mtl_debug_pass_buffers(mtl_session* s, const float** out16);
 /* LayerNorm(dropout(y)+res)*rowmask (+pe)  -- modules/common_layers.py:129-131,303-304 */
 int mtl_ln_fwd(const float* y, const float* res, const float* gamma, const float* beta,
                const float* rowmask, const float* pe, int pe_period, float drop_p,

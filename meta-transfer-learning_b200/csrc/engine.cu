@@ -142,6 +142,7 @@ struct Pass {
   size_t wz_off = 0, wz_cap = 0;
   uintptr_t ws_base;
   size_t ws_cap;
+  const float* dbg[16] = {};          // mtl_debug_pass_buffers: VGG intermediates and their gradients of the last pass
 };
 
 // Side streams of one pass.  A forward/backward pass is a DAG, not a chain: the k / v projections run beside the
@@ -840,6 +841,8 @@ static int backward(Run& R, float loss_scale, const float* dpred_ext, int ld_ext
   K(k_maxpool2_relu_bwd(P.cv[0].y, dp2, dc2, B, P.F, P.T, 64, R.st));
   float* dc1 = R.ws.f((size_t)B * P.F * P.T * 64);
   MTL_TRY(conv_bwd(R, P.cv[0], dc2, dc1, P.c1));
+  { const float* d[16] = {P.c1, P.cv[0].y, P.p2, P.cv[1].y, P.cv[2].y, P.p4, P.feat, dfeat, dp4, dc4, dc3, dp2, dc2, dc1, dh, nullptr};
+    for (int i = 0; i < 16; ++i) P.dbg[i] = d[i]; }
   K(k_conv1_wgrad(P.b.x, dc1, R.grad + L.conv_w[0], R.grad + L.conv_b[0], B, P.F, P.T, 64, R.st));
   MTL_TRY(join_all(R));
   return MTL_OK;
@@ -1257,6 +1260,13 @@ extern "C" int mtl_gemm_repeat(int reps, int mode, int transA, int transB, int M
   return MTL_OK;
 }
 int k_gemm_tc_debug_span(unsigned long long* host512);
+// debug: device pointers of the VGG intermediates of the last forward+backward of the plain (mtl_asr_*) pass:
+// c1, c2, p2, c3, c4, p4, feat, dfeat, dp4, dc4, dc3, dp2, dc2, dc1, dh (NHWC / row-major, inside the caller's workspace)
+extern "C" int mtl_debug_pass_buffers(mtl_session* s, const float** out16) {
+  MTL_REQUIRE(s && out16, "null argument");
+  for (int i = 0; i < 16; ++i) out16[i] = s->pass.dbg[i];
+  return MTL_OK;
+}
 extern "C" int mtl_debug_gemm_span(unsigned long long* host512) { return k_gemm_tc_debug_span(host512); }
 int k_attn_debug_stamps(long long* host32);
 extern "C" int mtl_debug_attn_stamps(long long* host32) { return k_attn_debug_stamps(host32); }

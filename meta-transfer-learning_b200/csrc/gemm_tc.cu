@@ -250,6 +250,10 @@ __device__ __forceinline__ void tma_epilogue_rows(const TcParams& P, const CUten
   const int nch = min(CHUNKS, (g.N - n0 + 31) / 32);            // chunks with at least one valid column
   mbar_wait(tmem_full, 0);                                       // accumulator complete => operand buffers are dead
   tc_fence_after();
+  // The staging tile aliases operand stages these same four warps read / rewrote as splitters.  The mbarrier chain
+  // (splitter -> ready -> MMA -> commit -> tmem_full) already orders those accesses before the stores below; the named
+  // barrier states the same order in a form compute-sanitizer's racecheck can see (it does not model mbarriers).
+  asm volatile("bar.sync 1, 128;" ::: "memory");
   if (threadIdx.x == 64) DBG_STAMP(5);
   if (mask && threadIdx.x == 64) {
     mbar_expect_tx(aux_full, (uint32_t)(nch * CHUNK_BYTES));
@@ -553,6 +557,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
   if (warp >= 2) {
     mbar_wait(tmem_full, 0);
     tc_fence_after();
+    asm volatile("bar.sync 1, 128;" ::: "memory");   // see tma_epilogue_rows: staging aliases the splitter's operand stages
     if (threadIdx.x == 64) DBG_STAMP(5);
     float* dst = stg + (q * 32 + lane) * LDS;
 #pragma unroll 1

@@ -82,6 +82,7 @@ SIGNATURES = {
     "mtl_debug_gemm_stamps": (_I, [_P]),
     "mtl_debug_attn_stamps": (_I, [_P]),
     "mtl_debug_gemm_span": (_I, [_P]),
+    "mtl_debug_pass_buffers": (_I, [_P, _P]),
     "mtl_ln_fwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _F, _ULL, _U, _P, _P, _P, _I, _I, _P]),
     "mtl_ln_bwd": (_I, [_P, _P, _P, _P, _P, _F, _ULL, _U, _P, _P, _I, _P, _P, _I, _I, _P]),
     "mtl_attn_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _ULL, _U, _P, _P, _P]),

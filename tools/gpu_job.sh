@@ -9,7 +9,7 @@ for step in "$@"; do
   echo "=== $step ($(date +%T))"
   case "$step" in
     pytest)      timeout 1500 $PY -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $OUT/pytest_gpu.log; tail -5 $OUT/pytest_gpu.log ;;
-    pytest_new)  timeout 1200 $PY -m pytest tests -m gpu -q -k "full_tensor or unchanged_reference or two_gpu or empty_transcript or varying_shapes or checkpoint" > $OUT/pytest_new.log 2>&1; echo "pytest rc=$?" >> $OUT/pytest_new.log; tail -15 $OUT/pytest_new.log ;;
+    pytest_new)  timeout 1200 $PY -m pytest tests -m gpu -q -k "full_tensor or decision_flips or unchanged_reference or two_gpu or empty_transcript or varying_shapes or checkpoint" > $OUT/pytest_new.log 2>&1; echo "pytest rc=$?" >> $OUT/pytest_new.log; tail -15 $OUT/pytest_new.log ;;
     precision)   timeout 900 $PY tools/probes/precision_table.py > $OUT/precision_table.log 2>&1; tail -80 $OUT/precision_table.log ;;
     bench)       timeout 900 $PY bench.py > $OUT/bench.json 2> $OUT/bench.err; tail -c 3000 $OUT/bench.json; tail -3 $OUT/bench.err ;;
     bench_tf32)  MTL_GEMM_MODE=1 timeout 600 $PY bench.py --no-cpu-baseline > $OUT/bench_tf32.json 2> $OUT/bench_tf32.err; tail -c 1500 $OUT/bench_tf32.json ;;

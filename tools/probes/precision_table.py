@@ -35,7 +35,8 @@ def main():
     policies = sys.argv[1:] or (
         [""] + ["%s=1" % c for c in CLASSES] +
         ["conv_fwd=1,conv_dgrad=1", "conv_fwd=1,conv_dgrad=1,conv_wgrad=1", "lin_fwd=1,lin_dgrad=1,lin_wgrad=1,stem=1,vocab=1",
-         "lin_fwd=1,lin_dgrad=1", "lin_wgrad=1,conv_wgrad=1",
+         "lin_fwd=1,lin_dgrad=1", "lin_wgrad=1,conv_wgrad=1", "conv_dgrad=1,conv_wgrad=1", "conv_dgrad=1,conv_wgrad=1,vocab=1",
+         "conv_dgrad=1,conv_wgrad=1,vocab=1,lin_wgrad=1",
          ",".join("%s=1" % c for c in CLASSES)])
     table = {}
     for pol in policies:
@@ -51,17 +52,21 @@ def main():
         torch.cuda.synchronize()
         gv = s.views(grad)
         errs = {k: rel_err(gv[k], g_o[k]) for k in g_o if float(g_o[k].abs().max()) > 1e-7}
+        l2 = {k: float((gv[k].cpu().double() - g_o[k].double()).norm() / g_o[k].double().norm()) for k in errs}
         keep = gold_o != 0
         hyp_ok = bool(torch.equal(out["hyp"].cpu().long()[keep], hyp_o[keep]))
         top = sorted(errs.items(), key=lambda kv: -kv[1])[:6]
         row = {"pred": rel_err(pred, pred_o), "loss": abs(float(out["ce"][0]) - loss_o) / abs(loss_o), "hyp_exact": hyp_ok,
                "worst": top[0][1], "n_over_1e-3": sum(1 for v in errs.values() if v > 1e-3),
-               "n_over_5e-4": sum(1 for v in errs.values() if v > 5e-4), "top": top, "all": errs}
+               "n_over_5e-4": sum(1 for v in errs.values() if v > 5e-4), "top": top, "all": errs,
+               "l2_worst": max(l2.values()), "l2_n_over_1e-3": sum(1 for v in l2.values() if v > 1e-3),
+               "l2_top": sorted(l2.items(), key=lambda kv: -kv[1])[:4], "l2_all": l2}
         table[pol or "all=2"] = row
         print("%-60s pred %.1e loss %.1e hyp %s worst %.2e  >1e-3: %d  >5e-4: %d" % (
             pol or "all=2", row["pred"], row["loss"], hyp_ok, row["worst"], row["n_over_1e-3"], row["n_over_5e-4"]))
         for k, v in top[:4]:
             print("      %-55s %.2e" % (k, v))
+        print("      L2-relative: worst %.2e (%s), > 1e-3: %d" % (row["l2_worst"], row["l2_top"][0][0], row["l2_n_over_1e-3"]))
         sys.stdout.flush()
         del s
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
