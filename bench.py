@@ -35,13 +35,10 @@ T_FRAMES, L_TOKENS = 101, 32
 TASKS_PER_GPU = 3
 LR, META_LR, DROPOUT = 1e-4, 1e-4, 0.1
 METRIC = "meta-step utterances/sec (enc2/dec4/d512, k=8)"
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE conv.2-forward launch (conv3x3_kw_kernel<64>) from the committed
-# `ncu --set full` captures, per gemm mode; None until a capture of that mode exists
-ROOFLINE_TRAFFIC_BYTES = {1: 33474816 + 765184, 2: 33627648 + 661760}   # profiles/r01_f_ncu_full_conv2_kw_{tf32,3xtf32}.txt
-# sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active of the same captures: how busy the tcgen05 pipe is with
-# the instruction mix the mode issues (3xTF32 issues 3 MMA-products per useful product)
-ROOFLINE_TENSOR_PIPE_PCT = {1: 30.7, 2: 50.4}
 UNIT = "utterance-passes/s"
+# algorithmic FLOPs of one cfg-2 meta-step with 3 tasks (48 utterance passes, forward + backward = 3 x the
+# forward MACs x 2): all dense contractions, and the attention + FFN + projection share the north_star names
+STEP_TFLOP_3TASKS, ATTN_FFN_TFLOP_3TASKS = 0.533, 0.0653
 
 
 def _peaks():
@@ -52,6 +49,31 @@ def _peaks():
                     src="measured")
     except Exception:
         return dict(hbm=6650.0, bf16=1590.0, bf16_sus=1400.0, src="fallback")
+
+
+def _ncu(role, mode):
+    """Metrics of the committed `ncu --set full` capture that documents `role` (profiles/ncu_metrics.json, written by
+    tools/ncu_extract.py from profiles/*_ncu_full_*.txt); {} when there is no capture for this engine mode."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_metrics.json")) as f:
+            caps = json.load(f)
+    except Exception:
+        return {}
+    best = {}
+    for v in caps.values():
+        if v.get("role") == role and v.get("gemm_mode") == mode and v.get("source", "") > best.get("source", ""):
+            best = v
+    return best
+
+
+def workload_config(n_total, world, scaling):
+    """The `config` object, identical in both arms (the reference arm times a bounded sample of the same workload)."""
+    w = "cfg2: meta_transfer_train.py 3 synthetic tasks k-train=8 enc2/dec4 d512 --copy-grad"
+    if world > 1:
+        w += (f", {n_total} tasks over {world} GPUs ({scaling} scaling), one exchange of copy_grad per step")
+    return {"workload": w, "tasks": n_total, "k_train": K_TRAIN, "k_valid": K_VALID, "frames": T_FRAMES,
+            "tokens": L_TOKENS, "dropout": DROPOUT,
+            "l2": "per-pass working set ~1.1 GB of activations + 56 MB x 6 arenas >> 126 MB L2"}
 
 
 def synth_task(spec, k, seed):
@@ -91,13 +113,15 @@ def run_reference(args, rank, world):
     dt = time.perf_counter() - t0
     u = n_tasks * (K_TRAIN + K_VALID)
     val = u * args.steps / dt
-    sample = f"{args.steps} full meta-steps ({n_tasks} tasks x ({K_TRAIN}+{K_VALID}) utterances, T={T_FRAMES}, L={L_TOKENS}, dropout {DROPOUT})"
+    sample = (f"{args.steps} full meta-steps of {n_tasks} tasks x ({K_TRAIN}+{K_VALID}) utterances (T={T_FRAMES}, L={L_TOKENS}, "
+              f"dropout {DROPOUT}) on {cores} host threads: the CPU port of the reference step (oracle/ref_meta.meta_step; "
+              "in the build container it runs 15 % faster than the live TransientTrainer, 1.99 vs 2.36 s/step on 8 cores)")
+    n_total = TASKS_PER_GPU * max(1, args.gpus)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "cfg2: meta_transfer_train.py 3 synthetic tasks k-train=8 enc2/dec4 d512 --copy-grad",
-                   "tasks": n_tasks, "k_train": K_TRAIN, "k_valid": K_VALID, "frames": T_FRAMES, "tokens": L_TOKENS},
+        "config": workload_config(n_total, max(1, args.gpus), "weak"),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -148,7 +172,7 @@ class ClockSampler:
 def run_ours(args, rank, world, local_rank):
     import mtl_b200
     from mtl_b200 import lib as L
-    from mtl_b200.shard import exchange_copy_grad
+    from mtl_b200.shard import MetaExchange, task_shard
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     dist = None
@@ -165,7 +189,7 @@ def run_ours(args, rank, world, local_rank):
 
     # parameters: reference init distributions (xavier_uniform on >=2-D), same on every rank
     g = torch.Generator().manual_seed(0)
-    theta, theta0, grad, cg, m, v = (s.new_arena() for _ in range(6))
+    theta, grad, cg, m, v = (s.new_arena() for _ in range(5))
     adam_state = s.new_adam_state()
     views = s.views(theta)
     for name, shape, off, n in s.table:
@@ -179,95 +203,148 @@ def run_ours(args, rank, world, local_rank):
             views[name].zero_()
         else:
             views[name].copy_((torch.rand(shape, generator=g) * 2 - 1) * 0.05)
+    theta_init = theta.clone()
+    exchange = MetaExchange(s, dist, mode=args.exchange)
 
     total_steps = args.warmup + args.steps
-    # host batches (pinned) for every step; device copies for the device-resident measurement
-    host = []
-    for i in range(total_steps):
-        tasks = [synth_task(spec, K_TRAIN, 1000 * i + rank * n_local + t) for t in range(n_local)]
-        val = synth_task(spec, K_VALID, 1000 * i + 999)
-        host.append(([tuple(t.pin_memory() for t in b) for b in tasks], tuple(t.pin_memory() for t in val)))
-    resident = [([tuple(t.to(dev) for t in b) for b in tasks], tuple(t.to(dev) for t in val)) for tasks, val in host]
     n_tok = L_TOKENS + 1
-    stepper = mtl_b200.MetaStepper(s, n_local, n_lanes=args.lanes or n_local, use_graph=not args.no_graph)
-    all_results = torch.zeros(total_steps, n_local, 16, device=dev)
-    torch.cuda.synchronize()
 
-    def meta_step(i, tasks, val):
-        # snapshot / reset of the weights (transient_trainer.py:160,237) are folded into the per-lane
-        # theta copies inside mtl_meta_tasks; theta itself only changes in the Adam step below
-        for t, b in enumerate(tasks):
-            stepper.load_task(t, *b, n=n_tok)                   # H2D (e2e) or D2D (resident) into the static slots
-        stepper.load_val(*val, n=n_tok)
-        res = stepper.run(theta, cg, LR, 1.0 / n_total, dropout=DROPOUT, seed=i * 64 + rank)
-        all_results[i].copy_(res, non_blocking=True)
-        exchange_copy_grad(cg, dist)                            # the one exchange step
-        s.meta_finish(theta, grad, cg, m, v, adam_state, META_LR)
+    def make_data(task_ids):
+        """pinned host batches for every step (task `t` of step i has seed 1000 i + t) + device copies"""
+        host = []
+        for i in range(total_steps):
+            tasks = [synth_task(spec, K_TRAIN, 1000 * i + t) for t in task_ids]
+            val = synth_task(spec, K_VALID, 1000 * i + 999)
+            host.append(([tuple(t.pin_memory() for t in b) for b in tasks], tuple(t.pin_memory() for t in val)))
+        resident = [([tuple(t.to(dev) for t in b) for b in tasks], tuple(t.to(dev) for t in val)) for tasks, val in host]
+        return host, resident
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---------------- device-resident throughput
+    def timed(fn, first, last):
+        """device time of fn(first..last-1): barrier + synchronize on both sides, max over ranks"""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(first, last):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if dist is not None:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    class Leg:
+        """One measured configuration: `task_ids` are this rank's tasks out of `n_tasks_total`."""
+
+        def __init__(self, task_ids, n_tasks_total):
+            self.ids, self.n_total = list(task_ids), n_tasks_total
+            self.host, self.resident = make_data(self.ids)
+            self.stepper = (mtl_b200.MetaStepper(s, len(self.ids), n_lanes=args.lanes or len(self.ids),
+                                                 use_graph=not args.no_graph) if self.ids else None)
+            self.results = torch.zeros(total_steps, max(1, len(self.ids)), 16, device=dev)
+            self.host_res = torch.zeros(max(1, len(self.ids)), 16).pin_memory()
+
+        def step(self, i, data):
+            # snapshot / reset of the weights (transient_trainer.py:160,237) are folded into the per-lane theta copies
+            # inside mtl_meta_tasks; theta itself only changes in the Adam step at the end
+            tasks, val = data[i]
+            if self.stepper is not None:
+                for t, b in enumerate(tasks):
+                    self.stepper.load_task(t, *b, n=n_tok)      # H2D (e2e) or D2D (resident) into the static slots
+                self.stepper.load_val(*val, n=n_tok)
+                res = self.stepper.run(theta, cg, LR, 1.0 / self.n_total, dropout=DROPOUT, seed=i * 64 + rank)
+                self.results[i].copy_(res, non_blocking=True)
+            else:
+                s.zero(cg)                                      # a rank without a task still joins the exchange
+            exchange.finish(theta, grad, cg, m, v, adam_state, META_LR)   # the one exchange step (SURVEY 8e) + Adam
+
+        def e2e_step(self, i):
+            self.step(i, self.host)
+            if self.stepper is not None:
+                self.host_res.copy_(self.stepper.results, non_blocking=True)
+            torch.cuda.current_stream().synchronize()           # the trainer prints the loss every step
+
+        def measure(self):
+            for i in range(args.warmup):
+                self.step(i, self.resident)
+            l0 = lib.mtl_launch_count()
+            ms = timed(lambda i: self.step(i, self.resident), args.warmup, total_steps)
+            launches = lib.mtl_launch_count() - l0
+            for i in range(min(2, args.warmup)):
+                self.e2e_step(i)
+            ms_e2e = timed(self.e2e_step, args.warmup, total_steps)
+            return ms, ms_e2e, launches
+
+    # ---------------- weak scaling (the headline): TASKS_PER_GPU tasks on every rank
     # the clock sampler starts before the warm-up steps (nvidia-smi needs ~0.2 s to produce its first line and the
     # timed region is only ~0.15 s long): its samples cover warm-up + timed region, all under load
     clocks = ClockSampler(local_rank) if rank == 0 else None
-    for i in range(args.warmup):
-        meta_step(i, *resident[i])
-    barrier()
-    l0 = lib.mtl_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.warmup, total_steps):
-        meta_step(i, *resident[i])
-    e1.record()
-    barrier()
-    launches = lib.mtl_launch_count() - l0
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if dist is not None:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms)
+    weak = Leg(range(rank * n_local, (rank + 1) * n_local), n_total)
+    ms_total, ms_e2e, launches = weak.measure()
     clk = clocks.stop() if clocks else None
-    losses = all_results[args.warmup:, :, 8].mean(dim=1).tolist()
-
-    # ---------------- end to end: host (pinned) batches in, losses out, every step
-    h2d = sum(t.numel() * t.element_size() for b in host[0][0] for t in b) + \
-        sum(t.numel() * t.element_size() for t in host[0][1])
+    losses = weak.results[args.warmup:, :, 8].mean(dim=1).tolist()
+    h2d = sum(t.numel() * t.element_size() for b in weak.host[0][0] for t in b) + \
+        sum(t.numel() * t.element_size() for t in weak.host[0][1])
     d2h = n_local * 16 * 4
-    host_res = torch.zeros(n_local, 16).pin_memory()
-
-    def e2e_step(i):
-        tasks, val = host[i]
-        meta_step(i, tasks, val)
-        host_res.copy_(stepper.results, non_blocking=True)
-        torch.cuda.current_stream().synchronize()               # the trainer prints the loss every step
-        return float(host_res[:, 8].mean())
-
-    for i in range(min(2, args.warmup)):
-        e2e_step(i)
-    barrier()
-    e0.record()
-    for i in range(args.warmup, total_steps):
-        e2e_step(i)
-    e1.record()
-    barrier()
-    ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if dist is not None:
-        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
-    ms_e2e = float(ms2)
     graph_caps, graph_reps = s.graph_stats()
 
-    if args.timeline and rank == 0:
-        dump_timeline(args.timeline, lambda: [meta_step(i, *resident[i]) for i in range(total_steps - 2, total_steps)])
+    # replicas must hold bit-identical weights after the same sequence of exchanged steps
+    chk = torch.stack([theta.double().sum(), theta.view(torch.int32).sum(dtype=torch.int64).double()])
+    allchk = [chk.clone() for _ in range(world)]
+    if dist is not None:
+        dist.all_gather(allchk, chk)
+    replicas_identical = all(torch.equal(c, allchk[0]) for c in allchk)
+    assert replicas_identical, "replicas diverged: " + str([c.tolist() for c in allchk])
 
-    # ---------------- roofline of the dominant kernel: conv.2 forward contraction (130088 x 64 x 576)
+    # ---------------- strong scaling (BASELINE configs[2]: the SAME 3-task meta-batch, one task per GPU)
+    strong = None
+    if world > 1 and not args.no_strong:
+        theta.copy_(theta_init); m.zero_(); v.zero_(); adam_state.zero_()
+        leg = Leg(task_shard(TASKS_PER_GPU, rank, world), TASKS_PER_GPU)
+        ms_s, ms_s_e2e, _ = leg.measure()
+        u3 = TASKS_PER_GPU * (K_TRAIN + K_VALID)
+        strong = {"tasks": TASKS_PER_GPU, "value": u3 * args.steps / (ms_s / 1e3), "ms_per_step": ms_s / args.steps,
+                  "e2e_value": u3 * args.steps / (ms_s_e2e / 1e3), "unit": UNIT,
+                  "gpus_with_a_task": min(world, TASKS_PER_GPU),
+                  "note": "total work fixed at the cfg-2 meta-batch (3 tasks): rank r runs tasks r, r + N, ...; one task is one "
+                          "dependent chain of 2 passes, so a rank with a single task is bound by that chain's latency"}
+
+    if args.timeline and rank == 0:
+        dump_timeline(args.timeline, lambda: [weak.step(i, weak.resident) for i in range(total_steps - 2, total_steps)])
+
+    # ---------------- roofline: kernel families by TIME (CUPTI pass), FLOP-dominant kernel timed alone, whole step
     roof = None
-    if rank == 0:
+    if rank == 0 and not args.no_roofline:
+        fam = kernel_families(lambda: [weak.step(i, weak.resident) for i in range(total_steps - 2, total_steps)], 2)
         roof = roofline_conv_gemm(s, lib, dev, args.gemm_mode)
+        pk = _peaks()
+        tf_step = STEP_TFLOP_3TASKS * n_local / 3.0                 # this rank's share of the step
+        af_step = ATTN_FFN_TFLOP_3TASKS * n_local / 3.0
+        ach = tf_step / (ms_total / args.steps / 1e3)
+        roof["whole_step"] = {"tflop_per_step_per_gpu": tf_step, "achieved": ach, "peak": pk["bf16_sus"], "unit": "TFLOP/s",
+                              "frac": ach / pk["bf16_sus"], "peak_source": pk["src"] + " dense bf16 cuBLAS sustained"}
+        if fam:
+            a = fam["families"]["attn_ffn"]
+            ach_a = af_step / (a["busy_ms_per_step"] / 1e3) if a["busy_ms_per_step"] > 0 else 0.0
+            roof["attn_ffn"] = {"tflop_per_step_per_gpu": af_step, "busy_ms_per_step": a["busy_ms_per_step"],
+                                "sum_kernel_ms_per_step": a["sum_ms_per_step"], "launches_per_step": a["launches_per_step"],
+                                "achieved": ach_a, "peak": pk["bf16_sus"], "unit": "TFLOP/s", "frac": ach_a / pk["bf16_sus"],
+                                "how": "attention + FFN + projection FLOPs (SURVEY 8d) over the time at least one kernel of "
+                                       "the family (block nn.Linear GEMMs, attention, LayerNorm, bias column sums) is running: "
+                                       "union of CUPTI kernel intervals, traced outside the timed region"}
+            roof["time_dominant"] = fam["top"]
+            roof["kernel_time_shares"] = {k: round(f["share"], 4) for k, f in fam["families"].items()}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline()
+    gpu_base = None
+    if rank == 0 and world == 1 and not args.no_gpu_baseline:
+        gpu_base = gpu_eager_baseline()
 
     if rank == 0:
         val = u_total * args.steps / (ms_total / 1e3)
@@ -275,23 +352,109 @@ def run_ours(args, rank, world, local_rank):
             "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {0: "f32", 1: "tf32", 2: "3xtf32"}[args.gemm_mode], "data": "synthetic",
-            "config": {"workload": "cfg2: meta_transfer_train.py 3 synthetic tasks k-train=8 enc2/dec4 d512 --copy-grad"
-                       + (f", {n_local} tasks per GPU x {world} GPUs, one all-reduce of copy_grad" if world > 1 else ""),
-                       "tasks": n_total, "k_train": K_TRAIN, "k_valid": K_VALID, "frames": T_FRAMES,
-                       "tokens": L_TOKENS, "dropout": DROPOUT, "gemm_mode": args.gemm_mode,
-                       "l2": "per-pass working set ~1.1 GB of activations + 56 MB x 6 arenas >> 126 MB L2"},
+            "config": workload_config(n_total, world, "weak"),
+            "engine": {"gemm_mode": args.gemm_mode, "op_modes": os.environ.get("MTL_OP_MODES", "default: 3xTF32 everywhere "
+                       "except the VGG input / weight gradients (single-pass TF32)") if args.gemm_mode == 2 else "session mode",
+                       "exchange": args.exchange, "lanes": weak.stepper.n_lanes},
             "e2e": {"value": u_total * args.steps / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
-            "cuda_graph": {"captures": graph_caps, "replays": graph_reps, "lanes": stepper.n_lanes},
+            "cuda_graph": {"captures": graph_caps, "replays": graph_reps, "lanes": weak.stepper.n_lanes},
             "clocks": clk,
+            "replicas": {"world": world, "bit_identical": replicas_identical, "theta_checksum": allchk[0].tolist()},
+            "strong": strong,
             "roofline": roof,
             "cpu_baseline": cpu,
+            "gpu_eager_baseline": gpu_base,
             "loss_first_last": [losses[0], losses[-1]],
         }
         print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()
+
+
+FAMILIES = (
+    # (family, predicate on (name, grid)) -- first match wins.  The tcgen05 GEMM kernel serves the block nn.Linear layers,
+    # the stem / vocabulary projections (grids with >= 30 tiles along M or N) and, under its own name, the implicit convs.
+    ("vgg", lambda n, g: n.startswith(("conv3x3", "conv_gemm_tc", "conv1_", "conv_w", "maxpool", "feat_transpose", "im2col"))),
+    ("stem_vocab", lambda n, g: n.startswith("gemm_") and max(g[:2] or [0]) >= 30),
+    ("attn_ffn", lambda n, g: n.startswith(("gemm_", "attn_", "ln_", "colsum"))),
+    ("loss_embed", lambda n, g: n.startswith(("ce_", "embed_", "dec_preprocess", "enc_masks"))),
+    ("arena", lambda n, g: n.startswith(("ew_kernel", "sumsq", "clip_", "adam_", "set_u64", "scale_"))),
+)
+
+
+def kernel_families(fn, n_steps):
+    """CUPTI pass (torch.profiler) over `n_steps` steps OUTSIDE any timed region: kernel time by family, the union of the
+    busy intervals of each family, and the time-dominant kernel.  Durations of kernels launched with programmatic
+    dependent launch include their wait for the predecessor, so the union (wall time with >= 1 kernel of the family in
+    flight) is the meaningful denominator."""
+    import collections
+    from torch.profiler import ProfilerActivity, profile
+    try:
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            fn()
+            torch.cuda.synchronize()
+        path = tempfile.mktemp(suffix=".json")
+        prof.export_chrome_trace(path)
+        with open(path) as f:
+            ev = json.load(f)["traceEvents"]
+        os.remove(path)
+    except Exception as e:
+        return {"error": str(e)[:200]} and None
+    per = collections.defaultdict(lambda: [0, 0.0])
+    fam_iv = collections.defaultdict(list)
+    fam_sum = collections.defaultdict(lambda: [0, 0.0])
+    total = 0.0
+    for e in ev:
+        if e.get("cat") != "kernel":
+            continue
+        name = e["name"].replace("(anonymous namespace)::", "").replace("void ", "")
+        grid = list(e.get("args", {}).get("grid", []))
+        short = name.split("(")[0]
+        fam = next((f for f, pred in FAMILIES if pred(short, grid)), "other")
+        per[short][0] += 1
+        per[short][1] += e["dur"]
+        fam_iv[fam].append((e["ts"], e["ts"] + e["dur"]))
+        fam_sum[fam][0] += 1
+        fam_sum[fam][1] += e["dur"]
+        total += e["dur"]
+    if not total:
+        return None
+
+    def union(iv):
+        iv.sort()
+        busy, end = 0.0, None
+        for a, b in iv:
+            if end is None or a > end:
+                busy += b - a
+                end = b
+            elif b > end:
+                busy += b - end
+                end = b
+        return busy
+    fams = {f: {"share": fam_sum[f][1] / total, "sum_ms_per_step": fam_sum[f][1] / 1e3 / n_steps,
+                "busy_ms_per_step": union(fam_iv[f]) / 1e3 / n_steps, "launches_per_step": fam_sum[f][0] // n_steps}
+            for f in fam_sum}
+    for f, _ in FAMILIES:
+        fams.setdefault(f, {"share": 0.0, "sum_ms_per_step": 0.0, "busy_ms_per_step": 0.0, "launches_per_step": 0})
+    k, (n, us) = max(per.items(), key=lambda kv: kv[1][1])
+    top = {"kernel": k, "share_of_summed_kernel_time": us / total, "launches_per_step": n // n_steps, "avg_us": us / n,
+           "note": "time-dominant kernel of the step (CUPTI, traced outside the timed region)"}
+    return {"families": fams, "top": top}
+
+
+def gpu_eager_baseline():
+    """Secondary baseline (SURVEY 8d / BASELINE.md 3.5): the reference model with PyTorch's own GPU kernels on this B200
+    (tools/gpu_eager_baseline.py, run in its own process so that its allocator / cuDNN state never touches the engine)."""
+    try:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gpu_eager_baseline.py")], capture_output=True,
+                           text=True, timeout=600)
+        line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
+        return json.loads(line)
+    except Exception as e:
+        return {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}
 
 
 def dump_timeline(path, fn):
@@ -308,11 +471,15 @@ def dump_timeline(path, fn):
         ev = json.load(f)["traceEvents"]
     os.remove(tmp)
     with gzip.open(path, "wt") as f:
-        f.write("name,stream,start_us,dur_us\n")
+        f.write("name,grid,block,smem,stream,start_us,dur_us\n")
         for e in ev:
             if e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset"):
                 name = e["name"].replace(",", ";")[:120]
-                f.write("%s,%s,%.3f,%.3f\n" % (name, e.get("args", {}).get("stream", e.get("tid")), e["ts"], e["dur"]))
+                a = e.get("args", {})
+                grid = "x".join(str(v) for v in a.get("grid", [])) or "-"
+                block = "x".join(str(v) for v in a.get("block", [])) or "-"
+                f.write("%s,%s,%s,%s,%s,%.3f,%.3f\n" % (name, grid, block, a.get("shared memory", 0),
+                                                       a.get("stream", e.get("tid")), e["ts"], e["dur"]))
 
 
 def roofline_conv_gemm(s, lib, dev, mode):
@@ -353,8 +520,9 @@ def roofline_conv_gemm(s, lib, dev, mode):
     flops = 2.0 * M * N * Kd
     ach = flops / (ms * 1e-3) / 1e12
     return {"bound": "tensor", "achieved": ach, "peak": pk["bf16"], "unit": "TFLOP/s", "frac": ach / pk["bf16"],
-            "traffic": ROOFLINE_TRAFFIC_BYTES.get(mode),
-            "tensor_pipe_active_pct_ncu": ROOFLINE_TENSOR_PIPE_PCT.get(mode),
+            "traffic": _ncu("conv2_fwd", mode).get("dram_bytes"),
+            "tensor_pipe_active_pct_ncu": _ncu("conv2_fwd", mode).get("tensor_pipe_active_pct"),
+            "ncu_capture": _ncu("conv2_fwd", mode).get("source"),
             "algorithmic_bytes": 4 * (M * Cin + M * Cout + N * Kd), "flops_per_launch": flops,
             "kernel": "conv.2 forward implicit GEMM %dx%dx%d (%s), incl. its weight re-layout launch" % (
                 M, N, Kd, {0: "im2col + gemm_simt_kernel fp32 CUDA cores", 1: "conv3x3_kw_kernel<64> tcgen05 tf32",
@@ -396,6 +564,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--gemm-mode", type=int, default=int(os.environ.get("MTL_GEMM_MODE", "2")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true", help="skip the per-kernel roofline leg (A/B runs)")
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the PyTorch-on-GPU baseline leg (N = 1 only)")
+    ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the strong-scaling leg (3 tasks in total)")
+    ap.add_argument("--exchange", default="allreduce", choices=["allreduce", "sharded"],
+                    help="N > 1: all-reduce + full Adam, or reduce-scatter -> Adam on the 1/N slice -> all-gather")
     ap.add_argument("--no-graph", action="store_true", help="run the meta-step eagerly (no CUDA graph replay)")
     ap.add_argument("--lanes", type=int, default=0, help="concurrent task lanes (default: one per task)")
     ap.add_argument("--timeline", default="", help="after the measurements, trace 2 more steps with torch.profiler "

@@ -66,6 +66,9 @@ int mtl_session_set_gemm_mode(mtl_session* s, int mode);
 #define MTL_OP_VOCAB 7
 #define MTL_OP_CLASSES 8
 int mtl_session_set_op_mode(mtl_session* s, int op_class, int mode);
+/* Engine variants kept for A/B measurements.  "merge_lowrank" (default 0): run each low-rank projection pair
+ * B(A x) of modules/common_layers.py:287-289,303 as ONE GEMM against W = B.A formed once per pass. */
+int mtl_session_set_flag(mtl_session* s, const char* name, int value);
 long long mtl_param_arena_floats(const mtl_session* s);
 int mtl_param_count(const mtl_session* s);
 int mtl_param_info(const mtl_session* s, int idx, long long* offset_floats, long long* numel);

@@ -23,6 +23,7 @@ void mtl_set_error(const char* fmt, ...);
   } while (0)
 
 extern int g_mtl_concurrency;                 // task lanes being enqueued together (1 outside mtl_meta_tasks)
+extern int g_mtl_launch_prio;                 // CUDA launch priority of the kernels being enqueued (0 = default / lowest; < 0 = more urgent)
 extern unsigned long long g_mtl_launches;   // kernels enqueued by this library (bench.py reports it)
 #define MTL_CHECK_LAUNCH()               \
   do {                                   \
@@ -63,10 +64,19 @@ static inline cudaError_t mtl_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at; cfg.numAttrs = mtl_pdl_enabled() ? 1 : 0;
+  cudaLaunchAttribute at[2];
+  int na = 0;
+  if (mtl_pdl_enabled()) {
+    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (g_mtl_launch_prio != 0) {              // latency-critical chain kernel: ahead of GPU-filling / deferred work
+    at[na].id = cudaLaunchAttributePriority;
+    at[na].val.priority = g_mtl_launch_prio;
+    ++na;
+  }
+  cfg.attrs = at; cfg.numAttrs = na;
   return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 __device__ __forceinline__ float warp_sum(float v) {

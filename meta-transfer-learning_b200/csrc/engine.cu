@@ -26,6 +26,7 @@ void mtl_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 unsigned long long g_mtl_launches = 0;
+int g_mtl_launch_prio = 0;
 int g_mtl_concurrency = 1;   // task lanes whose kernels are being enqueued together (set by mtl_meta_tasks; GEMM CTA budgets read it)
 bool mtl_pdl_enabled() {
   static int v = -1;
@@ -98,7 +99,7 @@ static void build_layout(Layout& L, const mtl_model_cfg& c) {
 }
 
 // ----------------------------------------------------------------------------- activation records
-struct LowRankAct { const float* x; float* a; float* y; int M, K, N; size_t offA, offBw, offBb; };
+struct LowRankAct { const float* x; float* a; float* y; int M, K, N, ldy; size_t offA, offBw, offBb; const float* W; };
 struct AttnAct {
   LowRankAct q, k, v, o;
   float *oh, *lse, *xhat, *rstd, *out;
@@ -108,6 +109,7 @@ struct AttnAct {
   const float* rowmask;
   MtlDrop drop_attn, drop_out;
   AttnP p;
+  float *Wqkv = nullptr, *Wo = nullptr;   // merged projection weights of this pass (merge_lowrank), null = factored path
 };
 struct FfnAct {
   const float* x;
@@ -198,6 +200,7 @@ struct mtl_session {
   mtl_model_cfg cfg;
   Layout L;
   int mode = MTL_GEMM_SIMT_FP32;
+  int merge_lowrank = 0;              // mtl_session_set_flag("merge_lowrank"): merged projection weights on the chain
   int op_mode[MTL_OP_CLASSES];        // per-operation-class engine (see mtl_session_set_op_mode); -1 = follow `mode`
   Pass pass;                          // record of the plain mtl_asr_forward / mtl_meta_task API
   Branches br;                        // its side streams
@@ -246,6 +249,7 @@ struct Run {
   unsigned long long seed;                    // effective seed = seed + (*seed_dev) * seed_mul
   const unsigned long long* seed_dev = nullptr;
   unsigned long long seed_mul = 0;
+  int bulk = 0;                               // > 0: inside a GPU-filling / deferred section (convolutions): default priority
   uint32_t site;
   MtlDrop next_drop() { return p_drop > 0.f ? mtl_drop(p_drop, seed, site++, seed_dev, seed_mul) : mtl_nodrop(); }
   bool par() const { return br != nullptr && !dry; }
@@ -266,6 +270,13 @@ struct On {
   On(Run& r, cudaStream_t s) : R(r), saved(r.st) { r.st = s; }
   ~On() { R.st = saved; }
 };
+static int chain_prio();
+static inline int prio_of(const Run& R) {
+  if (R.bulk > 0 || !R.br) return 0;
+  if (R.st == R.br->side[S_W0] || R.st == R.br->side[S_W1]) return 0;   // parameter gradients: nothing waits for them
+  return chain_prio();
+}
+struct Bulk { Run& R; explicit Bulk(Run& r) : R(r) { ++R.bulk; } ~Bulk() { --R.bulk; } };
 // Records "everything enqueued on s so far" (null event when the pass runs serially).
 static int ev_mark(Run& R, cudaStream_t s, cudaEvent_t* out) {
   *out = nullptr;
@@ -297,9 +308,44 @@ static int join_all(Run& R) {
   return MTL_OK;
 }
 
+// Launch priority of the kernel about to be enqueued.  The activation / activation-gradient chain of a pass (small
+// GEMMs, LayerNorm, attention: a few dozen CTAs each, ~200 deep) is latency-bound; the VGG convolutions and every
+// parameter-gradient contraction are GPU-filling or deferred.  With several task lanes in flight the chain kernels of one
+// lane otherwise queue behind thousands of convolution CTAs of another: they get the higher priority, so the block
+// scheduler hands them the next free SM.  MTL_PRIO=0 disables (A/B).
+static int chain_prio() {
+  static int v = 1;
+  static bool init = false;
+  if (!init) {
+    init = true;
+    const char* e = getenv("MTL_PRIO");
+    int lo = 0, hi = 0;
+    if ((e && e[0] == '0') || cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess) v = 0;
+    else v = hi;                                  // numerically lowest = most urgent (e.g. -5)
+  }
+  return v;
+}
+static inline int prio_of(const Run& R);
+// MTL_DBG_SKIP=vgg | tf: timing experiments only (results are garbage) -- do not launch the VGG front-end kernels /
+// anything but them, to measure how the two halves of a pass interfere when several task lanes run concurrently.
+static int dbg_skip() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MTL_DBG_SKIP"); v = !e ? 0 : (e[0] == 'v' ? 1 : (e[0] == 't' ? 2 : (e[0] == 'w' ? 3 : (e[0] == 'x' ? 4 : 0)))); }
+  return v;
+}
+static bool dbg_skip_now(const Run& R) {
+  const int m = dbg_skip();
+  if (m == 0) return false;
+  if (m == 1) return R.bulk > 0;
+  if (m == 2) return R.bulk == 0;
+  const bool wside = R.br && (R.st == R.br->side[S_W0] || R.st == R.br->side[S_W1]);
+  if (m == 3) return wside;                  // w: no parameter-gradient side work
+  return wside || R.bulk > 0;                // x: neither that nor the VGG front-end (the bare activation chain)
+}
 #define K(call)                        \
   do {                                 \
-    if (!R.dry) { MTL_TRY(call); }     \
+    if (!R.dry && !dbg_skip_now(R)) {                   \
+      g_mtl_launch_prio = prio_of(R); int rc_ = (call); g_mtl_launch_prio = 0; MTL_TRY(rc_); }               \
   } while (0)
 
 // ----------------------------------------------------------------------------- GEMM wrappers
@@ -392,7 +438,7 @@ static int lin_wgrad(Run& R, const float* dy, int ldy, const float* x, int ldx, 
 // ----------------------------------------------------------------------------- low-rank projection
 static int lowrank_fwd(Run& R, LowRankAct& A, const float* x, int M, int Kd, int N, int r, size_t offA,
                        size_t offBw, size_t offBb) {
-  A.x = x; A.M = M; A.K = Kd; A.N = N; A.offA = offA; A.offBw = offBw; A.offBb = offBb;
+  A.x = x; A.M = M; A.K = Kd; A.N = N; A.ldy = N; A.W = nullptr; A.offA = offA; A.offBw = offBw; A.offBb = offBb;
   const bool za = use_zslab(R, M, r, Kd);
   A.a = za ? R.wz.f((size_t)M * r) : R.ws.f((size_t)M * r);
   A.y = R.ws.f((size_t)M * N);
@@ -433,13 +479,85 @@ static int lowrank_bwd_tail(Run& R, const LowRankAct& A, const LrBwd& h, float* 
   return lin_dgrad(R, h.da, r, R.theta + A.offA, dx, A.K, A.M, r, A.K, beta_dx, EPI_NONE, nullptr);
 }
 
+// ----------------------------------------------------------------------------- merged low-rank projections
+// y = B(A x) + b with A: d -> r (no bias) and B: r -> N (modules/common_layers.py:250-257, 287-289, 303) is ONE linear map
+// W = B.A.  On the activation chain of a pass the pair of skinny GEMMs (K or N = 100: 9.7 + 11.1 us as dependent graph
+// nodes) is replaced by one d x N GEMM against W (10.5 us), and the two dgrad GEMMs by one; W is formed once per pass
+// from theta on the parameter-gradient streams while the VGG front-end runs.  What the parameter gradients need -- a = A x
+// and da = dy.B -- is computed beside them, off the chain.
+// MEASURED NEGATIVE RESULT (cfg 2, ms / meta-step, 1 lane | 3 lanes): the bare activation chain gets shorter (7.94 vs 8.53 |
+// 4.17 vs 4.36, 43 % fewer chain kernels) but the whole step gets slower (14.1 vs 12.2 | 8.43 vs 7.67): the d x d GEMMs
+// carry 2.5x the FLOPs through the 3xTF32 splitter and every projection needs five side kernels instead of three.  The
+// factored chain therefore stays the default; mtl_session_set_flag("merge_lowrank", 1) / MTL_MERGE_LOWRANK=1 selects this
+// path (kept under test: tests/test_gpu_parity.py::test_merged_lowrank_path_matches_oracle).
+static bool merge_default() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MTL_MERGE_LOWRANK"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v != 0;
+}
+// W[N, Kd] = Bw[N, r] . A[r, Kd]
+static int merge_lowrank(Run& R, float* W, size_t offA, size_t offBw, int N, int Kd) {
+  const int r = R.S->cfg.rank;
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.A = R.theta + offBw; g.lda = r; g.transA = 0; g.B = R.theta + offA; g.ldb = Kd; g.transB = 0; g.C = W; g.ldc = Kd;
+  g.M = N; g.N = Kd; g.K = r; g.alpha = 1.f; g.beta = 0.f; g.epi = EPI_NONE; g.split_k = 1;
+  K(k_gemm(g, op_mode(R.S, MTL_OP_LIN_FWD), R.st));
+  return MTL_OK;
+}
+static int merged_fwd(Run& R, LowRankAct& A, const float* x, int M, int Kd, int N, const float* W, float* y, int ldy,
+                      size_t offA, size_t offBw, size_t offBb) {
+  A.x = x; A.M = M; A.K = Kd; A.N = N; A.offA = offA; A.offBw = offBw; A.offBb = offBb; A.W = W; A.a = nullptr;
+  A.y = y; A.ldy = ldy;
+  return lin_fwd(R, x, Kd, W, R.theta + offBb, y, ldy, M, N, Kd, EPI_NONE);
+}
+// Parameter gradients of one merged projection on s_w (after e_dy): da = dy.Bw, a = x.A^T, dBw += dy^T a, db += colsum dy,
+// dA += da^T x.  dy has row stride ldy.
+static int merged_param_grads(Run& R, const LowRankAct& A, const float* dy, int ldy, cudaEvent_t e_dy, cudaStream_t s_w) {
+  const int r = R.S->cfg.rank;
+  float* da = R.ws.f((size_t)A.M * r);
+  float* a = R.ws.f((size_t)A.M * r);
+  MTL_TRY(ev_wait(R, s_w, e_dy));
+  On on(R, s_w);
+  MTL_TRY(lin_dgrad(R, dy, ldy, R.theta + A.offBw, da, r, A.M, A.N, r, 0.f, EPI_NONE, nullptr));
+  MTL_TRY(lin_fwd(R, A.x, A.K, R.theta + A.offA, nullptr, a, r, A.M, r, A.K, EPI_NONE));
+  MTL_TRY(lin_wgrad(R, dy, ldy, a, r, R.grad + A.offBw, A.M, A.N, r));
+  K(k_colsum_acc(dy, A.M, A.N, ldy, R.grad + A.offBb, R.st));
+  MTL_TRY(lin_wgrad(R, da, r, A.x, A.K, R.grad + A.offA, A.M, r, A.K));
+  return MTL_OK;
+}
+// Forms the merged weights of one attention block on stream s (they depend on theta only).
+static int attn_merge_weights(Run& R, AttnAct& A, const AttnP& p, cudaStream_t s) {
+  const mtl_model_cfg& c = R.S->cfg;
+  const int d = c.d_model, hk = c.n_heads * c.d_k, hv = c.n_heads * c.d_v;
+  A.Wqkv = R.ws.f((size_t)(2 * hk + hv) * d);
+  A.Wo = R.ws.f((size_t)d * hv);
+  On on(R, s);
+  MTL_TRY(merge_lowrank(R, A.Wqkv, p.qa, p.qb_w, hk, d));
+  MTL_TRY(merge_lowrank(R, A.Wqkv + (size_t)hk * d, p.ka, p.kb_w, hk, d));
+  MTL_TRY(merge_lowrank(R, A.Wqkv + (size_t)2 * hk * d, p.va, p.vb_w, hv, d));
+  MTL_TRY(merge_lowrank(R, A.Wo, p.oa, p.ob_w, d, hv));
+  return MTL_OK;
+}
+
 // ----------------------------------------------------------------------------- attention block
 // kv_pre: the k / v projections of this block were already enqueued on S_X / S_AUX (decoder cross-attention:
 // they depend on the encoder output only).
-static int attn_kv_fwd(Run& R, AttnAct& A, const AttnP& p, const float* xkv, int Mk, cudaStream_t sk, cudaStream_t sv) {
+static int attn_kv_fwd(Run& R, AttnAct& A, const AttnP& p, const float* xkv, int Mk, cudaStream_t sk, cudaStream_t sv,
+                       float* kbuf = nullptr, float* vbuf = nullptr, int ldkv = 0) {
   const mtl_model_cfg& c = R.S->cfg;
   cudaEvent_t e;
   MTL_TRY(ev_mark(R, R.main, &e));
+  if (A.Wqkv) {
+    // merged: k | v share one [Mk, hk + hv] buffer so that their input gradient is ONE K-concatenated GEMM in the backward
+    const int d = c.d_model, hk = c.n_heads * c.d_k, hv = c.n_heads * c.d_v;
+    if (!kbuf) { kbuf = R.ws.f((size_t)Mk * (hk + hv)); vbuf = kbuf + hk; ldkv = hk + hv; }
+    MTL_TRY(ev_wait(R, sk, e));
+    { On on(R, sk); MTL_TRY(merged_fwd(R, A.k, xkv, Mk, d, hk, A.Wqkv + (size_t)hk * d, kbuf, ldkv, p.ka, p.kb_w, p.kb_b)); }
+    MTL_TRY(ev_wait(R, sv, e));
+    { On on(R, sv); MTL_TRY(merged_fwd(R, A.v, xkv, Mk, d, hv, A.Wqkv + (size_t)2 * hk * d, vbuf, ldkv, p.va, p.vb_w, p.vb_b)); }
+    return MTL_OK;
+  }
   MTL_TRY(ev_wait(R, sk, e));
   { On on(R, sk); MTL_TRY(lowrank_fwd(R, A.k, xkv, Mk, c.d_model, c.n_heads * c.d_k, c.rank, p.ka, p.kb_w, p.kb_b)); }
   MTL_TRY(ev_wait(R, sv, e));
@@ -454,8 +572,19 @@ static int attn_block_fwd(Run& R, AttnAct& A, const AttnP& p, const float* xq, c
   A.p = p; A.xq = xq; A.xkv = xkv; A.B = B; A.Tq = Tq; A.Tk = Tk; A.causal = causal; A.keypad = keypad;
   A.rowmask = rowmask;
   const cudaStream_t sk = R.side(kv_pre ? S_X : S_K), sv = R.side(kv_pre ? S_AUX : S_V);
-  if (!kv_pre) MTL_TRY(attn_kv_fwd(R, A, p, xkv, Mk, sk, sv));
-  MTL_TRY(lowrank_fwd(R, A.q, xq, Mq, d, H * dk, r, p.qa, p.qb_w, p.qb_b));
+  if (A.Wqkv && !kv_pre) {
+    // self-attention, merged: q | k | v are column blocks of ONE [M, hk + hk + hv] buffer (so are their gradients)
+    const int ld = 2 * H * dk + H * dv;
+    float* qkv = R.ws.f((size_t)Mq * ld);
+    MTL_TRY(attn_kv_fwd(R, A, p, xkv, Mk, sk, sv, qkv + H * dk, qkv + 2 * H * dk, ld));
+    MTL_TRY(merged_fwd(R, A.q, xq, Mq, d, H * dk, A.Wqkv, qkv, ld, p.qa, p.qb_w, p.qb_b));
+  } else if (A.Wqkv) {
+    float* qb = R.ws.f((size_t)Mq * H * dk);
+    MTL_TRY(merged_fwd(R, A.q, xq, Mq, d, H * dk, A.Wqkv, qb, H * dk, p.qa, p.qb_w, p.qb_b));
+  } else {
+    if (!kv_pre) MTL_TRY(attn_kv_fwd(R, A, p, xkv, Mk, sk, sv));
+    MTL_TRY(lowrank_fwd(R, A.q, xq, Mq, d, H * dk, r, p.qa, p.qb_w, p.qb_b));
+  }
   MTL_TRY(chain(R, sk, R.main));
   MTL_TRY(chain(R, sv, R.main));
   A.oh = R.ws.f((size_t)Mq * H * dv);
@@ -465,10 +594,15 @@ static int attn_block_fwd(Run& R, AttnAct& A, const AttnP& p, const float* xq, c
   memset(&a, 0, sizeof(a));
   a.q = A.q.y; a.k = A.k.y; a.v = A.v.y; a.o = A.oh; a.lse = A.lse; a.keypad = keypad;
   a.B = B; a.H = H; a.Tq = Tq; a.Tk = Tk; a.dk = dk;
-  a.ldq = H * dk; a.ldk = H * dk; a.ldv = H * dv; a.ldo = H * dv;
+  a.ldq = A.q.ldy; a.ldk = A.k.ldy; a.ldv = A.v.ldy; a.ldo = H * dv;
   a.causal = causal; a.inv_temp = 1.0f / sqrtf((float)dk); a.drop = A.drop_attn;
   K(k_attn_fwd(a, R.st));
-  MTL_TRY(lowrank_fwd(R, A.o, A.oh, Mq, H * dv, d, r, p.oa, p.ob_w, p.ob_b));
+  if (A.Wo) {
+    float* ob = R.ws.f((size_t)Mq * d);
+    MTL_TRY(merged_fwd(R, A.o, A.oh, Mq, H * dv, d, A.Wo, ob, d, p.oa, p.ob_w, p.ob_b));
+  } else {
+    MTL_TRY(lowrank_fwd(R, A.o, A.oh, Mq, H * dv, d, r, p.oa, p.ob_w, p.ob_b));
+  }
   A.xhat = R.ws.f((size_t)Mq * d);
   A.rstd = R.ws.f(Mq);
   A.out = R.ws.f((size_t)Mq * d);
@@ -486,10 +620,58 @@ static int attn_block_bwd(Run& R, const AttnAct& A, const float* dout, float* dx
   const int Mq = A.B * A.Tq, Mk = A.B * A.Tk;
   float* do2 = R.ws.f((size_t)Mq * d);
   float* d_oh = R.ws.f((size_t)Mq * H * dv);
+  float* delta = R.ws.f((size_t)A.B * H * A.Tq);
+  if (A.Wqkv) {
+    // ---- merged projections: one dgrad GEMM per projection (group) on the chain, parameter gradients beside it
+    const int hk = H * dk, hv = H * dv;
+    K(k_ln_bwd(dout, A.xhat, A.rstd, R.theta + A.p.ln_w, A.rowmask, A.drop_out, do2, dxq, 0, R.grad + A.p.ln_w,
+               R.grad + A.p.ln_b, Mq, d, R.st));
+    cudaEvent_t e_do;
+    MTL_TRY(ev_mark(R, R.main, &e_do));
+    MTL_TRY(merged_param_grads(R, A.o, do2, d, e_do, R.wside()));
+    MTL_TRY(lin_dgrad(R, do2, d, A.Wo, d_oh, hv, Mq, d, hv, 0.f, EPI_NONE, nullptr));
+    // gradients of q | k | v in the forward's column layout: self-attention [M, hk + hk + hv], cross [Mq, hk] and [Mk, hk + hv]
+    float *dq, *dkk, *dvv;
+    if (cross) {
+      dq = R.ws.f((size_t)Mq * hk);
+      dkk = R.ws.f((size_t)Mk * (hk + hv));
+      dvv = dkk + hk;
+    } else {
+      dq = R.ws.f((size_t)Mq * (2 * hk + hv));
+      dkk = dq + hk;
+      dvv = dq + 2 * hk;
+    }
+    AttnBwdArgs b;
+    memset(&b, 0, sizeof(b));
+    b.f.q = A.q.y; b.f.k = A.k.y; b.f.v = A.v.y; b.f.o = A.oh; b.f.lse = A.lse; b.f.keypad = A.keypad;
+    b.f.B = A.B; b.f.H = H; b.f.Tq = A.Tq; b.f.Tk = A.Tk; b.f.dk = dk;
+    b.f.ldq = A.q.ldy; b.f.ldk = A.k.ldy; b.f.ldv = A.v.ldy; b.f.ldo = hv;
+    b.f.causal = A.causal; b.f.inv_temp = 1.0f / sqrtf((float)dk); b.f.drop = A.drop_attn;
+    b.d_o = d_oh; b.delta = delta; b.dq = dq; b.dk = dkk; b.dv = dvv;
+    K(k_attn_bwd(b, R.st));
+    cudaEvent_t e_qkv;
+    MTL_TRY(ev_mark(R, R.main, &e_qkv));
+    if (cross) {
+      const cudaStream_t sx = R.side(S_X);
+      MTL_TRY(ev_wait(R, sx, e_qkv));
+      { On on(R, sx);   // encoder-side gradient: dxkv += [dk | dv] . [Wk ; Wv], ordered on S_X
+        MTL_TRY(lin_dgrad(R, dkk, hk + hv, A.Wqkv + (size_t)hk * d, dxkv, d, Mk, hk + hv, d, 1.f, EPI_NONE, nullptr)); }
+      MTL_TRY(lin_dgrad(R, dq, hk, A.Wqkv, dxq, d, Mq, hk, d, 1.f, EPI_NONE, nullptr));
+      MTL_TRY(merged_param_grads(R, A.q, dq, hk, e_qkv, R.wside()));
+      MTL_TRY(merged_param_grads(R, A.k, dkk, hk + hv, e_qkv, R.wside()));
+      MTL_TRY(merged_param_grads(R, A.v, dvv, hk + hv, e_qkv, R.wside()));
+    } else {
+      // dx += [dq | dk | dv] . [Wq ; Wk ; Wv]: one K-concatenated GEMM (dxkv aliases dxq for self-attention)
+      MTL_TRY(lin_dgrad(R, dq, 2 * hk + hv, A.Wqkv, dxq, d, Mq, 2 * hk + hv, d, 1.f, EPI_NONE, nullptr));
+      MTL_TRY(merged_param_grads(R, A.q, dq, 2 * hk + hv, e_qkv, R.wside()));
+      MTL_TRY(merged_param_grads(R, A.k, dkk, 2 * hk + hv, e_qkv, R.wside()));
+      MTL_TRY(merged_param_grads(R, A.v, dvv, 2 * hk + hv, e_qkv, R.wside()));
+    }
+    return MTL_OK;
+  }
   float* dq = R.ws.f((size_t)Mq * H * dk);
   float* dkk = R.ws.f((size_t)Mk * H * dk);
   float* dvv = R.ws.f((size_t)Mk * H * dv);
-  float* delta = R.ws.f((size_t)A.B * H * A.Tq);
   K(k_ln_bwd(dout, A.xhat, A.rstd, R.theta + A.p.ln_w, A.rowmask, A.drop_out, do2, dxq, 0, R.grad + A.p.ln_w,
              R.grad + A.p.ln_b, Mq, d, R.st));
   LrBwd ho, hq, hk, hv;
@@ -673,7 +855,26 @@ static int forward(Run& R, const mtl_batch& b, const float* pe_enc, const float*
     }
   }
 
+  // ---- merged projection weights W = B.A of every attention block (theta only): on the two parameter-gradient streams,
+  //      idle during a forward, while the VGG front-end runs
+  P.enc_sa.assign(c.n_enc, AttnAct());
+  P.enc_ff.assign(c.n_enc, FfnAct());
+  P.dec_sa.assign(c.n_dec, AttnAct());
+  P.dec_ca.assign(c.n_dec, AttnAct());
+  P.dec_ff.assign(c.n_dec, FfnAct());
+  if (S->merge_lowrank && S->mode != MTL_GEMM_SIMT_FP32) {
+    MTL_TRY(chain(R, R.main, R.side(S_W0)));
+    MTL_TRY(chain(R, R.main, R.side(S_W1)));
+    for (int l = 0; l < c.n_enc; ++l) MTL_TRY(attn_merge_weights(R, P.enc_sa[l], L.enc_sa[l], R.wside()));
+    for (int l = 0; l < c.n_dec; ++l) {
+      MTL_TRY(attn_merge_weights(R, P.dec_ca[l], L.dec_ca[l], R.wside()));     // their k / v projections start first
+      MTL_TRY(attn_merge_weights(R, P.dec_sa[l], L.dec_sa[l], R.wside()));
+    }
+  }
+
   // ---- VGG front-end (transformer.py:47-59), NHWC
+  {
+  Bulk bulk(R);
   P.c1 = R.ws.f((size_t)B * P.F * P.T * 64);
   MTL_TRY(conv_weight_layouts(R, P));
   K(k_conv1_fwd(b.x, R.theta + L.conv_w[0], R.theta + L.conv_b[0], P.c1, B, P.F, P.T, 64, R.st));
@@ -687,6 +888,7 @@ static int forward(Run& R, const mtl_batch& b, const float* pe_enc, const float*
   K(k_maxpool2_fwd(P.cv[2].y, P.p4, B, P.F2, P.T2, 128, R.st));
   P.feat = R.ws.f((size_t)P.Me * P.d_in);
   K(k_feat_transpose(P.p4, P.feat, B, P.F4, P.T4, 128, R.st));
+  }
 
   // ---- encoder (encoder.py:53-80)
   P.enc_rowmask = R.ws.f(P.Me);
@@ -701,8 +903,10 @@ static int forward(Run& R, const mtl_batch& b, const float* pe_enc, const float*
   K(k_ln_fwd(P.h, nullptr, R.theta + L.lnin_w, R.theta + L.lnin_b, nullptr, pe_enc, Tp, mtl_nodrop(), P.e0,
              P.stem_xhat, P.stem_rstd, P.Me, d, R.st));
   const float* x = P.e0;
-  P.enc_sa.assign(c.n_enc, AttnAct());
-  P.enc_ff.assign(c.n_enc, FfnAct());
+  if (S->merge_lowrank && S->mode != MTL_GEMM_SIMT_FP32) {
+    MTL_TRY(chain(R, R.side(S_W0), R.main));   // merged weights ready
+    MTL_TRY(chain(R, R.side(S_W1), R.main));
+  }
   for (int l = 0; l < c.n_enc; ++l) {
     MTL_TRY(attn_block_fwd(R, P.enc_sa[l], L.enc_sa[l], x, x, B, Tp, Tp, P.enc_keypad, 0, P.enc_rowmask, false));
     x = P.enc_sa[l].out;
@@ -721,9 +925,6 @@ static int forward(Run& R, const mtl_batch& b, const float* pe_enc, const float*
   P.drop_emb = R.next_drop();
   K(k_embed_fwd(P.seq_in, R.theta + L.emb, pe_dec, P.drop_emb, P.x0, B, n, d, R.st));
   x = P.x0;
-  P.dec_sa.assign(c.n_dec, AttnAct());
-  P.dec_ca.assign(c.n_dec, AttnAct());
-  P.dec_ff.assign(c.n_dec, FfnAct());
   // every cross-attention k / v projection depends on the encoder output only: start them all now on S_X / S_AUX
   for (int l = 0; l < c.n_dec; ++l)
     MTL_TRY(attn_kv_fwd(R, P.dec_ca[l], L.dec_ca[l], P.enc_out, P.Me, R.side(S_X), R.side(S_AUX)));
@@ -829,6 +1030,7 @@ static int backward(Run& R, float loss_scale, const float* dpred_ext, int ld_ext
   float* dfeat = R.ws.f((size_t)P.Me * P.d_in);
   MTL_TRY(lin_dgrad(R, dh, d, R.theta + L.in_w, dfeat, P.d_in, P.Me, d, P.d_in, 0.f, EPI_NONE, nullptr, false, MTL_OP_STEM));
   // VGG front-end
+  Bulk bulk(R);
   float* dp4 = R.ws.f((size_t)B * P.F4 * P.T4 * 128);
   K(k_feat_transpose_bwd(dfeat, dp4, B, P.F4, P.T4, 128, R.st));
   float* dc4 = R.ws.f((size_t)B * P.F2 * P.T2 * 128);
@@ -862,10 +1064,16 @@ extern "C" int mtl_session_create(const mtl_model_cfg* cfg, mtl_session** out) {
   s->cfg = *cfg;
   build_layout(s->L, s->cfg);
   for (int i = 0; i < MTL_OP_CLASSES; ++i) s->op_mode[i] = -1;
+  // default precision policy: the VGG input / weight gradients in single-pass TF32 (a 3xTF32 session otherwise): measured
+  // on the ragged cfg-2 batch they leave every gradient where the all-3xTF32 engine puts it (profiles/r02_a_precision_table.log:
+  // worst tensor 2.00e-3 either way, set by ReLU / max-pool decision flips), and the step goes from 7.7 to 7.0 ms
+  s->op_mode[MTL_OP_CONV_DGRAD] = MTL_GEMM_TC_TF32;
+  s->op_mode[MTL_OP_CONV_WGRAD] = MTL_GEMM_TC_TF32;
+  s->merge_lowrank = merge_default() ? 1 : 0;
   if (const char* e = getenv("MTL_OP_MODES")) {                 // A/B: comma-separated engine per class, e.g. "1,1,2,1,1,2,2,2"
     for (int i = 0; i < MTL_OP_CLASSES && *e; ++i) {
       const int v = atoi(e);
-      if (v == MTL_GEMM_TC_TF32 || v == MTL_GEMM_TC_3XTF32) s->op_mode[i] = v;
+      if (v == MTL_GEMM_TC_TF32 || v == MTL_GEMM_TC_3XTF32 || v == -1) s->op_mode[i] = v;
       while (*e && *e != ',') ++e;
       if (*e == ',') ++e;
     }
@@ -893,6 +1101,12 @@ extern "C" int mtl_session_set_op_mode(mtl_session* s, int op_class, int mode) {
   MTL_REQUIRE(mode == -1 || mode == MTL_GEMM_TC_TF32 || mode == MTL_GEMM_TC_3XTF32, "op mode: -1 (session mode), 1 (TF32) or 2 (3xTF32)");
   s->op_mode[op_class] = mode;
   return MTL_OK;
+}
+extern "C" int mtl_session_set_flag(mtl_session* s, const char* name, int value) {
+  MTL_REQUIRE(s && name, "null argument");
+  if (!strcmp(name, "merge_lowrank")) { s->merge_lowrank = value != 0; return MTL_OK; }
+  mtl_set_error("unknown session flag '%s'", name);
+  return MTL_ERR_ARG;
 }
 extern "C" long long mtl_param_arena_floats(const mtl_session* s) { return s ? (long long)s->L.total : -1; }
 extern "C" int mtl_param_count(const mtl_session* s) { return s ? (int)s->L.tensors.size() : -1; }
@@ -1124,6 +1338,7 @@ extern "C" int mtl_meta_tasks(mtl_session* s, const mtl_meta_step_args* a, void*
   key.push_back((unsigned long long)(uintptr_t)a->results); key.push_back((unsigned long long)(uintptr_t)a->seed_slot);
   key.push_back((unsigned long long)s->mode);
   for (int i = 0; i < MTL_OP_CLASSES; ++i) key.push_back((unsigned long long)(unsigned)s->op_mode[i]);
+  key.push_back((unsigned long long)s->merge_lowrank);
 
   GraphEntry* e = nullptr;
   for (auto& g : s->graphs) if (g.key == key) { e = &g; break; }
@@ -1166,7 +1381,7 @@ extern "C" int mtl_meta_tasks(mtl_session* s, const mtl_meta_step_args* a, void*
       if (cudaGraphKernelNodeGetParams(nodes[i], &kp) == cudaSuccess && kp.func == (void*)set_u64_kernel) e->seed_node = nodes[i];
     }
     cudaGraphExec_t exec = nullptr;
-    ce = cudaGraphInstantiate(&exec, graph, 0);
+    ce = cudaGraphInstantiate(&exec, graph, chain_prio() != 0 ? cudaGraphInstantiateFlagUseNodePriority : 0);   // per-node launch priorities (K macro)
     if (ce != cudaSuccess || !e->seed_node) {
       if (exec) cudaGraphExecDestroy(exec);
       cudaGraphDestroy(graph);

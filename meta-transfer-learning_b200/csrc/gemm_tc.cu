@@ -229,6 +229,7 @@ struct TcParams {
   int epi_test;      // measurement only (MTL_EPI_TEST): 1 = conv epilogue computes but does not store
   int cluster_k;     // > 1: grid.z CTAs form one cluster that splits K and reduces over distributed shared memory
   int split_trunc;   // 3xTF32 splitter: 1 = truncating split (hi stays the raw tile), 0 = round-to-nearest hi written in place
+  int lin_stages;    // > 0: plain GEMM on the small-footprint pipeline (this many stages; see lin_small_stages)
 };
 
 // ---- TMA epilogue (shared by the GEMM / tap-box convolution kernel and the kw-box convolution kernel).
@@ -311,10 +312,8 @@ __device__ __forceinline__ void tma_epilogue_rows(const TcParams& P, const CUten
 }
 
 template <int BN, int STAGES, bool A_MN, bool B_MN, bool SPLIT3>
-__global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                      const __grid_constant__ CUtensorMap tmB,
-                                                      const __grid_constant__ CUtensorMap tmC,
-                                                      const __grid_constant__ CUtensorMap tmX, const TcParams P) {
+__device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
+                                             const CUtensorMap& tmX, const TcParams& P) {
   constexpr int B_STAGE_BYTES = BN * BK * 4;
   constexpr int HI_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   constexpr int STAGE_BYTES = HI_BYTES * (SPLIT3 ? 2 : 1);
@@ -753,6 +752,23 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
   DBG_SPAN(1);
+}
+
+// Two names for one body, so that a kernel timeline tells the nn.Linear GEMMs from the implicit convolutions that share it
+// (bench.py attributes kernel time to the attention / FFN family by name).
+template <int BN, int STAGES, bool A_MN, bool B_MN, bool SPLIT3>
+__global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                      const __grid_constant__ CUtensorMap tmB,
+                                                      const __grid_constant__ CUtensorMap tmC,
+                                                      const __grid_constant__ CUtensorMap tmX, const TcParams P) {
+  gemm_tc_body<BN, STAGES, A_MN, B_MN, SPLIT3>(tmA, tmB, tmC, tmX, P);
+}
+template <int BN, int STAGES, bool A_MN, bool B_MN, bool SPLIT3>
+__global__ void __launch_bounds__(192) conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                           const __grid_constant__ CUtensorMap tmB,
+                                                           const __grid_constant__ CUtensorMap tmC,
+                                                           const __grid_constant__ CUtensorMap tmX, const TcParams P) {
+  gemm_tc_body<BN, STAGES, A_MN, B_MN, SPLIT3>(tmA, tmB, tmC, tmX, P);
 }
 
 // ----------------------------------------------------------------------------- kw-box 3x3 convolution
@@ -1233,11 +1249,12 @@ int launch(const Maps& tm, const TcParams& P_in, dim3 grid, cudaStream_t s) {
   constexpr int SMEM_MAX = AUX_INSIDE ? SMEM : SMEM + TILE;
   static_assert(SMEM_MAX <= 227 * 1024, "shared memory budget");
   static bool configured = false;
-  auto kern = gemm_tc_kernel<BN, STAGES, A_MN, B_MN, SPLIT3>;
   if (!configured) {
-    MTL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
+    MTL_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, A_MN, B_MN, SPLIT3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
+    MTL_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, STAGES, A_MN, B_MN, SPLIT3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
     configured = true;
   }
+  auto kern = P_in.conv_mode != CONV_NONE ? conv_gemm_tc_kernel<BN, STAGES, A_MN, B_MN, SPLIT3> : gemm_tc_kernel<BN, STAGES, A_MN, B_MN, SPLIT3>;
   // ReLU-mask tile of the TMA epilogue: beside the staging tile inside the (dead) operand stages when they are
   // large enough, else in extra dynamic shared memory behind the barrier block
   TcParams P = P_in;
@@ -1250,8 +1267,13 @@ int launch(const Maps& tm, const TcParams& P_in, dim3 grid, cudaStream_t s) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = grid; cfg.blockDim = dim3(192, 1, 1); cfg.dynamicSmemBytes = smem; cfg.stream = s;
-  cudaLaunchAttribute at[2];
+  cudaLaunchAttribute at[3];
   int na = 0;
+  if (g_mtl_launch_prio != 0) {
+    at[na].id = cudaLaunchAttributePriority;
+    at[na].val.priority = g_mtl_launch_prio;
+    ++na;
+  }
   if (P.cluster_k > 1) {
     at[na].id = cudaLaunchAttributeClusterDimension;
     at[na].val.clusterDim.x = 1; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = (unsigned)P.cluster_k;
@@ -1283,9 +1305,41 @@ bool conv_wgrad_two_cta() {
   return v != 0;
 }
 
+// Small-footprint pipeline for the nn.Linear GEMMs (M = 200-264 rows).  Those CTAs stream 2-16 k-blocks and spend most of
+// their life waiting (first TMA, splitter, commit, epilogue); with 3 x 64 KB of stages each one owned a whole SM, and with
+// three task lanes in flight they crowd each other out.  Two 48 KB stages (3xTF32, 64-wide tile: A hi|lo 32 KB + B hi|lo
+// 16 KB; the staged output tile aliases them) let two CTAs share an SM -- 128 TMEM columns each -- and fit beside a
+// convolution CTA.  Measured (3 lanes, ms / meta-step): 3 x 64 KB stages 7.95, 2 x 48 KB 7.70, 1 x 48 KB (four CTAs per SM,
+// no TMA / MMA overlap inside a CTA) 8.49, 2 stages with 128-wide tiles 8.22.  MTL_LIN_STAGES: 0 = the 3 / 4-stage
+// pipelines, 1, 2 (default).
+int lin_small_stages() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MTL_LIN_STAGES"); v = e ? atoi(e) : 2; if (v < 0 || v > 2) v = 2; }
+  return v;
+}
+int lin_small_bn() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MTL_LIN_BN"); v = (e && atoi(e) == 128) ? 128 : 64; }
+  return v;
+}
 template <int BN, bool SPLIT3>
 int dispatch_major(bool a_mn, bool b_mn, const Maps& tm, const TcParams& P, dim3 grid, cudaStream_t s) {
   constexpr int STAGES = SPLIT3 ? (BN == 64 ? 4 : 3) : (BN == 64 ? 4 : 3);
+  if (P.lin_stages > 0 && P.conv_mode == CONV_NONE) {
+    // smallest legal ring: the staged output tile (TMA or padded row-major) has to fit in the operand stages
+    constexpr int S1 = SPLIT3 ? (BN == 64 ? 1 : 2) : (BN == 64 ? 2 : 3);
+    constexpr int S2 = SPLIT3 ? 2 : 3;
+    if (P.lin_stages == 1) {
+      if (!a_mn && !b_mn) return launch<BN, S1, false, false, SPLIT3>(tm, P, grid, s);
+      if (!a_mn && b_mn) return launch<BN, S1, false, true, SPLIT3>(tm, P, grid, s);
+      if (a_mn && !b_mn) return launch<BN, S1, true, false, SPLIT3>(tm, P, grid, s);
+      return launch<BN, S1, true, true, SPLIT3>(tm, P, grid, s);
+    }
+    if (!a_mn && !b_mn) return launch<BN, S2, false, false, SPLIT3>(tm, P, grid, s);
+    if (!a_mn && b_mn) return launch<BN, S2, false, true, SPLIT3>(tm, P, grid, s);
+    if (a_mn && !b_mn) return launch<BN, S2, true, false, SPLIT3>(tm, P, grid, s);
+    return launch<BN, S2, true, true, SPLIT3>(tm, P, grid, s);
+  }
   if (BN == 64 && SPLIT3 && !a_mn && !b_mn && P.conv_mode == CONV_FWD && conv_two_cta()) {
     // 2 stages x 48 KB: two CTAs share an SM, so one tile's epilogue overlaps the other's main loop
     return launch<BN, (BN == 64 && SPLIT3) ? 2 : STAGES, false, false, SPLIT3>(tm, P, grid, s);
@@ -1435,7 +1489,8 @@ int k_gemm_tc(const GemmArgs& g, int precision_mode, cudaStream_t s) {
   const bool tf = !split3;
   const bool a_mn = g.transA != 0;     // A stored [K,M]: M contiguous
   const bool b_mn = g.transB == 0;     // B stored [K,N]: N contiguous
-  const int bn = g.N <= 64 ? 64 : 128;
+  const int lin_stages = lin_small_stages();
+  const int bn = g.N <= 64 ? 64 : (lin_stages > 0 ? lin_small_bn() : 128);
   Maps tm;
   CUtensorMap& ta = tm.a;
   CUtensorMap& tb = tm.b;
@@ -1446,6 +1501,7 @@ int k_gemm_tc(const GemmArgs& g, int precision_mode, cudaStream_t s) {
   P.split_trunc = split_trunc_enabled();
   P.g = g;
   P.conv_mode = CONV_NONE;
+  P.lin_stages = lin_stages;
   P.kb_total = mtl_cdiv(g.K, BK);
   if (g.split_k > 1) MTL_REQUIRE(g.beta == 1.f && g.epi == EPI_NONE, "split-K needs beta=1, no activation epilogue");
   int split = plan_split(P, g.split_k);

@@ -59,6 +59,7 @@ SIGNATURES = {
     "mtl_session_destroy": (None, [_P]),
     "mtl_session_set_gemm_mode": (_I, [_P, _I]),
     "mtl_session_set_op_mode": (_I, [_P, _I, _I]),
+    "mtl_session_set_flag": (_I, [_P, C.c_char_p, _I]),
     "mtl_param_arena_floats": (_LL, [_P]),
     "mtl_param_count": (_I, [_P]),
     "mtl_param_info": (_I, [_P, _I, C.POINTER(_LL), C.POINTER(_LL)]),

@@ -103,6 +103,9 @@ class Session:
         idx = self.OP_CLASSES.index(op_class) if isinstance(op_class, str) else int(op_class)
         _l.check(self.lib.mtl_session_set_op_mode(self._h, idx, int(mode)))
 
+    def set_flag(self, name: str, value: int):
+        _l.check(self.lib.mtl_session_set_flag(self._h, name.encode(), int(value)))
+
     def new_arena(self) -> torch.Tensor:
         return torch.zeros(self.n_floats, dtype=torch.float32, device=self.device)
 

@@ -564,3 +564,51 @@ def test_cfg2_full_tensor_meta_step_copy_grad_vs_oracle():
     for k in po:
         d = (theta[k].cpu() - po[k]).abs()
         assert float(d.max()) <= 2.1 * m["meta_lr"], k
+
+
+def test_merged_lowrank_path_matches_oracle():
+    """mtl_session_set_flag("merge_lowrank", 1): every projection pair B(A x) (modules/common_layers.py:287-289,303) runs
+    as one GEMM against W = B.A on the activation chain; a = A x and da = dy.B are formed beside the parameter
+    gradients.  Same outputs and gradients as the factored default (kept as a measured A/B variant)."""
+    cfg = ref_asr.SMALL
+    p = ref_asr.init_params(cfg, 2)
+    batch = ref_meta.synth_batch(cfg, 4, 41, 7, 10, lengths=[41, 30, 9, 5], tgt_lengths=[7, 5, 3, 1])
+    loss_o, g_o, gold_o, hyp_o, pred_o = ref_meta.loss_and_grads(p, cfg, batch)
+    s = _session(cfg)
+    s.set_flag("merge_lowrank", 1)
+    out, pred, grads = _fwd_bwd(s, p, batch)
+    keep = gold_o != 0
+    assert torch.equal(out["hyp"].cpu().long()[keep], hyp_o[keep])
+    assert rel_err(pred, pred_o) < TOL_OUT
+    bad = {k: rel_err(grads[k], g_o[k]) for k in g_o if float(g_o[k].abs().max()) > 1e-7}
+    worst = max(bad, key=bad.get)
+    assert bad[worst] < _tol(worst), (worst, bad[worst])
+
+
+def test_precision_policy_classes():
+    """mtl_session_set_op_mode: the default policy runs the VGG input / weight gradients in single-pass TF32; forcing them
+    back to 3xTF32 or everything to TF32 changes the arithmetic (different bits) but stays inside the per-mode bounds."""
+    cfg = ref_asr.SMALL
+    p = ref_asr.init_params(cfg, 2)
+    batch = ref_meta.synth_batch(cfg, 4, 41, 7, 10)
+    _, g_o, *_ = ref_meta.loss_and_grads(p, cfg, batch)
+    res = {}
+    for name, over in (("default", {}), ("all3x", {"conv_dgrad": 2, "conv_wgrad": 2}), ("convfwd_tf32", {"conv_fwd": 1})):
+        s = _session(cfg)
+        for k, v in over.items():
+            s.set_op_mode(k, v)
+        _, pred, grads = _fwd_bwd(s, p, batch)
+        res[name] = (pred.clone(), {k: v.clone() for k, v in grads.items()})
+    if GEMM_MODE == 2:
+        assert not torch.equal(res["default"][1]["conv.2.weight"], res["all3x"][1]["conv.2.weight"])
+        assert torch.equal(res["default"][0], res["all3x"][0])                    # the forward is untouched by the policy
+        assert rel_err(res["default"][0], res["convfwd_tf32"][0]) > 1e-6          # ... and a forward class changes it
+    for name, (pred, grads) in res.items():
+        for k in g_o:
+            if float(g_o[k].abs().max()) > 1e-7:
+                tol = 5e-2 if (name == "convfwd_tf32" or k.startswith("conv.")) else TOL_GRAD
+                assert rel_err(grads[k], g_o[k]) < tol, (name, k)
+    with pytest.raises(mtl_b200.MtlError):
+        _session(cfg).set_op_mode(3, 7)
+    with pytest.raises(mtl_b200.MtlError):
+        _session(cfg).set_flag("no_such_flag", 1)

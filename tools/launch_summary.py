@@ -16,11 +16,11 @@ def main_timeline(path):
     with gzip.open(path, "rt") as f:
         next(f)
         for line in f:
-            name, _, start, dur = line.rstrip("\n").rsplit(",", 3)
-            start, dur = float(start), float(dur)
+            parts = line.rstrip("\n").split(",")
+            name, start, dur = parts[0], float(parts[-2]), float(parts[-1])
             t0 = start if t0 is None else min(t0, start)
             t1 = start + dur if t1 is None else max(t1, start + dur)
-            k = name.split("(")[0][-90:]
+            k = name.replace("(anonymous namespace)::", "").replace("void ", "").split("(")[0][-90:]
             agg[k][0] += 1
             agg[k][1] += dur
     tot = sum(v[1] for v in agg.values())
