@@ -383,13 +383,16 @@ static int dgrad_ctas() {
   if (v < 0) { const char* e = getenv("MTL_DGRAD_CTAS"); v = e ? atoi(e) : 0; }
   return v > 0 ? v : (g_mtl_concurrency >= 2 ? 24 : 296);
 }
-// Slab budget of a zero-pool GEMM (on the critical path).  A pass running alone is latency-bound and takes the slabs
-// (14.1 -> 13.4 ms/step with one lane); with several lanes in flight the step is SM-time-bound, slabs and clusters
-// measure the same (8.18 vs 8.21 ms/step) and the cluster path keeps the forward bit-reproducible: 1 = no slabs.
+// Slab budget of a zero-pool GEMM (on the critical path): K slabs merged by TMA reduce-add replace the cluster split-K
+// with its DSMEM reduction (~3.5 us of a ~9 us GEMM).  A pass running alone takes 160 CTAs (14.1 -> 13.4 ms/step with one
+// lane).  With several lanes in flight round 1 measured no difference while every GEMM CTA owned a whole SM (192 KB of
+// stages: 8.18 vs 8.21 ms/step); with the two-stage 96 KB pipeline the slabs win: 7.01 (clusters) -> 6.83 (48) -> 6.76 (96)
+// -> 6.85 (160) ms/step.  The price: the forward is no longer bit-reproducible run to run (reduce-add order), only to
+// ~1e-6.  MTL_ZSLAB_CTAS=1 restores the clusters.
 static int zslab_ctas() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("MTL_ZSLAB_CTAS"); v = e ? atoi(e) : 0; }
-  return v > 0 ? v : (g_mtl_concurrency >= 2 ? 1 : 160);
+  return v > 0 ? v : (g_mtl_concurrency >= 2 ? 96 : 160);
 }
 // MTL_ZSLAB=0 keeps the cluster split-K path for every beta == 0 GEMM (A/B measurements)
 static bool zslab_enabled() {

@@ -138,7 +138,7 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, ui
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -148,7 +148,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
         "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  tmem_ld32_issue(taddr, v);
+  tmem_ld_wait();
 }
 // round-to-nearest (ties away from zero) fp32 -> tf32: 10 explicit mantissa bits, low 13 bits zero.  Same result as
 // cvt.rna.tf32.f32 for finite inputs, but two full-rate integer ops instead of a quarter-rate conversion-pipe
@@ -271,12 +275,16 @@ __device__ __forceinline__ void tma_epilogue_rows(const TcParams& P, const CUten
 #pragma unroll 1
   for (int c = 0; c < nch; ++c) {
     uint32_t v[32];
-    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
     if (SPLIT3) {                                                // 3xTF32: columns [BN, 2BN) hold the a_hi*b_lo products
       uint32_t w[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + c * 32), w);
+      // both TMEM loads in flight before the one wait (each round trip is ~300 cycles of a latency-bound epilogue)
+      tmem_ld32_issue(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+      tmem_ld32_issue(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + c * 32), w);
+      tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
+    } else {
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -562,12 +570,15 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tmA, const CUten
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
       if (SPLIT3) {
         uint32_t w[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + c * 32), w);
+        tmem_ld32_issue(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+        tmem_ld32_issue(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + c * 32), w);
+        tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
+      } else {
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
       }
 #pragma unroll
       for (int j = 0; j < 32; j += 4)

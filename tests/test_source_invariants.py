@@ -17,12 +17,18 @@ def _sources():
 
 
 def _kernel_body(src, name):
-    m = re.search(r"__global__[^;{]*?\b" + re.escape(name) + r"\s*\(", src)
+    m = re.search(r"(__global__|__device__ __forceinline__ void)[^;{]*?\b" + re.escape(name) + r"\s*\(", src)
     if not m:
         return None
     rest = src[m.end():]
     nxt = rest.find("__global__")
-    return rest if nxt < 0 else rest[:nxt]
+    body = rest if nxt < 0 else rest[:nxt]
+    # a kernel that is only a named wrapper around a shared device body (gemm_tc_kernel / conv_gemm_tc_kernel):
+    # the rule applies to the body it calls
+    call = re.search(r"\b([A-Za-z0-9_]+_body)\s*<", body[:600])
+    if call and "pdl_wait()" not in body[:600]:
+        return _kernel_body(src, call.group(1))
+    return body
 
 
 def test_every_pdl_launched_kernel_waits_before_touching_memory():
@@ -31,7 +37,7 @@ def test_every_pdl_launched_kernel_waits_before_touching_memory():
     for s in src.values():
         names.update(re.findall(r"mtl_launch_pdl\(\s*([A-Za-z0-9_]+)", s))
     names.discard("kern")                                   # template launchers of gemm_tc.cu: listed explicitly below
-    names.update({"gemm_tc_kernel", "conv3x3_kw_kernel", "conv3x3_wgrad_kw_kernel"})
+    names.update({"gemm_tc_kernel", "conv_gemm_tc_kernel", "conv3x3_kw_kernel", "conv3x3_wgrad_kw_kernel"})
     assert len(names) >= 10, names
     for n in sorted(names):
         bodies = [b for b in (_kernel_body(s, n) for s in src.values()) if b is not None]

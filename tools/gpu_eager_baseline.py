@@ -35,7 +35,7 @@ def _setup(tf32, benchmark=True):
 def _batches(cfg, ref_meta, i, dev):
     tasks = [ref_meta.synth_batch(cfg, K_TRAIN, T_FRAMES, L_TOKENS, 1000 * i + t) for t in range(N_TASKS)]
     val = ref_meta.synth_batch(cfg, K_VALID, T_FRAMES, L_TOKENS, 1000 * i + 999)
-    mv = lambda b: (b[0].to(dev), b[1], b[2].to(dev))          # lengths stay on the host (Python mask loops read them)
+    mv = lambda b: (b[0].to(dev), [int(v) for v in b[1].tolist()], b[2].to(dev))   # lengths: host ints (Python mask loops read them)
     return [mv(b) for b in tasks], mv(val)
 
 
@@ -89,7 +89,7 @@ def graphed(steps=20, warmup=3, tf32=False):
         orig_mask, masks = ref_asr.length_row_mask, {}
 
         def cached_mask(n_rows, lengths, like):
-            key = (n_rows, tuple(int(l) for l in lengths), like.dtype)
+            key = (n_rows, tuple(lengths), like.dtype)
             if key not in masks:
                 masks[key] = orig_mask(n_rows, lengths, like)
             return masks[key]

@@ -1,8 +1,8 @@
 """Ad-hoc GPU timing (not pytest): latency of ONE small GEMM as a node of a dependent chain inside a CUDA graph
 (what the meta-step graph pays per node), plus the per-CTA %globaltimer span of the last launch (MTL_GEMM_DBG=99)."""
 import ctypes, os, sys
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
-import conftest  # noqa
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path[:0] = [os.path.join(ROOT, "meta-transfer-learning_b200"), ROOT, os.path.join(ROOT, "tests")]
 import torch
 from gpu_util import P, dev, lib, ok
 
@@ -42,4 +42,11 @@ for (tA, tB, M, N, K, beta, split) in SHAPES:
         v = [(s, e) for s, e in v if last - s < 50000]
         s0 = min(s for s, _ in v)
         line += f" | ctas {len(v):3d} start skew {max(s for s, _ in v) - s0:5d} ns, span {last - s0:6d} ns, mean cta {sum(e - s for s, e in v) / len(v):7.0f} ns"
+    if os.environ.get("MTL_GEMM_DBG") == "1":
+        st_ = (ctypes.c_longlong * 160)()
+        ok(lib().mtl_debug_gemm_stamps(st_))
+        t0 = st_[0]
+        names = {1: "pdl_wait done", 2: "first TMA", 3: "MMA sees operands", 4: "MMAs issued", 5: "tmem_full seen", 9: "staged",
+                 10: "cluster sync", 6: "stored", 7: "end"}
+        line += " | cycles from entry: " + ", ".join("%s %d" % (names[i], st_[i] - t0) for i in (1, 2, 3, 4, 5, 9, 10, 6, 7) if st_[i] > t0)
     print(line)
