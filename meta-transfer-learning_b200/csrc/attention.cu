@@ -583,6 +583,232 @@ __global__ void __launch_bounds__(NT) attn_small_bwd_kernel(AttnBwdArgs a) {
   SA_STAMP(20);
 }
 
+// ----------------------------------------------------------------------------- short sequences on the tensor cores
+// The same two kernels with every product on mma.sync.m16n8k8 TF32 fragments, 3xTF32 in registers (hi = rna_tf32(a),
+// lo = rna_tf32(a - hi); lo*hi + hi*lo + hi*hi accumulate in fp32): fp32-grade scores and gradients.  A (b, h) problem is
+// 33 x 33 x 64 -- far below one tcgen05 tile (M = 128) and not worth a TMEM allocation and a TMA descriptor fetch on a
+// latency-bound chain kernel -- so the warp-level MMA is the tensor-core path that fits: a warp owns 16 x 8 output tiles
+// and reads its fragments straight from the row-major shared-memory operands (row stride 68 floats: the 8 rows x 4
+// columns of an A / NT-B fragment fall into 32 distinct banks).  The CUDA-core version spent 6.8 k of its 17 k cycles on
+// the scores alone (shared-memory wavefronts of a 4 x 4 register-blocked FFMA loop).  MTL_ATTN_MMA=0 selects it (A/B).
+__device__ __forceinline__ uint32_t f2tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = f2tf32(x);
+  lo = f2tf32(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ void mma_3x(float (&c)[4], const float (&a)[4], const float (&b)[2]) {
+  uint32_t ah[4], al[4], bh[2], bl[2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) split_tf32(a[i], ah[i], al[i]);
+#pragma unroll
+  for (int i = 0; i < 2; ++i) split_tf32(b[i], bh[i], bl[i]);
+  mma_tf32(c, al, bh);
+  mma_tf32(c, ah, bl);
+  mma_tf32(c, ah, bh);
+}
+// Fragment coordinates of lane = 4 g + t:  A (16 x 8): (g, t) (g + 8, t) (g, t + 4) (g + 8, t + 4);  B (8 x 8): (k = t, n = g)
+// (k = t + 4, n = g);  C (16 x 8): (g, 2t) (g, 2t + 1) (g + 8, 2t) (g + 8, 2t + 1).
+// c += X[m0.., k] * Y[n0.., k]^T over k < K8 (multiple of 8)           (both operands row-major, contraction along columns)
+__device__ __forceinline__ void sa_mma_nt(float (&c)[4], const float (*X)[SA_LD], const float (*Y)[SA_LD], int m0, int n0,
+                                          int K8, int g, int t) {
+  for (int k0 = 0; k0 < K8; k0 += 8) {
+    const float a[4] = {X[m0 + g][k0 + t], X[m0 + g + 8][k0 + t], X[m0 + g][k0 + t + 4], X[m0 + g + 8][k0 + t + 4]};
+    const float b[2] = {Y[n0 + g][k0 + t], Y[n0 + g][k0 + t + 4]};
+    mma_3x(c, a, b);
+  }
+}
+// c += W[m0.., k] * Y[k, n0..] over k < K8                                (A row-major, B row-major [k][n])
+__device__ __forceinline__ void sa_mma_nn(float (&c)[4], const float (*W)[SA_LD], const float (*Y)[SA_LD], int m0, int n0,
+                                          int K8, int g, int t) {
+  for (int k0 = 0; k0 < K8; k0 += 8) {
+    const float a[4] = {W[m0 + g][k0 + t], W[m0 + g + 8][k0 + t], W[m0 + g][k0 + t + 4], W[m0 + g + 8][k0 + t + 4]};
+    const float b[2] = {Y[k0 + t][n0 + g], Y[k0 + t + 4][n0 + g]};
+    mma_3x(c, a, b);
+  }
+}
+// c += W[k, m0..]^T * Y[k, n0..] over k < K8                              (contraction over the ROWS of both operands)
+__device__ __forceinline__ void sa_mma_tn(float (&c)[4], const float (*W)[SA_LD], const float (*Y)[SA_LD], int m0, int n0,
+                                          int K8, int g, int t) {
+  for (int k0 = 0; k0 < K8; k0 += 8) {
+    const float a[4] = {W[k0 + t][m0 + g], W[k0 + t][m0 + g + 8], W[k0 + t + 4][m0 + g], W[k0 + t + 4][m0 + g + 8]};
+    const float b[2] = {Y[k0 + t][n0 + g], Y[k0 + t + 4][n0 + g]};
+    mma_3x(c, a, b);
+  }
+}
+// fragment -> global rows [0, rows) of a (.., ld) matrix, columns n0 + 2t, n0 + 2t + 1
+__device__ __forceinline__ void sa_store_frag(float* out, int ld, const float (&c)[4], int m0, int n0, int rows, int g, int t,
+                                              float scale) {
+  if (m0 + g < rows) *reinterpret_cast<float2*>(out + (size_t)(m0 + g) * ld + n0 + 2 * t) = make_float2(c[0] * scale, c[1] * scale);
+  if (m0 + g + 8 < rows) *reinterpret_cast<float2*>(out + (size_t)(m0 + g + 8) * ld + n0 + 2 * t) = make_float2(c[2] * scale, c[3] * scale);
+}
+
+template <int DK, int NT>
+__global__ void __launch_bounds__(NT) attn_small_fwd_mma_kernel(AttnArgs a) {
+  constexpr int NW = NT / 32;
+  extern __shared__ __align__(16) unsigned char sa_raw[];
+  SaSmem& S = *reinterpret_cast<SaSmem*>(sa_raw);
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  pdl_wait();
+  pdl_trigger();
+  SA_STAMP(0);
+  {
+    SaTile<DK, NT> tq, tk, tv;
+    sa_fetch<DK, NT>(tq, a.q, b, a.Tq, a.ldq, h);
+    sa_fetch<DK, NT>(tk, a.k, b, a.Tk, a.ldk, h);
+    sa_fetch<DK, NT>(tv, a.v, b, a.Tk, a.ldv, h);
+    sa_load_kmask(S.kmask, a.keypad, b, a.Tk);
+    sa_store<DK, NT>(S.q, tq); sa_store<DK, NT>(S.k, tk); sa_store<DK, NT>(S.v, tv);
+  }
+  __syncthreads();
+  SA_STAMP(1);
+  const int Tq = a.Tq, Tk = a.Tk;
+  const int mt = (Tq + 15) >> 4, nt = (Tk + 7) >> 3;
+  for (int tile = w; tile < mt * nt; tile += NW) {               // masked, scaled scores -> S.p
+    const int m0 = (tile / nt) << 4, n0 = (tile % nt) << 3;
+    float c[4] = {0.f, 0.f, 0.f, 0.f};
+    sa_mma_nt(c, S.q, S.k, m0, n0, DK, g, t);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int i = m0 + g + ((e >> 1) << 3), j = n0 + 2 * t + (e & 1);
+      const bool ok = i < Tq && !S.kmask[j] && !(a.causal && j > i);
+      S.p[i][j] = ok ? c[e] * a.inv_temp : -INFINITY;
+    }
+  }
+  __syncthreads();
+  SA_STAMP(2);
+  const unsigned long long seed = a.drop.p > 0.f ? mtl_eff_seed(a.drop) : 0ull;
+  const float drop_p = a.drop.p, inv_keep = a.drop.inv_keep;
+  const uint32_t site = a.drop.site;
+  const int nt8 = nt << 3;                                        // columns the score tiles wrote
+#pragma unroll
+  for (int u = 0; u < SA_T / NW; ++u) {                           // softmax over keys, one warp per query row
+    const int i = w + NW * u;
+    if (i >= ((Tq + 15) & ~15)) continue;                         // warp-uniform; rows [Tq, 16 mt) become zeros for P.V
+    const float s0 = lane < nt8 ? S.p[i][lane] : -INFINITY, s1 = lane + 32 < nt8 ? S.p[i][lane + 32] : -INFINITY;
+    const float m = warp_max(fmaxf(s0, s1));
+    float p0 = 0.f, p1 = 0.f;
+    if (m != -INFINITY) { p0 = __expf(s0 - m); p1 = __expf(s1 - m); }
+    const float l = warp_sum(p0 + p1);
+    const float inv = i < Tq ? 1.f / l : 0.f;                     // fully masked REAL row -> 0 * inf = NaN, like the reference
+    p0 *= inv; p1 *= inv;
+    if (drop_p > 0.f && i < Tq) {
+      const unsigned long long base = ((unsigned long long)(b * a.H + h) * Tq + i) * Tk;
+      if (s0 != -INFINITY) p0 *= dropout_scale(seed, site, base + lane, drop_p, inv_keep);
+      if (s1 != -INFINITY) p1 *= dropout_scale(seed, site, base + lane + 32, drop_p, inv_keep);
+    }
+    S.p[i][lane] = p0; S.p[i][lane + 32] = p1;
+    if (lane == 0 && i < Tq) a.lse[((size_t)b * a.H + h) * Tq + i] = m + logf(l);
+  }
+  __syncthreads();
+  SA_STAMP(3);
+  float* out = a.o + (size_t)b * Tq * a.ldo + h * DK;
+  for (int tile = w; tile < mt * (DK / 8); tile += NW) {          // O = P . V
+    const int m0 = (tile / (DK / 8)) << 4, n0 = (tile % (DK / 8)) << 3;
+    float c[4] = {0.f, 0.f, 0.f, 0.f};
+    sa_mma_nn(c, S.p, S.v, m0, n0, nt8, g, t);
+    sa_store_frag(out, a.ldo, c, m0, n0, Tq, g, t, 1.f);
+  }
+  SA_STAMP(4);
+}
+
+template <int DK, int NT>
+__global__ void __launch_bounds__(NT) attn_small_bwd_mma_kernel(AttnBwdArgs a) {
+  constexpr int NW = NT / 32;
+  extern __shared__ __align__(16) unsigned char sa_raw[];
+  SaSmem& S = *reinterpret_cast<SaSmem*>(sa_raw);
+  const AttnArgs& f = a.f;
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  pdl_wait();
+  pdl_trigger();
+  SA_STAMP(16);
+  {
+    SaTile<DK, NT> tq, tk, tv, tg, to;
+    sa_fetch<DK, NT>(tq, f.q, b, f.Tq, f.ldq, h);
+    sa_fetch<DK, NT>(tk, f.k, b, f.Tk, f.ldk, h);
+    sa_fetch<DK, NT>(tv, f.v, b, f.Tk, f.ldv, h);
+    sa_fetch<DK, NT>(tg, a.d_o, b, f.Tq, f.ldo, h);
+    sa_fetch<DK, NT>(to, f.o, b, f.Tq, f.ldo, h);      // O rows, only for delta (S.p is rewritten below)
+    sa_load_kmask(S.kmask, f.keypad, b, f.Tk);
+    if (threadIdx.x >= 64 && threadIdx.x < 64 + SA_T) {
+      const int i = threadIdx.x - 64;
+      S.lse[i] = i < f.Tq ? f.lse[((size_t)b * f.H + h) * f.Tq + i] : 0.f;
+    }
+    sa_store<DK, NT>(S.q, tq); sa_store<DK, NT>(S.k, tk); sa_store<DK, NT>(S.v, tv); sa_store<DK, NT>(S.g, tg); sa_store<DK, NT>(S.p, to);
+  }
+  __syncthreads();
+  SA_STAMP(17);
+  for (int i = w; i < SA_T; i += NW) {         // delta_i = dO_i . O_i (== sum_j P_ij dP_ij, also with dropout)
+    float s = 0.f;
+#pragma unroll
+    for (int v = 0; v < DK / 32; ++v) s += S.g[i][lane + 32 * v] * S.p[i][lane + 32 * v];
+    s = warp_sum(s);
+    if (lane == 0) S.delta[i] = s;
+  }
+  __syncthreads();
+  SA_STAMP(18);
+  const int Tq = f.Tq, Tk = f.Tk;
+  const int mt = (Tq + 15) >> 4, nt = (Tk + 7) >> 3;
+  {
+    const unsigned long long seed = f.drop.p > 0.f ? mtl_eff_seed(f.drop) : 0ull;
+    for (int tile = w; tile < mt * nt; tile += NW) {              // scores and dP of one 16 x 8 tile -> P (dropped), dS
+      const int m0 = (tile / nt) << 4, n0 = (tile % nt) << 3;
+      float sc[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
+      sa_mma_nt(sc, S.q, S.k, m0, n0, DK, g, t);
+      sa_mma_nt(dp, S.g, S.v, m0, n0, DK, g, t);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int i = m0 + g + ((e >> 1) << 3), j = n0 + 2 * t + (e & 1);
+        const bool ok = i < Tq && !S.kmask[j] && !(f.causal && j > i);
+        const float p = ok ? __expf(sc[e] * f.inv_temp - S.lse[i]) : 0.f;
+        float pd = p, d = dp[e];
+        if (f.drop.p > 0.f && ok) {
+          const unsigned long long idx = (((unsigned long long)(b * f.H + h) * Tq + i) * Tk + j);
+          const float s = dropout_scale(seed, f.drop.site, idx, f.drop.p, f.drop.inv_keep);
+          pd = p * s; d *= s;
+        }
+        S.p[i][j] = pd;
+        S.ds[i][j] = ok ? p * (d - S.delta[i]) : 0.f;
+      }
+    }
+  }
+  __syncthreads();
+  SA_STAMP(19);
+  // dQ = dS . K / temp ; dK = dS^T . Q / temp ; dV = P^T . dO -- (mt + 2 mk) x DK / 8 tiles of 16 x 8 shared by the warps
+  const int mk = (Tk + 15) >> 4, ND = DK / 8;
+  const int i8 = mt << 4, j8 = nt << 3;                           // extents of P / dS written above (zeros beyond Tq / Tk)
+  // dK / dV tiles read COLUMNS of dS / P up to 16 mk, beyond the 8 nt written above (stale O values there): column j of the
+  // transposed operand only reaches output row j, and rows >= Tk are never stored
+  float* dq = a.dq + (size_t)b * Tq * f.ldq + h * DK;
+  float* dk = a.dk + (size_t)b * Tk * f.ldk + h * DK;
+  float* dv = a.dv + (size_t)b * Tk * f.ldv + h * DK;
+  for (int tile = w; tile < (mt + 2 * mk) * ND; tile += NW) {
+    const int r = tile / ND, n0 = (tile % ND) << 3;
+    float c[4] = {0.f, 0.f, 0.f, 0.f};
+    if (r < mt) {
+      sa_mma_nn(c, S.ds, S.k, r << 4, n0, j8, g, t);
+      sa_store_frag(dq, f.ldq, c, r << 4, n0, Tq, g, t, f.inv_temp);
+    } else if (r < mt + mk) {
+      sa_mma_tn(c, S.ds, S.q, (r - mt) << 4, n0, i8, g, t);
+      sa_store_frag(dk, f.ldk, c, (r - mt) << 4, n0, Tk, g, t, f.inv_temp);
+    } else {
+      sa_mma_tn(c, S.p, S.g, (r - mt - mk) << 4, n0, i8, g, t);
+      sa_store_frag(dv, f.ldv, c, (r - mt - mk) << 4, n0, Tk, g, t, 1.f);
+    }
+  }
+  SA_STAMP(20);
+}
+
 // MTL_ATTN_SMALL=0 keeps the tiled kernels for short sequences too (A/B measurements)
 static bool attn_small_enabled() {
   static int v = -1;
@@ -600,14 +826,22 @@ static int attn_small_threads() {
   if (v < 0) { const char* e = getenv("MTL_ATTN_THREADS"); v = (e && atoi(e) == 256) ? 256 : 512; }
   return v;
 }
+// MTL_ATTN_MMA=0: the CUDA-core FFMA versions of the short-sequence kernels (A/B measurements)
+static bool attn_mma_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MTL_ATTN_MMA"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v != 0;
+}
 template <int DK, int NT>
 static int attn_small_fwd_launch(const AttnArgs& a, cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
     MTL_CHECK_CUDA(cudaFuncSetAttribute(attn_small_fwd_kernel<DK, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SaSmem)));
+    MTL_CHECK_CUDA(cudaFuncSetAttribute(attn_small_fwd_mma_kernel<DK, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SaSmem)));
     configured = true;
   }
-  MTL_CHECK_CUDA(mtl_launch_pdl(attn_small_fwd_kernel<DK, NT>, dim3(a.H, a.B), dim3(NT), sizeof(SaSmem), s, a));
+  auto kern = attn_mma_enabled() ? attn_small_fwd_mma_kernel<DK, NT> : attn_small_fwd_kernel<DK, NT>;
+  MTL_CHECK_CUDA(mtl_launch_pdl(kern, dim3(a.H, a.B), dim3(NT), sizeof(SaSmem), s, a));
   ++g_mtl_launches;
   return MTL_OK;
 }
@@ -616,9 +850,11 @@ static int attn_small_bwd_launch(const AttnBwdArgs& a, cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
     MTL_CHECK_CUDA(cudaFuncSetAttribute(attn_small_bwd_kernel<DK, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SaSmem)));
+    MTL_CHECK_CUDA(cudaFuncSetAttribute(attn_small_bwd_mma_kernel<DK, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SaSmem)));
     configured = true;
   }
-  MTL_CHECK_CUDA(mtl_launch_pdl(attn_small_bwd_kernel<DK, NT>, dim3(a.f.H, a.f.B), dim3(NT), sizeof(SaSmem), s, a));
+  auto kern = attn_mma_enabled() ? attn_small_bwd_mma_kernel<DK, NT> : attn_small_bwd_kernel<DK, NT>;
+  MTL_CHECK_CUDA(mtl_launch_pdl(kern, dim3(a.f.H, a.f.B), dim3(NT), sizeof(SaSmem), s, a));
   ++g_mtl_launches;
   return MTL_OK;
 }

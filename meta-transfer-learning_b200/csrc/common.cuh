@@ -23,6 +23,7 @@ void mtl_set_error(const char* fmt, ...);
   } while (0)
 
 extern int g_mtl_concurrency;                 // task lanes being enqueued together (1 outside mtl_meta_tasks)
+bool mtl_pdl_chain_only();                    // MTL_PDL_SIDE=0: programmatic dependent launch only for chain kernels
 extern int g_mtl_launch_prio;                 // CUDA launch priority of the kernels being enqueued (0 = default / lowest; < 0 = more urgent)
 extern unsigned long long g_mtl_launches;   // kernels enqueued by this library (bench.py reports it)
 #define MTL_CHECK_LAUNCH()               \
@@ -66,7 +67,7 @@ static inline cudaError_t mtl_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
   cudaLaunchAttribute at[2];
   int na = 0;
-  if (mtl_pdl_enabled()) {
+  if (mtl_pdl_enabled() && (g_mtl_launch_prio != 0 || !mtl_pdl_chain_only())) {
     at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[na].val.programmaticStreamSerializationAllowed = 1;
     ++na;

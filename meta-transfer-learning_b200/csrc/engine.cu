@@ -33,6 +33,11 @@ bool mtl_pdl_enabled() {
   if (v < 0) { const char* e = getenv("MTL_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
   return v != 0;
 }
+bool mtl_pdl_chain_only() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MTL_PDL_SIDE"); v = (e && e[0] == '0') ? 1 : 0; }
+  return v != 0;
+}
 extern "C" const char* mtl_last_error(void) { return g_err; }
 extern "C" unsigned long long mtl_launch_count(void) { return g_mtl_launches; }
 extern "C" int mtl_abi_version(void) { return MTL_ABI_VERSION; }

@@ -1290,7 +1290,7 @@ int launch(const Maps& tm, const TcParams& P_in, dim3 grid, cudaStream_t s) {
     at[na].val.clusterDim.x = 1; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = (unsigned)P.cluster_k;
     ++na;
   }
-  if (mtl_pdl_enabled()) {
+  if (mtl_pdl_enabled() && (g_mtl_launch_prio != 0 || !mtl_pdl_chain_only())) {
     at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[na].val.programmaticStreamSerializationAllowed = 1;
     ++na;
