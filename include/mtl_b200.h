@@ -107,6 +107,20 @@ int mtl_asr_forward(mtl_session* s, const float* theta, const float* pe_enc, con
 int mtl_asr_backward(mtl_session* s, const float* theta, float* grad, float loss_scale,
                      const float* dpred_ext, int ld_ext, void* stream);
 
+/* ------------------------------------------------------------------ inference: encode + greedy search
+ * mtl_asr_encode: Transformer.encode (models/asr/transformer.py:151-160): VGG front-end, flatten, Encoder.forward;
+ * enc_out (device) receives (B * T') x d_model rows, T' = (T / 2) / 2.
+ * mtl_asr_greedy: Decoder.greedy_search (modules/decoder.py:131-184) on an encoder output: out_tokens (device,
+ * B x max_steps int32) receives the arg-max token of every step (the caller cuts each row at the first EOS, :175-183).
+ * Masks as in the reference: all-ones non-pad mask, subsequent-only self-attention mask, no encoder-side key mask. */
+long long mtl_encode_workspace_bytes(mtl_session* s, int B, int T);
+int mtl_asr_encode(mtl_session* s, const float* theta, const float* pe_enc, void* workspace,
+                   long long workspace_bytes, const mtl_batch* batch, float* enc_out, void* stream);
+long long mtl_greedy_workspace_bytes(mtl_session* s, int B, int Tp, int max_steps);
+int mtl_asr_greedy(mtl_session* s, const float* theta, const float* pe_dec, void* workspace,
+                   long long workspace_bytes, const float* enc_out, int B, int Tp, int start_token, int max_steps,
+                   int* out_tokens, void* stream);
+
 /* ------------------------------------------------------------------ meta-step pieces
  * trainer/asr/transient_trainer.py:178-237 for ONE task, is_copy_grad=True:
  *   grad <- d CE(theta; train)            (:188-199)

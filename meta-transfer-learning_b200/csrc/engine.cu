@@ -254,6 +254,8 @@ struct Run {
   unsigned long long seed;                    // effective seed = seed + (*seed_dev) * seed_mul
   const unsigned long long* seed_dev = nullptr;
   unsigned long long seed_mul = 0;
+  bool enc_only = false;                      // forward() stops after the encoder (mtl_asr_encode)
+  bool no_zslab = false;                      // greedy decoding re-uses its scratch every step: no zero-pool outputs
   int bulk = 0;                               // > 0: inside a GPU-filling / deferred section (convolutions): default priority
   uint32_t site;
   MtlDrop next_drop() { return p_drop > 0.f ? mtl_drop(p_drop, seed, site++, seed_dev, seed_mul) : mtl_nodrop(); }
@@ -407,7 +409,7 @@ static bool zslab_enabled() {
 }
 // Should the [M, N] output of a K-deep beta == 0 GEMM live in the zero pool?
 static bool use_zslab(const Run& R, int M, int N, int Kd) {
-  if (!zslab_enabled() || R.S->mode == MTL_GEMM_SIMT_FP32 || N % 4 != 0 || Kd < 256) return false;
+  if (!zslab_enabled() || R.no_zslab || R.S->mode == MTL_GEMM_SIMT_FP32 || N % 4 != 0 || Kd < 256) return false;
   return (long long)mtl_cdiv(M, 128) * mtl_cdiv(N, N <= 64 ? 64 : 128) <= 16;
 }
 static int wgrad_ctas() {
@@ -842,7 +844,7 @@ static int forward(Run& R, const mtl_batch& b, const float* pe_enc, const float*
   const Layout& L = S->L;
   Pass& P = *R.P;
   P.valid = false;
-  MTL_REQUIRE(b.B > 0 && b.T > 0 && b.L >= 0 && b.n >= 1, "empty batch");   // n == 1: every transcript empty (SOS -> EOS only)
+  MTL_REQUIRE(b.B > 0 && b.T > 0 && b.L >= 0 && (b.n >= 1 || R.enc_only), "empty batch");   // n == 1: every transcript empty (SOS -> EOS only)
   P.b = b;
   P.B = b.B; P.T = b.T; P.F = c.n_freq; P.F2 = P.F / 2; P.T2 = P.T / 2; P.F4 = P.F2 / 2; P.T4 = P.T2 / 2;
   MTL_REQUIRE(P.T4 >= 1 && P.F4 >= 1, "input shorter than 4 frames / 4 bins");
@@ -922,6 +924,11 @@ static int forward(Run& R, const mtl_batch& b, const float* pe_enc, const float*
     x = P.enc_ff[l].out;
   }
   P.enc_out = x;
+  if (R.enc_only) {
+    MTL_TRY(join_all(R));
+    P.ws_after_fwd = R.ws.off;
+    return MTL_OK;
+  }
 
   // ---- decoder (decoder.py:71-115)
   P.seq_in = R.ws.i(P.Md);
@@ -1208,6 +1215,164 @@ extern "C" int mtl_asr_backward(mtl_session* s, const float* theta, float* grad,
                                 const float* dpred_ext, int ld_ext, void* stream) {
   MTL_REQUIRE(s, "null argument");
   return run_backward(s, &s->pass, &s->br, theta, grad, loss_scale, dpred_ext, ld_ext, (cudaStream_t)stream);
+}
+
+// ----------------------------------------------------------------------------- C ABI: inference (encode + greedy search)
+// Transformer.encode (models/asr/transformer.py:151-160: VGG front-end + flatten + Encoder.forward) into a caller buffer,
+// and Decoder.greedy_search (modules/decoder.py:131-184): start token, then `max_steps` times the whole decoder over the
+// prefix decoded so far -- all-ones non-pad mask, subsequent-only self-attention mask, NO encoder-side key mask
+// (dec_enc_attn_mask=None), eval-mode dropout -- and the arg-max of the last position appended.  The reference rebuilds
+// the prefix pass from Python 300 times with ~60 host syncs each; here the loop is enqueued once, without a host sync,
+// the encoder-side k / v projections of every layer are formed once, and each step re-uses one scratch region.
+__global__ void greedy_prefix_kernel(const int* ys, int cap, int B, int n, int* seq) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B * n) seq[i] = ys[(i / n) * cap + (i % n)];
+}
+__global__ void greedy_append_kernel(const int* hyp, int* ys, int cap, int t, int* out, int max_steps, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) { ys[b * cap + t + 1] = hyp[b]; out[b * max_steps + t] = hyp[b]; }
+}
+__global__ void greedy_init_kernel(int* ys, int cap, int B, int start_token, float* ones, unsigned char* zeros, int n_mask) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B) ys[i * cap] = start_token;
+  if (i < n_mask) { ones[i] = 1.f; zeros[i] = 0; }
+}
+
+static int encode_run(mtl_session* s, Run& R, const mtl_batch* batch, const float* pe_enc) {
+  R.enc_only = true;
+  mtl_batch b = *batch;
+  b.trg = nullptr; b.L = 0; b.n = 0; b.hyp_out = nullptr; b.gold_out = nullptr; b.ce_out = nullptr;
+  return forward(R, b, pe_enc, nullptr, 0.f);
+}
+extern "C" long long mtl_encode_workspace_bytes(mtl_session* s, int B, int T) {
+  if (!s) return -1;
+  Pass scratch;
+  Run R;
+  R.S = s; R.P = &scratch; R.st = 0; R.dry = true; R.theta = nullptr; R.grad = nullptr; R.p_drop = 0.f; R.seed = 0; R.site = 0;
+  R.ws.base = 0; R.ws.cap = ~(size_t)0;
+  mtl_batch b;
+  memset(&b, 0, sizeof(b));
+  b.B = B; b.T = T;
+  if (encode_run(s, R, &b, nullptr) != MTL_OK) return -1;
+  return (long long)(R.ws.peak + ((R.wz.peak + 255) & ~(size_t)255) + 512);
+}
+extern "C" int mtl_asr_encode(mtl_session* s, const float* theta, const float* pe_enc, void* workspace,
+                              long long workspace_bytes, const mtl_batch* batch, float* enc_out, void* stream) {
+  MTL_REQUIRE(s && theta && pe_enc && workspace && batch && batch->x && batch->lens && enc_out, "null argument");
+  MTL_REQUIRE((((uintptr_t)workspace) & 255u) == 0, "workspace must be 256B aligned");
+  const long long need = mtl_encode_workspace_bytes(s, batch->B, batch->T);
+  MTL_REQUIRE(need > 0 && need <= workspace_bytes, "workspace too small for mtl_asr_encode (mtl_encode_workspace_bytes)");
+  // zero-pool size of this pass
+  Pass scratch;
+  Run D;
+  D.S = s; D.P = &scratch; D.st = 0; D.dry = true; D.theta = nullptr; D.grad = nullptr; D.p_drop = 0.f; D.seed = 0; D.site = 0;
+  D.ws.base = 0; D.ws.cap = ~(size_t)0;
+  MTL_TRY(encode_run(s, D, batch, nullptr));
+  Run R;
+  R.zbytes = (D.wz.peak + 255) & ~(size_t)255;
+  R.S = s; R.P = &s->pass; R.st = (cudaStream_t)stream; R.main = R.st; R.dry = false; R.theta = theta; R.grad = nullptr;
+  if (branches_enabled()) { MTL_TRY(branches_init(s->br)); R.br = &s->br; }
+  R.p_drop = 0.f; R.seed = 0; R.site = 0;
+  R.ws.base = (uintptr_t)workspace; R.ws.cap = (size_t)workspace_bytes;
+  MTL_TRY(encode_run(s, R, batch, pe_enc));
+  s->pass.valid = false;                                   // no backward after an encode-only pass
+  const Pass& P = s->pass;
+  MTL_CHECK_CUDA(cudaMemcpyAsync(enc_out, P.enc_out, sizeof(float) * (size_t)P.Me * s->cfg.d_model, cudaMemcpyDeviceToDevice, R.st));
+  return MTL_OK;
+}
+
+// decoder over the prefix ys[:, :n] (B x n tokens) -> hyp[b] = arg-max of the last position's logits
+struct GreedyState {
+  std::vector<AttnAct> ca;             // cross-attention records: k / v of the encoder output, formed once
+  int* ys; int* seq; int* hyp; int* gold0;
+  float *ones, *row_lse, *row_loss, *logits;
+  unsigned char* nokeypad;
+  CeOut* ce;
+  int cap, ldp;
+};
+static int greedy_step(Run& R, GreedyState& G, const float* enc_out, const float* pe_dec, int B, int Tp, int n) {
+  mtl_session* S = R.S;
+  const mtl_model_cfg& c = S->cfg;
+  const Layout& L = S->L;
+  const int d = c.d_model, M = B * n;
+  if (!R.dry) { greedy_prefix_kernel<<<mtl_cdiv(M, 256), 256, 0, R.st>>>(G.ys, G.cap, B, n, G.seq); MTL_CHECK_LAUNCH(); ++g_mtl_launches; }
+  float* x0 = R.ws.f((size_t)M * d);
+  K(k_embed_fwd(G.seq, R.theta + L.emb, pe_dec, mtl_nodrop(), x0, B, n, d, R.st));
+  const float* x = x0;
+  for (int l = 0; l < c.n_dec; ++l) {
+    AttnAct sa;
+    FfnAct ff;
+    MTL_TRY(attn_block_fwd(R, sa, L.dec_sa[l], x, x, B, n, n, G.nokeypad, 1, G.ones, false));
+    x = sa.out;
+    MTL_TRY(attn_block_fwd(R, G.ca[l], L.dec_ca[l], x, enc_out, B, n, Tp, G.nokeypad, 0, G.ones, true));
+    x = G.ca[l].out;
+    MTL_TRY(ffn_block_fwd(R, ff, L.dec_ff[l], x, M, G.ones));
+    x = ff.out;
+  }
+  // logits of the LAST position of every sequence only: rows b * n + n - 1, i.e. a [B, d] matrix of row stride n * d
+  MTL_TRY(lin_fwd(R, x + (size_t)(n - 1) * d, n * d, R.theta + L.out_w, nullptr, G.logits, G.ldp, B, c.vocab, d, EPI_NONE, false,
+                  MTL_OP_VOCAB));
+  K(k_ce_fwd(G.logits, G.ldp, G.gold0, B, c.vocab, 0.f, 0, G.row_lse, G.row_loss, G.hyp, G.ce, R.st));
+  return MTL_OK;
+}
+static int greedy_run(mtl_session* s, Run& R, const float* enc_out, const float* pe_dec, int B, int Tp, int start_token,
+                      int max_steps, int* out_tokens) {
+  const mtl_model_cfg& c = s->cfg;
+  const Layout& L = s->L;
+  const int cap = max_steps + 1, n_mask = B * (cap > Tp ? cap : Tp);
+  GreedyState G;
+  G.cap = cap; G.ldp = (c.vocab + 3) & ~3;
+  G.ys = R.ws.i((size_t)B * cap); G.seq = R.ws.i((size_t)B * cap); G.hyp = R.ws.i(B); G.gold0 = R.ws.i(B);
+  G.ones = R.ws.f(n_mask); G.nokeypad = R.ws.u8(n_mask);
+  G.row_lse = R.ws.f(B); G.row_loss = R.ws.f(B); G.logits = R.ws.f((size_t)B * G.ldp); G.ce = (CeOut*)R.ws.f(8);
+  if (!R.dry) {
+    MTL_CHECK_CUDA(cudaMemsetAsync(G.gold0, 0, sizeof(int) * B, R.st));
+    greedy_init_kernel<<<mtl_cdiv(n_mask, 256), 256, 0, R.st>>>(G.ys, cap, B, start_token, G.ones, G.nokeypad, n_mask);
+    MTL_CHECK_LAUNCH();
+  }
+  G.ca.assign(c.n_dec, AttnAct());
+  for (int l = 0; l < c.n_dec; ++l)
+    MTL_TRY(attn_kv_fwd(R, G.ca[l], L.dec_ca[l], enc_out, B * Tp, R.main, R.main));
+  const size_t mark = R.ws.off;
+  for (int t = 0; t < max_steps; ++t) {
+    if (R.dry && t + 1 < max_steps) continue;            // planning: only the longest prefix matters
+    R.ws.off = mark;                                     // one stream, strictly ordered: every step re-uses the scratch
+    MTL_TRY(greedy_step(R, G, enc_out, pe_dec, B, Tp, t + 1));
+    if (!R.dry) {
+      greedy_append_kernel<<<mtl_cdiv(B, 128), 128, 0, R.st>>>(G.hyp, G.ys, cap, t, out_tokens, max_steps, B);
+      MTL_CHECK_LAUNCH();
+      ++g_mtl_launches;
+    }
+  }
+  return MTL_OK;
+}
+static void greedy_run_init(mtl_session* s, Run& R, Pass* scratch, bool dry) {
+  R.S = s; R.P = scratch; R.st = 0; R.main = 0; R.dry = dry; R.theta = nullptr; R.grad = nullptr; R.p_drop = 0.f; R.seed = 0;
+  R.site = 0; R.no_zslab = true; R.br = nullptr;
+  R.ws.base = 0; R.ws.cap = ~(size_t)0;
+}
+extern "C" long long mtl_greedy_workspace_bytes(mtl_session* s, int B, int Tp, int max_steps) {
+  if (!s || B < 1 || Tp < 1 || max_steps < 1) return -1;
+  Pass scratch;
+  Run R;
+  greedy_run_init(s, R, &scratch, true);
+  if (greedy_run(s, R, nullptr, nullptr, B, Tp, 0, max_steps, nullptr) != MTL_OK) return -1;
+  return (long long)(R.ws.peak + 512);
+}
+extern "C" int mtl_asr_greedy(mtl_session* s, const float* theta, const float* pe_dec, void* workspace,
+                              long long workspace_bytes, const float* enc_out, int B, int Tp, int start_token,
+                              int max_steps, int* out_tokens, void* stream) {
+  MTL_REQUIRE(s && theta && pe_dec && workspace && enc_out && out_tokens, "null argument");
+  MTL_REQUIRE(B >= 1 && Tp >= 1 && max_steps >= 1, "B, Tp, max_steps >= 1");
+  MTL_REQUIRE((((uintptr_t)workspace) & 255u) == 0, "workspace must be 256B aligned");
+  const long long need = mtl_greedy_workspace_bytes(s, B, Tp, max_steps);
+  MTL_REQUIRE(need > 0 && need <= workspace_bytes, "workspace too small for mtl_asr_greedy (mtl_greedy_workspace_bytes)");
+  Pass scratch;
+  Run R;
+  greedy_run_init(s, R, &scratch, false);
+  R.st = (cudaStream_t)stream; R.main = R.st; R.theta = theta;
+  R.ws.base = (uintptr_t)workspace; R.ws.cap = (size_t)workspace_bytes;
+  return greedy_run(s, R, enc_out, pe_dec, B, Tp, start_token, max_steps, out_tokens);
 }
 
 // ----------------------------------------------------------------------------- C ABI: meta-step pieces

@@ -19,6 +19,8 @@ from __future__ import annotations
 
 import itertools
 
+import weakref
+
 import torch
 import torch.nn as nn
 
@@ -137,6 +139,7 @@ class Transformer(nn.Module):
         s.pe_enc = self.encoder.positional_encoding.pe[0]
         s.pe_dec = self.decoder.positional_encoding.pe[0]
         self._hook = torch.zeros(1, device=device, requires_grad=True)
+        self.decoder.__dict__["_owner"] = weakref.ref(self)      # Decoder.greedy_search reaches the engine through the model
 
     def cuda(self, device=None):
         if not torch.cuda.is_available():
@@ -252,13 +255,32 @@ class Transformer(nn.Module):
         return _FusedLoss.apply(self._hook, self, owner[1])
 
     def encode(self, padded_input, input_lengths):
-        raise NotImplementedError("encode/decode are fused in the engine: call the model (forward) instead")
+        """(B,1,F,T) spectrograms, (B) raw frame counts -> encoder_padded_outputs (B, T', H)  (transformer.py:78-98)."""
+        s = self.session
+        x = padded_input.to(device=s.device, dtype=torch.float32).contiguous()
+        if x.size(2) != s.spec.n_freq:
+            self._rebuild_session(x.size(2))
+            s = self._session
+        lens = torch.as_tensor(input_lengths).to(device=s.device, dtype=torch.int32).contiguous()
+        return s.encode(self._theta, x, lens)
 
     def decode(self, encoder_padded_outputs, input_lengths, padded_target):
-        raise NotImplementedError("encode/decode are fused in the engine: call the model (forward) instead")
+        raise NotImplementedError("teacher-forced decoding from a detached encoder output is not exposed: the engine runs "
+                                  "encoder and decoder as one pass -- call the model (forward) instead")
 
-    def evaluate(self, *a, **k):
-        raise NotImplementedError("beam/greedy search evaluation (transformer.py:162-202) is outside the training hot path")
+    def evaluate(self, padded_input, input_lengths, padded_target, args, beam_search=False, beam_width=0, beam_nbest=0,
+                 lm=None, lm_rescoring=False, lm_weight=0.1, c_weight=1, start_token=-1, verbose=False, max_steps=300):
+        """-> (None, strs_hyps, strs_gold)  (transformer.py:162-202): greedy 1-best strings of the batch and the gold
+        strings (every position of <y><EOS><PAD>..., special tokens included, as the reference joins them)."""
+        if beam_search or lm is not None or lm_rescoring:
+            raise NotImplementedError("beam search / LM rescoring (decoder.py:186-291) are outside the B200 hot path; "
+                                      "greedy search (the reference's own fallback, transformer.py:191-199) is implemented")
+        enc = self.encode(padded_input, input_lengths)
+        _, gold = self.decoder.preprocess(padded_target.cpu())
+        strs_gold = ["".join(self.vocab.id2label[int(x)] for x in row) for row in gold]
+        strs_hyps = self.decoder.greedy_search(enc, args, start_token=start_token, max_steps=max_steps)
+        return None, strs_hyps, strs_gold
+
 
     # ------------------------------------------------------------------ copy-grad buffer (transformer.py:204-240)
     def init_copy_grad_(self):

@@ -51,7 +51,27 @@ class Decoder(FusedOnly):
         seq_out = pad_list([torch.cat([y, eos]) for y in seqs], v.PAD_ID)
         return seq_in, seq_out
 
-    def greedy_search(self, *a, **k):
-        raise NotImplementedError("inference-time search (decoder.py:131-291) is outside the training hot path")
+    def greedy_search(self, encoder_padded_outputs, args=None, beam_width=2, lm_rescoring=False, lm=None, lm_weight=0.1,
+                      c_weight=1, start_token=-1, max_steps=300):
+        """Greedy 1-best decoding (decoder.py:131-184): start token, `max_steps` (the reference hard-codes 300) arg-max
+        steps over the whole prefix, each row cut at its first EOS.  -> list of B strings.  One engine call
+        (mtl_asr_greedy) without host syncs instead of 300 Python-driven decoder passes."""
+        if lm is not None or lm_rescoring:
+            raise NotImplementedError("LM rescoring is outside the B200 hot path")
+        model = self._owner() if getattr(self, "_owner", None) is not None else None
+        if model is None:
+            raise RuntimeError("the decoder is not attached to a Transformer on a CUDA device")
+        ids = model.session.greedy(model._theta, encoder_padded_outputs, int(start_token), int(max_steps)).cpu().tolist()
+        v = self.vocab
+        out = []
+        for row in ids:
+            st = ""
+            for t in row:
+                if t == v.EOS_ID:
+                    break
+                st += v.id2label[t]
+            out.append(st)
+        return out
 
-    beam_search = greedy_search
+    def beam_search(self, *a, **k):
+        raise NotImplementedError("beam search (decoder.py:186-291) is outside the B200 hot path")

@@ -161,6 +161,42 @@ class Session:
         pred = flat.view(B, n, ldp.value)[:, :, :self.spec.vocab]
         return dict(pred=pred, gold=gold.view(B, n), hyp=hyp.view(B, n), ce=ce)
 
+    # ------------------------------------------------------------------ inference
+    def encode(self, theta: torch.Tensor, x: torch.Tensor, lens: torch.Tensor) -> torch.Tensor:
+        """Transformer.encode (models/asr/transformer.py:78-98): (B,1,F,T) spectrograms + raw frame counts ->
+        encoder output (B, T', d_model) with T' = (T // 2) // 2."""
+        B, _, F, T = x.shape
+        need = int(self.lib.mtl_encode_workspace_bytes(self._h, B, T))
+        if need < 0:
+            _l.check(-2)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(need + (64 << 20), dtype=torch.uint8, device=self.device)
+        b = Batch(x, lens, torch.zeros(B, 0, dtype=torch.int64, device=self.device), 0)
+        cb = self._cbatch(b)
+        out = torch.empty(B, (T // 2) // 2, self.spec.d_model, dtype=torch.float32, device=self.device)
+        _l.check(self.lib.mtl_asr_encode(self._h, _ptr(theta), _ptr(self.pe_enc), _ptr(self._ws), self._ws.numel(),
+                                         C.byref(cb), _ptr(out), _stream()))
+        self._live = (b, theta)
+        return out
+
+    def greedy(self, theta: torch.Tensor, enc_out: torch.Tensor, start_token: int, max_steps: int = 300) -> torch.Tensor:
+        """Decoder.greedy_search (modules/decoder.py:131-184) -> (B, max_steps) int32 arg-max tokens (not yet cut at EOS)."""
+        enc_out = enc_out.to(device=self.device, dtype=torch.float32).contiguous()
+        B, Tp, d = enc_out.shape
+        assert d == self.spec.d_model
+        if max_steps + 1 > self.pe_dec.shape[0]:
+            raise ValueError(f"max_steps {max_steps} exceeds the decoder positional table ({self.pe_dec.shape[0]} rows)")
+        need = int(self.lib.mtl_greedy_workspace_bytes(self._h, B, Tp, int(max_steps)))
+        if need < 0:
+            _l.check(-2)
+        ws = torch.empty(need + 4096, dtype=torch.uint8, device=self.device)
+        out = torch.empty(B, max_steps, dtype=torch.int32, device=self.device)
+        _l.check(self.lib.mtl_asr_greedy(self._h, _ptr(theta), _ptr(self.pe_dec), _ptr(ws), ws.numel(), _ptr(enc_out),
+                                         B, Tp, int(start_token), int(max_steps), _ptr(out), _stream()))
+        self._live_greedy = (ws, enc_out, theta)      # keep the buffers alive until the stream has consumed them
+        return out
+
     def backward(self, theta: torch.Tensor, grad: torch.Tensor, scale: float = 1.0,
                  dpred: Optional[torch.Tensor] = None):
         """Accumulates d(scale*CE)/dtheta (or the vjp of ``dpred``) of the last forward into ``grad``."""

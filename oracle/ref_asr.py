@@ -308,3 +308,36 @@ def num_correct(pred, gold):
     am = pred.reshape(-1, v).max(1)[1]
     gd = gold.reshape(-1)
     return int(am.eq(gd).masked_select(gd.ne(PAD_ID)).sum())
+
+
+def greedy_search(p, c: ModelConfig, enc_out, start_token: int = SOS_ID, max_steps: int = 300, bufs=None):
+    """Decoder.greedy_search (modules/decoder.py:131-184): ys = [start]; `max_steps` times the whole decoder over ys with an
+    all-ones non-pad mask, the subsequent mask only, NO encoder-side mask (dec_enc_attn_mask=None) and eval-mode
+    dropout; arg-max of the last position is appended.  Returns the (B, max_steps) token matrix (the reference then
+    cuts each row at the first EOS, :175-183)."""
+    bufs = bufs or buffers(c)
+    pe = bufs["decoder.positional_encoding.pe"]
+    b = enc_out.shape[0]
+    ys = torch.full((b, 1), start_token, dtype=torch.long)
+    out = []
+    for _ in range(max_steps):
+        n = ys.shape[1]
+        causal = torch.triu(torch.ones(n, n, dtype=torch.bool), diagonal=1).unsqueeze(0).expand(b, -1, -1)
+        nomask = torch.zeros(b, n, enc_out.shape[1], dtype=torch.bool)
+        x = F.embedding(ys, p["decoder.trg_embedding.weight"]) * 1.0 + pe[:, :n]
+        for l in range(c.n_dec):
+            pre = f"decoder.layers.{l}"
+            x = lowrank_attention(p, f"{pre}.self_attn", c, x, x, causal)
+            x = lowrank_attention(p, f"{pre}.encoder_attn", c, x, enc_out, nomask)
+            x = ffn(p, f"{pre}.pos_ffn", c, x)
+        prob = F.linear(x, p["decoder.output_linear.weight"])
+        nxt = prob[:, -1].max(dim=1)[1]
+        out.append(nxt)
+        ys = torch.cat([ys, nxt.unsqueeze(-1)], dim=1)
+    return torch.stack(out, dim=1)
+
+
+def encode(p, c: ModelConfig, x, lengths, bufs=None):
+    """Transformer.encode (models/asr/transformer.py:78-98)."""
+    bufs = bufs or buffers(c)
+    return encoder_forward(p, c, vgg_frontend(p, x), lengths, bufs["encoder.positional_encoding.pe"])

@@ -141,3 +141,28 @@ def test_joint_step_matches_reference_trainer():
     for s in range(n_steps):
         ref_meta.joint_step(po, adam, CFG, steps_tasks[s], lr=1e-3)
     _assert_params_close(model, po, 1e-3, n_steps)
+
+
+def test_greedy_search_and_encode_match_live_reference():
+    """Transformer.encode (models/asr/transformer.py:78-98) and Decoder.greedy_search (modules/decoder.py:131-184: 300
+    hard-coded steps, strings cut at the first EOS) of the live reference vs the restatement."""
+    import dataclasses
+    cfg = dataclasses.replace(CFG, tgt_max_len=320)              # the reference indexes the PE table up to 300 positions
+    p = ref_asr.init_params(cfg, 4)
+    model, vocab, args = live.build_model(cfg, p)
+    model.eval()
+    x, lens, y = ref_meta.synth_batch(cfg, 3, 41, 7, 77, lengths=[41, 25, 9], tgt_lengths=[7, 4, 2])
+    args.cuda = False
+    with torch.no_grad():
+        enc_ref = model.encode(x, lens)
+        strs_ref = model.decoder.greedy_search(enc_ref, args, start_token=vocab.SOS_ID)
+        enc_o = ref_asr.encode(p, cfg, x, lens)
+        ids = ref_asr.greedy_search(p, cfg, enc_o, start_token=vocab.SOS_ID, max_steps=300)
+    assert torch.equal(enc_o, enc_ref)
+    for b in range(3):
+        st = ""
+        for t in ids[b].tolist():
+            if t == vocab.EOS_ID:
+                break
+            st += vocab.id2label[t]
+        assert st == strs_ref[b], b
