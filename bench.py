@@ -319,8 +319,16 @@ def run_ours(args, rank, world, local_rank):
 
     # ---------------- roofline: kernel families by TIME (CUPTI pass), FLOP-dominant kernel timed alone, whole step
     roof = None
+    fam = None
+    if not args.no_roofline:
+        # every rank runs the two traced steps (they contain the collective); only rank 0 records them
+        run2 = lambda: [weak.step(i, weak.resident) for i in range(total_steps - 2, total_steps)]
+        if rank == 0:
+            fam = kernel_families(run2, 2)
+        else:
+            run2()
+        barrier()
     if rank == 0 and not args.no_roofline:
-        fam = kernel_families(lambda: [weak.step(i, weak.resident) for i in range(total_steps - 2, total_steps)], 2)
         roof = roofline_conv_gemm(s, lib, dev, args.gemm_mode)
         pk = _peaks()
         tf_step = STEP_TFLOP_3TASKS * n_local / 3.0                 # this rank's share of the step
@@ -381,6 +389,7 @@ FAMILIES = (
     ("attn_ffn", lambda n, g: n.startswith(("gemm_", "attn_", "ln_", "colsum"))),
     ("loss_embed", lambda n, g: n.startswith(("ce_", "embed_", "dec_preprocess", "enc_masks"))),
     ("arena", lambda n, g: n.startswith(("ew_kernel", "sumsq", "clip_", "adam_", "set_u64", "scale_"))),
+    ("exchange", lambda n, g: n.startswith("nccl")),
 )
 
 
