@@ -39,6 +39,24 @@ UNIT = "utterance-passes/s"
 # algorithmic FLOPs of one cfg-2 meta-step with 3 tasks (48 utterance passes, forward + backward = 3 x the
 # forward MACs x 2): all dense contractions, and the attention + FFN + projection share the north_star names
 STEP_TFLOP_3TASKS, ATTN_FFN_TFLOP_3TASKS = 0.533, 0.0653
+MODEL = dict()                      # ModelSpec overrides (cfg 2 = the defaults: enc2 / dec4 / d512 / 8 heads)
+WORKLOAD = "cfg2: meta_transfer_train.py 3 synthetic tasks k-train=8 enc2/dec4 d512 --copy-grad"
+
+
+def select_config(name):
+    """cfg2 (default, the BASELINE metric) or cfg4 = BASELINE configs[3]: enc4/dec6, d_model 768, 12 heads, --src-max-len
+    5000 (T = 5000 frames, T' = 1250), L = 256 target tokens and d_inner = 768 (not given by BASELINE.json,
+    assumed), 8 tasks on 8 GPUs = ONE task per GPU.  Arithmetic stays 3xTF32 / TF32 on fp32 storage (>= the bf16 the
+    config names); SURVEY 8d FLOPs: 82.73 TFLOP per 8-task meta-step, 21.26 of them attention + FFN + projections."""
+    global T_FRAMES, L_TOKENS, TASKS_PER_GPU, STEP_TFLOP_3TASKS, ATTN_FFN_TFLOP_3TASKS, MODEL, WORKLOAD
+    if name == "cfg4":
+        T_FRAMES, L_TOKENS, TASKS_PER_GPU = 5000, 256, 1
+        STEP_TFLOP_3TASKS, ATTN_FFN_TFLOP_3TASKS = 82.73 * 3 / 8, 21.26 * 3 / 8       # per 3 tasks, like the cfg-2 constants
+        MODEL = dict(n_enc=4, n_dec=6, d_model=768, n_heads=12, d_k=64, d_v=64, d_inner=768)
+        global METRIC
+        METRIC = "meta-step utterances/sec (enc4/dec6/d768/h12, k=8, T=5000)"
+        WORKLOAD = ("cfg4: meta_transfer_train.py enc4/dec6 d768 h12 --src-max-len 5000 (T=5000, L=256, d_inner=768 assumed), "
+                    "1 task per GPU, --copy-grad")
 
 
 def _peaks():
@@ -68,7 +86,7 @@ def _ncu(role, mode):
 
 def workload_config(n_total, world, scaling):
     """The `config` object, identical in both arms (the reference arm times a bounded sample of the same workload)."""
-    w = "cfg2: meta_transfer_train.py 3 synthetic tasks k-train=8 enc2/dec4 d512 --copy-grad"
+    w = WORKLOAD
     if world > 1:
         w += (f", {n_total} tasks over {world} GPUs ({scaling} scaling), one exchange of copy_grad per step")
     return {"workload": w, "tasks": n_total, "k_train": K_TRAIN, "k_valid": K_VALID, "frames": T_FRAMES,
@@ -180,7 +198,7 @@ def run_ours(args, rank, world, local_rank):
         import torch.distributed as dist_
         dist = dist_
         dist.init_process_group("nccl", device_id=dev)
-    spec = mtl_b200.ModelSpec()
+    spec = mtl_b200.ModelSpec(**MODEL)
     s = mtl_b200.Session(spec, dev, gemm_mode=args.gemm_mode)
     lib = L.get_lib()
     n_local = TASKS_PER_GPU
@@ -582,7 +600,12 @@ def main():
     ap.add_argument("--lanes", type=int, default=0, help="concurrent task lanes (default: one per task)")
     ap.add_argument("--timeline", default="", help="after the measurements, trace 2 more steps with torch.profiler "
                     "(CUPTI kernel records) and write name/stream/start/duration rows to this .csv.gz (diagnostic)")
+    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg4"], help="cfg2 = the BASELINE metric; cfg4 = "
+                    "BASELINE configs[3] (enc4/dec6 d768, T = 5000), one task per GPU")
     args = ap.parse_args()
+    select_config(args.config)
+    if args.config != "cfg2":
+        args.no_cpu_baseline = args.no_gpu_baseline = args.no_strong = True     # hour-long on the host / not defined
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

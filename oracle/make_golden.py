@@ -12,6 +12,7 @@ PCG64 seeds by oracle.ref_asr.init_params / oracle.ref_meta.synth_batch.
                       copy_grad after the last step, all parameters after the last Adam step
   cfg2_fwd_bwd.npz    BASELINE cfg 2 (enc2/dec4/d512, B=8, T=101, L=32): loss, gold, hyp,
                       pred samples, per-tensor grad L2 norms + 32 strided samples per tensor
+  ref_checkpoint_small.th  a checkpoint written by the reference's save_meta_model (SMALL cfg, after 2 Adam steps)
   cfg2_meta.npz       cfg 2, ONE TransientTrainer iteration (3 tasks, k=8): printed loss,
                       per-tensor L2 norm + samples of copy_grad and of (theta_after - theta_before)
 """
@@ -139,12 +140,51 @@ def cfg2_meta():
     np.savez_compressed(os.path.join(OUT, "cfg2_meta.npz"), **d)
 
 
+REF_CKPT = dict(seed=23, lr=1e-2, meta_lr=1e-3, epoch=7)
+
+
+def ref_checkpoint():
+    """A checkpoint written by the REFERENCE's own save_meta_model (utils/functions.py:101-126) after two real Adam steps:
+    pickled Vocab + argparse Namespace + model_state_dict + the live torch.optim.SGD / Adam objects.  The -m gpu test
+    loads it through OUR load_meta_model and resumes training (checkpoint wire format)."""
+    import shutil
+    import tempfile
+    cfg = ref_asr.SMALL
+    m = REF_CKPT
+    params = ref_asr.init_params(cfg, m["seed"])
+    tmp = tempfile.mkdtemp()
+    model, vocab, args = live.build_model(cfg, params, lr=m["lr"], meta_lr=m["meta_lr"], save_folder=tmp, name="ref",
+                                          is_factorized=False, r=cfg.rank, model="TRFS")
+    inner = torch.optim.SGD(model.parameters(), lr=m["lr"])
+    outer = torch.optim.Adam(model.parameters(), lr=m["meta_lr"])
+    model.train()
+    for step in range(2):
+        x, lens, y = ref_meta.synth_batch(cfg, 4, 41, 7, 2300 + step)
+        outer.zero_grad()
+        pred, gold, _ = model(x, lens, y)
+        torch.nn.functional.cross_entropy(pred.view(-1, pred.size(2)), gold.view(-1), ignore_index=0).backward()
+        outer.step()
+    with live.reference_imports():
+        from utils.data import Vocab
+        from utils.functions import save_meta_model
+        import contextlib, io
+        v2 = Vocab()                         # same class object as the one pickle will look up in this import context
+        v2.__dict__.update(vocab.__dict__)
+        with contextlib.redirect_stdout(io.StringIO()):
+            save_meta_model(model, v2, m["epoch"], inner, outer, {"avg_valid_loss": 1.25}, args, best_model=False)
+    shutil.copyfile(os.path.join(tmp, "ref", "epoch_%d.th" % m["epoch"]), os.path.join(OUT, "ref_checkpoint_small.th"))
+    shutil.rmtree(tmp)
+
+
 def main():
     if not live.available():
         sys.exit("needs the reference at /root/reference")
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
-    for fn in (small_fwd_bwd, small_meta, cfg2_fwd_bwd, cfg2_meta):
+    only = sys.argv[1:]
+    for fn in (small_fwd_bwd, small_meta, cfg2_fwd_bwd, cfg2_meta, ref_checkpoint):
+        if only and fn.__name__ not in only:
+            continue
         fn()
         print("wrote", fn.__name__)
 

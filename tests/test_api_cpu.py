@@ -174,3 +174,27 @@ def test_unchanged_reference_script_runs_against_our_packages_until_it_needs_the
     out = p.stdout + p.stderr
     assert "TRAINING FROM SCRATCH" in out and "feat extractor: vgg_cnn" in out, out[-2000:]
     assert p.returncode != 0 and "MtlError" in out and "CUDA device" in out, out[-2000:]
+
+
+def test_checkpoint_written_by_the_reference_unpickles_and_loads_into_our_model():
+    """tests/golden/ref_checkpoint_small.th was written by the REFERENCE's save_meta_model (oracle/make_golden.py:
+    ref_checkpoint).  With only our packages importable it must unpickle (utils.data.Vocab, argparse.Namespace,
+    torch.optim objects) and its model_state_dict must load key for key (utils/functions.py:158-188)."""
+    import oracle.make_golden as mg
+    path = os.path.join(ROOT, "tests", "golden", "ref_checkpoint_small.th")
+    ck = torch.load(path, map_location="cpu", weights_only=False)
+    assert set(ck) == {"vocab", "args", "epoch", "model_state_dict", "inner_opt", "outer_opt", "metrics"}
+    assert ck["epoch"] == mg.REF_CKPT["epoch"] and ck["metrics"]["avg_valid_loss"] == 1.25
+    from utils.data import Vocab
+    assert type(ck["vocab"]) is Vocab and ck["vocab"].id2label[:4] == ["<PAD>", "<SOS>", "<EOS>", "<OOV>"]
+    assert isinstance(ck["outer_opt"], torch.optim.Adam) and isinstance(ck["inner_opt"], torch.optim.SGD)
+    sd_opt = ck["outer_opt"].state_dict()
+    assert len(sd_opt["state"]) == len(ref_asr.param_specs(ref_asr.SMALL)) and int(sd_opt["state"][0]["step"]) == 2
+    from utils.functions import init_transformer_model
+    args = ck["args"]
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = init_transformer_model(args, ck["vocab"], is_factorized=args.is_factorized, r=args.r)
+    res = model.load_state_dict(ck["model_state_dict"])
+    assert not res.missing_keys and not res.unexpected_keys
+    for k, v in model.state_dict().items():
+        assert torch.equal(v, ck["model_state_dict"][k]), k

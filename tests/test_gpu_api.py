@@ -366,3 +366,48 @@ def test_greedy_search_long_prefix_uses_the_tiled_attention():
     # one near-tie between two logits flips a token and everything after it: demand the common prefix, not luck
     first_diff = int((ids != ids_o).float().argmax(dim=1).min()) if agree < 1.0 else 70
     assert agree == 1.0 or first_diff >= 20, (agree, first_diff)
+
+
+def test_resume_from_a_checkpoint_written_by_the_reference(tmp_path):
+    """load_meta_model on a file the REFERENCE's save_meta_model wrote (tests/golden/ref_checkpoint_small.th, generated by
+    oracle/make_golden.py: ref_checkpoint): weights, Adam moments and step count arrive in the arenas, training resumes,
+    and the checkpoint we write back is readable WITHOUT this package (plain torch.optim objects, utils.data.Vocab)."""
+    import pickle
+    from trainer.asr.transient_trainer import TransientTrainer
+    from utils.functions import load_meta_model, save_meta_model
+    path = os.path.join(ROOT, "tests", "golden", "ref_checkpoint_small.th")
+    raw = torch.load(path, map_location="cpu", weights_only=False)
+    with contextlib.redirect_stdout(io.StringIO()):
+        model, vocab, inner, outer, epoch, metrics, args = load_meta_model(path)
+    assert epoch == 7 and outer.step_count == 2
+    for k, v in model.state_dict().items():
+        assert torch.equal(v.cpu(), raw["model_state_dict"][k]), k
+    st = raw["outer_opt"].state_dict()["state"]
+    mv = model.session.views(outer.m)
+    for i, (name, _) in enumerate(model.named_parameters()):
+        assert torch.equal(mv[name].cpu(), st[i]["exp_avg"]), name
+    cfg = ref_asr.SMALL
+    batch = ref_meta.synth_batch(cfg, 4, 41, 7, 5)
+    samplers = [ListSampler([(_sampler(batch), _sampler(batch))]) for _ in range(2)]
+    args.save_folder, args.name, args.k_train, args.k_valid = str(tmp_path), "resumed", 4, 4
+    (inner2, outer2), losses, _, _ = _train_log(lambda: TransientTrainer().train(
+        model, vocab, samplers, [], "ce", epoch, epoch + 1, args, inner_opt=inner, outer_opt=outer,
+        evaluate_every=10 ** 9, early_stop="loss,10", is_copy_grad=True))
+    assert outer2.step_count == 3 and len(losses) == 1 and np.isfinite(losses[0])
+    with contextlib.redirect_stdout(io.StringIO()):
+        save_meta_model(model, vocab, epoch + 1, inner2, outer2, {"avg_valid_loss": 1.0}, args, best_model=False)
+    out_path = os.path.join(str(tmp_path), "resumed", "epoch_8.th")
+
+    class NoMtl(pickle.Unpickler):                                # what the reference's torch.load would have available
+        def find_class(self, module, name):
+            assert not module.startswith(("mtl_b200", "models", "modules", "trainer")), (module, name)
+            return super().find_class(module, name)
+
+    class _P:                                                     # torch.load(pickle_module=...) protocol
+        Unpickler = NoMtl
+        load = staticmethod(pickle.load)
+        __name__ = "pickle"
+    back = torch.load(out_path, map_location="cpu", weights_only=False, pickle_module=_P)
+    assert type(back["outer_opt"]) is torch.optim.Adam and type(back["inner_opt"]) is torch.optim.SGD
+    assert int(back["outer_opt"].state_dict()["state"][0]["step"]) == 3
+    assert list(back["model_state_dict"].keys()) == list(raw["model_state_dict"].keys())
