@@ -107,6 +107,16 @@ int mtl_asr_forward(mtl_session* s, const float* theta, const float* pe_enc, con
 int mtl_asr_backward(mtl_session* s, const float* theta, float* grad, float loss_scale,
                      const float* dpred_ext, int ld_ext, void* stream);
 
+/* ------------------------------------------------------------------ input features
+ * SpectrogramParser.parse_audio (utils/data_loader.py:65-96): log1p(|STFT|) of one utterance, n_fft = window =
+ * sample_rate * window_size samples, hop = sample_rate * window_stride, centred frames with reflect padding (the
+ * librosa.stft defaults the reference relies on), optional utterance-level (x - mean) / std (unbiased).
+ * wav: n_samples floats (device); window: n_fft floats (device); out: (n_fft / 2 + 1) rows of ld_out floats, the first
+ * 1 + n_samples / hop of each row are written -- so an utterance can be written straight into its slice
+ * x[b, 0, :, :T_b] of the zero-padded batch tensor (ld_out = T_max).  stat2: 2 doubles of device scratch. */
+int mtl_spectrogram(const float* wav, int n_samples, int n_fft, int hop, const float* window, float* out, int ld_out,
+                    int normalize, double* stat2, void* stream);
+
 /* ------------------------------------------------------------------ inference: encode + greedy search
  * mtl_asr_encode: Transformer.encode (models/asr/transformer.py:151-160): VGG front-end, flatten, Encoder.forward;
  * enc_out (device) receives (B * T') x d_model rows, T' = (T / 2) / 2.

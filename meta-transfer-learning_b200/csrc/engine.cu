@@ -1766,6 +1766,10 @@ extern "C" int mtl_conv3x3_bwd(int mode, const float* x, const float* w, const f
   g.M = (int)P; g.N = Cin; g.K = 9 * Cout; g.alpha = 1.f; g.epi = epi; g.aux = relu_aux; g.split_k = 1;
   return k_gemm(g, mode, st);
 }
+extern "C" int mtl_spectrogram(const float* wav, int n_samples, int n_fft, int hop, const float* window, float* out,
+                               int ld_out, int normalize, double* stat2, void* stream) {
+  return k_spectrogram(wav, n_samples, n_fft, hop, window, out, ld_out, normalize, stat2, (cudaStream_t)stream);
+}
 extern "C" int mtl_maxpool2_fwd(const float* x, float* out, int B, int F, int T, int C, void* stream) {
   return k_maxpool2_fwd(x, out, B, F, T, C, (cudaStream_t)stream);
 }

@@ -125,3 +125,9 @@ int k_maxpool2_relu_bwd(const float* x, const float* dpool, float* dx, int B, in
 // p4 [B,F4,T4,C] -> feat [B,T4,C*F4] (feature index c*F4+f), and back
 int k_feat_transpose(const float* p4, float* feat, int B, int F4, int T4, int C, cudaStream_t s);
 int k_feat_transpose_bwd(const float* dfeat, float* dp4, int B, int F4, int T4, int C, cudaStream_t s);
+
+// ----------------------------------------------------------------------------- spectrogram.cu
+// log1p(|STFT|) of a wave (centred, reflect-padded frames) into out[bin * ld_out + frame], optionally normalised over
+// the utterance (unbiased std); stat2 = 2 doubles of device scratch
+int k_spectrogram(const float* wav, int n, int n_fft, int hop, const float* window, float* out, int ld_out, int normalize,
+                  double* stat2, cudaStream_t s);

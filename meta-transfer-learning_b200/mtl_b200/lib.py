@@ -67,6 +67,7 @@ SIGNATURES = {
     "mtl_asr_forward": (_I, [_P, _P, _P, _P, _P, _LL, C.POINTER(CBatch), _F, _ULL, _F, _P, C.POINTER(_P),
                              C.POINTER(_I)]),
     "mtl_asr_backward": (_I, [_P, _P, _P, _F, _P, _I, _P]),
+    "mtl_spectrogram": (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _P, _P]),
     "mtl_encode_workspace_bytes": (_LL, [_P, _I, _I]),
     "mtl_asr_encode": (_I, [_P, _P, _P, _P, _LL, C.POINTER(CBatch), _P, _P]),
     "mtl_greedy_workspace_bytes": (_LL, [_P, _I, _I, _I]),

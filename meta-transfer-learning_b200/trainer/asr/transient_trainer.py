@@ -143,9 +143,15 @@ class TransientTrainer():
         # one sampling thread ahead of the step, as in the reference (:120-139)
         buffers = [[] for _ in range(n_tasks)]
 
+        def _pin(batch):
+            # host batches go up asynchronously from pinned memory (the copy into the static slots never blocks the host);
+            # device-computed features (utils/data_loader.py: feature_device) are already there
+            return tuple(t.pin_memory() if (torch.is_tensor(t) and not t.is_cuda) else t for t in batch)
+
         def fetch(buf):
             for manifest_id in range(n_tasks):
-                buf[manifest_id].insert(0, train_data_list[manifest_id].sample(k_train, k_valid, manifest_id))
+                tr, va = train_data_list[manifest_id].sample(k_train, k_valid, manifest_id)
+                buf[manifest_id].insert(0, (_pin(tr), _pin(va)))
 
         prefetch = threading.Thread(target=fetch, args=(buffers,))
         prefetch.start()

@@ -10,7 +10,13 @@
                                   input_sizes, target_sizes) sorted by length     (data_loader.py:401-477)
   BucketingSampler                fixed-size index bins                        (data_loader.py:480-500)
 
-Everything here is host-side; the tensors it returns are what the CUDA engine consumes."""
+Host-side by default (numpy STFT).  With ``audio_conf['device'] = 'cuda'`` (or MTL_FEATURES_ON_DEVICE=1) the K-shot sampler
+computes the features on the GPU instead (csrc/spectrogram.cu through mtl_spectrogram): the raw waves go up through one
+pinned staging buffer per batch, every utterance's log-spectrogram is written straight into its zero-padded slice of
+the (k,1,F,Tmax) batch tensor, and ``sample`` returns CUDA tensors that the trainer's static input slots take with a
+device-to-device copy -- the sampling thread of the trainer (transient_trainer.py:127-139) then overlaps disk reads and
+uploads with the running meta-step."""
+import os
 import random
 
 import numpy as np
@@ -40,6 +46,41 @@ def stft_magnitude(y, n_fft, hop_length, window):
     return np.abs(np.fft.rfft(frames, n=n_fft, axis=1)).T.astype(np.float32)
 
 
+def device_batch_features(waves, n_fft, hop, window, normalize, max_frames, device):
+    """k waves (1-D float arrays) -> (inputs (k,1,F,Tmax) float32 on `device`, zero padded; frames per utterance).  Frames
+    beyond `max_frames` are dropped AFTER the utterance-level normalisation, like ``parse_audio(...)[:, :src_max_len]``."""
+    import ctypes as C
+    from mtl_b200 import lib as L
+    lib = L.get_lib()
+    dev = torch.device(device)
+    k = len(waves)
+    frames = [1 + len(w) // hop for w in waves]
+    t_full = max(frames)
+    F = n_fft // 2 + 1
+    total = sum(len(w) for w in waves)
+    stage = torch.empty(total, dtype=torch.float32).pin_memory()           # one upload for the whole batch
+    off, offs = 0, []
+    for w in waves:
+        stage[off:off + len(w)] = torch.from_numpy(np.ascontiguousarray(w, dtype=np.float32))
+        offs.append(off)
+        off += len(w)
+    with torch.cuda.device(dev):
+        st = torch.cuda.current_stream()
+        wav_d = stage.to(dev, non_blocking=True)
+        win_d = torch.from_numpy(np.asarray(window, dtype=np.float32)).to(dev, non_blocking=True)
+        out = torch.zeros(k, 1, F, t_full, dtype=torch.float32, device=dev)
+        stat = torch.zeros(2, dtype=torch.float64, device=dev)
+        for i, w in enumerate(waves):
+            L.check(lib.mtl_spectrogram(C.c_void_p(wav_d.data_ptr() + 4 * offs[i]), len(w), n_fft, hop,
+                                        C.c_void_p(win_d.data_ptr()), C.c_void_p(out[i, 0].data_ptr()), t_full,
+                                        int(bool(normalize)), C.c_void_p(stat.data_ptr()), C.c_void_p(st.cuda_stream)))
+        st.synchronize()                                                   # the staging buffer may be released now
+    if t_full > max_frames:
+        out = out[:, :, :, :max_frames].contiguous()
+        frames = [min(f, max_frames) for f in frames]
+    return out, frames
+
+
 class AudioParser(object):
     def parse_transcript(self, transcript_path):
         raise NotImplementedError
@@ -61,9 +102,14 @@ class SpectrogramParser(AudioParser):
             raise NotImplementedError("noise injection needs sox (data_loader.py:367-399): not available in this build")
         self.noiseInjector = None
         self.noise_prob = audio_conf.get('noise_prob')
+        dev = audio_conf.get('device') or ("cuda" if os.environ.get("MTL_FEATURES_ON_DEVICE") == "1" else None)
+        self.feature_device = dev if (dev and torch.cuda.is_available()) else None
+
+    def _load_wave(self, audio_path):
+        return load_randomly_augmented_audio(audio_path, self.sample_rate) if self.augment else load_audio(audio_path)
 
     def parse_audio(self, audio_path):
-        y = load_randomly_augmented_audio(audio_path, self.sample_rate) if self.augment else load_audio(audio_path)
+        y = self._load_wave(audio_path)
         n_fft = int(self.sample_rate * self.window_size)
         hop = int(self.sample_rate * self.window_stride)
         spect = torch.from_numpy(np.log1p(stft_magnitude(y, n_fft, hop, self.window(n_fft))))
@@ -126,10 +172,31 @@ class SpectrogramDataset(Dataset, SpectrogramParser):
         spect = self.parse_audio(row[0])[:, :self.args.src_max_len]
         return spect, self.parse_transcript(row[1])
 
+    def _device_batch(self, rows):
+        """One K-shot batch with the features computed on the GPU: same five fields as ``_pad_batch``, inputs on the device."""
+        n_fft, hop = int(self.sample_rate * self.window_size), int(self.sample_rate * self.window_stride)
+        waves = [np.asarray(self._load_wave(r[0]), dtype=np.float32) for r in rows]
+        transcripts = [self.parse_transcript(r[1]) for r in rows]
+        inputs, frames = device_batch_features(waves, n_fft, hop, self.window(n_fft), self.normalize,
+                                               self.args.src_max_len, self.feature_device)
+        k, t_max = len(rows), inputs.size(3)
+        l_max = max(len(t) for t in transcripts)
+        sizes = torch.tensor(frames, dtype=torch.int32)
+        pct = sizes.float() / float(t_max)
+        targets = torch.full((k, l_max), self.vocab.PAD_ID).long()
+        target_sizes = torch.tensor([len(t) for t in transcripts], dtype=torch.int32)
+        for i, t in enumerate(transcripts):
+            if len(t):
+                targets[i, :len(t)] = torch.as_tensor(t, dtype=torch.long)
+        return inputs, sizes, pct, targets, target_sizes
+
     def sample(self, k_train, k_val, manifest_id):
         """k_train + k_val rows of one manifest, drawn with replacement (np.random.choice, the reference's RNG)."""
         ids = self.ids_list[manifest_id]
         picks = np.random.choice(np.arange(0, len(ids)), k_train + k_val, p=self.proba[manifest_id], replace=True)
+        if self.feature_device is not None:
+            return (self._device_batch([ids[i] for i in picks[:k_train]]),
+                    self._device_batch([ids[i] for i in picks[k_train:k_train + k_val]]))
         tr = [self._load(ids[i]) for i in picks[:k_train]]
         va = [self._load(ids[i]) for i in picks[k_train:k_train + k_val]]
         pad = self.vocab.PAD_ID

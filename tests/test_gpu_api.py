@@ -411,3 +411,45 @@ def test_resume_from_a_checkpoint_written_by_the_reference(tmp_path):
     assert type(back["outer_opt"]) is torch.optim.Adam and type(back["inner_opt"]) is torch.optim.SGD
     assert int(back["outer_opt"].state_dict()["state"][0]["step"]) == 3
     assert list(back["model_state_dict"].keys()) == list(raw["model_state_dict"].keys())
+
+
+def test_device_spectrogram_matches_the_host_parser(tmp_path):
+    """mtl_spectrogram (csrc/spectrogram.cu) vs the host restatement of SpectrogramParser.parse_audio
+    (utils/data_loader.py:65-96): log1p|STFT| with centred reflect-padded frames, utterance normalisation; and the
+    K-shot sampler contract (data_loader.py:245-321) with the features computed on the GPU."""
+    from utils.data_loader import SpectrogramDataset, SpectrogramParser, device_batch_features
+    import scipy.signal.windows
+    audio_conf = dict(sample_rate=16000, window_size=.02, window_stride=.01, window="hamming", noise_dir=None,
+                      noise_prob=0.4, noise_levels=(0.0, 0.5))
+    rng = np.random.default_rng(0)
+    waves = [rng.standard_normal(n).astype(np.float32) * 0.1 for n in (16000, 7777, 4001, 161)]
+    host = SpectrogramParser(audio_conf, normalize=True)
+    win = scipy.signal.windows.hamming(320)
+    for normalize in (False, True):
+        out, frames = device_batch_features(waves, 320, 160, win, normalize, 10 ** 6, "cuda")
+        assert out.shape == (4, 1, 161, 101) and frames == [101, 49, 26, 2]
+        for i, w in enumerate(waves):
+            from utils.data_loader import stft_magnitude
+            ref = torch.from_numpy(np.log1p(stft_magnitude(w, 320, 160, win)))
+            if normalize:
+                ref = (ref - ref.mean()) / ref.std()
+            got = out[i, 0, :, :frames[i]].cpu()
+            assert rel_err(got, ref) < 2e-4, (normalize, i, rel_err(got, ref))
+            assert float(out[i, 0, :, frames[i]:].abs().max()) == 0.0 if frames[i] < 101 else True
+    # truncation to src_max_len happens after the normalisation
+    out, frames = device_batch_features(waves[:1], 320, 160, win, True, 40, "cuda")
+    assert out.shape == (1, 1, 161, 40) and frames == [40]
+    # the sampler with device features: same fields, inputs on the GPU, everything else on the host
+    vocab = api_util.make_vocab(40)
+    args = api_util.script_args(src_max_len=90)
+    m0 = api_util.write_manifest(str(tmp_path), "m0", 5, seed=1)
+    conf = dict(audio_conf, device="cuda")
+    ds_d = SpectrogramDataset(vocab, args, conf, manifest_filepath_list=[m0], normalize=True, is_train=True)
+    ds_h = SpectrogramDataset(vocab, args, audio_conf, manifest_filepath_list=[m0], normalize=True, is_train=True)
+    np.random.seed(3)
+    (x, sizes, pct, y, ysz), _ = ds_d.sample(3, 2, 0)
+    np.random.seed(3)
+    (xh, sizes_h, pct_h, yh, ysz_h), _ = ds_h.sample(3, 2, 0)
+    assert x.is_cuda and not sizes.is_cuda and not y.is_cuda
+    assert torch.equal(sizes, sizes_h) and torch.equal(y, yh) and torch.allclose(pct, pct_h) and torch.equal(ysz, ysz_h)
+    assert x.shape == xh.shape and rel_err(x, xh) < 2e-4
