@@ -260,6 +260,14 @@ long long mtl_conv3x3_bwd_scratch_floats(int mode, int B, int F, int T, int Cin,
 int mtl_conv3x3_bwd(int mode, const float* x, const float* w, const float* dy, const float* relu_aux,
                     float* dw, float* db, float* dx, float* scratch, int B, int F, int T, int Cin, int Cout,
                     void* stream);
+/* conv.0 weight / bias gradient (models/asr/transformer.py:48, Cin = 1): dw (Cout,1,3,3) and db accumulate */
+int mtl_conv1_wgrad(const float* x, const float* dout, float* dw, float* db, int B, int F, int T, int Cout, void* stream);
+/* (B,F4,T4,C) NHWC <-> (B,T4,C*F4) encoder features (models/asr/transformer.py:133-138); backward != 0: the inverse map */
+int mtl_feat_transpose(const float* src, float* dst, int B, int F4, int T4, int C, int backward, void* stream);
+/* decoder input embedding + positional encoding + dropout (modules/decoder.py:96) and its scatter-add gradient;
+ * out (nullable): forward; dout + dE (nullable): backward into dE (vocab x d, accumulated; PAD row 0 skipped) */
+int mtl_embed(const int* tok, const float* E, const float* pe, float drop_p, unsigned long long seed, unsigned site,
+              float* out, const float* dout, float* dE, int B, int n, int d, void* stream);
 int mtl_maxpool2_fwd(const float* x, float* out, int B, int F, int T, int C, void* stream);
 int mtl_maxpool2_relu_bwd(const float* x, const float* dpool, float* dx, int B, int F, int T, int C,
                           void* stream);

@@ -1770,6 +1770,20 @@ extern "C" int mtl_spectrogram(const float* wav, int n_samples, int n_fft, int h
                                int ld_out, int normalize, double* stat2, void* stream) {
   return k_spectrogram(wav, n_samples, n_fft, hop, window, out, ld_out, normalize, stat2, (cudaStream_t)stream);
 }
+extern "C" int mtl_conv1_wgrad(const float* x, const float* dout, float* dw, float* db, int B, int F, int T, int Cout, void* stream) {
+  return k_conv1_wgrad(x, dout, dw, db, B, F, T, Cout, (cudaStream_t)stream);
+}
+extern "C" int mtl_feat_transpose(const float* p4, float* feat, int B, int F4, int T4, int C, int backward, void* stream) {
+  return backward ? k_feat_transpose_bwd(p4, feat, B, F4, T4, C, (cudaStream_t)stream)
+                  : k_feat_transpose(p4, feat, B, F4, T4, C, (cudaStream_t)stream);
+}
+extern "C" int mtl_embed(const int* tok, const float* E, const float* pe, float drop_p, unsigned long long seed, unsigned site,
+                         float* out, const float* dout, float* dE, int B, int n, int d, void* stream) {
+  const MtlDrop dr = drop_p > 0.f ? mtl_drop(drop_p, seed, site) : mtl_nodrop();
+  if (out) MTL_TRY(k_embed_fwd(tok, E, pe, dr, out, B, n, d, (cudaStream_t)stream));
+  if (dout && dE) MTL_TRY(k_embed_bwd(tok, dout, dr, dE, B, n, d, 0, (cudaStream_t)stream));
+  return MTL_OK;
+}
 extern "C" int mtl_maxpool2_fwd(const float* x, float* out, int B, int F, int T, int C, void* stream) {
   return k_maxpool2_fwd(x, out, B, F, T, C, (cudaStream_t)stream);
 }

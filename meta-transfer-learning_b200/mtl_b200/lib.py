@@ -99,6 +99,9 @@ SIGNATURES = {
     "mtl_conv3x3_relu_fwd": (_I, [_I, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "mtl_conv3x3_bwd_scratch_floats": (_LL, [_I, _I, _I, _I, _I, _I]),
     "mtl_conv3x3_bwd": (_I, [_I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "mtl_conv1_wgrad": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "mtl_feat_transpose": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
+    "mtl_embed": (_I, [_P, _P, _P, _F, _ULL, _U, _P, _P, _P, _I, _I, _I, _P]),
     "mtl_maxpool2_fwd": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "mtl_maxpool2_relu_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "mtl_dec_preprocess": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _P]),

@@ -46,6 +46,25 @@ def main():
         if "dram_read_bytes" in d:
             d["dram_bytes"] = d["dram_read_bytes"] + d.get("dram_write_bytes", 0.0)
         res[f] = d
+    # round-2 captures: one `ncu --set full --csv --page raw` run over a whole pass / over every operator once, reduced by
+    # tools/ncu_summary.py to one record per (kernel, grid)
+    KERNEL_ROLES = {("conv3x3_kw_kernel<64, 1>", 1144): ("conv2_fwd", 2), ("conv3x3_kw_kernel<64, 0>", 1144): ("conv2_fwd", 1),
+                    ("attn_small_fwd_mma_kernel<64, 512>", 64): ("attn_small_fwd", 2),
+                    ("attn_small_bwd_mma_kernel<64, 512>", 64): ("attn_small_bwd", 2),
+                    ("ln_fwd_kernel", 66): ("ln_fwd", 2), ("ln_bwd_kernel", 66): ("ln_bwd", 2)}
+    for f in sorted(os.listdir(PROF)):
+        if not f.endswith("_kernels.json"):
+            continue
+        for rec in json.load(open(os.path.join(PROF, f))):
+            name = rec["kernel"].replace("void ", "").replace("<unnamed>::", "")
+            key = (name, int(rec.get("grid") or 0))
+            role, mode = KERNEL_ROLES.get(key, (None, None))
+            d = {"role": role or name, "gemm_mode": mode, "source": "profiles/" + f, "kernel": name, "grid": key[1],
+                 "duration_us_under_ncu": rec.get("dur_us"), "dram_read_bytes": rec.get("dram_rd"),
+                 "dram_write_bytes": rec.get("dram_wr"), "dram_bytes": (rec.get("dram_rd") or 0) + (rec.get("dram_wr") or 0),
+                 "tensor_pipe_active_pct": rec.get("tensor_pct"), "sm_throughput_pct": rec.get("sm_pct"),
+                 "l2_to_sm_read_bytes": rec.get("l2_to_sm")}
+            res["%s::%s@%d" % (f, name, key[1])] = d
     with open(os.path.join(PROF, "ncu_metrics.json"), "w") as fh:
         json.dump(res, fh, indent=1, sort_keys=True)
     print("wrote %d captures" % len(res))
