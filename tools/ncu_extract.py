@@ -59,6 +59,8 @@ def main():
             name = rec["kernel"].replace("void ", "").replace("<unnamed>::", "")
             key = (name, int(rec.get("grid") or 0))
             role, mode = KERNEL_ROLES.get(key, (None, None))
+            if role == "conv2_fwd" and "forward" not in f:         # same kernel and grid serve conv.2's input gradient
+                role = "conv2_dgrad"
             d = {"role": role or name, "gemm_mode": mode, "source": "profiles/" + f, "kernel": name, "grid": key[1],
                  "duration_us_under_ncu": rec.get("dur_us"), "dram_read_bytes": rec.get("dram_rd"),
                  "dram_write_bytes": rec.get("dram_wr"), "dram_bytes": (rec.get("dram_rd") or 0) + (rec.get("dram_wr") or 0),
