@@ -222,7 +222,7 @@ def run_ours(args, rank, world, local_rank):
         else:
             views[name].copy_((torch.rand(shape, generator=g) * 2 - 1) * 0.05)
     theta_init = theta.clone()
-    exchange = MetaExchange(s, dist, mode=args.exchange)
+    exchange = MetaExchange(s, dist, mode=args.exchange, overlap=not args.no_overlap)
 
     total_steps = args.warmup + args.steps
     n_tok = L_TOKENS + 1
@@ -279,6 +279,7 @@ def run_ours(args, rank, world, local_rank):
                 self.results[i].copy_(res, non_blocking=True)
             else:
                 s.zero(cg)                                      # a rank without a task still joins the exchange
+            exchange.ran_tasks = self.stepper is not None
             exchange.finish(theta, grad, cg, m, v, adam_state, META_LR)   # the one exchange step + Adam
 
         def e2e_step(self, i):
@@ -596,6 +597,8 @@ def main():
     ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the strong-scaling leg (3 tasks in total)")
     ap.add_argument("--exchange", default="allreduce", choices=["allreduce", "sharded"],
                     help="N > 1: all-reduce + full Adam, or reduce-scatter -> Adam on the 1/N slice -> all-gather")
+    ap.add_argument("--no-overlap", action="store_true", help="N > 1: one blocking all-reduce after the step instead of "
+                    "exchanging region A under the convolution backward")
     ap.add_argument("--no-graph", action="store_true", help="run the meta-step eagerly (no CUDA graph replay)")
     ap.add_argument("--lanes", type=int, default=0, help="concurrent task lanes (default: one per task)")
     ap.add_argument("--timeline", default="", help="after the measurements, trace 2 more steps with torch.profiler "

@@ -187,6 +187,13 @@ typedef struct mtl_meta_step_args {
 } mtl_meta_step_args;
 int mtl_meta_tasks(mtl_session* s, const mtl_meta_step_args* args, void* stream);
 int mtl_graph_stats(const mtl_session* s, unsigned long long* captures, unsigned long long* replays);
+/* Early exchange of the outer gradient (trainer/asr/transient_trainer.py:229,248 across GPUs).  copy_grad is accumulated
+ * in two regions: A = the first mtl_region_a_floats() floats (every parameter except the VGG front-end, 98 % of the
+ * arena) is complete when the LAST task's validation pass reaches its VGG backward; B = the VGG tail at the end.
+ * mtl_stream_wait_region_a makes `stream` wait for region A of the most recent mtl_meta_tasks call (graph replay or
+ * eager), so a collective on region A can run under the remaining convolution backward. */
+long long mtl_region_a_floats(const mtl_session* s);
+int mtl_stream_wait_region_a(mtl_session* s, void* stream);
 /* transient_trainer.py:248-255: grad <- copy_grad; [clip]; theta <- Adam(theta, grad) with the outer optimizer's
  * betas / eps (torch.optim.Adam defaults 0.9, 0.999, 1e-8 at :109; a resumed optimizer keeps its own).
  * adam_state (device): int step, float step_size, float bc2_sqrt, pad (16 bytes). */

@@ -187,6 +187,8 @@ static void branches_destroy(Branches& b) {
 // One lane = one concurrently running task of a meta-step: its own stream and activation record.
 struct Lane {
   cudaStream_t st = nullptr;
+  cudaStream_t col = nullptr;         // collector: the early copy_grad accumulation of the leading arena region
+  cudaEvent_t col_done = nullptr;
   cudaEvent_t done = nullptr;
   Pass pass;
   Branches br;
@@ -212,7 +214,8 @@ struct mtl_session {
   std::vector<Lane> lanes;
   cudaEvent_t ev_fork = nullptr;
   cudaStream_t cap_st = nullptr;      // capture origin (the caller's stream may be the legacy stream, which cannot capture)
-  std::vector<cudaEvent_t> ev_axpy;
+  std::vector<cudaEvent_t> ev_axpy, ev_axpy_a;
+  cudaEvent_t ev_region_a = nullptr;  // leading region [0, conv.0.weight) of copy_grad holds every task's contribution
   std::vector<GraphEntry> graphs;
   unsigned long long tick = 0;
   unsigned long long graph_replays = 0, graph_captures = 0;
@@ -233,6 +236,15 @@ struct Bump {
   unsigned char* u8(size_t n) { return (unsigned char*)raw(n); }
 };
 
+// Hook a caller hangs into a backward pass: fired (on its own stream `st`, after every stream of the pass that writes
+// parameter gradients OUTSIDE the VGG front-end) right before the VGG backward is enqueued -- from that point on the
+// leading region [0, conv.0.weight) of the gradient arena is final while ~0.4 ms of convolution backward still runs.
+struct EarlyHook {
+  cudaStream_t st = nullptr;
+  int (*fn)(void*) = nullptr;
+  void* ctx = nullptr;
+  bool fired = false;
+};
 struct Run {
   mtl_session* S;
   Pass* P;                                    // activation record this run fills / consumes
@@ -254,6 +266,7 @@ struct Run {
   unsigned long long seed;                    // effective seed = seed + (*seed_dev) * seed_mul
   const unsigned long long* seed_dev = nullptr;
   unsigned long long seed_mul = 0;
+  EarlyHook* early = nullptr;                 // see EarlyHook
   bool enc_only = false;                      // forward() stops after the encoder (mtl_asr_encode)
   bool no_zslab = false;                      // greedy decoding re-uses its scratch every step: no zero-pool outputs
   int bulk = 0;                               // > 0: inside a GPU-filling / deferred section (convolutions): default priority
@@ -1045,6 +1058,14 @@ static int backward(Run& R, float loss_scale, const float* dpred_ext, int ld_ext
   float* dfeat = R.ws.f((size_t)P.Me * P.d_in);
   MTL_TRY(lin_dgrad(R, dh, d, R.theta + L.in_w, dfeat, P.d_in, P.Me, d, P.d_in, 0.f, EPI_NONE, nullptr, false, MTL_OP_STEM));
   // VGG front-end
+  if (R.early && R.early->fn && R.par()) {
+    // every kernel that writes a non-VGG parameter gradient has been enqueued: gather the streams that carry them
+    MTL_TRY(chain(R, R.main, R.early->st));
+    for (int i = 0; i < kSides; ++i)
+      if (R.br->dirty[i]) MTL_TRY(chain(R, R.br->side[i], R.early->st));    // (a clean side stream holds nothing un-joined)
+    MTL_TRY(R.early->fn(R.early->ctx));
+    R.early->fired = true;
+  }
   Bulk bulk(R);
   float* dp4 = R.ws.f((size_t)B * P.F4 * P.T4 * 128);
   K(k_feat_transpose_bwd(dfeat, dp4, B, P.F4, P.T4, 128, R.st));
@@ -1099,7 +1120,9 @@ extern "C" int mtl_session_create(const mtl_model_cfg* cfg, mtl_session** out) {
 extern "C" void mtl_session_destroy(mtl_session* s) {
   if (!s) return;
   for (auto& g : s->graphs) { if (g.exec) cudaGraphExecDestroy(g.exec); if (g.graph) cudaGraphDestroy(g.graph); }
-  for (auto& l : s->lanes) { branches_destroy(l.br); if (l.done) cudaEventDestroy(l.done); if (l.st) cudaStreamDestroy(l.st); }
+  for (auto& l : s->lanes) { branches_destroy(l.br); if (l.done) cudaEventDestroy(l.done); if (l.col_done) cudaEventDestroy(l.col_done); if (l.col) cudaStreamDestroy(l.col); if (l.st) cudaStreamDestroy(l.st); }
+  for (auto e : s->ev_axpy_a) cudaEventDestroy(e);
+  if (s->ev_region_a) cudaEventDestroy(s->ev_region_a);
   branches_destroy(s->br);
   for (auto e : s->ev_axpy) cudaEventDestroy(e);
   if (s->ev_fork) cudaEventDestroy(s->ev_fork);
@@ -1184,13 +1207,14 @@ static int run_forward(mtl_session* s, Pass* pass, Branches* br, const float* th
   return forward(R, *batch, pe_enc, pe_dec, label_smoothing);
 }
 static int run_backward(mtl_session* s, Pass* pass, Branches* br, const float* theta, float* grad, float loss_scale,
-                        const float* dpred_ext, int ld_ext, cudaStream_t st) {
+                        const float* dpred_ext, int ld_ext, cudaStream_t st, EarlyHook* early = nullptr) {
   MTL_REQUIRE(s && theta && grad, "null argument");
   MTL_REQUIRE(pass->valid, "backward without a preceding forward");
   Run R;
   R.S = s; R.P = pass; R.st = st; R.main = st; R.dry = false; R.theta = theta; R.grad = grad;
   if (br && branches_enabled()) { MTL_TRY(branches_init(*br)); R.br = br; }
   R.p_drop = 0.f; R.seed = 0; R.site = 0;
+  R.early = early;
   R.ws.base = pass->ws_base; R.ws.cap = pass->ws_cap; R.ws.off = pass->ws_after_fwd;
   R.wz.base = pass->wz_base; R.wz.cap = pass->wz_cap; R.wz.off = pass->wz_off;
   MTL_TRY(backward(R, loss_scale, dpred_ext, ld_ext));
@@ -1380,7 +1404,8 @@ extern "C" int mtl_asr_greedy(mtl_session* s, const float* theta, const float* p
 // (grad <- dCE_train; [clip]; theta -= lr*grad; grad += d(CE_val*val_scale)).
 static int task_body(mtl_session* s, Pass* pass, Branches* br, float* theta, float* grad, const float* pe_enc, const float* pe_dec,
                      void* workspace, long long workspace_bytes, const mtl_batch* train, const mtl_batch* val,
-                     const mtl_meta_hparams* hp, SeedRef seed_tr, SeedRef seed_va, float* results16, cudaStream_t st) {
+                     const mtl_meta_hparams* hp, SeedRef seed_tr, SeedRef seed_va, float* results16, cudaStream_t st,
+                     EarlyHook* early = nullptr) {
   const size_t n = s->L.total;
   // scratch for the clip coefficient lives at the very end of the workspace
   const long long tail = (long long)((MTL_NORM_PARTIALS + 8) * sizeof(float) + 256);
@@ -1400,7 +1425,7 @@ static int task_body(mtl_session* s, Pass* pass, Branches* br, float* theta, flo
   MTL_TRY(k_sgd(theta, grad, hp->lr, n, st));                                       // inner_opt.step()
   MTL_TRY(run_forward(s, pass, br, theta, pe_enc, pe_dec, workspace, ws_main, &va, hp->dropout, seed_va,
                       hp->label_smoothing, st));
-  MTL_TRY(run_backward(s, pass, br, theta, grad, hp->val_scale, nullptr, 0, st));   // (val_loss/N).backward(), no zero_grad
+  MTL_TRY(run_backward(s, pass, br, theta, grad, hp->val_scale, nullptr, 0, st, early));   // (val_loss/N).backward(), no zero_grad
   return MTL_OK;
 }
 
@@ -1426,16 +1451,21 @@ static int ensure_lanes(mtl_session* s, int n_lanes, int n_tasks) {
   while ((int)s->lanes.size() < n_lanes) {
     Lane l;
     MTL_CHECK_CUDA(cudaStreamCreateWithFlags(&l.st, cudaStreamNonBlocking));
+    MTL_CHECK_CUDA(cudaStreamCreateWithFlags(&l.col, cudaStreamNonBlocking));
+    MTL_CHECK_CUDA(cudaEventCreateWithFlags(&l.col_done, cudaEventDisableTiming));
     MTL_CHECK_CUDA(cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming));
     s->lanes.push_back(l);
   }
   if (!s->ev_fork) MTL_CHECK_CUDA(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
   if (!s->cap_st) MTL_CHECK_CUDA(cudaStreamCreateWithFlags(&s->cap_st, cudaStreamNonBlocking));
   while ((int)s->ev_axpy.size() < n_tasks) {
-    cudaEvent_t e;
+    cudaEvent_t e, ea;
     MTL_CHECK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    MTL_CHECK_CUDA(cudaEventCreateWithFlags(&ea, cudaEventDisableTiming));
     s->ev_axpy.push_back(e);
+    s->ev_axpy_a.push_back(ea);
   }
+  if (!s->ev_region_a) MTL_CHECK_CUDA(cudaEventCreateWithFlags(&s->ev_region_a, cudaEventDisableTiming));
   return MTL_OK;
 }
 
@@ -1463,10 +1493,37 @@ static int meta_tasks_body(mtl_session* s, const mtl_meta_step_args* a, cudaStre
     const unsigned long long lo0 = (unsigned long long)t * 2ull, lo1 = lo0 + 1ull;
     if (dev_seed) { s0 = {lo0, a->seed_slot, 128ull}; s1 = {lo1, a->seed_slot, 128ull}; }
     else { s0 = {a->hp.seed * 128ull + lo0, nullptr, 0}; s1 = {a->hp.seed * 128ull + lo1, nullptr, 0}; }
+    // model.add_copy_grad() in two regions.  A = [0, conv.0.weight): final as soon as the val pass reaches its VGG
+    // backward, accumulated then (collector stream), and after the LAST task signalled through ev_region_a so that the
+    // caller can start exchanging 98 % of the arena while the convolution backward still runs.  B = the VGG tail.
+    const size_t n_a = s->L.conv_w[0];
+    struct AccA { mtl_session* s; const mtl_meta_step_args* a; float* grad; cudaStream_t st; int t; size_t n_a; } acc{s, a, lb.grad, ln.col, t, n_a};
+    auto acc_a = [](void* p) -> int {
+      AccA& c = *(AccA*)p;
+      if (c.t > 0) MTL_CHECK_CUDA(cudaStreamWaitEvent(c.st, c.s->ev_axpy_a[c.t - 1], 0));   // the reference's summation order
+      MTL_TRY(k_axpy(c.a->copy_grad, c.grad, 1.f, c.n_a, c.st));
+      MTL_CHECK_CUDA(cudaEventRecord(c.s->ev_axpy_a[c.t], c.st));
+      if (c.t == c.a->n_tasks - 1) {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        MTL_CHECK_CUDA(cudaStreamIsCapturing(c.st, &cs));
+        MTL_CHECK_CUDA(cudaEventRecordWithFlags(c.s->ev_region_a, c.st,
+                                                cs == cudaStreamCaptureStatusActive ? cudaEventRecordExternal : cudaEventRecordDefault));
+      }
+      return MTL_OK;
+    };
+    EarlyHook hook;
+    hook.st = ln.col; hook.fn = acc_a; hook.ctx = &acc;
     MTL_TRY(task_body(s, &ln.pass, &ln.br, lb.theta, lb.grad, a->pe_enc, a->pe_dec, lb.workspace, lb.workspace_bytes,
-                      &a->train[t], &va, &a->hp, s0, s1, a->results ? a->results + 16 * t : nullptr, ln.st));
-    if (t > 0) MTL_CHECK_CUDA(cudaStreamWaitEvent(ln.st, s->ev_axpy[t - 1], 0));    // keep the reference's summation order
-    MTL_TRY(k_axpy(a->copy_grad, lb.grad, 1.f, n, ln.st));                          // model.add_copy_grad()
+                      &a->train[t], &va, &a->hp, s0, s1, a->results ? a->results + 16 * t : nullptr, ln.st, &hook));
+    if (hook.fired) {                                                               // the lane ends after its collector
+      MTL_CHECK_CUDA(cudaEventRecord(ln.col_done, ln.col));
+      MTL_CHECK_CUDA(cudaStreamWaitEvent(ln.st, ln.col_done, 0));
+    } else {                                                                        // serial pass (MTL_BRANCHES=0): region A now
+      acc.st = ln.st;
+      MTL_TRY(acc_a(&acc));
+    }
+    if (t > 0) MTL_CHECK_CUDA(cudaStreamWaitEvent(ln.st, s->ev_axpy[t - 1], 0));
+    MTL_TRY(k_axpy(a->copy_grad + n_a, lb.grad + n_a, 1.f, n - n_a, ln.st));
     MTL_CHECK_CUDA(cudaEventRecord(s->ev_axpy[t], ln.st));
   }
   for (int l = 0; l < used; ++l) {
@@ -1578,6 +1635,12 @@ extern "C" int mtl_meta_tasks(mtl_session* s, const mtl_meta_step_args* a, void*
   MTL_CHECK_CUDA(cudaGraphLaunch(e->exec, st));
   g_mtl_launches += e->kernels;
   ++s->graph_replays;
+  return MTL_OK;
+}
+extern "C" long long mtl_region_a_floats(const mtl_session* s) { return s ? (long long)s->L.conv_w[0] : -1; }
+extern "C" int mtl_stream_wait_region_a(mtl_session* s, void* stream) {
+  MTL_REQUIRE(s, "null argument");
+  if (s->ev_region_a) MTL_CHECK_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, s->ev_region_a, 0));
   return MTL_OK;
 }
 extern "C" int mtl_graph_stats(const mtl_session* s, unsigned long long* captures, unsigned long long* replays) {

@@ -75,6 +75,8 @@ SIGNATURES = {
     "mtl_meta_task": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _LL, C.POINTER(CBatch), C.POINTER(CBatch),
                            C.POINTER(MetaHParams), _P, _P]),
     "mtl_meta_tasks": (_I, [_P, C.POINTER(MetaStepArgs), _P]),
+    "mtl_region_a_floats": (_LL, [_P]),
+    "mtl_stream_wait_region_a": (_I, [_P, _P]),
     "mtl_graph_stats": (_I, [_P, C.POINTER(_ULL), C.POINTER(_ULL)]),
     "mtl_meta_finish": (_I, [_P, _P, _P, _P, _P, _P, _D, _D, _D, _D, _I, _F, _P, _LL, _P]),
     "mtl_arena_zero": (_I, [_P, _LL, _P]),

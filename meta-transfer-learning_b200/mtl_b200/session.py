@@ -222,6 +222,14 @@ class Session:
                                         _ptr(self.pe_enc), _ptr(self.pe_dec), _ptr(ws), ws.numel(),
                                         C.byref(ctr), C.byref(cva), C.byref(hp), _ptr(results), _stream()))
 
+    def region_a_floats(self) -> int:
+        """Leading floats of the arena (everything but the VGG front-end) whose copy_grad is final early (mtl_b200.h)."""
+        return int(self.lib.mtl_region_a_floats(self._h))
+
+    def wait_region_a(self, stream: torch.cuda.Stream):
+        """`stream` waits until region A of copy_grad of the latest MetaStepper.run holds every task's contribution."""
+        _l.check(self.lib.mtl_stream_wait_region_a(self._h, C.c_void_p(stream.cuda_stream)))
+
     def graph_stats(self):
         cap, rep = C.c_ulonglong(), C.c_ulonglong()
         _l.check(self.lib.mtl_graph_stats(self._h, C.byref(cap), C.byref(rep)))

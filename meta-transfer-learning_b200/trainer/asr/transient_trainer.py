@@ -181,6 +181,7 @@ class TransientTrainer():
                 else:
                     session.zero(copy_grad)
                 g = outer_opt.param_groups[0]
+                exchange.ran_tasks = stepper is not None
                 exchange.finish(theta, grad, copy_grad, outer_opt.m, outer_opt.v, outer_opt.dev_state, g['lr'],
                                 clip=args.clip, max_norm=args.max_norm, betas=g['betas'], eps=g['eps'])
 

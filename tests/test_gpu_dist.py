@@ -37,7 +37,7 @@ def _problem(n_tasks):
     return cfg, params, tasks, val
 
 
-def _run(dev, params, cfg, tasks, val, n_total, dist, steps=2, overlap=True):
+def _run(dev, params, cfg, tasks, val, n_total, dist, steps=3, overlap=True, use_graph=False):
     """`steps` meta-steps of the tasks given (already this rank's shard); returns (copy_grad of step 0, theta)."""
     import mtl_b200
     from gpu_util import spec_of
@@ -47,7 +47,7 @@ def _run(dev, params, cfg, tasks, val, n_total, dist, steps=2, overlap=True):
     st = s.new_adam_state()
     s.load(theta, params)
     ex = MetaExchange(s, dist, overlap=overlap)
-    stepper = mtl_b200.MetaStepper(s, max(1, len(tasks)), use_graph=False) if tasks else None
+    stepper = mtl_b200.MetaStepper(s, max(1, len(tasks)), use_graph=use_graph) if tasks else None
     cg0 = None
     for it in range(steps):
         if stepper is not None:
@@ -57,6 +57,7 @@ def _run(dev, params, cfg, tasks, val, n_total, dist, steps=2, overlap=True):
             stepper.run(theta, cg, 1e-2, 1.0 / n_total, seed=it)
         else:
             s.zero(cg)
+        ex.ran_tasks = stepper is not None
         ex.finish(theta, grad, cg, m, v, st, 1e-3)
         if it == 0:
             cg0 = ex.last_copy_grad(cg).clone()
@@ -64,7 +65,7 @@ def _run(dev, params, cfg, tasks, val, n_total, dist, steps=2, overlap=True):
     return cg0.cpu(), theta.cpu()
 
 
-def _worker(rank, world, port, n_tasks, out_dir, overlap):
+def _worker(rank, world, port, n_tasks, out_dir, overlap, use_graph):
     _setup_path()
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -75,22 +76,23 @@ def _worker(rank, world, port, n_tasks, out_dir, overlap):
         from mtl_b200.shard import task_shard
         cfg, params, tasks, val = _problem(n_tasks)
         mine = task_shard(n_tasks, rank, world)
-        cg0, theta = _run(dev, params, cfg, [tasks[t] for t in mine], val, n_tasks, dist, overlap=overlap)
+        cg0, theta = _run(dev, params, cfg, [tasks[t] for t in mine], val, n_tasks, dist, overlap=overlap, use_graph=use_graph)
         torch.save(dict(cg=cg0, theta=theta, mine=mine), os.path.join(out_dir, f"rank{rank}.pt"))
     finally:
         dist.destroy_process_group()
 
 
 @pytest.mark.timeout(600)
-@pytest.mark.parametrize("n_tasks,overlap", [(4, True), (3, True), (3, False)])
-def test_two_gpu_sharded_meta_step_matches_single_gpu(tmp_path, n_tasks, overlap):
+@pytest.mark.parametrize("n_tasks,overlap,use_graph", [(4, True, False), (4, True, True), (3, True, True), (3, False, False),
+                                                        (1, True, True)])
+def test_two_gpu_sharded_meta_step_matches_single_gpu(tmp_path, n_tasks, overlap, use_graph):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     _setup_path()
     import torch.multiprocessing as mp
     from gpu_util import rel_err
     world = 2
-    mp.spawn(_worker, args=(world, _free_port(), n_tasks, str(tmp_path), overlap), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), n_tasks, str(tmp_path), overlap, use_graph), nprocs=world, join=True)
     r0, r1 = torch.load(tmp_path / "rank0.pt"), torch.load(tmp_path / "rank1.pt")
     assert sorted(r0["mine"] + r1["mine"]) == list(range(n_tasks))
     assert torch.equal(r0["theta"], r1["theta"]), "replicas diverged"
@@ -98,7 +100,7 @@ def test_two_gpu_sharded_meta_step_matches_single_gpu(tmp_path, n_tasks, overlap
     cfg, params, tasks, val = _problem(n_tasks)
     cg_ref, theta_ref = _run(torch.device("cuda", 0), params, cfg, tasks, val, n_tasks, None)
     assert rel_err(r0["cg"], cg_ref) < 2e-5
-    # two Adam steps of lr 1e-3 (|update| <= lr each): entries with a solid gradient land where the single-GPU run lands;
+    # three Adam steps of lr 1e-3 (step 2 replays the captured graph when use_graph) (|update| <= lr each): entries with a solid gradient land where the single-GPU run lands;
     # the second step's gradient is taken at weights that already differ by the first step's rounding (measured 1.3e-4)
     solid = cg_ref.abs() > 1e-3 * float(cg_ref.abs().max())
-    assert float((r0["theta"] - theta_ref).abs()[solid].max()) <= 0.25 * 1e-3
+    assert float((r0["theta"] - theta_ref).abs()[solid].max()) <= 0.4 * 1e-3
