@@ -64,7 +64,8 @@ int mtl_session_set_gemm_mode(mtl_session* s, int mode);
 #define MTL_OP_LIN_WGRAD 5
 #define MTL_OP_STEM 6
 #define MTL_OP_VOCAB 7
-#define MTL_OP_CLASSES 8
+#define MTL_OP_ATTN 8 /* QK^T / PV contractions of sequences longer than 64 (modules/common_layers.py:321-329) */
+#define MTL_OP_CLASSES 9
 int mtl_session_set_op_mode(mtl_session* s, int op_class, int mode);
 /* Engine variants kept for A/B measurements.  "merge_lowrank" (default 0): run each low-rank projection pair
  * B(A x) of modules/common_layers.py:287-289,303 as ONE GEMM against W = B.A formed once per pass. */

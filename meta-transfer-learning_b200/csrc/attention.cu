@@ -12,6 +12,9 @@
 int k_attn_small_fwd(const AttnArgs& a, cudaStream_t s);
 int k_attn_small_bwd(const AttnBwdArgs& a, cudaStream_t s);
 bool k_attn_small_eligible(const AttnArgs& a);
+int k_attn_flash_fwd(const AttnArgs& a, cudaStream_t s);
+int k_attn_flash_bwd(const AttnBwdArgs& a, cudaStream_t s);
+bool k_attn_flash_eligible(const AttnArgs& a);
 
 #define ATT_TILE 32      // keys (fwd/dQ) or queries (dKV) per smem tile == warp width
 #define ATT_ROWS 16      // rows per CTA (4 warps x 4 rows)
@@ -98,6 +101,7 @@ int k_attn_fwd(const AttnArgs& a, cudaStream_t s) {
   MTL_REQUIRE(a.dk == 32 || a.dk == 64, "attention head dim must be 32 or 64");
   if (a.B * a.H * a.Tq == 0) return MTL_OK;
   if (k_attn_small_eligible(a)) return k_attn_small_fwd(a, s);
+  if (k_attn_flash_eligible(a)) return k_attn_flash_fwd(a, s);
   dim3 grid(mtl_cdiv(a.Tq, ATT_ROWS), a.H, a.B);
   if (a.dk == 64) attn_fwd_kernel<64><<<grid, 128, 0, s>>>(a);
   else attn_fwd_kernel<32><<<grid, 128, 0, s>>>(a);
@@ -298,6 +302,8 @@ int k_attn_bwd(const AttnBwdArgs& a, cudaStream_t s) {
   if (a.f.B * a.f.H * a.f.Tq == 0) return MTL_OK;
   if (k_attn_small_eligible(a.f) && (((uintptr_t)a.d_o | (uintptr_t)a.dq | (uintptr_t)a.dk | (uintptr_t)a.dv) & 15u) == 0)
     return k_attn_small_bwd(a, s);
+  if (k_attn_flash_eligible(a.f) && (((uintptr_t)a.d_o | (uintptr_t)a.dq | (uintptr_t)a.dk | (uintptr_t)a.dv) & 15u) == 0)
+    return k_attn_flash_bwd(a, s);
   return a.f.dk == 64 ? attn_bwd_launch<64>(a, s) : attn_bwd_launch<32>(a, s);
 }
 
@@ -591,11 +597,9 @@ __global__ void __launch_bounds__(NT) attn_small_bwd_kernel(AttnBwdArgs a) {
 // and reads its fragments straight from the row-major shared-memory operands (row stride 68 floats: the 8 rows x 4
 // columns of an A / NT-B fragment fall into 32 distinct banks).  The CUDA-core version spent 6.8 k of its 17 k cycles on
 // the scores alone (shared-memory wavefronts of a 4 x 4 register-blocked FFMA loop).  MTL_ATTN_MMA=0 selects it (A/B).
-__device__ __forceinline__ uint32_t f2tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
-}
+// round-to-nearest (ties away) fp32 -> tf32 with two full-rate integer ops (cvt.rna.tf32.f32 runs on the quarter-rate
+// conversion pipe; same result for finite inputs -- see tf32_rna in gemm_tc.cu)
+__device__ __forceinline__ uint32_t f2tf32(float x) { return (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u; }
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
   hi = f2tf32(x);
   lo = f2tf32(x - __uint_as_float(hi));
@@ -808,6 +812,393 @@ __global__ void __launch_bounds__(NT) attn_small_bwd_mma_kernel(AttnBwdArgs a) {
   }
   SA_STAMP(20);
 }
+
+// ----------------------------------------------------------------------------- long sequences on the tensor cores
+// Flash-style attention for Tq or Tk > 64 (every utterance longer than 2.6 s: T' = frames / 4; BASELINE configs[3] runs
+// T' = 1250) on the same mma.sync.m16n8k8 TF32 fragments as the short-sequence kernels.  A CTA of 4 warps owns 64 query
+// rows (forward, dQ) or 64 key rows (dK / dV) of one (b, h); the opposite side streams through shared memory in 64-row
+// tiles; a warp owns 16 rows, keeps its 16 x 64 score / probability tile in a warp-private shared-memory strip between the
+// two products, and the running max / sum / output accumulators in registers (online softmax).  Scores never reach HBM;
+// the backward recomputes probabilities from the saved log-sum-exp.  The CUDA-core tiled kernels above (16 rows per
+// CTA, shuffle-broadcast FFMA) took 62 % of the kernel time of a cfg-4 pass: 1.44 / 1.92 / 2.48 ms per launch.
+// X3 = 3xTF32 (fp32-grade, default) or single-pass TF32 (AttnArgs.prec = 1: the session's TF32 engine).
+constexpr int FA_T = 64;
+// pre-split operand fragment: hi / lo tf32 words (lo unused in single-pass TF32)
+template <bool X3, int N>
+__device__ __forceinline__ void fa_split(const float (&x)[N], uint32_t (&hi)[N], uint32_t (&lo)[N]) {
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    hi[i] = f2tf32(x[i]);
+    lo[i] = X3 ? f2tf32(x[i] - __uint_as_float(hi[i])) : 0u;
+  }
+}
+template <bool X3>
+__device__ __forceinline__ void fa_mma(float (&c)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], const uint32_t (&bh)[2],
+                                       const uint32_t (&bl)[2]) {
+  if (X3) { mma_tf32(c, al, bh); mma_tf32(c, ah, bl); }
+  mma_tf32(c, ah, bh);
+}
+// c[nt] += X[m0.., :K8] * Y[8 nt.., :K8]^T for the eight 8-column tiles nt: the A fragment is loaded and split ONCE per k-step
+template <bool X3>
+__device__ __forceinline__ void fa_nt8(float (&c)[8][4], const float (*X)[SA_LD], const float (*Y)[SA_LD], int m0, int K8, int g,
+                                       int t) {
+#pragma unroll 2
+  for (int k0 = 0; k0 < K8; k0 += 8) {
+    const float a[4] = {X[m0 + g][k0 + t], X[m0 + g + 8][k0 + t], X[m0 + g][k0 + t + 4], X[m0 + g + 8][k0 + t + 4]};
+    uint32_t ah[4], al[4];
+    fa_split<X3, 4>(a, ah, al);
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const float b[2] = {Y[8 * nt + g][k0 + t], Y[8 * nt + g][k0 + t + 4]};
+      uint32_t bh[2], bl[2];
+      fa_split<X3, 2>(b, bh, bl);
+      fa_mma<X3>(c[nt], ah, al, bh, bl);
+    }
+  }
+}
+// c[d] += W[0..16, :K8] * Y[:K8, 8 d..] for the ND 8-column tiles d
+template <bool X3, int ND>
+__device__ __forceinline__ void fa_nn8(float (&c)[ND][4], const float (*W)[SA_LD], const float (*Y)[SA_LD], int K8, int g, int t) {
+#pragma unroll 2
+  for (int k0 = 0; k0 < K8; k0 += 8) {
+    const float a[4] = {W[g][k0 + t], W[g + 8][k0 + t], W[g][k0 + t + 4], W[g + 8][k0 + t + 4]};
+    uint32_t ah[4], al[4];
+    fa_split<X3, 4>(a, ah, al);
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+      const float b[2] = {Y[k0 + t][8 * d + g], Y[k0 + t + 4][8 * d + g]};
+      uint32_t bh[2], bl[2];
+      fa_split<X3, 2>(b, bh, bl);
+      fa_mma<X3>(c[d], ah, al, bh, bl);
+    }
+  }
+}
+// rows [row0, row0 + 64) of the head-h column block of a (B*T, ld) matrix -> tile (rows >= T zero), 128 threads
+template <int DK>
+__device__ __forceinline__ void fa_load(float (*dst)[SA_LD], const float* src, int b, int T, int ld, int h, int row0) {
+  constexpr int C4 = DK / 4;
+#pragma unroll
+  for (int u = 0; u < FA_T * C4 / 128; ++u) {
+    const int i = threadIdx.x + u * 128, r = i / C4, c4 = i % C4, gr = row0 + r;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (gr < T) v = __ldg(reinterpret_cast<const float4*>(src + (size_t)(b * T + gr) * ld + h * DK + c4 * 4));
+    *reinterpret_cast<float4*>(&dst[r][c4 * 4]) = v;
+  }
+}
+// dropout scales of two ADJACENT elements idx, idx + 1 (one Philox block when they share it)
+__device__ __forceinline__ void drop2(unsigned long long seed, uint32_t site, unsigned long long idx, float p, float inv_keep,
+                                      float& s0, float& s1) {
+  if ((idx & 3ull) != 3ull) {
+    const float4 q = dropout_scale4(seed, site, idx & ~3ull, p, inv_keep);
+    const int e = (int)(idx & 3ull);
+    s0 = e == 0 ? q.x : (e == 1 ? q.y : q.z);
+    s1 = e == 0 ? q.y : (e == 1 ? q.z : q.w);
+  } else {
+    s0 = dropout_scale(seed, site, idx, p, inv_keep);
+    s1 = dropout_scale(seed, site, idx + 1, p, inv_keep);
+  }
+}
+struct FaFwdSmem {
+  float q[FA_T][SA_LD], k[FA_T][SA_LD], v[FA_T][SA_LD], p[4][16][SA_LD];
+  int kmask[FA_T];
+};
+struct FaBwdSmem {
+  float q[FA_T][SA_LD], g[FA_T][SA_LD], k[FA_T][SA_LD], v[FA_T][SA_LD], p[4][16][SA_LD], ds[4][16][SA_LD];
+  float lse[FA_T], delta[FA_T];
+  int kmask[FA_T];
+};
+static_assert(sizeof(FaBwdSmem) <= 227 * 1024, "shared memory budget");
+
+template <int DK, bool X3>
+__global__ void __launch_bounds__(128) attn_flash_fwd_kernel(AttnArgs a) {
+  constexpr int ND = DK / 8;
+  extern __shared__ __align__(16) unsigned char fa_raw[];
+  FaFwdSmem& S = *reinterpret_cast<FaFwdSmem*>(fa_raw);
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * FA_T;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const int Tq = a.Tq, Tk = a.Tk;
+  fa_load<DK>(S.q, a.q, b, Tq, a.ldq, h, q0);
+  float m_[2] = {-INFINITY, -INFINITY}, l_[2] = {0.f, 0.f}, o[ND][4];
+#pragma unroll
+  for (int d = 0; d < ND; ++d) o[d][0] = o[d][1] = o[d][2] = o[d][3] = 0.f;
+  const int row[2] = {q0 + 16 * w + g, q0 + 16 * w + g + 8};
+  const unsigned long long seed = a.drop.p > 0.f ? mtl_eff_seed(a.drop) : 0ull;
+  const int k_end = a.causal ? min(Tk, q0 + FA_T) : Tk;         // causal: keys beyond this CTA's last query never contribute
+  for (int k0 = 0; k0 < k_end; k0 += FA_T) {
+    __syncthreads();
+    fa_load<DK>(S.k, a.k, b, Tk, a.ldk, h, k0);
+    fa_load<DK>(S.v, a.v, b, Tk, a.ldv, h, k0);
+    if (threadIdx.x < FA_T) {
+      const int kj = k0 + threadIdx.x;
+      S.kmask[threadIdx.x] = (kj >= Tk || (a.keypad && a.keypad[(size_t)b * Tk + kj])) ? 1 : 0;
+    }
+    __syncthreads();
+    float s[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+    fa_nt8<X3>(s, S.q, S.k, 16 * w, DK, g, t);
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int jl = 8 * nt + 2 * t + (e & 1), i = row[e >> 1];
+        const bool ok = i < Tq && !S.kmask[jl] && !(a.causal && k0 + jl > i);
+        s[nt][e] = ok ? s[nt][e] * a.inv_temp : -INFINITY;
+        mx[e >> 1] = fmaxf(mx[e >> 1], s[nt][e]);
+      }
+    float corr[2], sum[2] = {0.f, 0.f};
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+      const float mn = fmaxf(m_[r], mx[r]);
+      corr[r] = (mn == -INFINITY) ? 1.f : (m_[r] == -INFINITY ? 0.f : __expf(m_[r] - mn));
+      m_[r] = mn;
+    }
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float p = (s[nt][e] == -INFINITY) ? 0.f : __expf(s[nt][e] - m_[e >> 1]);
+        s[nt][e] = p;
+        sum[e >> 1] += p;
+      }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], 1);
+      sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], 2);
+      l_[r] = l_[r] * corr[r] + sum[r];
+    }
+#pragma unroll
+    for (int d = 0; d < ND; ++d) { o[d][0] *= corr[0]; o[d][1] *= corr[0]; o[d][2] *= corr[1]; o[d][3] *= corr[1]; }
+    // probabilities (after dropout) -> the warp's strip
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        float p0 = s[nt][2 * r], p1 = s[nt][2 * r + 1];
+        if (a.drop.p > 0.f && row[r] < Tq) {
+          float d0, d1;
+          drop2(seed, a.drop.site, (((unsigned long long)(b * a.H + h) * Tq + row[r]) * Tk + k0 + 8 * nt + 2 * t), a.drop.p,
+                a.drop.inv_keep, d0, d1);
+          p0 *= d0; p1 *= d1;
+        }
+        *reinterpret_cast<float2*>(&S.p[w][g + 8 * r][8 * nt + 2 * t]) = make_float2(p0, p1);
+      }
+    __syncwarp();
+    fa_nn8<X3, ND>(o, S.p[w], S.v, FA_T, g, t);
+  }
+  float* out = a.o + (size_t)b * Tq * a.ldo + h * DK;
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    if (row[r] >= Tq) continue;
+    const float inv = 1.f / l_[r];                               // fully masked row -> NaN, like softmax over a row of -inf
+#pragma unroll
+    for (int d = 0; d < ND; ++d)
+      *reinterpret_cast<float2*>(out + (size_t)row[r] * a.ldo + 8 * d + 2 * t) = make_float2(o[d][2 * r] * inv, o[d][2 * r + 1] * inv);
+    if (t == 0) a.lse[((size_t)b * a.H + h) * Tq + row[r]] = m_[r] + logf(l_[r]);
+  }
+}
+
+// dQ: 64 query rows per CTA, key tiles stream by
+template <int DK, bool X3>
+__global__ void __launch_bounds__(128) attn_flash_dq_kernel(AttnBwdArgs a) {
+  constexpr int ND = DK / 8;
+  extern __shared__ __align__(16) unsigned char fa_raw[];
+  FaBwdSmem& S = *reinterpret_cast<FaBwdSmem*>(fa_raw);
+  const AttnArgs& f = a.f;
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * FA_T;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const int Tq = f.Tq, Tk = f.Tk;
+  fa_load<DK>(S.q, f.q, b, Tq, f.ldq, h, q0);
+  fa_load<DK>(S.g, a.d_o, b, Tq, f.ldo, h, q0);
+  const int row[2] = {q0 + 16 * w + g, q0 + 16 * w + g + 8};
+  float lse[2], dl[2], acc[ND][4];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const size_t si = ((size_t)b * f.H + h) * Tq + min(row[r], Tq - 1);
+    lse[r] = f.lse[si]; dl[r] = a.delta[si];
+  }
+#pragma unroll
+  for (int d = 0; d < ND; ++d) acc[d][0] = acc[d][1] = acc[d][2] = acc[d][3] = 0.f;
+  const unsigned long long seed = f.drop.p > 0.f ? mtl_eff_seed(f.drop) : 0ull;
+  const int k_end = f.causal ? min(Tk, q0 + FA_T) : Tk;
+  for (int k0 = 0; k0 < k_end; k0 += FA_T) {
+    __syncthreads();
+    fa_load<DK>(S.k, f.k, b, Tk, f.ldk, h, k0);
+    fa_load<DK>(S.v, f.v, b, Tk, f.ldv, h, k0);
+    if (threadIdx.x < FA_T) {
+      const int kj = k0 + threadIdx.x;
+      S.kmask[threadIdx.x] = (kj >= Tk || (f.keypad && f.keypad[(size_t)b * Tk + kj])) ? 1 : 0;
+    }
+    __syncthreads();
+    float sc8[8][4], dp8[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) { sc8[nt][0] = sc8[nt][1] = sc8[nt][2] = sc8[nt][3] = 0.f; dp8[nt][0] = dp8[nt][1] = dp8[nt][2] = dp8[nt][3] = 0.f; }
+    fa_nt8<X3>(sc8, S.q, S.k, 16 * w, DK, g, t);
+    fa_nt8<X3>(dp8, S.g, S.v, 16 * w, DK, g, t);
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const float (&sc)[4] = sc8[nt];
+      const float (&dp)[4] = dp8[nt];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        float ds2[2];
+        float d0 = 1.f, d1 = 1.f;
+        if (f.drop.p > 0.f && row[r] < Tq)
+          drop2(seed, f.drop.site, (((unsigned long long)(b * f.H + h) * Tq + row[r]) * Tk + k0 + 8 * nt + 2 * t), f.drop.p,
+                f.drop.inv_keep, d0, d1);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int jl = 8 * nt + 2 * t + c, i = row[r];
+          const bool ok = i < Tq && !S.kmask[jl] && !(f.causal && k0 + jl > i);
+          const float p = ok ? __expf(sc[2 * r + c] * f.inv_temp - lse[r]) : 0.f;
+          ds2[c] = ok ? p * (dp[2 * r + c] * (c ? d1 : d0) - dl[r]) : 0.f;
+        }
+        *reinterpret_cast<float2*>(&S.ds[w][g + 8 * r][8 * nt + 2 * t]) = make_float2(ds2[0], ds2[1]);
+      }
+    }
+    __syncwarp();
+    fa_nn8<X3, ND>(acc, S.ds[w], S.k, FA_T, g, t);
+  }
+  float* dq = a.dq + (size_t)b * Tq * f.ldq + h * DK;
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    if (row[r] >= Tq) continue;
+#pragma unroll
+    for (int d = 0; d < ND; ++d)
+      *reinterpret_cast<float2*>(dq + (size_t)row[r] * f.ldq + 8 * d + 2 * t) =
+          make_float2(acc[d][2 * r] * f.inv_temp, acc[d][2 * r + 1] * f.inv_temp);
+  }
+}
+
+// dK, dV: 64 key rows per CTA, query tiles stream by; the warp's tiles are TRANSPOSED (rows = its 16 keys, columns = queries)
+template <int DK, bool X3>
+__global__ void __launch_bounds__(128) attn_flash_dkv_kernel(AttnBwdArgs a) {
+  constexpr int ND = DK / 8;
+  extern __shared__ __align__(16) unsigned char fa_raw[];
+  FaBwdSmem& S = *reinterpret_cast<FaBwdSmem*>(fa_raw);
+  const AttnArgs& f = a.f;
+  const int b = blockIdx.z, h = blockIdx.y, kb0 = blockIdx.x * FA_T;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const int Tq = f.Tq, Tk = f.Tk;
+  fa_load<DK>(S.k, f.k, b, Tk, f.ldk, h, kb0);
+  fa_load<DK>(S.v, f.v, b, Tk, f.ldv, h, kb0);
+  const int key[2] = {kb0 + 16 * w + g, kb0 + 16 * w + g + 8};
+  bool kvalid[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) kvalid[r] = key[r] < Tk && !(f.keypad && f.keypad[(size_t)b * Tk + key[r]]);
+  float accK[ND][4], accV[ND][4];
+#pragma unroll
+  for (int d = 0; d < ND; ++d) { accK[d][0] = accK[d][1] = accK[d][2] = accK[d][3] = 0.f; accV[d][0] = accV[d][1] = accV[d][2] = accV[d][3] = 0.f; }
+  const unsigned long long seed = f.drop.p > 0.f ? mtl_eff_seed(f.drop) : 0ull;
+  const int q_begin = f.causal ? kb0 : 0;                       // causal: earlier queries never see these keys (kb0 % 64 == 0)
+  for (int q0 = q_begin; q0 < Tq; q0 += FA_T) {
+    __syncthreads();
+    fa_load<DK>(S.q, f.q, b, Tq, f.ldq, h, q0);
+    fa_load<DK>(S.g, a.d_o, b, Tq, f.ldo, h, q0);
+    if (threadIdx.x < FA_T) {
+      const size_t si = ((size_t)b * f.H + h) * Tq + min(q0 + (int)threadIdx.x, Tq - 1);
+      S.lse[threadIdx.x] = f.lse[si];
+      S.delta[threadIdx.x] = a.delta[si];
+    }
+    __syncthreads();
+    float sc8[8][4], dp8[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) { sc8[nt][0] = sc8[nt][1] = sc8[nt][2] = sc8[nt][3] = 0.f; dp8[nt][0] = dp8[nt][1] = dp8[nt][2] = dp8[nt][3] = 0.f; }
+    fa_nt8<X3>(sc8, S.k, S.q, 16 * w, DK, g, t);                   // S^T: rows = keys, columns = queries
+    fa_nt8<X3>(dp8, S.v, S.g, 16 * w, DK, g, t);                   // dP^T
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const float (&sc)[4] = sc8[nt];
+      const float (&dp)[4] = dp8[nt];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        float pd2[2], ds2[2];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int il = 8 * nt + 2 * t + c, i = q0 + il, j = key[r];
+          const bool ok = kvalid[r] && i < Tq && !(f.causal && j > i);
+          const float p = ok ? __expf(sc[2 * r + c] * f.inv_temp - S.lse[il]) : 0.f;
+          float scale = 1.f;
+          if (f.drop.p > 0.f && ok)
+            scale = dropout_scale(seed, f.drop.site, (((unsigned long long)(b * f.H + h) * Tq + i) * Tk + j), f.drop.p, f.drop.inv_keep);
+          pd2[c] = p * scale;
+          ds2[c] = ok ? p * (dp[2 * r + c] * scale - S.delta[il]) : 0.f;
+        }
+        *reinterpret_cast<float2*>(&S.p[w][g + 8 * r][8 * nt + 2 * t]) = make_float2(pd2[0], pd2[1]);
+        *reinterpret_cast<float2*>(&S.ds[w][g + 8 * r][8 * nt + 2 * t]) = make_float2(ds2[0], ds2[1]);
+      }
+    }
+    __syncwarp();
+    fa_nn8<X3, ND>(accV, S.p[w], S.g, FA_T, g, t);                 // dV += P_dropped^T . dO
+    fa_nn8<X3, ND>(accK, S.ds[w], S.q, FA_T, g, t);                // dK += dS^T . Q
+  }
+  float* dk = a.dk + (size_t)b * Tk * f.ldk + h * DK;
+  float* dv = a.dv + (size_t)b * Tk * f.ldv + h * DK;
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    if (key[r] >= Tk) continue;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+      *reinterpret_cast<float2*>(dk + (size_t)key[r] * f.ldk + 8 * d + 2 * t) =
+          make_float2(accK[d][2 * r] * f.inv_temp, accK[d][2 * r + 1] * f.inv_temp);
+      *reinterpret_cast<float2*>(dv + (size_t)key[r] * f.ldv + 8 * d + 2 * t) = make_float2(accV[d][2 * r], accV[d][2 * r + 1]);
+    }
+  }
+}
+
+// MTL_ATTN_FLASH=0: the CUDA-core tiled kernels for long sequences (A/B measurements; also AttnArgs.prec = 2, the fp32 engine)
+static bool attn_flash_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MTL_ATTN_FLASH"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v != 0;
+}
+static bool attn_flash_ok(const AttnArgs& a) {
+  auto al = [](const void* p) { return (((uintptr_t)p) & 15u) == 0; };
+  return attn_flash_enabled() && a.prec != 2 && a.ldq % 4 == 0 && a.ldk % 4 == 0 && a.ldv % 4 == 0 && a.ldo % 4 == 0 &&
+         al(a.q) && al(a.k) && al(a.v) && al(a.o);
+}
+template <int DK, bool X3>
+static int attn_flash_fwd_launch(const AttnArgs& a, cudaStream_t s) {
+  static bool configured = false;
+  if (!configured) {
+    MTL_CHECK_CUDA(cudaFuncSetAttribute(attn_flash_fwd_kernel<DK, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FaFwdSmem)));
+    configured = true;
+  }
+  attn_flash_fwd_kernel<DK, X3><<<dim3(mtl_cdiv(a.Tq, FA_T), a.H, a.B), 128, sizeof(FaFwdSmem), s>>>(a);
+  MTL_CHECK_LAUNCH();
+  ++g_mtl_launches;
+  return MTL_OK;
+}
+template <int DK, bool X3>
+static int attn_flash_bwd_launch(const AttnBwdArgs& a, cudaStream_t s) {
+  static bool configured = false;
+  if (!configured) {
+    MTL_CHECK_CUDA(cudaFuncSetAttribute(attn_flash_dq_kernel<DK, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FaBwdSmem)));
+    MTL_CHECK_CUDA(cudaFuncSetAttribute(attn_flash_dkv_kernel<DK, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FaBwdSmem)));
+    configured = true;
+  }
+  const AttnArgs& f = a.f;
+  attn_delta_kernel<DK><<<mtl_cdiv(f.B * f.Tq * f.H, 4), 128, 0, s>>>(a);
+  MTL_CHECK_LAUNCH();
+  attn_flash_dq_kernel<DK, X3><<<dim3(mtl_cdiv(f.Tq, FA_T), f.H, f.B), 128, sizeof(FaBwdSmem), s>>>(a);
+  MTL_CHECK_LAUNCH();
+  attn_flash_dkv_kernel<DK, X3><<<dim3(mtl_cdiv(f.Tk, FA_T), f.H, f.B), 128, sizeof(FaBwdSmem), s>>>(a);
+  MTL_CHECK_LAUNCH();
+  g_mtl_launches += 3;
+  return MTL_OK;
+}
+int k_attn_flash_fwd(const AttnArgs& a, cudaStream_t s) {
+  if (a.prec == 1) return a.dk == 64 ? attn_flash_fwd_launch<64, false>(a, s) : attn_flash_fwd_launch<32, false>(a, s);
+  return a.dk == 64 ? attn_flash_fwd_launch<64, true>(a, s) : attn_flash_fwd_launch<32, true>(a, s);
+}
+int k_attn_flash_bwd(const AttnBwdArgs& a, cudaStream_t s) {
+  if (a.f.prec == 1) return a.f.dk == 64 ? attn_flash_bwd_launch<64, false>(a, s) : attn_flash_bwd_launch<32, false>(a, s);
+  return a.f.dk == 64 ? attn_flash_bwd_launch<64, true>(a, s) : attn_flash_bwd_launch<32, true>(a, s);
+}
+bool k_attn_flash_eligible(const AttnArgs& a) { return attn_flash_ok(a); }
 
 // MTL_ATTN_SMALL=0 keeps the tiled kernels for short sequences too (A/B measurements)
 static bool attn_small_enabled() {

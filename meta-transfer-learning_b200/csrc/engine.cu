@@ -283,6 +283,12 @@ static inline int op_mode(const mtl_session* S, int cls) {
   const int m = S->op_mode[cls];
   return m > 0 ? m : S->mode;
 }
+// Arithmetic of the long-sequence attention kernels (AttnArgs.prec): fp32 CUDA-core kernels with the fp32 engine, else the
+// tensor-core flash kernels in 3xTF32 or, under a TF32 policy for MTL_OP_ATTN, single-pass TF32.
+static inline int attn_prec(const mtl_session* S) {
+  if (S->mode == MTL_GEMM_SIMT_FP32) return 2;
+  return op_mode(S, MTL_OP_ATTN) == MTL_GEMM_TC_TF32 ? 1 : 0;
+}
 // Scope in which the launch wrappers enqueue on `s` instead of the main stream.
 struct On {
   Run& R;
@@ -618,7 +624,7 @@ static int attn_block_fwd(Run& R, AttnAct& A, const AttnP& p, const float* xq, c
   a.q = A.q.y; a.k = A.k.y; a.v = A.v.y; a.o = A.oh; a.lse = A.lse; a.keypad = keypad;
   a.B = B; a.H = H; a.Tq = Tq; a.Tk = Tk; a.dk = dk;
   a.ldq = A.q.ldy; a.ldk = A.k.ldy; a.ldv = A.v.ldy; a.ldo = H * dv;
-  a.causal = causal; a.inv_temp = 1.0f / sqrtf((float)dk); a.drop = A.drop_attn;
+  a.causal = causal; a.inv_temp = 1.0f / sqrtf((float)dk); a.drop = A.drop_attn; a.prec = attn_prec(R.S);
   K(k_attn_fwd(a, R.st));
   if (A.Wo) {
     float* ob = R.ws.f((size_t)Mq * d);
@@ -669,7 +675,7 @@ static int attn_block_bwd(Run& R, const AttnAct& A, const float* dout, float* dx
     b.f.q = A.q.y; b.f.k = A.k.y; b.f.v = A.v.y; b.f.o = A.oh; b.f.lse = A.lse; b.f.keypad = A.keypad;
     b.f.B = A.B; b.f.H = H; b.f.Tq = A.Tq; b.f.Tk = A.Tk; b.f.dk = dk;
     b.f.ldq = A.q.ldy; b.f.ldk = A.k.ldy; b.f.ldv = A.v.ldy; b.f.ldo = hv;
-    b.f.causal = A.causal; b.f.inv_temp = 1.0f / sqrtf((float)dk); b.f.drop = A.drop_attn;
+    b.f.causal = A.causal; b.f.inv_temp = 1.0f / sqrtf((float)dk); b.f.drop = A.drop_attn; b.f.prec = attn_prec(R.S);
     b.d_o = d_oh; b.delta = delta; b.dq = dq; b.dk = dkk; b.dv = dvv;
     K(k_attn_bwd(b, R.st));
     cudaEvent_t e_qkv;
@@ -705,7 +711,7 @@ static int attn_block_bwd(Run& R, const AttnAct& A, const float* dout, float* dx
   b.f.q = A.q.y; b.f.k = A.k.y; b.f.v = A.v.y; b.f.o = A.oh; b.f.lse = A.lse; b.f.keypad = A.keypad;
   b.f.B = A.B; b.f.H = H; b.f.Tq = A.Tq; b.f.Tk = A.Tk; b.f.dk = dk;
   b.f.ldq = H * dk; b.f.ldk = H * dk; b.f.ldv = H * dv; b.f.ldo = H * dv;
-  b.f.causal = A.causal; b.f.inv_temp = 1.0f / sqrtf((float)dk); b.f.drop = A.drop_attn;
+  b.f.causal = A.causal; b.f.inv_temp = 1.0f / sqrtf((float)dk); b.f.drop = A.drop_attn; b.f.prec = attn_prec(R.S);
   b.d_o = d_oh; b.delta = delta; b.dq = dq; b.dk = dkk; b.dv = dvv;
   K(k_attn_bwd(b, R.st));
   cudaEvent_t e_qkv;

@@ -99,6 +99,7 @@ struct AttnArgs {
   int causal;
   float inv_temp;              // 1/sqrt(dk)
   MtlDrop drop;
+  int prec;                    // tensor-core kernels: 0 = 3xTF32 (fp32-grade), 1 = single-pass TF32; 2 = CUDA-core fp32 kernels
 };
 int k_attn_fwd(const AttnArgs& a, cudaStream_t s);
 struct AttnBwdArgs {

@@ -96,7 +96,7 @@ class Session:
         _l.check(self.lib.mtl_session_set_gemm_mode(self._h, int(mode)))
         self.gemm_mode = int(mode)
 
-    OP_CLASSES = ("conv_fwd", "conv_dgrad", "conv_wgrad", "lin_fwd", "lin_dgrad", "lin_wgrad", "stem", "vocab")
+    OP_CLASSES = ("conv_fwd", "conv_dgrad", "conv_wgrad", "lin_fwd", "lin_dgrad", "lin_wgrad", "stem", "vocab", "attn")
 
     def set_op_mode(self, op_class, mode: int):
         """Per-operation-class engine (include/mtl_b200.h: mtl_session_set_op_mode); mode -1 = follow gemm_mode."""
