@@ -219,6 +219,16 @@ int mtl_arena_adam(float* p, const float* g, float* m, float* v, void* adam_stat
 int mtl_gemm(int mode, int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda,
              const float* B, int ldb, float beta, float* C, int ldc, const float* bias, int epi,
              const float* aux, int split_k, void* stream);
+/* The rank-r factorised nn.Linear pair of the attention blocks, linear_b(linear_a(x)) (modules/common_layers.py:250-257,
+ * 287-289, 303), as ONE kernel -- forward (bwd = 0) or its input gradient (bwd = 1) -- for G <= 3 problems of equal shape
+ * (q | k | v).  Pointer arrays hold G entries.  K slabs are merged by reduce-add: a [M, r] and y [M, N2] (row stride ldy)
+ * must be zero (y may instead hold a sum to accumulate into) before the call.
+ *   bwd = 0: x [M, K1] (ldx), w1 = linear_a.weight [r, K1], w2 = linear_b.weight [N2, r], bias[g] [N2] or null
+ *   bwd = 1: x = dy [M, K1] (ldx), w1 = linear_b.weight [K1, r], w2 = linear_a.weight [r, N2], bias ignored
+ * mode: MTL_GEMM_TC_TF32 or MTL_GEMM_TC_3XTF32.  ctas: CTA budget sizing the K split (0 = none). */
+int mtl_lowrank_pair(int mode, int bwd, int G, int M, int K1, int r, int N2, const float* const* x, int ldx,
+                     const float* const* w1, const float* const* w2, const float* const* bias, float* const* a,
+                     float* const* y, int ldy, int ctas, void* stream);
 /* measurement hook: `reps` back-to-back launches of the same GEMM (alpha = 1, no bias / epilogue) */
 int mtl_gemm_repeat(int reps, int mode, int transA, int transB, int M, int N, int K, const float* A, int lda,
                     const float* B, int ldb, float beta, float* C, int ldc, int split_k, void* stream);

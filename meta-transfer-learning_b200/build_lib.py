@@ -14,7 +14,7 @@ LIB = os.path.join(OUT_DIR, "libmtl_b200.so")
 BUILD = os.path.join(HERE, "build")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-         "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+         "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"] + os.environ.get("MTL_NVCC_DEFS", "").split()
 SOURCES = ["arena.cu", "norm_embed.cu", "ce.cu", "attention.cu", "conv.cu", "spectrogram.cu", "gemm_simt.cu", "gemm_tc.cu",
            "engine.cu"]
 

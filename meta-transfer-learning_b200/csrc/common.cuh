@@ -57,7 +57,17 @@ static inline int mtl_cdiv(long long a, long long b) { return (int)((a + b - 1) 
 // global memory.  pdl_trigger: the next kernel's CTAs may become resident and run their prologue (barrier init, TMEM
 // allocation, descriptor fetch, index math) while this one finishes.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#ifndef MTL_PDL_LATE
+#define MTL_PDL_LATE 0
+#endif
+// MTL_PDL_LATE (build-time A/B): 1 = no explicit trigger (dependents become resident when this grid's CTAs exit);
+// 0 = trigger where the kernel says.  A dependent grid that is resident but parked in pdl_wait holds its shared memory
+// and TMEM: free with one task lane, SM-time with several.
+__device__ __forceinline__ void pdl_trigger() {
+#if !MTL_PDL_LATE
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
 // <<<grid, block, smem, s>>> with the programmatic-stream-serialization attribute (the kernel MUST call pdl_wait)
 template <typename... KArgs, typename... Args>
 static inline cudaError_t mtl_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,

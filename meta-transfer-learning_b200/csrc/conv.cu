@@ -42,9 +42,63 @@ __global__ void __launch_bounds__(256) conv1_fwd_kernel(const float* __restrict_
     *reinterpret_cast<float4*>(out + (size_t)p * Cout + c4) = acc;
   }
 }
+// Cout == 64 (the model's conv.0): one warp per quarter of a (b, f) row, the two half-warps take alternate time steps, a
+// lane owns 4 channels whose 36 weights + bias live in registers -- no shared memory, no division in the loop; every store
+// is one coalesced float4 per lane (512 contiguous bytes per warp) and four pixels per thread are in flight.  Same
+// accumulation order (bias, then taps in (kh, kw) order, FMA) as the generic kernel: bit-identical results.
+__global__ void __launch_bounds__(128) conv1_fwd64_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                          const float* __restrict__ bias, float* __restrict__ out, int B,
+                                                          int F, int T) {
+  pdl_wait();
+  pdl_trigger();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int TS = 4;
+  const int unit = blockIdx.x * 4 + warp;
+  const int row = unit / TS, seg = unit % TS;
+  if (row >= B * F) return;
+  const int tlen = (T + TS - 1) / TS, t0 = seg * tlen, t1 = min(T, t0 + tlen);
+  const int half = lane >> 4, c4 = (lane & 15) * 4;
+  float wr[9][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) wr[tap][j] = __ldg(w + (c4 + j) * 9 + tap);
+  const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c4));
+  const int f = row % F, b = row / F;
+  const float* xr[3];
+  bool rv[3];
+#pragma unroll
+  for (int kh = 0; kh < 3; ++kh) {
+    const int ff = f + kh - 1;
+    rv[kh] = ff >= 0 && ff < F;
+    xr[kh] = x + ((size_t)b * F + (rv[kh] ? ff : f)) * T;
+  }
+  float* o = out + (size_t)row * T * 64 + c4;
+#pragma unroll 4
+  for (int t = t0 + half; t < t1; t += 2) {
+    float4 acc = b4;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int tt = t + kw - 1;
+        if (!rv[kh] || tt < 0 || tt >= T) continue;        // the generic kernel skips padded taps too (no +0 term)
+        const float xv = __ldg(xr[kh] + tt);
+        acc.x += xv * wr[kh * 3 + kw][0]; acc.y += xv * wr[kh * 3 + kw][1];
+        acc.z += xv * wr[kh * 3 + kw][2]; acc.w += xv * wr[kh * 3 + kw][3];
+      }
+    acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f);
+    *reinterpret_cast<float4*>(o + (size_t)t * 64) = acc;
+  }
+}
 int k_conv1_fwd(const float* x, const float* w, const float* b, float* out, int B, int F, int T, int Cout,
                 cudaStream_t s) {
   MTL_REQUIRE(Cout % 4 == 0, "conv1 Cout % 4");
+  if (Cout == 64 && B * F > 0 && T > 0 && (((uintptr_t)out) & 15u) == 0 && (((uintptr_t)b) & 15u) == 0) {
+    MTL_CHECK_CUDA(mtl_launch_pdl(conv1_fwd64_kernel, dim3(B * F), dim3(128), 0, s, x, w, b, out, B, F, T));
+    ++g_mtl_launches;
+    return MTL_OK;
+  }
   size_t total = (size_t)B * F * T * (Cout / 4);
   if (!total) return MTL_OK;
   MTL_REQUIRE(total < (1ull << 31), "conv1: B*F*T*Cout/4 must stay below 2^31");
@@ -344,45 +398,91 @@ int k_maxpool2_relu_bwd(const float* x, const float* dpool, float* dx, int B, in
 }
 
 // ------------------------------------------------------------------ (B,F4,T4,C) <-> (B,T4,C*F4)
-__global__ void __launch_bounds__(256) feat_transpose_kernel(const float* __restrict__ p4, float* __restrict__ feat,
+// One block per (b, t, 32-channel chunk): the F4 x 32 slice p4[b, :, t, c0:c0+32] (128-byte rows, T4*C floats apart) is
+// transposed through shared memory into the contiguous run feat[b, t, c0*F4 : (c0+32)*F4] (feature index c*F4 + f) --
+// both global sides move whole 128-byte lines (the element-per-thread version read with a stride of T4*C floats), every
+// thread has all of its loads in flight before the first store.  The backward is the same tile read the other way.
+constexpr int FT_CH = 32, FT_MAX_PER = 8;                    // channels per block; elements per thread (F4 <= 64)
+template <bool BWD>
+__global__ void __launch_bounds__(256) feat_transpose_kernel(const float* __restrict__ src, float* __restrict__ dst,
                                                              int B, int F4, int T4, int C) {
   pdl_wait();
   pdl_trigger();
+  __shared__ float tile[64 * (FT_CH + 1)];                   // [F4][33]
+  const int chunks = C / FT_CH;
+  const int cc = blockIdx.x % chunks, bt = blockIdx.x / chunks, b = bt / T4, t = bt - b * T4;
+  const int n = F4 * FT_CH;
+  // NHWC side: element (f, c) at p4[((b*F4 + f)*T4 + t)*C + cc*32 + c]; feature side: feat[bt*C*F4 + (cc*32 + c)*F4 + f]
+  const size_t nhwc0 = ((size_t)b * F4 * T4 + t) * C + cc * FT_CH, feat0 = (size_t)bt * C * F4 + (size_t)cc * FT_CH * F4;
+  const size_t fstride = (size_t)T4 * C;
+  float v[FT_MAX_PER];
+  if (!BWD) {
+#pragma unroll
+    for (int k = 0; k < FT_MAX_PER; ++k) {
+      const int i = threadIdx.x + k * 256;
+      if (i < n) v[k] = src[nhwc0 + (size_t)(i >> 5) * fstride + (i & 31)];
+    }
+#pragma unroll
+    for (int k = 0; k < FT_MAX_PER; ++k) {
+      const int i = threadIdx.x + k * 256;
+      if (i < n) tile[(i >> 5) * (FT_CH + 1) + (i & 31)] = v[k];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < FT_MAX_PER; ++k) {
+      const int i = threadIdx.x + k * 256;
+      if (i < n) { const int c = i / F4, f = i - c * F4; dst[feat0 + i] = tile[f * (FT_CH + 1) + c]; }
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < FT_MAX_PER; ++k) {
+      const int i = threadIdx.x + k * 256;
+      if (i < n) v[k] = src[feat0 + i];
+    }
+#pragma unroll
+    for (int k = 0; k < FT_MAX_PER; ++k) {
+      const int i = threadIdx.x + k * 256;
+      if (i < n) { const int c = i / F4, f = i - c * F4; tile[f * (FT_CH + 1) + c] = v[k]; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < FT_MAX_PER; ++k) {
+      const int i = threadIdx.x + k * 256;
+      if (i < n) dst[nhwc0 + (size_t)(i >> 5) * fstride + (i & 31)] = tile[(i >> 5) * (FT_CH + 1) + (i & 31)];
+    }
+  }
+}
+// generic fallback (C % 32 != 0 or F4 > 64): one element per thread
+__global__ void __launch_bounds__(256) feat_transpose_generic_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                                     int B, int F4, int T4, int C, int bwd) {
   const size_t total = (size_t)B * T4 * C * F4;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int f = (int)(i % F4), c = (int)((i / F4) % C);
     const size_t bt = i / ((size_t)F4 * C);
     const int t = (int)(bt % T4);
     const size_t b = bt / T4;
-    feat[i] = p4[((b * F4 + f) * T4 + t) * C + c];
+    const size_t j = ((b * F4 + f) * T4 + t) * C + c;
+    if (bwd) dst[j] = src[i]; else dst[i] = src[j];
   }
 }
-__global__ void __launch_bounds__(256) feat_transpose_bwd_kernel(const float* __restrict__ dfeat,
-                                                                 float* __restrict__ dp4, int B, int F4, int T4, int C) {
-  pdl_wait();
-  pdl_trigger();
+static int feat_transpose_launch(bool bwd, const float* src, float* dst, int B, int F4, int T4, int C, cudaStream_t s) {
   const size_t total = (size_t)B * T4 * C * F4;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C), t = (int)((i / C) % T4);
-    const size_t bf = i / ((size_t)C * T4);
-    const int f = (int)(bf % F4);
-    const size_t b = bf / F4;
-    dp4[i] = dfeat[((b * T4 + t) * C + c) * F4 + f];
+  if (total == 0) return MTL_OK;
+  if (C % FT_CH == 0 && F4 <= 64) {
+    const dim3 grid((unsigned)((size_t)B * T4 * (C / FT_CH)));
+    if (bwd) MTL_CHECK_CUDA(mtl_launch_pdl(feat_transpose_kernel<true>, grid, dim3(256), 0, s, src, dst, B, F4, T4, C));
+    else MTL_CHECK_CUDA(mtl_launch_pdl(feat_transpose_kernel<false>, grid, dim3(256), 0, s, src, dst, B, F4, T4, C));
+    ++g_mtl_launches;
+    return MTL_OK;
   }
+  size_t g = (total + 255) / 256; if (g > 148 * 16) g = 148 * 16;
+  feat_transpose_generic_kernel<<<(unsigned)g, 256, 0, s>>>(src, dst, B, F4, T4, C, bwd ? 1 : 0);
+  MTL_CHECK_LAUNCH();
+  return MTL_OK;
 }
 int k_feat_transpose(const float* p4, float* feat, int B, int F4, int T4, int C, cudaStream_t s) {
-  size_t total = (size_t)B * T4 * C * F4;
-  if (!total) return MTL_OK;
-  size_t g = (total + 255) / 256; if (g > 148 * 16) g = 148 * 16;
-  MTL_CHECK_CUDA(mtl_launch_pdl(feat_transpose_kernel, dim3((unsigned)g), dim3(256), 0, s, p4, feat, B, F4, T4, C));
-  ++g_mtl_launches;
-  return MTL_OK;
+  return feat_transpose_launch(false, p4, feat, B, F4, T4, C, s);
 }
 int k_feat_transpose_bwd(const float* dfeat, float* dp4, int B, int F4, int T4, int C, cudaStream_t s) {
-  size_t total = (size_t)B * T4 * C * F4;
-  if (!total) return MTL_OK;
-  size_t g = (total + 255) / 256; if (g > 148 * 16) g = 148 * 16;
-  MTL_CHECK_CUDA(mtl_launch_pdl(feat_transpose_bwd_kernel, dim3((unsigned)g), dim3(256), 0, s, dfeat, dp4, B, F4, T4, C));
-  ++g_mtl_launches;
-  return MTL_OK;
+  return feat_transpose_launch(true, dfeat, dp4, B, F4, T4, C, s);
 }

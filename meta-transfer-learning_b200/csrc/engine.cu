@@ -208,6 +208,7 @@ struct mtl_session {
   Layout L;
   int mode = MTL_GEMM_SIMT_FP32;
   int merge_lowrank = 0;              // mtl_session_set_flag("merge_lowrank"): merged projection weights on the chain
+  int fuse_lowrank = 0;               // mtl_session_set_flag("fuse_lowrank"): linear_b(linear_a(x)) pairs as one kernel (k_lowrank_pair)
   int op_mode[MTL_OP_CLASSES];        // per-operation-class engine (see mtl_session_set_op_mode); -1 = follow `mode`
   Pass pass;                          // record of the plain mtl_asr_forward / mtl_meta_task API
   Branches br;                        // its side streams
@@ -508,6 +509,81 @@ static int lowrank_bwd_tail(Run& R, const LowRankAct& A, const LrBwd& h, float* 
   return lin_dgrad(R, h.da, r, R.theta + A.offA, dx, A.K, A.M, r, A.K, beta_dx, EPI_NONE, nullptr);
 }
 
+// ----------------------------------------------------------------------------- fused low-rank projection pairs
+// linear_b(linear_a(x)) (modules/common_layers.py:287-289,303) and its input gradient as ONE kernel per group of up to
+// three projections of equal shape (k_lowrank_pair: the rank-r tile stays on chip, K slabs merge by TMA reduce-add into
+// zero-pool outputs).  Per attention block the activation chain is [q|k|v, attention, out, LN] forward and [LN, out,
+// attention, q|k|v] backward -- 4 + 4 kernels instead of 6 + 8, and 4 GEMM-class launches instead of 16.
+// MEASURED NEGATIVE RESULT (cfg 2, three lanes, ms / meta-step): 2696 -> 2024 launches per step, but 6.53 -> 7.10 (CTA
+// budget 24) / 7.54 (74) / 8.39 (148): a pair CTA needs 194 KB of shared memory (the rank-r tile as hi | lo operand is
+// 128 KB by itself), so it owns a whole SM, and every one of the N / 64 column chunks repeats phase 1 -- eight times the
+// operand traffic of the stand-alone linear_a GEMM, in a pipeline that is shared-memory-bandwidth bound in 3xTF32.  The
+// two-launch path spreads phase 1 over K slabs and phase 2 over column tiles at two CTAs per SM and stays the default;
+// mtl_session_set_flag("fuse_lowrank", 1) / MTL_FUSE_LOWRANK=1 selects the fused path (kept under test:
+// tests/test_gpu_ops.py::test_lowrank_pair, tests/test_gpu_parity.py::test_fused_lowrank_path_matches_oracle).
+static bool fuse_default() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MTL_FUSE_LOWRANK"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v != 0;
+}
+static bool fuse_lowrank(const Run& R) {
+  const mtl_model_cfg& c = R.S->cfg;
+  return R.S->fuse_lowrank && !R.S->merge_lowrank && R.S->mode != MTL_GEMM_SIMT_FP32 && !R.no_zslab && zslab_enabled() &&
+         c.rank <= 128 && c.d_k == c.d_v;
+}
+// CTA budget that sizes the K slabs of a fused pair (every CTA owns a whole SM: 194 KB of shared memory)
+static int lrp_ctas() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MTL_LRP_CTAS"); v = e ? atoi(e) : 0; }
+  return v > 0 ? v : (g_mtl_concurrency >= 2 ? 74 : 148);
+}
+struct LrProj { LowRankAct* act; size_t offA, offBw, offBb; };
+static int lowrank_fwd_fused(Run& R, const LrProj* pr, int G, const float* x, int M, int Kd, int N) {
+  const int r = R.S->cfg.rank;
+  LrPairArgs a;
+  memset(&a, 0, sizeof(a));
+  a.G = G; a.M = M; a.K1 = Kd; a.r = r; a.N2 = N; a.bwd = 0; a.ctas = lrp_ctas();
+  for (int g = 0; g < G; ++g) {
+    LowRankAct& A = *pr[g].act;
+    A.x = x; A.M = M; A.K = Kd; A.N = N; A.ldy = N; A.W = nullptr; A.offA = pr[g].offA; A.offBw = pr[g].offBw; A.offBb = pr[g].offBb;
+    A.a = R.wz.f((size_t)M * r);
+    A.y = R.wz.f((size_t)M * N);
+    a.x[g] = x; a.ldx[g] = Kd; a.a[g] = A.a; a.y[g] = A.y; a.ldy[g] = N;
+    if (!R.dry) { a.w1[g] = R.theta + A.offA; a.w2[g] = R.theta + A.offBw; a.bias[g] = R.theta + A.offBb; }
+  }
+  K(k_lowrank_pair(a, op_mode(R.S, MTL_OP_LIN_FWD), R.st));
+  return MTL_OK;
+}
+// dx[g] += (dy[g] . Bw_g) . A_g on the current stream; da_g = dy[g] . Bw_g is left in the zero pool for the weight gradients,
+// which follow on parameter-gradient streams: dBw += dy^T a, db += colsum dy, dA += da^T x.
+static int lowrank_bwd_fused(Run& R, const LowRankAct* const* acts, int G, const float* const* dy, float* const* dx) {
+  const int r = R.S->cfg.rank;
+  const LowRankAct& A0 = *acts[0];
+  LrPairArgs a;
+  memset(&a, 0, sizeof(a));
+  a.G = G; a.M = A0.M; a.K1 = A0.N; a.r = r; a.N2 = A0.K; a.bwd = 1; a.ctas = lrp_ctas();
+  float* da[3] = {nullptr, nullptr, nullptr};
+  for (int g = 0; g < G; ++g) {
+    const LowRankAct& A = *acts[g];
+    da[g] = R.wz.f((size_t)A.M * r);
+    a.x[g] = dy[g]; a.ldx[g] = A.N; a.a[g] = da[g]; a.y[g] = dx[g]; a.ldy[g] = A.K;
+    if (!R.dry) { a.w1[g] = R.theta + A.offBw; a.w2[g] = R.theta + A.offA; }
+  }
+  K(k_lowrank_pair(a, op_mode(R.S, MTL_OP_LIN_DGRAD), R.st));
+  cudaEvent_t e;
+  MTL_TRY(ev_mark(R, R.st, &e));
+  for (int g = 0; g < G; ++g) {
+    const LowRankAct& A = *acts[g];
+    const cudaStream_t sw = R.wside();
+    MTL_TRY(ev_wait(R, sw, e));
+    On on(R, sw);
+    MTL_TRY(lin_wgrad(R, dy[g], A.N, A.a, r, R.grad + A.offBw, A.M, A.N, r));
+    K(k_colsum_acc(dy[g], A.M, A.N, A.N, R.grad + A.offBb, R.st));
+    MTL_TRY(lin_wgrad(R, da[g], r, A.x, A.K, R.grad + A.offA, A.M, r, A.K));
+  }
+  return MTL_OK;
+}
+
 // ----------------------------------------------------------------------------- merged low-rank projections
 // y = B(A x) + b with A: d -> r (no bias) and B: r -> N (modules/common_layers.py:250-257, 287-289, 303) is ONE linear map
 // W = B.A.  On the activation chain of a pass the pair of skinny GEMMs (K or N = 100: 9.7 + 11.1 us as dependent graph
@@ -587,6 +663,12 @@ static int attn_kv_fwd(Run& R, AttnAct& A, const AttnP& p, const float* xkv, int
     { On on(R, sv); MTL_TRY(merged_fwd(R, A.v, xkv, Mk, d, hv, A.Wqkv + (size_t)2 * hk * d, vbuf, ldkv, p.va, p.vb_w, p.vb_b)); }
     return MTL_OK;
   }
+  if (fuse_lowrank(R)) {               // k | v as one launch on sk
+    const LrProj pr[2] = {{&A.k, p.ka, p.kb_w, p.kb_b}, {&A.v, p.va, p.vb_w, p.vb_b}};
+    MTL_TRY(ev_wait(R, sk, e));
+    On on(R, sk);
+    return lowrank_fwd_fused(R, pr, 2, xkv, Mk, c.d_model, c.n_heads * c.d_k);
+  }
   MTL_TRY(ev_wait(R, sk, e));
   { On on(R, sk); MTL_TRY(lowrank_fwd(R, A.k, xkv, Mk, c.d_model, c.n_heads * c.d_k, c.rank, p.ka, p.kb_w, p.kb_b)); }
   MTL_TRY(ev_wait(R, sv, e));
@@ -610,12 +692,22 @@ static int attn_block_fwd(Run& R, AttnAct& A, const AttnP& p, const float* xq, c
   } else if (A.Wqkv) {
     float* qb = R.ws.f((size_t)Mq * H * dk);
     MTL_TRY(merged_fwd(R, A.q, xq, Mq, d, H * dk, A.Wqkv, qb, H * dk, p.qa, p.qb_w, p.qb_b));
+  } else if (fuse_lowrank(R) && !kv_pre && xq == xkv) {
+    // self-attention: q | k | v in one launch on the chain (no fork / join)
+    const LrProj pr[3] = {{&A.q, p.qa, p.qb_w, p.qb_b}, {&A.k, p.ka, p.kb_w, p.kb_b}, {&A.v, p.va, p.vb_w, p.vb_b}};
+    MTL_TRY(lowrank_fwd_fused(R, pr, 3, xq, Mq, d, H * dk));
+  } else if (fuse_lowrank(R)) {
+    if (!kv_pre) MTL_TRY(attn_kv_fwd(R, A, p, xkv, Mk, sk, sv));
+    const LrProj pr[1] = {{&A.q, p.qa, p.qb_w, p.qb_b}};
+    MTL_TRY(lowrank_fwd_fused(R, pr, 1, xq, Mq, d, H * dk));
   } else {
     if (!kv_pre) MTL_TRY(attn_kv_fwd(R, A, p, xkv, Mk, sk, sv));
     MTL_TRY(lowrank_fwd(R, A.q, xq, Mq, d, H * dk, r, p.qa, p.qb_w, p.qb_b));
   }
-  MTL_TRY(chain(R, sk, R.main));
-  MTL_TRY(chain(R, sv, R.main));
+  if (!(fuse_lowrank(R) && !kv_pre && xq == xkv)) {
+    MTL_TRY(chain(R, sk, R.main));
+    if (!fuse_lowrank(R)) MTL_TRY(chain(R, sv, R.main));
+  }
   A.oh = R.ws.f((size_t)Mq * H * dv);
   A.lse = R.ws.f((size_t)B * H * Tq);
   A.drop_attn = R.next_drop();
@@ -629,6 +721,9 @@ static int attn_block_fwd(Run& R, AttnAct& A, const AttnP& p, const float* xq, c
   if (A.Wo) {
     float* ob = R.ws.f((size_t)Mq * d);
     MTL_TRY(merged_fwd(R, A.o, A.oh, Mq, H * dv, d, A.Wo, ob, d, p.oa, p.ob_w, p.ob_b));
+  } else if (fuse_lowrank(R)) {
+    const LrProj pr[1] = {{&A.o, p.oa, p.ob_w, p.ob_b}};
+    MTL_TRY(lowrank_fwd_fused(R, pr, 1, A.oh, Mq, H * dv, d));
   } else {
     MTL_TRY(lowrank_fwd(R, A.o, A.oh, Mq, H * dv, d, r, p.oa, p.ob_w, p.ob_b));
   }
@@ -703,9 +798,18 @@ static int attn_block_bwd(Run& R, const AttnAct& A, const float* dout, float* dx
   float* dvv = R.ws.f((size_t)Mk * H * dv);
   K(k_ln_bwd(dout, A.xhat, A.rstd, R.theta + A.p.ln_w, A.rowmask, A.drop_out, do2, dxq, 0, R.grad + A.p.ln_w,
              R.grad + A.p.ln_b, Mq, d, R.st));
+  const bool fuse = fuse_lowrank(R);
   LrBwd ho, hq, hk, hv;
-  MTL_TRY(lowrank_bwd_head(R, A.o, do2, nullptr, R.main, R.wside(), &ho));
-  MTL_TRY(lowrank_bwd_tail(R, A.o, ho, d_oh, 0.f, R.main));
+  if (fuse) {
+    d_oh = R.wz.f((size_t)Mq * H * dv);                          // the pair accumulates K slabs: zero-pool output
+    const LowRankAct* acts[1] = {&A.o};
+    const float* dys[1] = {do2};
+    float* dxs[1] = {d_oh};
+    MTL_TRY(lowrank_bwd_fused(R, acts, 1, dys, dxs));
+  } else {
+    MTL_TRY(lowrank_bwd_head(R, A.o, do2, nullptr, R.main, R.wside(), &ho));
+    MTL_TRY(lowrank_bwd_tail(R, A.o, ho, d_oh, 0.f, R.main));
+  }
   AttnBwdArgs b;
   memset(&b, 0, sizeof(b));
   b.f.q = A.q.y; b.f.k = A.k.y; b.f.v = A.v.y; b.f.o = A.oh; b.f.lse = A.lse; b.f.keypad = A.keypad;
@@ -716,6 +820,31 @@ static int attn_block_bwd(Run& R, const AttnAct& A, const float* dout, float* dx
   K(k_attn_bwd(b, R.st));
   cudaEvent_t e_qkv;
   MTL_TRY(ev_mark(R, R.main, &e_qkv));
+  if (fuse && cross) {
+    // encoder-side gradient: dxkv += k | v pairs in one launch, ordered on S_X; query side on the chain
+    const cudaStream_t sx = R.side(S_X);
+    MTL_TRY(ev_wait(R, sx, e_qkv));
+    {
+      On on(R, sx);
+      const LowRankAct* acts[2] = {&A.k, &A.v};
+      const float* dys[2] = {dkk, dvv};
+      float* dxs[2] = {dxkv, dxkv};
+      MTL_TRY(lowrank_bwd_fused(R, acts, 2, dys, dxs));
+    }
+    const LowRankAct* acts[1] = {&A.q};
+    const float* dys[1] = {dq};
+    float* dxs[1] = {dxq};
+    MTL_TRY(lowrank_bwd_fused(R, acts, 1, dys, dxs));
+    return MTL_OK;
+  }
+  if (fuse) {
+    // self-attention: dx += q | k | v pairs in ONE launch (dxkv aliases dxq; the three problems reduce-add into it)
+    const LowRankAct* acts[3] = {&A.q, &A.k, &A.v};
+    const float* dys[3] = {dq, dkk, dvv};
+    float* dxs[3] = {dxq, dxkv, dxkv};
+    MTL_TRY(lowrank_bwd_fused(R, acts, 3, dys, dxs));
+    return MTL_OK;
+  }
   if (cross) {
     // key / value side: dgrads accumulate into the shared encoder-side gradient, one stream keeps them ordered
     const cudaStream_t sx = R.side(S_X);
@@ -1112,6 +1241,7 @@ extern "C" int mtl_session_create(const mtl_model_cfg* cfg, mtl_session** out) {
   s->op_mode[MTL_OP_CONV_DGRAD] = MTL_GEMM_TC_TF32;
   s->op_mode[MTL_OP_CONV_WGRAD] = MTL_GEMM_TC_TF32;
   s->merge_lowrank = merge_default() ? 1 : 0;
+  s->fuse_lowrank = fuse_default() ? 1 : 0;
   if (const char* e = getenv("MTL_OP_MODES")) {                 // A/B: comma-separated engine per class, e.g. "1,1,2,1,1,2,2,2"
     for (int i = 0; i < MTL_OP_CLASSES && *e; ++i) {
       const int v = atoi(e);
@@ -1149,6 +1279,7 @@ extern "C" int mtl_session_set_op_mode(mtl_session* s, int op_class, int mode) {
 extern "C" int mtl_session_set_flag(mtl_session* s, const char* name, int value) {
   MTL_REQUIRE(s && name, "null argument");
   if (!strcmp(name, "merge_lowrank")) { s->merge_lowrank = value != 0; return MTL_OK; }
+  if (!strcmp(name, "fuse_lowrank")) { s->fuse_lowrank = value != 0; return MTL_OK; }
   mtl_set_error("unknown session flag '%s'", name);
   return MTL_ERR_ARG;
 }
@@ -1575,6 +1706,7 @@ extern "C" int mtl_meta_tasks(mtl_session* s, const mtl_meta_step_args* a, void*
   key.push_back((unsigned long long)s->mode);
   for (int i = 0; i < MTL_OP_CLASSES; ++i) key.push_back((unsigned long long)(unsigned)s->op_mode[i]);
   key.push_back((unsigned long long)s->merge_lowrank);
+  key.push_back((unsigned long long)s->fuse_lowrank);
 
   GraphEntry* e = nullptr;
   for (auto& g : s->graphs) if (g.key == key) { e = &g; break; }
@@ -1715,6 +1847,20 @@ extern "C" int mtl_gemm_repeat(int reps, int mode, int transA, int transB, int M
   g.transA = transA; g.transB = transB; g.alpha = 1.f; g.beta = beta; g.split_k = split_k;
   for (int i = 0; i < reps; ++i) MTL_TRY(k_gemm(g, mode, (cudaStream_t)stream));
   return MTL_OK;
+}
+extern "C" int mtl_lowrank_pair(int mode, int bwd, int G, int M, int K1, int r, int N2, const float* const* x, int ldx,
+                                const float* const* w1, const float* const* w2, const float* const* bias, float* const* a,
+                                float* const* y, int ldy, int ctas, void* stream) {
+  MTL_REQUIRE(x && w1 && w2 && a && y && G >= 1 && G <= 3, "null argument / 1 <= G <= 3");
+  MTL_REQUIRE(mode == MTL_GEMM_TC_TF32 || mode == MTL_GEMM_TC_3XTF32, "the fused pair runs on the tensor-core engines only");
+  LrPairArgs p;
+  memset(&p, 0, sizeof(p));
+  p.G = G; p.M = M; p.K1 = K1; p.r = r; p.N2 = N2; p.bwd = bwd; p.ctas = ctas;
+  for (int g = 0; g < G; ++g) {
+    p.x[g] = x[g]; p.ldx[g] = ldx; p.w1[g] = w1[g]; p.w2[g] = w2[g]; p.bias[g] = (bias && !bwd) ? bias[g] : nullptr;
+    p.a[g] = a[g]; p.y[g] = y[g]; p.ldy[g] = ldy;
+  }
+  return k_lowrank_pair(p, mode, (cudaStream_t)stream);
 }
 int k_gemm_tc_debug_span(unsigned long long* host512);
 // debug: device pointers of the VGG intermediates of the last forward+backward of the plain (mtl_asr_*) pass:

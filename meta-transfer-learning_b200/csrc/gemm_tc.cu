@@ -1168,6 +1168,321 @@ __global__ void __launch_bounds__(192) conv3x3_wgrad_kw_kernel(const __grid_cons
   }
 }
 
+// ----------------------------------------------------------------------------- fused low-rank projection pair
+// y (+)= (x . W1) . W2 (+ bias) for the rank-r factorised nn.Linear pairs of the attention blocks
+// (modules/common_layers.py:250-257,287-289,303: q / k / v / output = linear_b(linear_a(x))) in ONE kernel: the rank-r
+// intermediate never makes a round trip through global memory between the two contractions.
+//   forward  (B_MN = false): x [M, K1], W1 = A [r, K1], W2 = Bw [N2, r] (nn.Linear weights: K-major B operands), bias [N2]
+//   backward (B_MN = true) : x = dy [M, K1], W1 = Bw [K1, r], W2 = A [r, N2] (the same weights read as [K, N]: MN-major)
+// Phase 1 accumulates the [128, r <= 128] tile of a = x . W1 over this CTA's K slab in TMEM; the epilogue warps drain
+// it, split it into tf32 hi / lo in registers and park it in shared memory in the K-major 128B-swizzled layout the UMMA
+// descriptors of phase 2 read -- which is also the layout of a TMA store box, so the same tile is reduce-added to the
+// global `a` (the weight-gradient contractions need it).  Phase 2 multiplies the tile by this CTA's 64 columns of W2
+// (all of its <= 4 k-blocks were fetched, and split, while phase 1 ran) into a second accumulator; the result goes out
+// through the TMA reduce-add staging path.  K slabs (blockIdx.z) are merged in L2 by linearity of BOTH phases:
+// y = sum_s (x_s . W1_s) . W2, so y and a must be zero (zero pool) or hold the running sum (dx of a backward).
+// Up to three problems that share the shapes (q | k | v of a self-attention, k | v of a cross-attention) run as one
+// launch: blockIdx.z = problem * slabs + slab.
+//   warp 0: TMA producer; warp 1: TMEM allocator + MMA issuer (both phases); warps 2..5: splitter, then both epilogues.
+constexpr int LR_BN1 = 128;                    // rank, padded (TMA zero-fills rows / columns >= r)
+constexpr int LR_BN2 = 64;                     // output columns per CTA
+constexpr int LR_K2B = 4;                      // k-blocks of phase 2 (r <= 128)
+constexpr int LR_MAXG = 3;
+struct LrMaps { CUtensorMap x, w1, w2, y, a; };
+struct LrParams {
+  LrMaps tm[LR_MAXG];
+  const float* bias[LR_MAXG];
+  int M, r, N2;
+  int kb_total, kb_per_slab, slabs;
+  int k2b;                                     // ceil(r / 32)
+  int store_a;
+};
+template <bool SPLIT3>
+struct LrCfg {
+  static constexpr int STAGES = 2;
+  static constexpr int B1_BYTES = LR_BN1 * BK * 4;                             // 16 KB
+  static constexpr int HI1 = A_STAGE_BYTES + B1_BYTES;                         // bytes TMA delivers per stage
+  static constexpr int STAGE1 = HI1 * (SPLIT3 ? 2 : 1);                        // [A | A_lo | B1 | B1_lo]
+  static constexpr int B1_OFF = SPLIT3 ? 2 * A_STAGE_BYTES : A_STAGE_BYTES;
+  static constexpr int RING = STAGES * STAGE1;                                 // 128 KB / 64 KB
+  static constexpr int ATILE = LR_K2B * A_STAGE_BYTES;                         // a as the A operand of phase 2: 4 k-blocks
+  static constexpr int B2_KB = LR_BN2 * BK * 4;                                // one k-block of W2 (hi)
+  static constexpr int B2_SLOT = B2_KB * (SPLIT3 ? 2 : 1);                     // [hi | lo]
+  static constexpr int B2_BYTES = LR_K2B * B2_SLOT;                            // 64 KB / 32 KB (later: the y staging tile)
+  static constexpr int TM1 = SPLIT3 ? 2 * LR_BN1 : LR_BN1;                     // accumulator columns of phase 1
+  static constexpr int TMEM_COLS = SPLIT3 ? 512 : 256;                         // TM1 + (2 x) LR_BN2, power of two
+  static constexpr int SMEM = RING + B2_BYTES + 1024 /*barriers + bias*/ + 1024 /*align slack*/;
+  static_assert(ATILE * (SPLIT3 ? 2 : 1) <= RING, "the a tile (hi | lo) aliases the phase-1 ring");
+  static_assert((LR_BN2 / 32) * BM * 128 <= B2_BYTES, "the y staging tile aliases the W2 k-blocks");
+};
+
+template <bool B_MN, bool SPLIT3>
+__global__ void __launch_bounds__(192) lowrank_pair_kernel(const __grid_constant__ LrParams P) {
+  using Cfg = LrCfg<SPLIT3>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t b2_u = base + Cfg::RING;
+  uint8_t* b2 = smem + Cfg::RING;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::RING + Cfg::B2_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* ready = empty + STAGES;
+  uint64_t* b2_full = ready + STAGES;
+  uint64_t* b2_ready = b2_full + 1;
+  uint64_t* tmem_full1 = b2_ready + 1;
+  uint64_t* a_ready = tmem_full1 + 1;
+  uint64_t* tmem_full2 = a_ready + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full2 + 1);
+  float* bias_s = reinterpret_cast<float*>(smem + Cfg::RING + Cfg::B2_BYTES + 256);   // LR_BN2 floats
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int prob = blockIdx.z / P.slabs, slab = blockIdx.z - prob * P.slabs;
+  const LrMaps& tm = P.tm[prob];
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * LR_BN2;
+  const int kb0 = slab * P.kb_per_slab, kb1 = min(P.kb_total, kb0 + P.kb_per_slab);
+  const int k2b = P.k2b;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&ready[s], 4); }
+    mbar_init(b2_full, 1); mbar_init(b2_ready, 4);
+    mbar_init(tmem_full1, 1); mbar_init(a_ready, 4); mbar_init(tmem_full2, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(Cfg::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem1 = *tmem_slot, tmem2 = tmem1 + (uint32_t)Cfg::TM1;
+  pdl_wait();
+  if (warp >= 2) {
+    const int t = threadIdx.x - 64, cn = n0 + t;
+    const float* bp = P.bias[prob];
+    if (t < LR_BN2) bias_s[t] = (bp && slab == 0 && cn < P.N2) ? __ldg(bp + cn) : 0.f;   // slab 0 alone adds the bias
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+  }
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      // W2 first: it does not depend on phase 1 and is needed (split) the moment the a tile is parked
+      mbar_expect_tx(b2_full, (uint32_t)(k2b * Cfg::B2_KB));
+      for (int kb = 0; kb < k2b; ++kb) {
+        const uint32_t dst = b2_u + kb * Cfg::B2_SLOT;
+        if (!B_MN) {
+          tma_load_2d(dst, &tm.w2, b2_full, kb * BK, n0);
+        } else {
+#pragma unroll
+          for (int i = 0; i < LR_BN2 / 32; ++i) tma_load_2d(dst + i * 4096, &tm.w2, b2_full, n0 + i * 32, kb * BK);
+        }
+      }
+      int it = 0;
+      for (int kb = kb0; kb < kb1; ++kb, ++it) {
+        const int s = it % STAGES;
+        mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
+        mbar_expect_tx(&full[s], Cfg::HI1);
+        const uint32_t sa = base + s * Cfg::STAGE1, sb = sa + Cfg::B1_OFF;
+        tma_load_2d(sa, &tm.x, &full[s], kb * BK, m0);
+        if (!B_MN) {
+          tma_load_2d(sb, &tm.w1, &full[s], kb * BK, 0);
+        } else {
+#pragma unroll
+          for (int i = 0; i < LR_BN1 / 32; ++i) tma_load_2d(sb + i * 4096, &tm.w1, &full[s], i * 32, kb * BK);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t IDB = (1u << 4) | (2u << 7) | (2u << 10) | ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BM >> 4) << 24);
+      constexpr uint32_t id1 = IDB | ((uint32_t)(LR_BN1 >> 3) << 17), id1x2 = IDB | ((uint32_t)((2 * LR_BN1) >> 3) << 17);
+      constexpr uint32_t id2 = IDB | ((uint32_t)(LR_BN2 >> 3) << 17), id2x2 = IDB | ((uint32_t)((2 * LR_BN2) >> 3) << 17);
+      constexpr uint64_t STEP_B = B_MN ? 64 : 2;
+      int it = 0;
+      for (int kb = kb0; kb < kb1; ++kb, ++it) {
+        const int s = it % STAGES;
+        mbar_wait(SPLIT3 ? &ready[s] : &full[s], (it / STAGES) & 1);
+        tc_fence_after();
+        const uint32_t sa = base + s * Cfg::STAGE1, sb = sa + Cfg::B1_OFF;
+        const uint64_t da0 = desc_kmajor(sa), la0 = desc_kmajor(sa + A_STAGE_BYTES);
+        const uint64_t db0 = B_MN ? desc_mnmajor(sb) : desc_kmajor(sb);
+#pragma unroll
+        for (int k = 0; k < BK / 8; ++k) {
+          const uint32_t acc0 = (it > 0 || k > 0) ? 1u : 0u;
+          if (SPLIT3) {
+            tc_mma_tf32(tmem1, da0 + 2 * k, db0 + k * STEP_B, id1x2, acc0);   // x_hi * [w_hi ; w_lo]
+            tc_mma_tf32(tmem1, la0 + 2 * k, db0 + k * STEP_B, id1, 1u);       // x_lo * w_hi
+          } else {
+            tc_mma_tf32(tmem1, da0 + 2 * k, db0 + k * STEP_B, id1, acc0);
+          }
+        }
+        tc_commit(&empty[s]);
+      }
+      tc_commit(tmem_full1);
+      // ---- phase 2: a tile (parked over the ring by the epilogue warps) x W2 k-blocks
+      mbar_wait(SPLIT3 ? b2_ready : b2_full, 0);
+      mbar_wait(a_ready, 0);
+      tc_fence_after();
+      for (int kb = 0; kb < k2b; ++kb) {
+        const uint64_t da0 = desc_kmajor(base + kb * A_STAGE_BYTES);
+        const uint64_t la0 = desc_kmajor(base + Cfg::ATILE + kb * A_STAGE_BYTES);
+        const uint32_t sb = b2_u + kb * Cfg::B2_SLOT;
+        const uint64_t db0 = B_MN ? desc_mnmajor(sb) : desc_kmajor(sb);
+#pragma unroll
+        for (int k = 0; k < BK / 8; ++k) {
+          const uint32_t acc0 = (kb > 0 || k > 0) ? 1u : 0u;
+          if (SPLIT3) {
+            tc_mma_tf32(tmem2, da0 + 2 * k, db0 + k * STEP_B, id2x2, acc0);
+            tc_mma_tf32(tmem2, la0 + 2 * k, db0 + k * STEP_B, id2, 1u);
+          } else {
+            tc_mma_tf32(tmem2, da0 + 2 * k, db0 + k * STEP_B, id2, acc0);
+          }
+        }
+      }
+      tc_commit(tmem_full2);
+      pdl_trigger();
+    }
+  } else {
+    const int tid = threadIdx.x - 64;
+    if (SPLIT3) {
+      // ===================== operand splitter (truncating: hi stays the raw tile, lo = rna_tf32(a - trunc(a))) =====================
+      int it = 0;
+      for (int kb = kb0; kb < kb1; ++kb, ++it) {
+        const int s = it % STAGES;
+        mbar_wait(&full[s], (it / STAGES) & 1);
+        float4* a_hi = reinterpret_cast<float4*>(smem + s * Cfg::STAGE1) + tid;
+        float4* b_hi = reinterpret_cast<float4*>(smem + s * Cfg::STAGE1 + Cfg::B1_OFF) + tid;
+        constexpr int PER_A = A_STAGE_BYTES / 16 / 128, PER_B = Cfg::B1_BYTES / 16 / 128;
+        float4 a[PER_A], b[PER_B];
+#pragma unroll
+        for (int j = 0; j < PER_A; ++j) a[j] = a_hi[j * 128];
+#pragma unroll
+        for (int j = 0; j < PER_B; ++j) b[j] = b_hi[j * 128];
+#pragma unroll
+        for (int j = 0; j < PER_A; ++j) {
+          float4 l;
+          l.x = tf32_lo_trunc(a[j].x); l.y = tf32_lo_trunc(a[j].y); l.z = tf32_lo_trunc(a[j].z); l.w = tf32_lo_trunc(a[j].w);
+          a_hi[j * 128 + A_STAGE_BYTES / 16] = l;
+        }
+#pragma unroll
+        for (int j = 0; j < PER_B; ++j) {
+          float4 l;
+          l.x = tf32_lo_trunc(b[j].x); l.y = tf32_lo_trunc(b[j].y); l.z = tf32_lo_trunc(b[j].z); l.w = tf32_lo_trunc(b[j].w);
+          b_hi[j * 128 + Cfg::B1_BYTES / 16] = l;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ready[s]);
+      }
+      // W2 k-blocks (landed long ago)
+      mbar_wait(b2_full, 0);
+      constexpr int PER_2 = Cfg::B2_KB / 16 / 128;
+      for (int kb = 0; kb < k2b; ++kb) {
+        float4* h = reinterpret_cast<float4*>(b2 + kb * Cfg::B2_SLOT) + tid;
+        float4 v[PER_2];
+#pragma unroll
+        for (int j = 0; j < PER_2; ++j) v[j] = h[j * 128];
+#pragma unroll
+        for (int j = 0; j < PER_2; ++j) {
+          float4 l;
+          l.x = tf32_lo_trunc(v[j].x); l.y = tf32_lo_trunc(v[j].y); l.z = tf32_lo_trunc(v[j].z); l.w = tf32_lo_trunc(v[j].w);
+          h[j * 128 + Cfg::B2_KB / 16] = l;
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(b2_ready);
+    }
+    // ===================== epilogue 1: a tile TMEM -> (hi | lo) K-major operand tiles over the dead ring =====================
+    const int q = warp & 3, row = q * 32 + lane;
+    const uint32_t row_u = (uint32_t)row * 128u, sw = (uint32_t)(row & 7);
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    mbar_wait(tmem_full1, 0);                                      // phase-1 MMAs complete => the ring is dead
+    tc_fence_after();
+    asm volatile("bar.sync 1, 128;" ::: "memory");                 // (racecheck-visible form of the same order)
+#pragma unroll 1
+    for (int c = 0; c < k2b; ++c) {
+      uint32_t v[32];
+      if (SPLIT3) {
+        uint32_t w[32];
+        tmem_ld32_issue(tmem1 + lane_addr + (uint32_t)(c * 32), v);
+        tmem_ld32_issue(tmem1 + lane_addr + (uint32_t)(LR_BN1 + c * 32), w);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
+      } else {
+        tmem_ld32(tmem1 + lane_addr + (uint32_t)(c * 32), v);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t slot = (uint32_t)c * A_STAGE_BYTES + row_u + ((((uint32_t)j) ^ sw) << 4);
+        const float x0 = __uint_as_float(v[4 * j + 0]), x1 = __uint_as_float(v[4 * j + 1]);
+        const float x2 = __uint_as_float(v[4 * j + 2]), x3 = __uint_as_float(v[4 * j + 3]);
+        // the hi tile is the raw fp32 sum (kind::tf32 reads its top 19 bits); it is also what `a` receives
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(base + slot), "f"(x0), "f"(x1), "f"(x2), "f"(x3) : "memory");
+        if (SPLIT3)
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(base + (uint32_t)Cfg::ATILE + slot), "f"(tf32_lo_trunc(x0)),
+                       "f"(tf32_lo_trunc(x1)), "f"(tf32_lo_trunc(x2)), "f"(tf32_lo_trunc(x3)) : "memory");
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // parked tiles -> visible to the MMA and TMA units
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(a_ready);
+    if (P.store_a && blockIdx.y == 0) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (threadIdx.x == 64) {
+        for (int c = 0; c < k2b; ++c) tma_store_2d(&tm.a, base + c * A_STAGE_BYTES, c * 32, m0, true);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    }
+    // ===================== epilogue 2: y tile -> staging (over the dead W2 k-blocks) -> TMA reduce-add =====================
+    const int nch = min(LR_BN2 / 32, (P.N2 - n0 + 31) / 32);
+    mbar_wait(tmem_full2, 0);
+    tc_fence_after();
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll 1
+    for (int c = 0; c < nch; ++c) {
+      uint32_t v[32];
+      if (SPLIT3) {
+        uint32_t w[32];
+        tmem_ld32_issue(tmem2 + lane_addr + (uint32_t)(c * 32), v);
+        tmem_ld32_issue(tmem2 + lane_addr + (uint32_t)(LR_BN2 + c * 32), w);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
+      } else {
+        tmem_ld32(tmem2 + lane_addr + (uint32_t)(c * 32), v);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c * 32 + j * 4);
+        const uint32_t slot = (uint32_t)c * (BM * 128) + row_u + ((((uint32_t)j) ^ sw) << 4);
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(b2_u + slot), "f"(__uint_as_float(v[4 * j + 0]) + b4.x),
+                     "f"(__uint_as_float(v[4 * j + 1]) + b4.y), "f"(__uint_as_float(v[4 * j + 2]) + b4.z),
+                     "f"(__uint_as_float(v[4 * j + 3]) + b4.w) : "memory");
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (threadIdx.x == 64) {
+      for (int c = 0; c < nch; ++c) tma_store_2d(&tm.y, b2_u + c * (BM * 128), n0 + c * 32, m0, true);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // both staged tiles (a, y) must outlive their reads
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem1), "r"(Cfg::TMEM_COLS) : "memory");
+  }
+}
+
 // ----------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -1396,10 +1711,12 @@ bool conv_wgrad_kw_enabled() {
   if (v < 0) { const char* e = getenv("MTL_CONV_WGRAD_KW"); v = (e && e[0] == '0') ? 0 : 1; }
   return v != 0;
 }
-// the Cin = 64 variants (conv.2, conv.3) of the kw-box weight gradient: MTL_CONV_WGRAD_KW64=1 until validated on the GPU
+// the Cin = 64 variants (conv.2, conv.3) of the kw-box weight gradient.  In 3xTF32 they were no faster than the tap-box
+// kernel (three MMAs per product without the N-concatenated operand); under the default single-pass TF32 policy for the
+// VGG weight gradients they are: 6.54 -> 6.41 ms / meta-step (3 lanes).  MTL_CONV_WGRAD_KW64=0 restores the tap-box kernel.
 bool conv_wgrad_kw64_enabled() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("MTL_CONV_WGRAD_KW64"); v = (e && e[0] == '1') ? 1 : 0; }
+  if (v < 0) { const char* e = getenv("MTL_CONV_WGRAD_KW64"); v = (e && e[0] == '0') ? 0 : 1; }
   return v != 0;
 }
 template <int CIN, int BN, bool SPLIT3>
@@ -1549,6 +1866,70 @@ int k_gemm_tc(const GemmArgs& g, int precision_mode, cudaStream_t s) {
   MTL_TRY(plan_epilogue(P, tm, [&](const float* ptr, CUtensorMap* out) { return make_map(ptr, N, M, ldc, BM, false, false, out); }));
   MTL_REQUIRE(!(g.split_k > 1 && g.bias) || P.tma_epi, "split-K with bias needs the TMA epilogue (16 B aligned C, N % 4 == 0)");
   return dispatch(bn, split3, a_mn, b_mn, tm, P, grid, s);
+}
+
+// ----------------------------------------------------------------------------- fused low-rank pair: host side
+namespace {
+template <bool B_MN, bool SPLIT3>
+int launch_lowrank(const LrParams& P, dim3 grid, cudaStream_t s) {
+  using Cfg = LrCfg<SPLIT3>;
+  static_assert(Cfg::SMEM <= 227 * 1024, "shared memory budget");
+  static bool configured = false;
+  auto kern = lowrank_pair_kernel<B_MN, SPLIT3>;
+  if (!configured) {
+    MTL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    configured = true;
+  }
+  MTL_CHECK_CUDA(mtl_launch_pdl(kern, grid, dim3(192, 1, 1), (size_t)Cfg::SMEM, s, P));
+  ++g_mtl_launches;
+  return MTL_OK;
+}
+}  // namespace
+
+bool k_lowrank_pair_eligible(const LrPairArgs& a) {
+  if (a.G < 1 || a.G > LR_MAXG || a.M < 1 || a.K1 < 1 || a.N2 < 1) return false;
+  if (a.r < 4 || a.r > LR_BN1 || a.r % 4 != 0 || a.K1 % 4 != 0 || a.N2 % 4 != 0) return false;
+  for (int g = 0; g < a.G; ++g) {
+    if (!al16(a.x[g]) || !al16(a.w1[g]) || !al16(a.w2[g]) || !al16(a.y[g]) || !al16(a.a[g])) return false;
+    if (a.ldx[g] % 4 != 0 || a.ldy[g] % 4 != 0) return false;
+  }
+  return true;
+}
+
+int k_lowrank_pair(const LrPairArgs& a, int precision_mode, cudaStream_t s) {
+  MTL_REQUIRE(k_lowrank_pair_eligible(a), "low-rank pair: rank <= 128, dims % 4 == 0, 16 B aligned operands");
+  const bool split3 = precision_mode == 2;
+  const bool tf = !split3;
+  LrParams P;
+  memset(&P, 0, sizeof(P));
+  P.M = a.M; P.r = a.r; P.N2 = a.N2;
+  P.kb_total = mtl_cdiv(a.K1, BK);
+  P.k2b = mtl_cdiv(a.r, BK);
+  P.store_a = 1;
+  const int tiles = mtl_cdiv(a.M, BM) * mtl_cdiv(a.N2, LR_BN2) * a.G;
+  int slabs = a.ctas > 0 ? a.ctas / tiles : 1;
+  if (slabs > P.kb_total) slabs = P.kb_total;
+  if (slabs < 1) slabs = 1;
+  P.kb_per_slab = mtl_cdiv(P.kb_total, slabs);
+  P.slabs = mtl_cdiv(P.kb_total, P.kb_per_slab);               // every slab owns at least one k-block
+  for (int g = 0; g < a.G; ++g) {
+    LrMaps& m = P.tm[g];
+    MTL_TRY(make_map(a.x[g], a.K1, a.M, a.ldx[g], BM, false, tf, &m.x));
+    if (!a.bwd) {
+      MTL_TRY(make_map(a.w1[g], a.K1, a.r, a.K1, LR_BN1, false, tf, &m.w1));      // A  [r, K1]: K-major B operand
+      MTL_TRY(make_map(a.w2[g], a.r, a.N2, a.r, LR_BN2, false, tf, &m.w2));       // Bw [N2, r]
+    } else {
+      MTL_TRY(make_map(a.w1[g], a.r, a.K1, a.r, 32, true, tf, &m.w1));            // Bw [K1, r]: MN-major B operand
+      MTL_TRY(make_map(a.w2[g], a.N2, a.r, a.N2, 32, true, tf, &m.w2));           // A  [r, N2]
+    }
+    MTL_TRY(make_map(a.y[g], a.N2, a.M, a.ldy[g], BM, false, false, &m.y));
+    MTL_TRY(make_map(a.a[g], a.r, a.M, a.r, BM, false, false, &m.a));
+    P.bias[g] = a.bias[g];
+  }
+  dim3 grid(mtl_cdiv(a.M, BM), mtl_cdiv(a.N2, LR_BN2), a.G * P.slabs);
+  MTL_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "low-rank pair grid too large");
+  if (split3) return a.bwd ? launch_lowrank<true, true>(P, grid, s) : launch_lowrank<false, true>(P, grid, s);
+  return a.bwd ? launch_lowrank<true, false>(P, grid, s) : launch_lowrank<false, false>(P, grid, s);
 }
 
 // MTL_CONV_KW=0 keeps the first-generation tap-box kernel for the forward / dgrad convolutions (A/B measurements)

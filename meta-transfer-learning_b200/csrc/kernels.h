@@ -44,6 +44,21 @@ int k_gemm_tc(const GemmArgs& g, int precision_mode, cudaStream_t s);   // tcgen
 bool k_gemm_tc_eligible(const GemmArgs& g);
 // Dispatcher: mode 0 = SIMT fp32 (exact), 1 = tcgen05 TF32, 2 = tcgen05 3xTF32.
 int k_gemm(const GemmArgs& g, int mode, cudaStream_t s);
+// Fused rank-r projection pair (tcgen05; modules/common_layers.py:250-257,287-289,303): for each of the G <= 3 problems
+//   a (+)= x . W1 ;  y (+)= (x . W1) . W2 (+ bias)          -- K slabs are merged by TMA reduce-add, so a and y must be
+// zero (or, for y, hold the sum being accumulated) when the kernel starts.
+//   bwd == 0: x [M, K1] (ldx), W1 = linear_a.weight [r, K1], W2 = linear_b.weight [N2, r], bias [N2] or null
+//   bwd == 1: x = dy [M, K1] (ldx), W1 = linear_b.weight [K1, r], W2 = linear_a.weight [r, N2]
+// a is [M, r] (row stride r), y is [M, N2] (ldy).  ctas: CTA budget that sizes the K slabs (0 = no K split).
+struct LrPairArgs {
+  int G;
+  const float* x[3]; int ldx[3];
+  const float* w1[3]; const float* w2[3]; const float* bias[3];
+  float* a[3]; float* y[3]; int ldy[3];
+  int M, K1, r, N2, bwd, ctas;
+};
+bool k_lowrank_pair_eligible(const LrPairArgs& a);
+int k_lowrank_pair(const LrPairArgs& a, int precision_mode, cudaStream_t s);
 // Implicit-GEMM 3x3 convolutions on NHWC activations (tcgen05; precision_mode 1 = TF32, 2 = 3xTF32):
 //   y[pixel,co] = epi(sum x[pixel+tap,ci] * wg[co, tap*Cin+ci] + bias[co])          (forward, and dgrad on dY with flipped taps)
 //   dwgT[tap*Cin+ci, co] += sum_pixel x[pixel+tap,ci] * dy[pixel,co]                  (weight gradient, atomics)

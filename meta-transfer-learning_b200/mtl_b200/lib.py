@@ -86,6 +86,7 @@ SIGNATURES = {
     "mtl_arena_clip": (_I, [_P, _LL, _F, _P, _P]),
     "mtl_arena_adam": (_I, [_P, _P, _P, _P, _P, _D, _D, _D, _D, _LL, _P]),
     "mtl_gemm": (_I, [_I, _I, _I, _I, _I, _I, _F, _P, _I, _P, _I, _F, _P, _I, _P, _I, _P, _I, _P]),
+    "mtl_lowrank_pair": (_I, [_I, _I, _I, _I, _I, _I, _I, _P, _I, _P, _P, _P, _P, _P, _I, _I, _P]),
     "mtl_gemm_repeat": (_I, [_I, _I, _I, _I, _I, _I, _I, _P, _I, _P, _I, _F, _P, _I, _I, _P]),
     "mtl_debug_gemm_stamps": (_I, [_P]),
     "mtl_debug_attn_stamps": (_I, [_P]),

@@ -67,6 +67,58 @@ def test_gemm_epilogues(mode):
     assert rel_err(Cd, dy.double().t() @ x.double() + 1.0) < tol
 
 
+# ----------------------------------------------------------------------------------------- fused low-rank pair
+def _ptrs(ts):
+    import ctypes as C
+    arr = (C.c_void_p * len(ts))(*[None if t is None else t.data_ptr() for t in ts])
+    return arr
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("bwd", [0, 1])
+@pytest.mark.parametrize("G,M,K1,r,N2,ctas", [(1, 264, 512, 100, 512, 0), (3, 264, 512, 100, 512, 148),
+                                              (2, 200, 512, 100, 512, 64), (1, 66, 768, 100, 768, 96),
+                                              (1, 7, 64, 20, 36, 0), (3, 130, 100, 128, 68, 1000), (1, 129, 36, 4, 512, 7)])
+def test_lowrank_pair(mode, bwd, G, M, K1, r, N2, ctas):
+    """y = linear_b(linear_a(x)) (common_layers.py:287-289,303) and its input gradient as ONE kernel, vs fp64."""
+    xs = [_r(M, K1, seed=10 + g) for g in range(G)]
+    # forward: w1 = A [r, K1], w2 = Bw [N2, r]; backward: w1 = Bw [K1, r], w2 = A [r, N2]
+    w1 = [(_r(K1, r, seed=20 + g) if bwd else _r(r, K1, seed=20 + g)) * 0.1 for g in range(G)]
+    w2 = [(_r(r, N2, seed=30 + g) if bwd else _r(N2, r, seed=30 + g)) * 0.1 for g in range(G)]
+    bias = [None if bwd else _r(N2, seed=40 + g) for g in range(G)]
+    y0 = [_r(M, N2, seed=50 + g) if bwd else torch.zeros(M, N2) for g in range(G)]       # backward accumulates into dx
+    xd, w1d, w2d = [[t.to(dev()) for t in ts] for ts in (xs, w1, w2)]
+    bd = [None if b is None else b.to(dev()) for b in bias]
+    ad = [torch.zeros(M, r, device=dev()) for _ in range(G)]
+    yd = [t.to(dev()) for t in y0]
+    ok(lib().mtl_lowrank_pair(mode, bwd, G, M, K1, r, N2, _ptrs(xd), K1, _ptrs(w1d), _ptrs(w2d), _ptrs(bd), _ptrs(ad),
+                              _ptrs(yd), N2, ctas, stream()))
+    tol = 2e-3 if mode == 1 else 5e-5
+    for g in range(G):
+        a_ref = xs[g].double() @ (w1[g].double() if bwd else w1[g].double().t())
+        y_ref = a_ref @ (w2[g].double() if bwd else w2[g].double().t()) + y0[g].double()
+        if not bwd:
+            y_ref = y_ref + bias[g].double()
+        assert rel_err(ad[g], a_ref) < tol, ("a", g)
+        assert rel_err(yd[g], y_ref) < tol, ("y", g)
+
+
+def test_lowrank_pair_shared_output_accumulates():
+    """q | k | v input gradients of a self-attention land in ONE dx (the three problems reduce-add into it)."""
+    M, K1, r, N2 = 264, 512, 100, 512
+    xs = [_r(M, K1, seed=60 + g) for g in range(3)]
+    w1 = [_r(K1, r, seed=70 + g) * 0.1 for g in range(3)]
+    w2 = [_r(r, N2, seed=80 + g) * 0.1 for g in range(3)]
+    dx0 = _r(M, N2, seed=90)
+    xd, w1d, w2d = [[t.to(dev()) for t in ts] for ts in (xs, w1, w2)]
+    ad = [torch.zeros(M, r, device=dev()) for _ in range(3)]
+    dx = dx0.to(dev())
+    ok(lib().mtl_lowrank_pair(2, 1, 3, M, K1, r, N2, _ptrs(xd), K1, _ptrs(w1d), _ptrs(w2d), None, _ptrs(ad),
+                              _ptrs([dx, dx, dx]), N2, 148, stream()))
+    ref = dx0.double() + sum(xs[g].double() @ w1[g].double() @ w2[g].double() for g in range(3))
+    assert rel_err(dx, ref) < 5e-5
+
+
 # ----------------------------------------------------------------------------------------- LayerNorm block
 @pytest.mark.parametrize("M,d", [(200, 512), (33, 64), (5, 768)])
 def test_ln_fwd_bwd(M, d):
@@ -239,8 +291,23 @@ def _nhwc(x):
 CONV_TOL = {0: 2e-5, 1: 2e-3, 2: 5e-5}
 
 
-def test_conv1_fwd():
-    B, Fq, T = 2, 21, 19
+@pytest.mark.parametrize("B,F4,T4,C", [(8, 40, 25, 128), (2, 5, 3, 128), (1, 40, 312, 128), (3, 7, 9, 64)])
+def test_feat_transpose_roundtrip(B, F4, T4, C):
+    """(B, C, F', T') -> view(B, C*F', T').transpose(1, 2) (models/asr/transformer.py:136-138) on the NHWC activation,
+    and its gradient: exact copies, compared bit for bit."""
+    p4 = _r(B, F4, T4, C, seed=4)                                     # NHWC: [B, F', T', C]
+    ref = p4.permute(0, 3, 1, 2).reshape(B, C * F4, T4).transpose(1, 2).contiguous()   # [B, T', C*F' ] index c*F'+f
+    p4d = p4.to(dev())
+    feat = torch.empty(B, T4, C * F4, device=dev())
+    ok(lib().mtl_feat_transpose(P(p4d), P(feat), B, F4, T4, C, 0, stream()))
+    assert torch.equal(feat.cpu(), ref)
+    back = torch.empty(B, F4, T4, C, device=dev())
+    ok(lib().mtl_feat_transpose(P(feat), P(back), B, F4, T4, C, 1, stream()))
+    assert torch.equal(back.cpu(), p4)
+
+
+@pytest.mark.parametrize("B,Fq,T", [(2, 21, 19), (2, 161, 101), (1, 4, 7)])
+def test_conv1_fwd(B, Fq, T):
     x = _r(B, 1, Fq, T, seed=1)
     w1, b1 = _r(64, 1, 3, 3, seed=2) * 0.3, _r(64, seed=3) * 0.1
     out = torch.empty(B, Fq, T, 64, device=dev())

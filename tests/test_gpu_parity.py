@@ -598,6 +598,46 @@ def test_merged_lowrank_path_matches_oracle():
     assert bad[worst] < _tol(worst), (worst, bad[worst])
 
 
+def test_fused_lowrank_path_matches_oracle():
+    """mtl_session_set_flag("fuse_lowrank", 1): every projection pair linear_b(linear_a(x)) (modules/common_layers.py:
+    287-289,303) and its input gradient run as ONE kernel (q | k | v grouped into one launch; the rank-r tile never leaves
+    the SM).  Same outputs and gradients as the two-launch default (kept as a measured A/B variant)."""
+    cfg = ref_asr.SMALL
+    batch = ref_meta.synth_batch(cfg, 4, 41, 7, 10, lengths=[41, 30, 9, 5], tgt_lengths=[7, 5, 3, 1])
+    p = ref_asr.init_params(cfg, 2)
+    loss_o, g_o, gold_o, hyp_o, pred_o = ref_meta.loss_and_grads(p, cfg, batch)
+    s = _session(cfg)
+    s.set_flag("fuse_lowrank", 1)
+    out, pred, grads = _fwd_bwd(s, p, batch)
+    keep = gold_o != 0
+    assert torch.equal(out["hyp"].cpu().long()[keep], hyp_o[keep])
+    assert rel_err(pred, pred_o) < TOL_OUT
+    bad = {k: rel_err(grads[k], g_o[k]) for k in g_o if float(g_o[k].abs().max()) > 1e-7}
+    worst = max(bad, key=bad.get)
+    assert bad[worst] < _tol(worst), (worst, bad[worst])
+
+
+def test_fused_lowrank_path_equals_default_path_at_cfg2():
+    """cfg-2 shapes (M = 200 / 264 rows, d = 512, rank 100), ragged batch: the fused pair path against the two-launch
+    default on the same device -- the VGG forward is shared, so every ReLU / max-pool decision is too, and all 190
+    gradients have to agree to accumulation-order noise."""
+    cfg = ref_asr.CFG2
+    batch = mg.cfg2_batch(3100, ragged=True)
+    p = ref_asr.init_params(cfg, 31)
+    res = []
+    for fuse in (0, 1):
+        s = _session(cfg)
+        s.set_flag("fuse_lowrank", fuse)
+        out, pred, grads = _fwd_bwd(s, p, batch)
+        res.append((out["hyp"].cpu().clone(), pred.cpu().clone(), {k: v.cpu().clone() for k, v in grads.items()}))
+    assert torch.equal(res[0][0], res[1][0])
+    tol = {0: 1e-5, 1: 5e-3, 2: 2e-5}[GEMM_MODE]
+    assert rel_err(res[1][1], res[0][1]) < tol
+    bad = {k: rel_err(res[1][2][k], res[0][2][k]) for k in res[0][2] if float(res[0][2][k].abs().max()) > 1e-7}
+    worst = max(bad, key=bad.get)
+    assert bad[worst] < 20 * tol, (worst, bad[worst])
+
+
 def test_precision_policy_classes():
     """mtl_session_set_op_mode: the default policy runs the VGG input / weight gradients in single-pass TF32; forcing them
     back to 3xTF32 or everything to TF32 changes the arithmetic (different bits) but stays inside the per-mode bounds."""
