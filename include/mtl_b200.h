@@ -213,6 +213,37 @@ int mtl_arena_clip(float* g, long long n, float max_norm, float* scratch1032, vo
 int mtl_arena_adam(float* p, const float* g, float* m, float* v, void* adam_state, double lr, double b1,
                    double b2, double eps, long long n, void* stream);
 
+/* ------------------------------------------------------------------ LSTM language-model meta-loop
+ * Replaces lm/model/rnn_model.py:12-62 (RNNModel: Embedding -> Dropout -> nn.LSTM -> Dropout -> Linear) and the loop
+ * body of lm/main_meta_transfer.py:277-372.  Parameters live in ONE flat fp32 arena in model.parameters() order
+ * (encoder.weight, rnn.{weight_ih,weight_hh,bias_ih,bias_hh}_l<k>, decoder.weight, decoder.bias); every tensor start is
+ * padded to 64 floats.  tokens are (T, B) int64 row-major (time-major, as LMDataset.get_batch returns them,
+ * lm/util/data.py:36-44), targets (T*B) int64; hidden state h / c are (nlayers, B, nhid) fp32. */
+typedef struct mtl_lm_cfg { int vocab, ninp, nhid, nlayers; } mtl_lm_cfg;
+long long mtl_lm_param_floats(const mtl_lm_cfg* cfg);
+int mtl_lm_param_count(const mtl_lm_cfg* cfg);
+int mtl_lm_param_info(const mtl_lm_cfg* cfg, int idx, long long* offset_floats, long long* numel);
+long long mtl_lm_workspace_bytes(const mtl_lm_cfg* cfg, int T, int B);
+/* RNNModel.forward (+ nn.CrossEntropyLoss + .backward() when grad != NULL: grad += loss_scale * dCE/dtheta).
+ * h0 / c0 NULL = zeros (init_hidden); hT / cT nullable, may alias h0 / c0.  loss_out8: device block {mean CE, n tokens,
+ * n correct, ...}; logits_out: optional (T*B, vocab) copy of the decoder output.  targets NULL = logits only. */
+int mtl_lm_pass(const mtl_lm_cfg* cfg, int gemm_mode, const float* theta, float* grad, const long long* tokens,
+                const long long* targets, int T, int B, const float* h0, const float* c0, float* hT, float* cT,
+                float dropout, unsigned long long seed, float loss_scale, void* workspace, long long workspace_bytes,
+                float* loss_out8, float* logits_out, void* stream);
+/* One meta-iteration (lm/main_meta_transfer.py:293-372), first-order: per task an inner SGD(lr / meta_lr_factor) step on
+ * the clipped train gradient at a working copy of theta, then the val gradient at the adapted weights scaled by
+ * task_weights[i] ((1-ratio)/2, (1-ratio)/2, ratio) accumulated in meta_grad; finally theta -= lr * clip(meta_grad).
+ * The hidden state is threaded exactly as the script does: every train forward starts from the previous train forward's
+ * (detached) state, the val forward from its own task's.  clip <= 0 disables clipping.  results: 16 floats per task
+ * (train loss block, val loss block), device memory, nullable.  scratch1032: 1032 floats of device scratch. */
+int mtl_lm_meta_step(const mtl_lm_cfg* cfg, int gemm_mode, float* theta, float* theta_work, float* grad, float* meta_grad,
+                     float* hidden_h, float* hidden_c, int n_tasks, const long long* const* train_tokens,
+                     const long long* const* train_targets, const long long* val_tokens, const long long* val_targets,
+                     int T, int B, const float* task_weights, float lr, float meta_lr_factor, float clip, float dropout,
+                     unsigned long long seed, void* workspace, long long workspace_bytes, float* results,
+                     float* scratch1032, void* stream);
+
 /* ------------------------------------------------------------------ single operators (unit-test surface) */
 /* nn.Linear / its two backward contractions: C = epi(alpha*op(A)op(B)+bias)+beta*C, row-major.
  * transA: A stored (K,M); transB: B stored (N,K).  epi: 0 none, 1 relu, 2 relu-backward (aux). */

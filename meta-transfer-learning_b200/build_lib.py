@@ -16,7 +16,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"] + os.environ.get("MTL_NVCC_DEFS", "").split()
 SOURCES = ["arena.cu", "norm_embed.cu", "ce.cu", "attention.cu", "conv.cu", "spectrogram.cu", "gemm_simt.cu", "gemm_tc.cu",
-           "engine.cu"]
+           "lstm_lm.cu", "engine.cu"]
 
 
 def _digest(path: str) -> str:

@@ -6,3 +6,4 @@ missing."""
 from .lib import MtlError, get_lib, library_path  # noqa: F401
 from .spec import ModelSpec, param_specs  # noqa: F401
 from .session import Batch, MetaStepper, Session  # noqa: F401
+from .lm_session import LmSession, LmSpec, lm_param_specs  # noqa: F401

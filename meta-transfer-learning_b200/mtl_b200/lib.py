@@ -30,6 +30,10 @@ class CBatch(C.Structure):
                 ("hyp_out", C.c_void_p), ("gold_out", C.c_void_p), ("ce_out", C.c_void_p)]
 
 
+class LmCfg(C.Structure):
+    _fields_ = [(k, C.c_int) for k in "vocab ninp nhid nlayers".split()]
+
+
 class MetaHParams(C.Structure):
     _fields_ = [("lr", C.c_float), ("val_scale", C.c_float), ("clip", C.c_int), ("max_norm", C.c_float),
                 ("dropout", C.c_float), ("label_smoothing", C.c_float), ("seed", C.c_ulonglong)]
@@ -85,6 +89,13 @@ SIGNATURES = {
     "mtl_arena_sgd": (_I, [_P, _P, _F, _LL, _P]),
     "mtl_arena_clip": (_I, [_P, _LL, _F, _P, _P]),
     "mtl_arena_adam": (_I, [_P, _P, _P, _P, _P, _D, _D, _D, _D, _LL, _P]),
+    "mtl_lm_param_floats": (_LL, [C.POINTER(LmCfg)]),
+    "mtl_lm_param_count": (_I, [C.POINTER(LmCfg)]),
+    "mtl_lm_param_info": (_I, [C.POINTER(LmCfg), _I, C.POINTER(_LL), C.POINTER(_LL)]),
+    "mtl_lm_workspace_bytes": (_LL, [C.POINTER(LmCfg), _I, _I]),
+    "mtl_lm_pass": (_I, [C.POINTER(LmCfg), _I, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _F, _ULL, _F, _P, _LL, _P, _P, _P]),
+    "mtl_lm_meta_step": (_I, [C.POINTER(LmCfg), _I, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _I, _I, _P, _F, _F, _F, _F,
+                              _ULL, _P, _LL, _P, _P, _P]),
     "mtl_gemm": (_I, [_I, _I, _I, _I, _I, _I, _F, _P, _I, _P, _I, _F, _P, _I, _P, _I, _P, _I, _P]),
     "mtl_lowrank_pair": (_I, [_I, _I, _I, _I, _I, _I, _I, _P, _I, _P, _P, _P, _P, _P, _I, _I, _P]),
     "mtl_gemm_repeat": (_I, [_I, _I, _I, _I, _I, _I, _I, _P, _I, _P, _I, _F, _P, _I, _I, _P]),

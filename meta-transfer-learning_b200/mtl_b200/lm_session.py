@@ -1,0 +1,150 @@
+"""Torch-tensor front of the LSTM language-model entry points of libmtl_b200 (mtl_lm_*): parameter arena layout,
+workspace, one forward(+backward) pass and the whole first-order meta-step of lm/main_meta_transfer.py:277-372."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import lib as _l
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+@dataclass(frozen=True)
+class LmSpec:
+    """RNNModel('LSTM', vocab, ninp, nhid, nlayers) -- lm/model/rnn_model.py:15-46."""
+    vocab: int
+    ninp: int = 200
+    nhid: int = 200
+    nlayers: int = 2
+
+
+def lm_param_specs(spec: LmSpec) -> List[Tuple[str, Tuple[int, ...]]]:
+    """(name, shape) in ``RNNModel.parameters()`` order (encoder, rnn layer by layer, decoder)."""
+    out = [("encoder.weight", (spec.vocab, spec.ninp))]
+    for l in range(spec.nlayers):
+        n_in = spec.ninp if l == 0 else spec.nhid
+        out += [(f"rnn.weight_ih_l{l}", (4 * spec.nhid, n_in)), (f"rnn.weight_hh_l{l}", (4 * spec.nhid, spec.nhid)),
+                (f"rnn.bias_ih_l{l}", (4 * spec.nhid,)), (f"rnn.bias_hh_l{l}", (4 * spec.nhid,))]
+    out += [("decoder.weight", (spec.vocab, spec.nhid)), ("decoder.bias", (spec.vocab,))]
+    return out
+
+
+class LmSession:
+    """Layout + workspace of one LSTM LM on one CUDA device.  There is no CPU path."""
+
+    def __init__(self, spec: LmSpec, device="cuda", gemm_mode: int = 2):
+        if not torch.cuda.is_available():
+            raise _l.MtlError("libmtl_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = _l.get_lib()
+        self.spec = spec
+        self.device = torch.device(device)
+        self.gemm_mode = int(gemm_mode)
+        self.cfg = _l.LmCfg(spec.vocab, spec.ninp, spec.nhid, spec.nlayers)
+        self.n_floats = int(self.lib.mtl_lm_param_floats(C.byref(self.cfg)))
+        if self.n_floats <= 0:
+            raise _l.MtlError(f"unsupported LM configuration {spec}: {self.lib.mtl_last_error().decode()}")
+        self.specs = lm_param_specs(spec)
+        assert self.lib.mtl_lm_param_count(C.byref(self.cfg)) == len(self.specs)
+        self.table = []
+        off, num = C.c_longlong(), C.c_longlong()
+        for i, (name, shape) in enumerate(self.specs):
+            _l.check(self.lib.mtl_lm_param_info(C.byref(self.cfg), i, C.byref(off), C.byref(num)))
+            n = 1
+            for s in shape:
+                n *= s
+            assert n == num.value, (name, shape, num.value)
+            self.table.append((name, shape, off.value, n))
+        self._ws = None
+        self._ws_key = None
+        self._scratch = torch.zeros(1032 + 64, device=self.device)
+
+    # ------------------------------------------------------------------ arenas
+    def new_arena(self) -> torch.Tensor:
+        return torch.zeros(self.n_floats, device=self.device, dtype=torch.float32)
+
+    def views(self, arena: torch.Tensor) -> Dict[str, torch.Tensor]:
+        return {name: arena[off:off + n].view(shape) for name, shape, off, n in self.table}
+
+    def load(self, arena: torch.Tensor, params: Dict[str, torch.Tensor]) -> None:
+        v = self.views(arena)
+        for name, *_ in self.table:
+            v[name].copy_(params[name].to(self.device, torch.float32))
+
+    def new_hidden(self, bsz: int):
+        z = torch.zeros(self.spec.nlayers, bsz, self.spec.nhid, device=self.device)
+        return z, z.clone()
+
+    def _workspace(self, T: int, B: int) -> torch.Tensor:
+        if self._ws_key != (T, B):
+            need = int(self.lib.mtl_lm_workspace_bytes(C.byref(self.cfg), T, B))
+            if need <= 0:
+                raise _l.MtlError("mtl_lm_workspace_bytes failed")
+            if self._ws is None or self._ws.numel() < need + 256:
+                self._ws = torch.empty(need + 256, device=self.device, dtype=torch.uint8)
+            self._ws_key = (T, B)
+        return self._ws
+
+    def _ws_ptr(self, ws):
+        p = ws.data_ptr()
+        a = (p + 255) & ~255
+        return C.c_void_p(a), ws.numel() - (a - p)
+
+    # ------------------------------------------------------------------ one pass
+    def run(self, theta, tokens, targets=None, hidden=None, grad=None, dropout=0.0, seed=0, scale=1.0,
+            want_logits=False, hidden_out=True):
+        """RNNModel.forward (+ CE + backward into ``grad`` when given).  tokens (T, B) int64, targets (T*B,) int64.
+        Returns dict(loss block (8,), logits (T, B, V) or None, hidden (h, c) or None)."""
+        tokens = tokens.to(self.device, torch.int64).contiguous()
+        T, B = tokens.shape
+        if targets is not None:
+            targets = targets.to(self.device, torch.int64).contiguous().view(-1)
+            assert targets.numel() == T * B
+        ws = self._workspace(T, B)
+        wp, wbytes = self._ws_ptr(ws)
+        h0 = c0 = None
+        if hidden is not None:
+            h0, c0 = (t.to(self.device, torch.float32).contiguous() for t in hidden)
+        hT = cT = None
+        if hidden_out:
+            hT, cT = self.new_hidden(B)
+        loss = torch.zeros(8, device=self.device) if targets is not None else None
+        logits = torch.empty(T, B, self.spec.vocab, device=self.device) if want_logits else None
+        _l.check(self.lib.mtl_lm_pass(C.byref(self.cfg), self.gemm_mode, _ptr(theta), _ptr(grad), _ptr(tokens), _ptr(targets),
+                                      T, B, _ptr(h0), _ptr(c0), _ptr(hT), _ptr(cT), float(dropout), int(seed), float(scale),
+                                      wp, wbytes, _ptr(loss), _ptr(logits), _stream()))
+        return {"loss": loss, "logits": logits, "hidden": (hT, cT) if hidden_out else None}
+
+    # ------------------------------------------------------------------ meta-step
+    def meta_step(self, theta, theta_work, grad, meta_grad, hidden, train: Sequence[Tuple[torch.Tensor, torch.Tensor]],
+                  val: Tuple[torch.Tensor, torch.Tensor], weights: Sequence[float], lr: float, meta_lr_factor: float,
+                  clip: float, dropout: float, seed: int, results: Optional[torch.Tensor] = None):
+        """One iteration of lm/main_meta_transfer.py:293-372 on the device, without a host sync.  ``hidden`` (h, c) is
+        updated in place; ``results`` (n_tasks, 16) receives the train / val loss blocks."""
+        n = len(train)
+        toks = [t.to(self.device, torch.int64).contiguous() for t, _ in train]
+        trgs = [y.to(self.device, torch.int64).contiguous().view(-1) for _, y in train]
+        vt = val[0].to(self.device, torch.int64).contiguous()
+        vy = val[1].to(self.device, torch.int64).contiguous().view(-1)
+        T, B = vt.shape
+        assert all(t.shape == (T, B) for t in toks), "every task block must have the val block's (bptt, batch) shape"
+        ws = self._workspace(T, B)
+        wp, wbytes = self._ws_ptr(ws)
+        tok_arr = (C.c_void_p * n)(*[t.data_ptr() for t in toks])
+        trg_arr = (C.c_void_p * n)(*[t.data_ptr() for t in trgs])
+        w_arr = (C.c_float * n)(*[float(w) for w in weights])
+        _l.check(self.lib.mtl_lm_meta_step(C.byref(self.cfg), self.gemm_mode, _ptr(theta), _ptr(theta_work), _ptr(grad),
+                                           _ptr(meta_grad), _ptr(hidden[0]), _ptr(hidden[1]), n, tok_arr, trg_arr, _ptr(vt),
+                                           _ptr(vy), T, B, w_arr, float(lr), float(meta_lr_factor), float(clip),
+                                           float(dropout), int(seed), wp, wbytes, _ptr(results), _ptr(self._scratch),
+                                           _stream()))
+        self._keep = (toks, trgs, vt, vy)          # alive until the stream has consumed them

@@ -160,3 +160,31 @@ def run_joint(model, vocab, args, steps_tasks, n_steps):
     if "Error:" in out:
         raise RuntimeError("reference trainer swallowed an exception:\n" + out[-2000:])
     return out
+
+
+# ----------------------------------------------------------------------------- LM sub-project (lm/model/rnn_model.py)
+def build_lm_model(cfg, params):
+    """The UNMODIFIED reference RNNModel('LSTM', ...) with `params` loaded (eval mode: dropout off).  The module is loaded
+    from its file by path so that neither `model` nor `util` of the reference's lm/ directory shadows anything here."""
+    import importlib.util
+    path = os.path.join(REFERENCE_ROOT, "lm", "model", "rnn_model.py")
+    spec = importlib.util.spec_from_file_location("_ref_lm_rnn_model", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    m = mod.RNNModel('LSTM', cfg.vocab, cfg.ninp, cfg.nhid, cfg.nlayers, dropout=0.2, tie_weights=False)
+    m.load_state_dict({k: v.clone() for k, v in params.items()})
+    m.eval()
+    return m
+
+
+def lm_fwd_bwd(cfg, params, tokens, targets, hidden=None):
+    """Reference forward + nn.CrossEntropyLoss + backward (lm/main_meta_transfer.py:268-319), eval-mode dropout."""
+    import torch
+    m = build_lm_model(cfg, params)
+    hid = m.init_hidden(tokens.shape[1]) if hidden is None else tuple(h.clone() for h in hidden)
+    m.zero_grad()
+    out, hid = m(tokens, hid)
+    loss = torch.nn.CrossEntropyLoss()(out.view(-1, cfg.vocab), targets)
+    loss.backward()
+    grads = {n: p.grad.detach().clone() for n, p in m.named_parameters()}
+    return float(loss.detach()), grads, out.detach(), (hid[0].detach(), hid[1].detach())

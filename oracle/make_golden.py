@@ -176,13 +176,35 @@ def ref_checkpoint():
     shutil.rmtree(tmp)
 
 
+LM_SMALL_GOLD = dict(seed=41, data_seed=4100, T=9, B=5)
+
+
+def lm_small():
+    """Reference RNNModel forward + CE + backward on a small LSTM LM, two chained blocks (the second starts from the first
+    one's hidden state, as forward_one_batch threads it)."""
+    from oracle import ref_lm
+    cfg, m = ref_lm.LM_SMALL, LM_SMALL_GOLD
+    p = ref_lm.init_params(cfg, m["seed"])
+    (b0, b1), _ = ref_lm.synth_blocks(cfg, 2, m["T"], m["B"], m["data_seed"])
+    d = {}
+    hidden = None
+    for i, (tok, trg) in enumerate((b0, b1)):
+        loss, grads, logits, hidden = live.lm_fwd_bwd(cfg, p, tok, trg, hidden)
+        d[f"loss{i}"] = np.float32(loss)
+        d[f"logits{i}"] = logits.numpy()
+        d[f"h{i}"], d[f"c{i}"] = hidden[0].numpy(), hidden[1].numpy()
+        for k, v in grads.items():
+            d[f"grad{i}/" + k] = v.numpy()
+    np.savez_compressed(os.path.join(OUT, "lm_small.npz"), **d)
+
+
 def main():
     if not live.available():
         sys.exit("needs the reference at /root/reference")
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
     only = sys.argv[1:]
-    for fn in (small_fwd_bwd, small_meta, cfg2_fwd_bwd, cfg2_meta, ref_checkpoint):
+    for fn in (small_fwd_bwd, small_meta, cfg2_fwd_bwd, cfg2_meta, ref_checkpoint, lm_small):
         if only and fn.__name__ not in only:
             continue
         fn()
