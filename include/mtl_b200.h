@@ -236,13 +236,15 @@ int mtl_lm_pass(const mtl_lm_cfg* cfg, int gemm_mode, const float* theta, float*
  * task_weights[i] ((1-ratio)/2, (1-ratio)/2, ratio) accumulated in meta_grad; finally theta -= lr * clip(meta_grad).
  * The hidden state is threaded exactly as the script does: every train forward starts from the previous train forward's
  * (detached) state, the val forward from its own task's.  clip <= 0 disables clipping.  results: 16 floats per task
- * (train loss block, val loss block), device memory, nullable.  scratch1032: 1032 floats of device scratch. */
+ * (train loss block, val loss block), device memory, nullable.  scratch1032: 1032 floats of device scratch.
+ * seed_slot (nullable): device word that holds the step's dropout seed instead of `seed`; with it the enqueued work
+ * depends on no per-step host value, so the call can be captured in a CUDA graph and replayed (no sync, no allocation). */
 int mtl_lm_meta_step(const mtl_lm_cfg* cfg, int gemm_mode, float* theta, float* theta_work, float* grad, float* meta_grad,
                      float* hidden_h, float* hidden_c, int n_tasks, const long long* const* train_tokens,
                      const long long* const* train_targets, const long long* val_tokens, const long long* val_targets,
                      int T, int B, const float* task_weights, float lr, float meta_lr_factor, float clip, float dropout,
-                     unsigned long long seed, void* workspace, long long workspace_bytes, float* results,
-                     float* scratch1032, void* stream);
+                     unsigned long long seed, const unsigned long long* seed_slot, void* workspace,
+                     long long workspace_bytes, float* results, float* scratch1032, void* stream);
 
 /* ------------------------------------------------------------------ single operators (unit-test surface) */
 /* nn.Linear / its two backward contractions: C = epi(alpha*op(A)op(B)+bias)+beta*C, row-major.

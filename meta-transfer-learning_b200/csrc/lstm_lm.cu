@@ -94,7 +94,7 @@ __global__ void lm_gold_kernel(const long long* __restrict__ trg, int* __restric
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) { long long t = trg[i]; gold[i] = (int)(t < 0 ? 0 : (t >= V ? V - 1 : t)); }
 }
-// W [4H, H] -> WT [H, 4H] (so that the forward step reads gate rows coalesced over the hidden index)
+// W [4H, H] -> WT [H, 4H] (so that the backward step's warp reads row j of W_hh^T coalesced)
 __global__ void lm_transpose_kernel(const float* __restrict__ W, float* __restrict__ WT, int rows, int cols) {
   __shared__ float t[32][33];
   const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
@@ -109,77 +109,149 @@ __global__ void lm_transpose_kernel(const float* __restrict__ W, float* __restri
   }
 }
 
-// One LSTM time step (torch.nn.LSTM cell; gate order i, f, g, o):  thread (b, j)
+// One LSTM time step (torch.nn.LSTM cell; gate order i, f, g, o).  One WARP per hidden unit j: its lanes stride the
+// K = H reduction of the four gate rows W_hh[g*H + j, :] (coalesced), the previous hidden state of a chunk of LM_BCH batch
+// rows sits in shared memory, partial sums are reduced by shuffles and lane b finishes unit (b, j):
 //   pre = xg[b, g*H + j] (x W_ih^T + b_ih, precomputed) + b_hh[g*H + j] + sum_k h_prev[b, k] * W_hh[g*H + j, k]
 //   c = sig(f) * c_prev + sig(i) * tanh(g);  h = sig(o) * tanh(c);  the four ACTIVATED gates are kept for the backward
-__global__ void __launch_bounds__(128) lstm_step_fwd_kernel(const float* __restrict__ xg, const float* __restrict__ h_prev,
-                                                            const float* __restrict__ c_prev, const float* __restrict__ WhhT,
-                                                            const float* __restrict__ b_hh, float* __restrict__ gates,
-                                                            float* __restrict__ c_out, float* __restrict__ h_out, int H) {
-  extern __shared__ float hs[];                   // h_prev[b, :]
-  const int b = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
-  for (int k = threadIdx.x; k < H; k += blockDim.x) hs[k] = h_prev[(size_t)b * H + k];
-  __syncthreads();
-  if (j >= H) return;
-  const int H4 = 4 * H;
-  float ai = 0.f, af = 0.f, ag = 0.f, ao = 0.f;
-  const float* w = WhhT + j;
-#pragma unroll 4
-  for (int k = 0; k < H; ++k) {
-    const float hv = hs[k];
-    const float* wk = w + (size_t)k * H4;
-    ai = fmaf(hv, __ldg(wk), ai);
-    af = fmaf(hv, __ldg(wk + H), af);
-    ag = fmaf(hv, __ldg(wk + 2 * H), ag);
-    ao = fmaf(hv, __ldg(wk + 3 * H), ao);
+// (the first version, one thread per (b, j) walking K alone, ran 40 CTAs at ~25 us per step.)
+// global -> shared copy of n floats (n % 4 == 0, both 16 B aligned) with eight float4 loads per thread in flight at once:
+// the copy is one round trip to the L2 instead of one per element (a scalar loop here was most of the step kernels' time)
+__device__ __forceinline__ void fill_smem(float* __restrict__ dst, const float* __restrict__ src, int n) {
+  const int n4 = n >> 2;
+  const float4* s4 = reinterpret_cast<const float4*>(src);
+  float4* d4 = reinterpret_cast<float4*>(dst);
+  for (int i0 = 0; i0 < n4; i0 += 8 * (int)blockDim.x) {
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { const int i = i0 + u * (int)blockDim.x + (int)threadIdx.x; if (i < n4) v[u] = __ldg(s4 + i); }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { const int i = i0 + u * (int)blockDim.x + (int)threadIdx.x; if (i < n4) d4[i] = v[u]; }
   }
-  const float* x = xg + (size_t)b * H4;
-  const float gi = sigmoidf_(x[j] + b_hh[j] + ai);
-  const float gf = sigmoidf_(x[H + j] + b_hh[H + j] + af);
-  const float gg = tanhf(x[2 * H + j] + b_hh[2 * H + j] + ag);
-  const float go = sigmoidf_(x[3 * H + j] + b_hh[3 * H + j] + ao);
-  const float c = gf * c_prev[(size_t)b * H + j] + gi * gg;
-  float* g = gates + (size_t)b * H4;
-  g[j] = gi; g[H + j] = gf; g[2 * H + j] = gg; g[3 * H + j] = go;
-  c_out[(size_t)b * H + j] = c;
-  h_out[(size_t)b * H + j] = go * tanhf(c);
 }
-// Backward of one time step: thread (b, j)
+constexpr int LM_BCH = 24, LM_WARPS = 8;      // batch rows per pass over the weights (the script's batch of 20 in one), warps per CTA
+constexpr int LM_KPF = 8, LM_KPB = 16;        // weight values per lane fetched together (all loads in flight before the first FMA)
+__global__ void __launch_bounds__(LM_WARPS * 32) lstm_step_fwd_kernel(const float* __restrict__ xg, const float* __restrict__ h_prev,
+                                                                      const float* __restrict__ c_prev, const float* __restrict__ Whh,
+                                                                      const float* __restrict__ b_hh, float* __restrict__ gates,
+                                                                      float* __restrict__ c_out, float* __restrict__ h_out, int B,
+                                                                      int H) {
+  extern __shared__ float hs[];                   // h_prev[b0 .. b0 + LM_BCH, :]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int j = blockIdx.x * LM_WARPS + warp;
+  const int H4 = 4 * H;
+  for (int b0 = 0; b0 < B; b0 += LM_BCH) {
+    const int nb = min(LM_BCH, B - b0);
+    __syncthreads();
+    fill_smem(hs, h_prev + (size_t)b0 * H, nb * H);
+    __syncthreads();
+    if (j >= H) continue;
+    float acc[4][LM_BCH];
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+#pragma unroll
+      for (int b = 0; b < LM_BCH; ++b) acc[g][b] = 0.f;
+    for (int k0 = 0; k0 < H; k0 += 32 * LM_KPF) {
+      float w[4][LM_KPF];
+#pragma unroll
+      for (int i = 0; i < LM_KPF; ++i) {
+        const int k = k0 + i * 32 + lane;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) w[g][i] = k < H ? __ldg(Whh + (size_t)(g * H + j) * H + k) : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < LM_KPF; ++i) {
+        const int k = k0 + i * 32 + lane;
+        if (k0 + i * 32 >= H) break;               // warp-uniform
+#pragma unroll
+        for (int b = 0; b < LM_BCH; ++b) {
+          const float hv = (b < nb && k < H) ? hs[b * H + k] : 0.f;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) acc[g][b] = fmaf(hv, w[g][i], acc[g][b]);
+        }
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+#pragma unroll
+      for (int b = 0; b < LM_BCH; ++b) acc[g][b] = warp_sum(acc[g][b]);
+    // lane b finishes batch row b0 + b (every lane holds every sum after the xor-reduction: pick without dynamic indexing)
+    float a4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int b = 0; b < LM_BCH; ++b)
+      if (lane == b) { a4[0] = acc[0][b]; a4[1] = acc[1][b]; a4[2] = acc[2][b]; a4[3] = acc[3][b]; }
+    if (lane < nb) {
+      const int b = b0 + lane;
+      const float* x = xg + (size_t)b * H4;
+      const float gi = sigmoidf_(x[j] + b_hh[j] + a4[0]);
+      const float gf = sigmoidf_(x[H + j] + b_hh[H + j] + a4[1]);
+      const float gg = tanhf(x[2 * H + j] + b_hh[2 * H + j] + a4[2]);
+      const float go = sigmoidf_(x[3 * H + j] + b_hh[3 * H + j] + a4[3]);
+      const float c = gf * c_prev[(size_t)b * H + j] + gi * gg;
+      float* g = gates + (size_t)b * H4;
+      g[j] = gi; g[H + j] = gf; g[2 * H + j] = gg; g[3 * H + j] = go;
+      c_out[(size_t)b * H + j] = c;
+      h_out[(size_t)b * H + j] = go * tanhf(c);
+    }
+  }
+}
+// Backward of one time step, one WARP per hidden unit j (lanes stride the 4H reduction over row j of W_hh^T):
 //   dh = dh_above[b, j] + sum_m dgates_next[b, m] * W_hh[m, j]      (recurrent input gradient of step t + 1; absent at t = T - 1)
 //   dc = dc_carry + dh * o * (1 - tanh(c)^2);  pre-activation gate gradients -> dgates[b, :];  dc_carry = dc * f
-__global__ void __launch_bounds__(128) lstm_step_bwd_kernel(const float* __restrict__ dh_above, const float* __restrict__ dg_next,
-                                                            const float* __restrict__ Whh, const float* __restrict__ gates,
-                                                            const float* __restrict__ c_t, const float* __restrict__ c_prev,
-                                                            float* __restrict__ dc_carry, float* __restrict__ dgates, int H) {
-  extern __shared__ float ds[];                   // dgates_next[b, :] (4H)
-  const int b = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(LM_WARPS * 32) lstm_step_bwd_kernel(const float* __restrict__ dh_above, const float* __restrict__ dg_next,
+                                                                      const float* __restrict__ WhhT, const float* __restrict__ gates,
+                                                                      const float* __restrict__ c_t, const float* __restrict__ c_prev,
+                                                                      float* __restrict__ dc_carry, float* __restrict__ dgates, int B,
+                                                                      int H) {
+  extern __shared__ float ds[];                   // dgates_next[b0 .. b0 + LM_BCH, :] (4H each)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int j = blockIdx.x * LM_WARPS + warp;
   const int H4 = 4 * H;
-  if (dg_next) {
-    for (int m = threadIdx.x; m < H4; m += blockDim.x) ds[m] = dg_next[(size_t)b * H4 + m];
-    __syncthreads();
-  }
-  if (j >= H) return;
-  float dh = dh_above[(size_t)b * H + j];
-  if (dg_next) {
-    float a0 = 0.f, a1 = 0.f;
-    const float* w = Whh + j;
-#pragma unroll 4
-    for (int m = 0; m < H4; m += 2) {
-      a0 = fmaf(ds[m], __ldg(w + (size_t)m * H), a0);
-      a1 = fmaf(ds[m + 1], __ldg(w + (size_t)(m + 1) * H), a1);
+  for (int b0 = 0; b0 < B; b0 += LM_BCH) {
+    const int nb = min(LM_BCH, B - b0);
+    float rec = 0.f;
+    if (dg_next) {
+      __syncthreads();
+      fill_smem(ds, dg_next + (size_t)b0 * H4, nb * H4);
+      __syncthreads();
+      if (j < H) {
+        float acc[LM_BCH];
+#pragma unroll
+        for (int b = 0; b < LM_BCH; ++b) acc[b] = 0.f;
+        const float* w = WhhT + (size_t)j * H4;
+        for (int m0 = 0; m0 < H4; m0 += 32 * LM_KPB) {
+          float wv[LM_KPB];
+#pragma unroll
+          for (int i = 0; i < LM_KPB; ++i) { const int m = m0 + i * 32 + lane; wv[i] = m < H4 ? __ldg(w + m) : 0.f; }
+#pragma unroll
+          for (int i = 0; i < LM_KPB; ++i) {
+            const int m = m0 + i * 32 + lane;
+            if (m0 + i * 32 >= H4) break;          // warp-uniform
+#pragma unroll
+            for (int b = 0; b < LM_BCH; ++b) acc[b] = fmaf((b < nb && m < H4) ? ds[b * H4 + m] : 0.f, wv[i], acc[b]);
+          }
+        }
+#pragma unroll
+        for (int b = 0; b < LM_BCH; ++b) acc[b] = warp_sum(acc[b]);
+#pragma unroll
+        for (int b = 0; b < LM_BCH; ++b)
+          if (lane == b) rec = acc[b];
+      }
     }
-    dh += a0 + a1;
+    if (j >= H || lane >= nb) continue;
+    const int b = b0 + lane;
+    const float dh = dh_above[(size_t)b * H + j] + rec;
+    const float* g = gates + (size_t)b * H4;
+    const float gi = g[j], gf = g[H + j], gg = g[2 * H + j], go = g[3 * H + j];
+    const float tc = tanhf(c_t[(size_t)b * H + j]);
+    const float dc = dc_carry[(size_t)b * H + j] + dh * go * (1.f - tc * tc);
+    float* d = dgates + (size_t)b * H4;
+    d[j] = dc * gg * gi * (1.f - gi);
+    d[H + j] = dc * c_prev[(size_t)b * H + j] * gf * (1.f - gf);
+    d[2 * H + j] = dc * gi * (1.f - gg * gg);
+    d[3 * H + j] = dh * tc * go * (1.f - go);
+    dc_carry[(size_t)b * H + j] = dc * gf;
   }
-  const float* g = gates + (size_t)b * H4;
-  const float gi = g[j], gf = g[H + j], gg = g[2 * H + j], go = g[3 * H + j];
-  const float tc = tanhf(c_t[(size_t)b * H + j]);
-  const float dc = dc_carry[(size_t)b * H + j] + dh * go * (1.f - tc * tc);
-  float* d = dgates + (size_t)b * H4;
-  d[j] = dc * gg * gi * (1.f - gi);
-  d[H + j] = dc * c_prev[(size_t)b * H + j] * gf * (1.f - gf);
-  d[2 * H + j] = dc * gi * (1.f - gg * gg);
-  d[3 * H + j] = dh * tc * go * (1.f - go);
-  dc_carry[(size_t)b * H + j] = dc * gf;
 }
 
 // ----------------------------------------------------------------------------- host helpers
@@ -250,7 +322,17 @@ int lm_pass(const mtl_lm_cfg& c, const LmLayout& L, int mode, const float* theta
   const int H = c.nhid, H4 = 4 * H, V = c.vocab, ldp = (V + 3) & ~3;
   const int R = T * B;
   const size_t BH = (size_t)B * H;
-  const dim3 sgrid(mtl_cdiv(H, 128), B);
+  const dim3 sgrid(mtl_cdiv(H, LM_WARPS));
+  const size_t fwd_smem = (size_t)LM_BCH * H * sizeof(float), bwd_smem = (size_t)LM_BCH * H4 * sizeof(float);
+  MTL_REQUIRE(bwd_smem <= 200 * 1024, "nhid too large for the recurrent step kernels (16 * 4 * nhid floats of shared memory)");
+  {
+    static size_t configured = 0;                  // opt in to > 48 KB of dynamic shared memory once per size
+    if (bwd_smem > configured) {
+      MTL_CHECK_CUDA(cudaFuncSetAttribute(lstm_step_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem));
+      MTL_CHECK_CUDA(cudaFuncSetAttribute(lstm_step_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem));
+      configured = bwd_smem;
+    }
+  }
 
   // ---- forward
   lm_embed_fwd_kernel<<<ew_grid((size_t)R * c.ninp), 256, 0, s>>>(tokens, theta + L.enc, lm_drop(p_drop, sd, 0), P.emb, R, c.ninp, V);
@@ -265,10 +347,10 @@ int lm_pass(const mtl_lm_cfg& c, const LmLayout& L, int mode, const float* theta
     MTL_TRY(k_copy(P.hseq[l], h0 ? h0 + (size_t)l * BH : P.zeros, BH, s));
     MTL_TRY(k_copy(P.cseq[l], c0 ? c0 + (size_t)l * BH : P.zeros, BH, s));
     for (int t = 0; t < T; ++t) {
-      lstm_step_fwd_kernel<<<sgrid, 128, H * sizeof(float), s>>>(P.xg + (size_t)t * B * H4, P.hseq[l] + (size_t)t * BH,
-                                                                 P.cseq[l] + (size_t)t * BH, P.whhT[l], theta + L.b_hh[l],
-                                                                 P.gates[l] + (size_t)t * B * H4, P.cseq[l] + (size_t)(t + 1) * BH,
-                                                                 P.hseq[l] + (size_t)(t + 1) * BH, H);
+      lstm_step_fwd_kernel<<<sgrid, LM_WARPS * 32, fwd_smem, s>>>(P.xg + (size_t)t * B * H4, P.hseq[l] + (size_t)t * BH,
+                                                                  P.cseq[l] + (size_t)t * BH, theta + L.w_hh[l], theta + L.b_hh[l],
+                                                                  P.gates[l] + (size_t)t * B * H4, P.cseq[l] + (size_t)(t + 1) * BH,
+                                                                  P.hseq[l] + (size_t)(t + 1) * BH, B, H);
       MTL_CHECK_LAUNCH();
     }
     const float* y = P.hseq[l] + BH;               // [T*B, H]
@@ -299,8 +381,12 @@ int lm_pass(const mtl_lm_cfg& c, const LmLayout& L, int mode, const float* theta
 
   // ---- backward
   MTL_TRY(k_ce_bwd(P.logits, ldp, P.gold, P.row_lse, P.ce, loss_scale, 0.f, -1, P.dlogits, R, V, s));
-  const int wsplit = 24;
-  MTL_TRY(gemm(mode, P.dlogits, ldp, 1, y_last, H, 0, grad + L.dec_w, H, V, H, R, 1.f, nullptr, wsplit, s));     // dW_dec += dlogits^T y
+  // K slabs of the weight-gradient contractions: about two waves of CTAs, at least one 32-row k-block each
+  auto slabs = [&](int M_, int N_) { const long long tiles = (long long)mtl_cdiv(M_, 128) * mtl_cdiv(N_, 64);
+                                     long long sp = (296 + tiles - 1) / tiles; const int kb = mtl_cdiv(R, 32);
+                                     return (int)(sp > kb ? kb : (sp > 1 ? sp : 2)); };
+  const int wsplit = slabs(H4, H);
+  MTL_TRY(gemm(mode, P.dlogits, ldp, 1, y_last, H, 0, grad + L.dec_w, H, V, H, R, 1.f, nullptr, slabs(V, H), s));   // dW_dec += dlogits^T y
   MTL_TRY(k_colsum_acc(P.dlogits, R, V, ldp, grad + L.dec_b, s));
   MTL_TRY(gemm(mode, P.dlogits, ldp, 0, theta + L.dec_w, H, 0, P.dy, H, R, H, V, 0.f, nullptr, 1, s));            // d(y_last) = dlogits W_dec
   for (int l = c.nlayers - 1; l >= 0; --l) {
@@ -310,11 +396,11 @@ int lm_pass(const mtl_lm_cfg& c, const LmLayout& L, int mode, const float* theta
     }
     MTL_TRY(k_zero(P.dc, BH, s));
     for (int t = T - 1; t >= 0; --t) {
-      lstm_step_bwd_kernel<<<sgrid, 128, H4 * sizeof(float), s>>>(P.dy + (size_t)t * BH,
+      lstm_step_bwd_kernel<<<sgrid, LM_WARPS * 32, bwd_smem, s>>>(P.dy + (size_t)t * BH,
                                                                   t + 1 < T ? P.dgates + (size_t)(t + 1) * B * H4 : nullptr,
-                                                                  theta + L.w_hh[l], P.gates[l] + (size_t)t * B * H4,
+                                                                  P.whhT[l], P.gates[l] + (size_t)t * B * H4,
                                                                   P.cseq[l] + (size_t)(t + 1) * BH, P.cseq[l] + (size_t)t * BH, P.dc,
-                                                                  P.dgates + (size_t)t * B * H4, H);
+                                                                  P.dgates + (size_t)t * B * H4, B, H);
       MTL_CHECK_LAUNCH();
     }
     const int lin = l == 0 ? c.ninp : H;
@@ -378,13 +464,15 @@ extern "C" int mtl_lm_pass(const mtl_lm_cfg* cfg, int gemm_mode, const float* th
 //   theta0 <- theta0 - lr * clip(G)
 // theta_work / grad / meta_grad are caller arenas of mtl_lm_param_floats floats; hidden_h / hidden_c [L, B, H] are carried
 // across calls (the reference never re-initialises them); results: 16 floats per task (train CeOut, val CeOut).
+// seed_slot (nullable): device word holding the step's seed -- nothing in the enqueued work then depends on a host value that
+// changes per step, so the caller may capture the call in a CUDA graph and replay it.
 extern "C" int mtl_lm_meta_step(const mtl_lm_cfg* cfg, int gemm_mode, float* theta, float* theta_work, float* grad,
                                 float* meta_grad, float* hidden_h, float* hidden_c, int n_tasks,
                                 const long long* const* train_tokens, const long long* const* train_targets,
                                 const long long* val_tokens, const long long* val_targets, int T, int B,
                                 const float* task_weights, float lr, float meta_lr_factor, float clip, float dropout,
-                                unsigned long long seed, void* workspace, long long workspace_bytes, float* results,
-                                float* scratch1032, void* stream) {
+                                unsigned long long seed, const unsigned long long* seed_slot, void* workspace,
+                                long long workspace_bytes, float* results, float* scratch1032, void* stream) {
   MTL_REQUIRE(cfg && theta && theta_work && grad && meta_grad && hidden_h && hidden_c && train_tokens && train_targets &&
                   val_tokens && val_targets && task_weights && scratch1032,
               "null argument");
@@ -398,7 +486,10 @@ extern "C" int mtl_lm_meta_step(const mtl_lm_cfg* cfg, int gemm_mode, float* the
   for (int i = 0; i < n_tasks; ++i) {
     MTL_TRY(k_copy(theta_work, theta, n, s));                                        // weights_original / load_state_dict
     MTL_TRY(k_zero(grad, n, s));
+    // dropout keys: seed * 128 + 2 * task + pass; with a device seed slot (a captured CUDA graph patches it per replay) the
+    // seed is read on the device
     LmSeed s0 = {seed * 128ull + 2ull * i, nullptr, 0}, s1 = {seed * 128ull + 2ull * i + 1ull, nullptr, 0};
+    if (seed_slot) { s0 = {2ull * i, seed_slot, 128ull}; s1 = {2ull * i + 1ull, seed_slot, 128ull}; }
     MTL_TRY(lm_pass(*cfg, L, gemm_mode, theta_work, grad, train_tokens[i], train_targets[i], T, B, hidden_h, hidden_c, hidden_h,
                     hidden_c, dropout, s0, 1.f, workspace, workspace_bytes, results ? results + 16 * i : nullptr, nullptr, s));
     if (clip > 0.f) {

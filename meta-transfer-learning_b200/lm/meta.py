@@ -31,6 +31,7 @@ class LMMetaTrainer(object):
         self.theta_work, self.grad, self.meta_grad = s.new_arena(), s.new_arena(), s.new_arena()
         self.hidden = s.new_hidden(args.batch_size)            # model.init_hidden(batch_size), carried across iterations
         self.lr = args.lr
+        self.use_graph = bool(getattr(args, "cuda_graph", True))   # replay the iteration from a CUDA graph (same shapes)
 
     def step(self, dataset, it: int, results: torch.Tensor = None):
         """One meta-iteration on ``dataset`` (an ``LMDataset``); returns the (n_tasks, 16) device loss blocks."""
@@ -46,7 +47,7 @@ class LMMetaTrainer(object):
         seed = (int(getattr(a, "seed", 0)) * 1000003 + it) & 0x7FFFFFFFFFFF
         s.meta_step(self.theta, self.theta_work, self.grad, self.meta_grad, self.hidden, train, (val_x, val_y),
                     task_weights(n, a.ratio), self.lr, a.meta_lr_factor, a.clip if a.clip else 0.0,
-                    a.dropout if self.model.training else 0.0, seed, results)
+                    a.dropout if self.model.training else 0.0, seed, results, graph=self.use_graph)
         return results
 
     def evaluate(self, data_source, eval_batch_size=10):

@@ -95,7 +95,7 @@ SIGNATURES = {
     "mtl_lm_workspace_bytes": (_LL, [C.POINTER(LmCfg), _I, _I]),
     "mtl_lm_pass": (_I, [C.POINTER(LmCfg), _I, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _F, _ULL, _F, _P, _LL, _P, _P, _P]),
     "mtl_lm_meta_step": (_I, [C.POINTER(LmCfg), _I, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _I, _I, _P, _F, _F, _F, _F,
-                              _ULL, _P, _LL, _P, _P, _P]),
+                              _ULL, _P, _P, _LL, _P, _P, _P]),
     "mtl_gemm": (_I, [_I, _I, _I, _I, _I, _I, _F, _P, _I, _P, _I, _F, _P, _I, _P, _I, _P, _I, _P]),
     "mtl_lowrank_pair": (_I, [_I, _I, _I, _I, _I, _I, _I, _P, _I, _P, _P, _P, _P, _P, _I, _I, _P]),
     "mtl_gemm_repeat": (_I, [_I, _I, _I, _I, _I, _I, _I, _P, _I, _P, _I, _F, _P, _I, _I, _P]),

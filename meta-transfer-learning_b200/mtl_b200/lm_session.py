@@ -125,18 +125,10 @@ class LmSession:
         return {"loss": loss, "logits": logits, "hidden": (hT, cT) if hidden_out else None}
 
     # ------------------------------------------------------------------ meta-step
-    def meta_step(self, theta, theta_work, grad, meta_grad, hidden, train: Sequence[Tuple[torch.Tensor, torch.Tensor]],
-                  val: Tuple[torch.Tensor, torch.Tensor], weights: Sequence[float], lr: float, meta_lr_factor: float,
-                  clip: float, dropout: float, seed: int, results: Optional[torch.Tensor] = None):
-        """One iteration of lm/main_meta_transfer.py:293-372 on the device, without a host sync.  ``hidden`` (h, c) is
-        updated in place; ``results`` (n_tasks, 16) receives the train / val loss blocks."""
-        n = len(train)
-        toks = [t.to(self.device, torch.int64).contiguous() for t, _ in train]
-        trgs = [y.to(self.device, torch.int64).contiguous().view(-1) for _, y in train]
-        vt = val[0].to(self.device, torch.int64).contiguous()
-        vy = val[1].to(self.device, torch.int64).contiguous().view(-1)
+    def _enqueue_meta(self, theta, theta_work, grad, meta_grad, hidden, toks, trgs, vt, vy, weights, lr, meta_lr_factor, clip,
+                      dropout, seed, seed_slot, results):
+        n = len(toks)
         T, B = vt.shape
-        assert all(t.shape == (T, B) for t in toks), "every task block must have the val block's (bptt, batch) shape"
         ws = self._workspace(T, B)
         wp, wbytes = self._ws_ptr(ws)
         tok_arr = (C.c_void_p * n)(*[t.data_ptr() for t in toks])
@@ -145,6 +137,58 @@ class LmSession:
         _l.check(self.lib.mtl_lm_meta_step(C.byref(self.cfg), self.gemm_mode, _ptr(theta), _ptr(theta_work), _ptr(grad),
                                            _ptr(meta_grad), _ptr(hidden[0]), _ptr(hidden[1]), n, tok_arr, trg_arr, _ptr(vt),
                                            _ptr(vy), T, B, w_arr, float(lr), float(meta_lr_factor), float(clip),
-                                           float(dropout), int(seed), wp, wbytes, _ptr(results), _ptr(self._scratch),
-                                           _stream()))
-        self._keep = (toks, trgs, vt, vy)          # alive until the stream has consumed them
+                                           float(dropout), int(seed), _ptr(seed_slot), wp, wbytes, _ptr(results),
+                                           _ptr(self._scratch), _stream()))
+
+    def meta_step(self, theta, theta_work, grad, meta_grad, hidden, train: Sequence[Tuple[torch.Tensor, torch.Tensor]],
+                  val: Tuple[torch.Tensor, torch.Tensor], weights: Sequence[float], lr: float, meta_lr_factor: float,
+                  clip: float, dropout: float, seed: int, results: Optional[torch.Tensor] = None, graph: bool = False):
+        """One iteration of lm/main_meta_transfer.py:293-372 on the device, without a host sync.  ``hidden`` (h, c) is
+        updated in place; ``results`` (n_tasks, 16) receives the train / val loss blocks.  graph=True: the token blocks are
+        copied into static device buffers and the step (about a thousand small kernels) is replayed from a CUDA graph
+        captured at the second call with the same shapes and hyper-parameters; the dropout seed lives in a device word."""
+        n = len(train)
+        T, B = val[0].shape
+        assert all(t.shape == (T, B) for t, _ in train), "every task block must have the val block's (bptt, batch) shape"
+        if not graph:
+            toks = [t.to(self.device, torch.int64).contiguous() for t, _ in train]
+            trgs = [y.to(self.device, torch.int64).contiguous().view(-1) for _, y in train]
+            vt = val[0].to(self.device, torch.int64).contiguous()
+            vy = val[1].to(self.device, torch.int64).contiguous().view(-1)
+            self._enqueue_meta(theta, theta_work, grad, meta_grad, hidden, toks, trgs, vt, vy, weights, lr, meta_lr_factor, clip,
+                               dropout, seed, None, results)
+            self._keep = (toks, trgs, vt, vy)      # alive until the stream has consumed them
+            return
+        key = (n, T, B, theta.data_ptr(), theta_work.data_ptr(), grad.data_ptr(), meta_grad.data_ptr(), hidden[0].data_ptr(),
+               hidden[1].data_ptr(), tuple(float(w) for w in weights), float(lr), float(meta_lr_factor), float(clip),
+               float(dropout), None if results is None else results.data_ptr())
+        g = getattr(self, "_graph", None)
+        if g is None or g["key"] != key:
+            mk = lambda *shape: torch.zeros(*shape, device=self.device, dtype=torch.int64)
+            g = {"key": key, "seen": 0, "graph": None, "toks": [mk(T, B) for _ in range(n)], "trgs": [mk(T * B) for _ in range(n)],
+                 "vt": mk(T, B), "vy": mk(T * B), "seed": torch.zeros(1, device=self.device, dtype=torch.int64)}
+            self._graph = g
+        for i, (t, y) in enumerate(train):
+            g["toks"][i].copy_(t, non_blocking=True)
+            g["trgs"][i].copy_(y.reshape(-1), non_blocking=True)
+        g["vt"].copy_(val[0], non_blocking=True)
+        g["vy"].copy_(val[1].reshape(-1), non_blocking=True)
+        g["seed"].fill_(int(seed))
+        run = lambda: self._enqueue_meta(theta, theta_work, grad, meta_grad, hidden, g["toks"], g["trgs"], g["vt"], g["vy"], weights,
+                                         lr, meta_lr_factor, clip, dropout, 0, g["seed"], results)
+        if g["graph"] is not None:
+            g["graph"].replay()
+        elif g["seen"] == 0:
+            g["seen"] = 1
+            run()                                  # first sighting: eager (warms every kernel / attribute / tensor map up)
+        else:
+            cur = torch.cuda.current_stream()
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(cur)
+            cg = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(side):
+                with torch.cuda.graph(cg, stream=side):
+                    run()
+            cur.wait_stream(side)
+            g["graph"] = cg
+            cg.replay()                            # the capture itself executed nothing

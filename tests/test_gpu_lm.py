@@ -155,3 +155,25 @@ def test_lm_model_and_trainer_api():
     for k, v in model.state_dict().items():                               # the parameters ARE the arena views
         assert rel_err(v, new_p[k]) < 5 * TOL, k
     assert res.shape == (3, 16)
+
+
+def test_lm_meta_step_graph_replay_equals_eager():
+    """graph=True: static token buffers + device seed word + CUDA-graph replay from the third call on; same parameters
+    and hidden state as the eager path after four iterations (dropout off: bit-for-bit up to reduce-add order)."""
+    cfg = ref_lm.LmConfig(vocab=500, ninp=32, nhid=32, nlayers=2)
+    p = ref_lm.init_params(cfg, 6)
+    out = []
+    for use_graph in (False, True):
+        s = _session(cfg)
+        theta, work, grad, meta = s.new_arena(), s.new_arena(), s.new_arena(), s.new_arena()
+        s.load(theta, p)
+        hidden = s.new_hidden(4)
+        res = torch.zeros(3, 16, device=dev())
+        for it in range(4):
+            train, val = ref_lm.synth_blocks(cfg, 3, 6, 4, 80 + it)
+            s.meta_step(theta, work, grad, meta, hidden, train, val, [0.1, 0.1, 0.8], lr=1.0, meta_lr_factor=3.0, clip=0.25,
+                        dropout=0.0, seed=it, results=res, graph=use_graph)
+        torch.cuda.synchronize()
+        out.append((theta.cpu().clone(), hidden[0].cpu().clone(), res.cpu().clone()))
+    assert rel_err(out[1][0], out[0][0]) < 1e-5 and rel_err(out[1][1], out[0][1]) < 1e-5
+    assert rel_err(out[1][2][:, 8], out[0][2][:, 8]) < 1e-5
