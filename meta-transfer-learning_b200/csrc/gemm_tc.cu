@@ -247,7 +247,8 @@ template <int BN, bool SPLIT3>
 __device__ __forceinline__ void tma_epilogue_rows(const TcParams& P, const CUtensorMap* tmC, const CUtensorMap* tmX,
                                                   uint32_t stg_u, uint32_t aux_u, uint64_t* tmem_full,
                                                   uint64_t* aux_full, const float* bias_s, uint32_t tmem_base, int warp,
-                                                  int lane, int m0, int n0, bool conv, int ct0, int cf0, int cb) {
+                                                  int lane, int m0, int n0, bool conv, int ct0, int cf0, int cb,
+                                                  uint32_t aux_par = 0) {
   constexpr int CHUNKS = BN / 32, CHUNK_BYTES = BM * 128;
   const GemmArgs& g = P.g;
   const int q = warp & 3;                                        // TMEM lane quarter this warp may access
@@ -271,7 +272,7 @@ __device__ __forceinline__ void tma_epilogue_rows(const TcParams& P, const CUten
   const uint32_t row_u = (uint32_t)row * 128u, sw = (uint32_t)(row & 7);
   const float alpha = g.alpha;
   const float lo = g.epi == EPI_RELU ? 0.f : -INFINITY;          // branch-free ReLU
-  if (mask) mbar_wait(aux_full, 0);
+  if (mask) mbar_wait(aux_full, aux_par);
 #pragma unroll 1
   for (int c = 0; c < nch; ++c) {
     uint32_t v[32];
@@ -793,37 +794,55 @@ __global__ void __launch_bounds__(192) conv_gemm_tc_kernel(const __grid_constant
 // splitter warps only touch activations.
 //   warp 0: TMA producer (A ring + B ring); warp 1: TMEM allocator + MMA issuer; warps 2..5: A splitter (3xTF32),
 //   then the TMA epilogue.
-constexpr int KW_BT = 8, KW_BF = 16;                       // pixel box of a tile
-constexpr int KW_A_ROWS = (KW_BF + 2) * KW_BT;             // 144 rows per A box
-constexpr int KW_A_BYTES = KW_A_ROWS * 128;                // 18 KB
-constexpr int KW_NA = 2;                                   // A slots
+constexpr int KW_BT = 8, KW_BF = 16;                       // pixel box of one 128-row accumulator tile
+#ifndef KW_TF32_NA64
+#define KW_TF32_NA64 2
+#endif
+#ifndef KW_TF32_NA128
+#define KW_TF32_NA128 2
+#endif
 
-template <int BN, bool SPLIT3>
+// MT = accumulator tiles per CTA.  The forward / dgrad convolutions are L2 -> SM bandwidth bound (ncu, conv.2 forward:
+// 464 MB through the L2 for 34 MB of DRAM reads, 6.8 TB/s): every CTA streams the whole weight matrix (hi + lo) for its 128
+// pixels.  With MT = 2 the pixel box is 8 (t) x 32 (f): ONE A box of 8 x 34 rows per (chunk, kw) whose row windows
+// [8 kh, 8 kh + 128) and [128 + 8 kh, 256 + 8 kh) feed two accumulators from the same weight k-block, so the weights are
+// fetched once per 256 pixels (and the f halo once per 32 rows instead of once per 16).
+template <int BN, bool SPLIT3, int MT>
 struct KwCfg {
+  static constexpr int A_ROWS = (KW_BF * MT + 2) * KW_BT;                  // 144 / 272 rows per A box
+  static constexpr int A_BYTES = A_ROWS * 128;                             // 18 / 34 KB
   static constexpr int B_BYTES = BN * 128;                                 // one (tap, chunk) weight k-block
-  static constexpr int A_SLOT = KW_A_BYTES * (SPLIT3 ? 2 : 1);             // [A_hi | A_lo]
+  static constexpr int A_SLOT = A_BYTES * (SPLIT3 ? 2 : 1);                // [A_hi | A_lo]
   static constexpr int B_SLOT = B_BYTES * (SPLIT3 ? 2 : 1);                // [B_hi | B_lo]
-  // weight slots: 3xTF32 Cout<=64 keeps the CTA at ~106 KB so that two CTAs share an SM (one tile's epilogue
+  // weight slots: 3xTF32 Cout<=64 keeps the one-tile CTA at ~106 KB so that two CTAs share an SM (one tile's epilogue
   // overlaps the other's main loop)
-  static constexpr int NB = BN == 64 ? (SPLIT3 ? 2 : 4) : 3;
-  static constexpr int RING = KW_NA * A_SLOT + NB * B_SLOT;
+  static constexpr int NB = BN == 64 ? (SPLIT3 ? 2 : 4) : (SPLIT3 && MT == 2 ? 2 : 3);
+  // A slots.  3xTF32: two (the [hi | lo] slots are 36 / 68 KB each).  Single-pass TF32: two as well -- four were measured
+  // for Cout = 128 (conv.7 dgrad 53.6 -> 52.0 us: not latency bound); KW_TF32_NA64 / KW_TF32_NA128 for A/B builds.
+  static constexpr int NA = SPLIT3 ? 2 : (BN == 64 ? KW_TF32_NA64 : KW_TF32_NA128);
+  static constexpr int RING = NA * A_SLOT + NB * B_SLOT;
   static constexpr int TILE = BM * BN * 4;                                 // staged output tile (aliases the rings)
   static constexpr int HEAD = 1024;                                        // barriers + bias slice, in front of the data
   static constexpr int DATA = RING > TILE ? RING : TILE;
   static constexpr int DATA_MASK = RING > 2 * TILE ? RING : 2 * TILE;      // + the ReLU-mask tile (EPI_RELU_BWD)
   static constexpr int SMEM = HEAD + DATA + 1024 /*align slack*/;
   static constexpr int SMEM_MASK = HEAD + DATA_MASK + 1024;
-  static constexpr int TMEM_COLS = SPLIT3 ? 2 * BN : BN;
+  static constexpr int ACC_COLS = SPLIT3 ? 2 * BN : BN;                    // TMEM columns of one accumulator tile
+  static constexpr int TMEM_COLS = MT * ACC_COLS;
+  static_assert(TMEM_COLS == 64 || TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM allocation: power of two");
+  static_assert(A_BYTES % (16 * 128) == 0, "splitter: whole float4 columns per thread");
 };
 
-template <int BN, bool SPLIT3>
+template <int BN, bool SPLIT3, int MT>
 __global__ void __launch_bounds__(192) conv3x3_kw_kernel(const __grid_constant__ CUtensorMap tmA,
                                                          const __grid_constant__ CUtensorMap tmBh,
                                                          const __grid_constant__ CUtensorMap tmBl,
                                                          const __grid_constant__ CUtensorMap tmC,
                                                          const __grid_constant__ CUtensorMap tmX, const TcParams P) {
-  using Cfg = KwCfg<BN, SPLIT3>;
+  using Cfg = KwCfg<BN, SPLIT3, MT>;
   constexpr int NB = Cfg::NB;
+  constexpr int KW_NA = Cfg::NA;
+  constexpr int KW_A_BYTES = Cfg::A_BYTES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t head = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_head = smem_raw + (head - smem_u32(smem_raw));
@@ -843,7 +862,7 @@ __global__ void __launch_bounds__(192) conv3x3_kw_kernel(const __grid_constant__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.y * BN;
   const int tt = blockIdx.x % P.tiles_t, rem = blockIdx.x / P.tiles_t;
-  const int ct0 = tt * KW_BT, cf0 = (rem % P.tiles_f) * KW_BF, cb = rem / P.tiles_f;
+  const int ct0 = tt * KW_BT, cf0 = (rem % P.tiles_f) * (KW_BF * MT), cb = rem / P.tiles_f;
   const int cpb = P.cCin >> 5;                               // 32-channel chunks
   const int n_stage = 3 * cpb;                               // (chunk, kw) A boxes per tile
 
@@ -925,17 +944,22 @@ __global__ void __launch_bounds__(192) conv3x3_kw_kernel(const __grid_constant__
           const int sb = ib % NB;
           mbar_wait(&b_full[sb], (ib / NB) & 1);
           tc_fence_after();
-          const uint64_t da0 = desc_kmajor(a_u + kh * 1024);                 // rows [8*kh, 8*kh + 128) of the box
-          const uint64_t la0 = desc_kmajor(a_u + KW_A_BYTES + kh * 1024);
           const uint64_t db0 = desc_kmajor(b_ring + sb * Cfg::B_SLOT);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint32_t acc0 = (st > 0 || kh > 0 || k > 0) ? 1u : 0u;
-            if (SPLIT3) {
-              tc_mma_tf32(tmem_base, da0 + 2 * k, db0 + 2 * k, idesc2, acc0);   // a_hi * [b_hi ; b_lo]
-              tc_mma_tf32(tmem_base, la0 + 2 * k, db0 + 2 * k, idesc, 1u);      // a_lo * b_hi
-            } else {
-              tc_mma_tf32(tmem_base, da0 + 2 * k, db0 + 2 * k, idesc, acc0);
+          for (int mt = 0; mt < MT; ++mt) {
+            // accumulator tile mt = rows [128 mt + 8 kh, 128 mt + 8 kh + 128) of the box (whole 1024 B swizzle atoms)
+            const uint64_t da0 = desc_kmajor(a_u + mt * (BM * 128) + kh * 1024);
+            const uint64_t la0 = desc_kmajor(a_u + KW_A_BYTES + mt * (BM * 128) + kh * 1024);
+            const uint32_t acc = tmem_base + (uint32_t)(mt * Cfg::ACC_COLS);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t acc0 = (st > 0 || kh > 0 || k > 0) ? 1u : 0u;
+              if (SPLIT3) {
+                tc_mma_tf32(acc, da0 + 2 * k, db0 + 2 * k, idesc2, acc0);   // a_hi * [b_hi ; b_lo]
+                tc_mma_tf32(acc, la0 + 2 * k, db0 + 2 * k, idesc, 1u);      // a_lo * b_hi
+              } else {
+                tc_mma_tf32(acc, da0 + 2 * k, db0 + 2 * k, idesc, acc0);
+              }
             }
           }
           tc_commit(&b_empty[sb]);
@@ -953,8 +977,7 @@ __global__ void __launch_bounds__(192) conv3x3_kw_kernel(const __grid_constant__
       const int sa = st % KW_NA;
       mbar_wait(&a_full[sa], (st / KW_NA) & 1);
       float4* hi = reinterpret_cast<float4*>(smem + sa * Cfg::A_SLOT) + tid;
-      constexpr int PER = KW_A_BYTES / 16 / 128;               // 9 float4 per thread
-      static_assert(KW_A_BYTES % (16 * 128) == 0, "whole float4 columns per thread");
+      constexpr int PER = KW_A_BYTES / 16 / 128;               // 9 / 17 float4 per thread
       float4 a[PER];
 #pragma unroll
       for (int j = 0; j < PER; ++j) a[j] = hi[j * 128];
@@ -979,9 +1002,23 @@ __global__ void __launch_bounds__(192) conv3x3_kw_kernel(const __grid_constant__
   }
 
   // ===================== epilogue =====================
-  if (warp >= 2)
-    tma_epilogue_rows<BN, SPLIT3>(P, &tmC, &tmX, base, base + Cfg::TILE, tmem_full, aux_full, bias_s, tmem_base, warp, lane,
-                                  0, n0, true, ct0, cf0, cb);
+  if (warp >= 2) {
+    int n_mask = 0;
+#pragma unroll 1
+    for (int mt = 0; mt < MT; ++mt) {
+      if (mt > 0) {
+        if (cf0 + mt * KW_BF >= P.cF) break;                  // the second 16-row tile lies outside the image (odd tile count)
+        // the staging / mask tiles are reused: their TMA reads are done (wait_group.read in the call above), order the
+        // generic-proxy accesses of every thread before the next tile's TMA mask load and staging stores
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      tma_epilogue_rows<BN, SPLIT3>(P, &tmC, &tmX, base, base + Cfg::TILE, tmem_full, aux_full, bias_s,
+                                    tmem_base + (uint32_t)(mt * Cfg::ACC_COLS), warp, lane, 0, n0, true, ct0, cf0 + mt * KW_BF, cb,
+                                    (uint32_t)(n_mask & 1));
+      ++n_mask;
+    }
+  }
   tc_fence_before();
   __syncthreads();
   if (threadIdx.x == 0) DBG_STAMP(7);
@@ -1006,13 +1043,19 @@ __global__ void __launch_bounds__(192) conv3x3_kw_kernel(const __grid_constant__
 //   warp 0: TMA producer; warp 1: TMEM allocator + MMA issuer; warps 2..5: splitter (3xTF32, truncating), then epilogue.
 constexpr int WK_ROWS_A = 48, WK_A_BOX = WK_ROWS_A * 128, WK_B_BOX = 32 * 128;      // 6144 B / 4096 B per 32-column box
 constexpr int WK_A_BYTES = 4 * WK_A_BOX;
-constexpr int WK_STAGES = 2, WK_HEAD = 1024;
+constexpr int WK_HEAD = 1024;
+#ifndef WK_TF32_STAGES
+#define WK_TF32_STAGES 4
+#endif
 template <int BN, bool SPLIT3>
 struct WkCfg {
   static constexpr int B_BYTES = (BN / 32) * WK_B_BOX;
   static constexpr int STAGE = (WK_A_BYTES + B_BYTES) * (SPLIT3 ? 2 : 1);            // [A | A_lo | B | B_lo]
   static constexpr int B_OFF = WK_A_BYTES * (SPLIT3 ? 2 : 1);
-  static constexpr int DATA = WK_STAGES * STAGE > BM * BN * 4 ? WK_STAGES * STAGE : BM * BN * 4;
+  // pipeline depth: 3xTF32 stages are 64-96 KB (two fit); single-pass TF32 stages are half that, and with one CTA per SM
+  // (one wave) only the ring hides the ~1 us TMA round trip of a 0.3-0.6 us stage: four stages in flight
+  static constexpr int STAGES = SPLIT3 ? 2 : WK_TF32_STAGES;
+  static constexpr int DATA = STAGES * STAGE > BM * BN * 4 ? STAGES * STAGE : BM * BN * 4;
   static constexpr int SMEM = WK_HEAD + DATA + 1024;
   static constexpr int TMEM_COLS = BN == 128 ? 512 : 256;                            // 3 * BN rounded up to a power of two
 };
@@ -1022,6 +1065,7 @@ __global__ void __launch_bounds__(192) conv3x3_wgrad_kw_kernel(const __grid_cons
                                                                const __grid_constant__ CUtensorMap tmC,
                                                                const __grid_constant__ CUtensorMap tmC64, const TcParams P) {
   using Cfg = WkCfg<BN, SPLIT3>;
+  constexpr int WK_STAGES = Cfg::STAGES;
   constexpr int NCH = CIN / 32;                                  // 32-channel chunks per tap: 4 or 2
   static_assert(NCH == 4 || NCH == 2, "Cin must be 64 or 128");
   extern __shared__ uint8_t smem_raw[];
@@ -1687,13 +1731,13 @@ int dispatch(int bn, bool split3, bool a_mn, bool b_mn, const Maps& tm, const Tc
 }
 
 struct KwMaps { CUtensorMap a, bh, bl, c, x; };
-template <int BN, bool SPLIT3>
+template <int BN, bool SPLIT3, int MT>
 int launch_kw(const KwMaps& tm, const TcParams& P, dim3 grid, cudaStream_t s) {
-  using Cfg = KwCfg<BN, SPLIT3>;
+  using Cfg = KwCfg<BN, SPLIT3, MT>;
   static_assert(Cfg::SMEM_MASK <= 227 * 1024, "shared memory budget");
   static_assert(256 + BN * 4 <= Cfg::HEAD, "bias slice must fit in the head block");
   static bool configured = false;
-  auto kern = conv3x3_kw_kernel<BN, SPLIT3>;
+  auto kern = conv3x3_kw_kernel<BN, SPLIT3, MT>;
   if (!configured) {
     MTL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_MASK));
     configured = true;
@@ -1972,13 +2016,20 @@ int k_conv3x3_tc(const float* x, const float* wg, const float* bias, float* y, i
   { const char* e = getenv("MTL_EPI_TEST"); P.epi_test = e ? atoi(e) : 0; }
   MTL_REQUIRE(!(split3 && w_split) || k_conv3x3_w_split(precision_mode, Cout), "conv3x3_tc: pre-split weights need the kw-box kernel");
   if (k_conv3x3_kw_enabled() && Cout % 32 == 0 && (!split3 || w_split)) {
-    // kw-box kernel: fixed 8 (t) x 16 (f) pixel tiles, A boxes 8 x 18
+    // kw-box kernel: 8 (t) x 16 (f) pixel tiles, one per CTA (A box 8 x 18).  MTL_CONV_KW_MT=2: two per CTA (A box 8 x 34,
+    // two accumulators fed by the same weight k-block: half the weight traffic per pixel).  MEASURED NEGATIVE RESULT (cfg 2,
+    // one lane, us per launch, MT = 1 -> 2): conv.2 forward 3xTF32 62 -> 96, conv.5 / conv.7 forward 3xTF32 41 -> 69, conv.7
+    // dgrad TF32 52 -> 64, conv.2 / conv.5 dgrad TF32 43 -> 41.5; step 6.28 -> 6.49 ms.  The 3xTF32 CTAs are bound by their four
+    // splitter warps and the shared-memory traffic of the split, not by the L2: one 174-205 KB CTA per SM halves the
+    // splitter warps per SM; at 80 x 50 pixels the 8 x 32 boxes pad 34 % (168 CTAs = two waves on 148 SMs).
+    static int mt = -1;
+    if (mt < 0) { const char* e = getenv("MTL_CONV_KW_MT"); mt = (e && e[0] == '2') ? 2 : 1; }
     P.bt_log2 = 3;
     P.tiles_t = mtl_cdiv(T, KW_BT);
-    P.tiles_f = mtl_cdiv(F, KW_BF);
+    P.tiles_f = mtl_cdiv(F, KW_BF * mt);
     P.tma_epi = 1;
     KwMaps km;
-    MTL_TRY(make_map_nhwc(x, B, F, T, Cin, KW_BT, KW_BF + 2, false, tf, &km.a));
+    MTL_TRY(make_map_nhwc(x, B, F, T, Cin, KW_BT, KW_BF * mt + 2, false, tf, &km.a));
     MTL_TRY(make_map(wg, 9LL * Cin, Cout, 9LL * Cin, bn, false, tf, &km.bh));
     km.bl = km.bh;
     if (split3) MTL_TRY(make_map(wg + (size_t)Cout * 9 * Cin, 9LL * Cin, Cout, 9LL * Cin, bn, false, false, &km.bl));
@@ -1986,8 +2037,12 @@ int k_conv3x3_tc(const float* x, const float* wg, const float* bias, float* y, i
     km.x = km.c;
     if (epi == EPI_RELU_BWD) MTL_TRY(make_map_nhwc(aux, B, F, T, Cout, KW_BT, KW_BF, false, false, &km.x));
     dim3 grid(B * P.tiles_f * P.tiles_t, mtl_cdiv(Cout, bn), 1);
-    if (bn == 64) return split3 ? launch_kw<64, true>(km, P, grid, s) : launch_kw<64, false>(km, P, grid, s);
-    return split3 ? launch_kw<128, true>(km, P, grid, s) : launch_kw<128, false>(km, P, grid, s);
+    if (mt == 1) {
+      if (bn == 64) return split3 ? launch_kw<64, true, 1>(km, P, grid, s) : launch_kw<64, false, 1>(km, P, grid, s);
+      return split3 ? launch_kw<128, true, 1>(km, P, grid, s) : launch_kw<128, false, 1>(km, P, grid, s);
+    }
+    if (bn == 64) return split3 ? launch_kw<64, true, 2>(km, P, grid, s) : launch_kw<64, false, 2>(km, P, grid, s);
+    return split3 ? launch_kw<128, true, 2>(km, P, grid, s) : launch_kw<128, false, 2>(km, P, grid, s);
   }
   P.bt_log2 = pick_bt_log2(BM, F, T, &P.tiles_t, &P.tiles_f);
   Maps tm;
