@@ -149,7 +149,11 @@ class LmSession:
         captured at the second call with the same shapes and hyper-parameters; the dropout seed lives in a device word."""
         n = len(train)
         T, B = val[0].shape
-        assert all(t.shape == (T, B) for t, _ in train), "every task block must have the val block's (bptt, batch) shape"
+        if not all(tuple(t.shape) == (T, B) for t, _ in train):
+            # blocks at the end of a corpus are shorter than bptt (lm/util/data.py:37): compose the same iteration from
+            # single passes and arena kernels (still no host sync)
+            return self._meta_step_ragged(theta, theta_work, grad, meta_grad, hidden, train, val, weights, lr, meta_lr_factor,
+                                          clip, dropout, seed, results)
         if not graph:
             toks = [t.to(self.device, torch.int64).contiguous() for t, _ in train]
             trgs = [y.to(self.device, torch.int64).contiguous().view(-1) for _, y in train]
@@ -192,3 +196,29 @@ class LmSession:
             cur.wait_stream(side)
             g["graph"] = cg
             cg.replay()                            # the capture itself executed nothing
+
+    def _meta_step_ragged(self, theta, theta_work, grad, meta_grad, hidden, train, val, weights, lr, meta_lr_factor, clip,
+                          dropout, seed, results):
+        """mtl_lm_meta_step restated over mtl_lm_pass + mtl_arena_* for task blocks of different lengths."""
+        n_f, st = self.n_floats, _stream
+        lib = self.lib
+        _l.check(lib.mtl_arena_zero(_ptr(meta_grad), n_f, st()))
+        for i, (tok, trg) in enumerate(train):
+            _l.check(lib.mtl_arena_copy(_ptr(theta_work), _ptr(theta), n_f, st()))
+            _l.check(lib.mtl_arena_zero(_ptr(grad), n_f, st()))
+            out = self.run(theta_work, tok, trg, hidden=hidden, grad=grad, dropout=dropout, seed=int(seed) * 128 + 2 * i)
+            if results is not None:
+                results[i, :8].copy_(out["loss"])
+            if clip and clip > 0:
+                _l.check(lib.mtl_arena_clip(_ptr(grad), n_f, float(clip), _ptr(self._scratch), st()))
+            _l.check(lib.mtl_arena_sgd(_ptr(theta_work), _ptr(grad), float(lr) / float(meta_lr_factor), n_f, st()))
+            hidden[0].copy_(out["hidden"][0])
+            hidden[1].copy_(out["hidden"][1])
+            # a val block of another batch width cannot take this hidden state; the reference would fail there as well
+            out = self.run(theta_work, val[0], val[1], hidden=hidden, grad=meta_grad, dropout=dropout,
+                           seed=int(seed) * 128 + 2 * i + 1, scale=float(weights[i]), hidden_out=False)
+            if results is not None:
+                results[i, 8:].copy_(out["loss"])
+        if clip and clip > 0:
+            _l.check(lib.mtl_arena_clip(_ptr(meta_grad), n_f, float(clip), _ptr(self._scratch), st()))
+        _l.check(lib.mtl_arena_sgd(_ptr(theta), _ptr(meta_grad), float(lr), n_f, st()))

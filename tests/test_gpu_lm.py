@@ -177,3 +177,58 @@ def test_lm_meta_step_graph_replay_equals_eager():
         out.append((theta.cpu().clone(), hidden[0].cpu().clone(), res.cpu().clone()))
     assert rel_err(out[1][0], out[0][0]) < 1e-5 and rel_err(out[1][1], out[0][1]) < 1e-5
     assert rel_err(out[1][2][:, 8], out[0][2][:, 8]) < 1e-5
+
+
+def test_lm_cli_runs_on_synthetic_corpora(tmp_path):
+    """lm/main_meta_transfer.py (the reference script's flags) end to end on nine tiny synthetic corpus files: model
+    build, LMDataset sampling, meta-iterations from the CUDA graph, a log line, validation / test evaluation, checkpoint."""
+    import random
+    import subprocess
+    pkg = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "meta-transfer-learning_b200")
+    rnd = random.Random(3)
+    words = [f"w{i}" for i in range(60)]
+    d = tmp_path / "data"
+    d.mkdir()
+    for name in ("seame_train", "seame_valid", "seame_test", "cv_train", "cv_valid", "cv_test", "hkust_train", "hkust_dev"):
+        n_lines = 120 if name.endswith("train") else 30
+        with open(d / f"{name}.txt", "w") as f:
+            for _ in range(n_lines):
+                f.write(" ".join(rnd.choice(words) for _ in range(rnd.randint(3, 12))) + "\n")
+    cmd = [sys.executable, os.path.join(pkg, "lm", "main_meta_transfer.py"), "--cuda", "--data-dir", str(d), "--emsize", "32",
+           "--nhid", "32", "--bptt", "5", "--batch_size", "4", "--lr", "1", "--iterations", "13", "--log-interval", "4",
+           "--valid-interval", "8", "--save", str(tmp_path / "model"), "--name", "t"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "| it   4 | lr" in r.stdout and "val loss" in r.stdout and "End of training" in r.stdout
+    assert os.path.exists(tmp_path / "model" / "t.pt")
+    sd = torch.load(tmp_path / "model" / "t.pt", map_location="cpu")
+    assert list(sd.keys())[0] == "encoder.weight" and sd["encoder.weight"].shape[1] == 32
+
+
+def test_lm_meta_step_with_ragged_blocks_matches_oracle():
+    """Task blocks of different lengths (the tail of a corpus is shorter than bptt, lm/util/data.py:37): the iteration is
+    composed from single passes and arena kernels and still equals the oracle."""
+    cfg = ref_lm.LmConfig(vocab=400, ninp=32, nhid=32, nlayers=2)
+    p = ref_lm.init_params(cfg, 8)
+    g = torch.Generator().manual_seed(12)
+
+    def block(T, B=4):
+        stream = torch.randint(0, cfg.vocab, (T + 1, B), generator=g)
+        return stream[:T].contiguous(), stream[1:].reshape(-1).contiguous()
+    train, val = [block(7), block(3), block(7)], block(5)
+    s = _session(cfg)
+    theta, work, grad, meta = s.new_arena(), s.new_arena(), s.new_arena(), s.new_arena()
+    s.load(theta, p)
+    hidden = s.new_hidden(4)
+    res = torch.zeros(3, 16, device=dev())
+    w = [0.1, 0.1, 0.8]
+    s.meta_step(theta, work, grad, meta, hidden, train, val, w, lr=1.5, meta_lr_factor=3.0, clip=0.25, dropout=0.0, seed=0,
+                results=res, graph=True)
+    torch.cuda.synchronize()
+    new_p, hid_o, trl, vall, _ = ref_lm.meta_step(p, cfg, train, val, w, None, lr=1.5, meta_lr_factor=3.0, clip=0.25)
+    tv = s.views(theta)
+    for k in ref_lm.param_names(cfg):
+        assert rel_err(tv[k], new_p[k]) < 5 * TOL, k
+    assert rel_err(hidden[0], hid_o[0]) < 5 * TOL
+    r = res.cpu()
+    assert all(abs(float(r[i, 8]) - vall[i]) < 5 * TOL * abs(vall[i]) for i in range(3))
