@@ -430,7 +430,11 @@ static bool zslab_enabled() {
 // Should the [M, N] output of a K-deep beta == 0 GEMM live in the zero pool?
 static bool use_zslab(const Run& R, int M, int N, int Kd) {
   if (!zslab_enabled() || R.no_zslab || R.S->mode == MTL_GEMM_SIMT_FP32 || N % 4 != 0 || Kd < 256) return false;
-  return (long long)mtl_cdiv(M, 128) * mtl_cdiv(N, N <= 64 ? 64 : 128) <= 16;
+  // <= 24 tiles: the d x d projections of cfg 2 (FFN W2 forward, the masked FFN dgrad) run as slabs too -- a cluster
+  // split-K GEMM spends 4.3 us after its MMAs on the cluster barrier + DSMEM pull (9.5 us per node vs 6.9 us as slabs)
+  static int lim = -1;
+  if (lim < 0) { const char* e = getenv("MTL_ZSLAB_TILES"); lim = e ? atoi(e) : 24; }
+  return (long long)mtl_cdiv(M, 128) * mtl_cdiv(N, N <= 64 ? 64 : 128) <= lim;
 }
 static int wgrad_ctas() {
   static int v = -1;
@@ -446,7 +450,7 @@ static int lin_dgrad(Run& R, const float* dy, int ldy, const float* W, float* dx
   g.M = M; g.N = Kd; g.K = N; g.alpha = 1.f; g.beta = beta; g.epi = epi; g.aux = aux; g.split_k = 1;
   if (beta == 1.f && epi == EPI_NONE)
     g.split_k = slab_split((long long)mtl_cdiv(M, 128) * mtl_cdiv(Kd, Kd <= 64 ? 64 : 128), N, dgrad_ctas());
-  else if (dx_zeroed && beta == 0.f && epi == EPI_NONE) {
+  else if (dx_zeroed && beta == 0.f && (epi == EPI_NONE || epi == EPI_RELU_BWD)) {     // the ReLU mask is linear: masked slabs add up
     const int sp = slab_split((long long)mtl_cdiv(M, 128) * mtl_cdiv(Kd, Kd <= 64 ? 64 : 128), N, zslab_ctas());
     if (sp > 1) { g.beta = 1.f; g.split_k = sp; }
   }
@@ -887,7 +891,8 @@ static int ffn_block_bwd(Run& R, const FfnAct& A, const float* dout, float* dx) 
   const mtl_model_cfg& c = R.S->cfg;
   const int d = c.d_model, f = c.d_inner, M = A.M;
   float* df2 = R.ws.f((size_t)M * d);
-  float* df1 = R.ws.f((size_t)M * f);
+  const bool z1 = use_zslab(R, M, f, d);
+  float* df1 = z1 ? R.wz.f((size_t)M * f) : R.ws.f((size_t)M * f);
   const cudaStream_t sw = R.wside();
   K(k_ln_bwd(dout, A.xhat, A.rstd, R.theta + A.p.ln_w, A.rowmask, A.drop, df2, dx, 0, R.grad + A.p.ln_w,
              R.grad + A.p.ln_b, M, d, R.st));
@@ -897,7 +902,7 @@ static int ffn_block_bwd(Run& R, const FfnAct& A, const float* dout, float* dx) 
     MTL_TRY(lin_wgrad(R, df2, d, A.f1, f, R.grad + A.p.w2, M, d, f));
     K(k_colsum_acc(df2, M, d, d, R.grad + A.p.b2, R.st));
   }
-  MTL_TRY(lin_dgrad(R, df2, d, R.theta + A.p.w2, df1, f, M, d, f, 0.f, EPI_RELU_BWD, A.f1));
+  MTL_TRY(lin_dgrad(R, df2, d, R.theta + A.p.w2, df1, f, M, d, f, 0.f, EPI_RELU_BWD, A.f1, z1));
   MTL_TRY(chain(R, R.main, sw));
   {
     On on(R, sw);

@@ -1875,7 +1875,9 @@ int k_gemm_tc(const GemmArgs& g, int precision_mode, cudaStream_t s) {
   P.conv_mode = CONV_NONE;
   P.lin_stages = lin_stages;
   P.kb_total = mtl_cdiv(g.K, BK);
-  if (g.split_k > 1) MTL_REQUIRE(g.beta == 1.f && g.epi == EPI_NONE, "split-K needs beta=1, no activation epilogue");
+  // K slabs accumulate into C: the epilogue has to be linear in the partial sum -- none, or the ReLU-backward mask (an
+  // element-wise 0 / 1 factor: every slab masks its partial; TMA epilogue only)
+  if (g.split_k > 1) MTL_REQUIRE(g.beta == 1.f && (g.epi == EPI_NONE || g.epi == EPI_RELU_BWD), "split-K needs beta=1 and a linear epilogue");
   int split = plan_split(P, g.split_k);
   P.cluster_k = 1;
   if (g.split_k <= 1 && cluster_split_enabled()) {
@@ -1908,7 +1910,8 @@ int k_gemm_tc(const GemmArgs& g, int precision_mode, cudaStream_t s) {
   MTL_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "gemm grid too large");
   const int M = g.M, N = g.N, ldc = g.ldc;
   MTL_TRY(plan_epilogue(P, tm, [&](const float* ptr, CUtensorMap* out) { return make_map(ptr, N, M, ldc, BM, false, false, out); }));
-  MTL_REQUIRE(!(g.split_k > 1 && g.bias) || P.tma_epi, "split-K with bias needs the TMA epilogue (16 B aligned C, N % 4 == 0)");
+  MTL_REQUIRE(!(g.split_k > 1 && (g.bias || g.epi == EPI_RELU_BWD)) || P.tma_epi,
+              "split-K with bias / ReLU mask needs the TMA epilogue (16 B aligned C, N % 4 == 0)");
   return dispatch(bn, split3, a_mn, b_mn, tm, P, grid, s);
 }
 

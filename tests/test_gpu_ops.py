@@ -57,6 +57,11 @@ def test_gemm_epilogues(mode):
     Cd = torch.empty(M, N, device=dev())
     ok(lib().mtl_gemm(mode, 0, 1, M, N, K, 1.0, P(Ad), K, P(Wd), K, 0.0, P(Cd), N, None, 2, P(auxd), 1, stream()))
     assert rel_err(Cd, F.linear(A.double(), W.double()) * (aux > 0).double()) < tol
+    # K slabs with the ReLU-backward mask (a linear epilogue: every slab masks its partial; the masked FFN dgrad of the engine)
+    if mode != 0:
+        Cd = torch.zeros(M, N, device=dev())
+        ok(lib().mtl_gemm(mode, 0, 1, M, N, K, 1.0, P(Ad), K, P(Wd), K, 1.0, P(Cd), N, None, 2, P(auxd), 4, stream()))
+        assert rel_err(Cd, F.linear(A.double(), W.double()) * (aux > 0).double()) < tol
     # split-K wgrad-style: C[N,K] += A^T[M,N]^T . X[M,K]
     Mr = 4000
     dy, x = _r(Mr, 64, seed=8), _r(Mr, 576, seed=9)
