@@ -1684,7 +1684,7 @@ bool conv_wgrad_two_cta() {
 // pipelines, 1, 2 (default).
 int lin_small_stages() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("MTL_LIN_STAGES"); v = e ? atoi(e) : 2; if (v < 0 || v > 2) v = 2; }
+  if (v < 0) { const char* e = getenv("MTL_LIN_STAGES"); v = e ? atoi(e) : 2; if (v < 0 || (v > 2 && v != 4)) v = 2; }   // 4: 64-wide tiles, 4 x 48 KB
   return v;
 }
 int lin_small_bn() {
@@ -1695,7 +1695,7 @@ int lin_small_bn() {
 template <int BN, bool SPLIT3>
 int dispatch_major(bool a_mn, bool b_mn, const Maps& tm, const TcParams& P, dim3 grid, cudaStream_t s) {
   constexpr int STAGES = SPLIT3 ? (BN == 64 ? 4 : 3) : (BN == 64 ? 4 : 3);
-  if (P.lin_stages > 0 && P.conv_mode == CONV_NONE) {
+  if (P.lin_stages > 0 && P.lin_stages <= 2 && P.conv_mode == CONV_NONE) {
     // smallest legal ring: the staged output tile (TMA or padded row-major) has to fit in the operand stages
     constexpr int S1 = SPLIT3 ? (BN == 64 ? 1 : 2) : (BN == 64 ? 2 : 3);
     constexpr int S2 = SPLIT3 ? 2 : 3;
