@@ -129,7 +129,10 @@ __device__ __forceinline__ void fill_smem(float* __restrict__ dst, const float* 
     for (int u = 0; u < 8; ++u) { const int i = i0 + u * (int)blockDim.x + (int)threadIdx.x; if (i < n4) d4[i] = v[u]; }
   }
 }
-constexpr int LM_BCH = 24, LM_WARPS = 8;      // batch rows per pass over the weights (the script's batch of 20 in one), warps per CTA
+#ifndef LM_WARPS_PER_CTA
+#define LM_WARPS_PER_CTA 4   // 8: 9.03, 4: 8.41, 2: 9.45 ms per meta-iteration (fewer shuffle reductions per SM vs. more state re-fills)
+#endif
+constexpr int LM_BCH = 24, LM_WARPS = LM_WARPS_PER_CTA;      // batch rows per pass over the weights (the script's batch of 20 in one), warps per CTA
 constexpr int LM_KPF = 8, LM_KPB = 16;        // weight values per lane fetched together (all loads in flight before the first FMA)
 __global__ void __launch_bounds__(LM_WARPS * 32) lstm_step_fwd_kernel(const float* __restrict__ xg, const float* __restrict__ h_prev,
                                                                       const float* __restrict__ c_prev, const float* __restrict__ Whh,
@@ -254,6 +257,161 @@ __global__ void __launch_bounds__(LM_WARPS * 32) lstm_step_bwd_kernel(const floa
   }
 }
 
+// ---- persistent variants: ALL time steps of one layer in ONE launch.  A warp keeps its unit's recurrent weights in
+// registers across the whole sequence (the step kernels re-read the 640 KB W_hh from the L2 at every step), the CTAs meet at
+// a global-memory barrier between steps (h_t / dgates_t of every unit must be visible before step t +- 1 starts) and the
+// cell-gradient carry never leaves its thread.  35 launches and launch gaps per layer become one; eligible when the batch
+// fits one chunk (B <= LM_BCH) and the weights fit the register budget (nhid <= 256); MTL_LM_SEQ=0 keeps the step kernels.
+constexpr int LM_KPS = 32;                    // W_hh^T values per lane held by the backward sequence kernel (4 * nhid <= 1024)
+__device__ __forceinline__ void fill_smem_cg(float* __restrict__ dst, const float* src, int n) {
+  // as fill_smem, but through the L2 (ld.global.cg): the data was written by other CTAs of THIS launch
+  const int n4 = n >> 2;
+  const float4* s4 = reinterpret_cast<const float4*>(src);
+  float4* d4 = reinterpret_cast<float4*>(dst);
+  for (int i0 = 0; i0 < n4; i0 += 8 * (int)blockDim.x) {
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { const int i = i0 + u * (int)blockDim.x + (int)threadIdx.x; if (i < n4) v[u] = __ldcg(s4 + i); }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { const int i = i0 + u * (int)blockDim.x + (int)threadIdx.x; if (i < n4) d4[i] = v[u]; }
+  }
+}
+// all CTAs of the grid have finished step `round` (1-based); bounded spin: a scheduling bug must trap, not hang the GPU
+__device__ __forceinline__ void lm_grid_barrier(unsigned* bar, unsigned round) {
+  __threadfence();                               // this thread's h / dgates stores -> device scope
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    atomicAdd(bar, 1u);
+    const unsigned target = round * gridDim.x;
+    const long long t0 = clock64();
+    while (true) {
+      unsigned v;
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+      if (v >= target) break;
+      if (clock64() - t0 > 4000000000LL) __trap();
+    }
+  }
+  __syncthreads();
+}
+__global__ void __launch_bounds__(LM_WARPS * 32) lstm_seq_fwd_kernel(const float* __restrict__ xg, float* hseq, float* cseq,
+                                                                     const float* __restrict__ Whh, const float* __restrict__ b_hh,
+                                                                     float* __restrict__ gates, int B, int H, int T, unsigned* bar) {
+  extern __shared__ float hs[];                   // h_{t-1}[0 .. B, :]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int j = blockIdx.x * LM_WARPS + warp;
+  const int H4 = 4 * H;
+  const size_t BH = (size_t)B * H;
+  float w[4][LM_KPF];
+  float bh[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < LM_KPF; ++i) {
+    const int k = i * 32 + lane;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) w[g][i] = (j < H && k < H) ? __ldg(Whh + (size_t)(g * H + j) * H + k) : 0.f;
+  }
+  if (j < H) { bh[0] = b_hh[j]; bh[1] = b_hh[H + j]; bh[2] = b_hh[2 * H + j]; bh[3] = b_hh[3 * H + j]; }
+  for (int t = 0; t < T; ++t) {
+    fill_smem_cg(hs, hseq + (size_t)t * BH, B * H);
+    __syncthreads();
+    if (j < H) {
+      // two half-chunks of 12 batch rows: 48 accumulators live beside the 32 weight registers (96 spilled)
+      float a4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+      for (int bb = 0; bb < LM_BCH; bb += LM_BCH / 2) {
+        float acc[4][LM_BCH / 2];
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+#pragma unroll
+          for (int b = 0; b < LM_BCH / 2; ++b) acc[g][b] = 0.f;
+#pragma unroll
+        for (int i = 0; i < LM_KPF; ++i) {
+          const int k = i * 32 + lane;
+          if (i * 32 >= H) break;                  // warp-uniform
+#pragma unroll
+          for (int b = 0; b < LM_BCH / 2; ++b) {
+            const float hv = (bb + b < B && k < H) ? hs[(bb + b) * H + k] : 0.f;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) acc[g][b] = fmaf(hv, w[g][i], acc[g][b]);
+          }
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+#pragma unroll
+          for (int b = 0; b < LM_BCH / 2; ++b) acc[g][b] = warp_sum(acc[g][b]);
+#pragma unroll
+        for (int b = 0; b < LM_BCH / 2; ++b)
+          if (lane == bb + b) { a4[0] = acc[0][b]; a4[1] = acc[1][b]; a4[2] = acc[2][b]; a4[3] = acc[3][b]; }
+      }
+      if (lane < B) {
+        const int b = lane;
+        const float* x = xg + ((size_t)t * B + b) * H4;
+        const float gi = sigmoidf_(x[j] + bh[0] + a4[0]);
+        const float gf = sigmoidf_(x[H + j] + bh[1] + a4[1]);
+        const float gg = tanhf(x[2 * H + j] + bh[2] + a4[2]);
+        const float go = sigmoidf_(x[3 * H + j] + bh[3] + a4[3]);
+        const float c = gf * __ldcg(cseq + (size_t)t * BH + (size_t)b * H + j) + gi * gg;
+        float* g = gates + ((size_t)t * B + b) * H4;
+        g[j] = gi; g[H + j] = gf; g[2 * H + j] = gg; g[3 * H + j] = go;
+        cseq[(size_t)(t + 1) * BH + (size_t)b * H + j] = c;
+        hseq[(size_t)(t + 1) * BH + (size_t)b * H + j] = go * tanhf(c);
+      }
+    }
+    if (t + 1 < T) lm_grid_barrier(bar, (unsigned)(t + 1));   // also protects hs against the next step's refill
+  }
+}
+__global__ void __launch_bounds__(LM_WARPS * 32) lstm_seq_bwd_kernel(const float* __restrict__ dh_above, const float* __restrict__ WhhT,
+                                                                     const float* __restrict__ gates, const float* __restrict__ cseq,
+                                                                     float* dgates, int B, int H, int T, unsigned* bar) {
+  extern __shared__ float ds[];                   // dgates_{t+1}[0 .. B, :] (4H each)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int j = blockIdx.x * LM_WARPS + warp;
+  const int H4 = 4 * H;
+  const size_t BH = (size_t)B * H;
+  float wv[LM_KPS];
+#pragma unroll
+  for (int i = 0; i < LM_KPS; ++i) { const int m = i * 32 + lane; wv[i] = (j < H && m < H4) ? __ldg(WhhT + (size_t)j * H4 + m) : 0.f; }
+  float dc_carry = 0.f;                            // of (b = lane, j): never leaves this thread
+  for (int t = T - 1; t >= 0; --t) {
+    float rec = 0.f;
+    if (t + 1 < T) {
+      fill_smem_cg(ds, dgates + (size_t)(t + 1) * B * H4, B * H4);
+      __syncthreads();
+      if (j < H) {
+        float acc[LM_BCH];
+#pragma unroll
+        for (int b = 0; b < LM_BCH; ++b) acc[b] = 0.f;
+#pragma unroll
+        for (int i = 0; i < LM_KPS; ++i) {
+          const int m = i * 32 + lane;
+          if (i * 32 >= H4) break;                 // warp-uniform
+#pragma unroll
+          for (int b = 0; b < LM_BCH; ++b) acc[b] = fmaf((b < B && m < H4) ? ds[b * H4 + m] : 0.f, wv[i], acc[b]);
+        }
+#pragma unroll
+        for (int b = 0; b < LM_BCH; ++b) acc[b] = warp_sum(acc[b]);
+#pragma unroll
+        for (int b = 0; b < LM_BCH; ++b)
+          if (lane == b) rec = acc[b];
+      }
+    }
+    if (j < H && lane < B) {
+      const int b = lane;
+      const float dh = dh_above[(size_t)t * BH + (size_t)b * H + j] + rec;
+      const float* g = gates + ((size_t)t * B + b) * H4;
+      const float gi = g[j], gf = g[H + j], gg = g[2 * H + j], go = g[3 * H + j];
+      const float tc = tanhf(cseq[(size_t)(t + 1) * BH + (size_t)b * H + j]);
+      const float dc = dc_carry + dh * go * (1.f - tc * tc);
+      float* d = dgates + ((size_t)t * B + b) * H4;
+      d[j] = dc * gg * gi * (1.f - gi);
+      d[H + j] = dc * cseq[(size_t)t * BH + (size_t)b * H + j] * gf * (1.f - gf);
+      d[2 * H + j] = dc * gi * (1.f - gg * gg);
+      d[3 * H + j] = dh * tc * go * (1.f - go);
+      dc_carry = dc * gf;
+    }
+    if (t > 0) lm_grid_barrier(bar, (unsigned)(T - t));
+  }
+}
+
 // ----------------------------------------------------------------------------- host helpers
 int gemm(int mode, const float* A, int lda, int tA, const float* B, int ldb, int tB, float* C, int ldc, int M, int N, int K,
          float beta, const float* bias, int split, cudaStream_t s) {
@@ -275,6 +433,7 @@ struct LmPlan {
   float *hseq[8], *cseq[8], *gates[8], *yd[8], *whhT[8];
   float *logits, *dlogits, *row_lse, *row_loss, *dy, *dgates, *dc;
   int *gold, *hyp;
+  unsigned* bar;                     // grid-barrier counters of the sequence kernels: 2 per layer
   CeOut* ce;
   size_t bytes;
 };
@@ -301,6 +460,7 @@ void plan_ws(const mtl_lm_cfg& c, int T, int B, uintptr_t base, LmPlan& P) {
   P.dc = w.f((size_t)B * H);
   P.gold = (int*)w.raw(R * sizeof(int)); P.hyp = (int*)w.raw(R * sizeof(int));
   P.ce = (CeOut*)w.f(8);
+  P.bar = (unsigned*)w.raw(64 * sizeof(unsigned));
   P.bytes = w.off + 256;
 }
 
@@ -334,6 +494,20 @@ int lm_pass(const mtl_lm_cfg& c, const LmLayout& L, int mode, const float* theta
     }
   }
 
+  // whole-sequence kernels (one launch per layer and direction) when the batch is one chunk and the weights fit registers
+  static int seq_env = -1;
+  if (seq_env < 0) { const char* e = getenv("MTL_LM_SEQ"); seq_env = (e && e[0] == '1') ? 1 : 0; }
+  const bool seq = seq_env && B <= LM_BCH && H <= 32 * LM_KPF && H4 <= 32 * LM_KPS && (int)sgrid.x <= 148;
+  if (seq) MTL_CHECK_CUDA(cudaMemsetAsync(P.bar, 0, 64 * sizeof(unsigned), s));
+  {
+    static size_t configured_seq = 0;
+    if (bwd_smem > configured_seq) {
+      MTL_CHECK_CUDA(cudaFuncSetAttribute(lstm_seq_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem));
+      MTL_CHECK_CUDA(cudaFuncSetAttribute(lstm_seq_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem));
+      configured_seq = bwd_smem;
+    }
+  }
+
   // ---- forward
   lm_embed_fwd_kernel<<<ew_grid((size_t)R * c.ninp), 256, 0, s>>>(tokens, theta + L.enc, lm_drop(p_drop, sd, 0), P.emb, R, c.ninp, V);
   MTL_CHECK_LAUNCH();
@@ -346,7 +520,12 @@ int lm_pass(const mtl_lm_cfg& c, const LmLayout& L, int mode, const float* theta
     MTL_TRY(gemm(mode, x, in, 0, theta + L.w_ih[l], in, 1, P.xg, H4, R, H4, in, 0.f, theta + L.b_ih[l], 1, s));
     MTL_TRY(k_copy(P.hseq[l], h0 ? h0 + (size_t)l * BH : P.zeros, BH, s));
     MTL_TRY(k_copy(P.cseq[l], c0 ? c0 + (size_t)l * BH : P.zeros, BH, s));
-    for (int t = 0; t < T; ++t) {
+    if (seq) {
+      lstm_seq_fwd_kernel<<<sgrid, LM_WARPS * 32, fwd_smem, s>>>(P.xg, P.hseq[l], P.cseq[l], theta + L.w_hh[l], theta + L.b_hh[l],
+                                                                 P.gates[l], B, H, T, P.bar + 2 * l);
+      MTL_CHECK_LAUNCH();
+    }
+    for (int t = 0; t < T && !seq; ++t) {
       lstm_step_fwd_kernel<<<sgrid, LM_WARPS * 32, fwd_smem, s>>>(P.xg + (size_t)t * B * H4, P.hseq[l] + (size_t)t * BH,
                                                                   P.cseq[l] + (size_t)t * BH, theta + L.w_hh[l], theta + L.b_hh[l],
                                                                   P.gates[l] + (size_t)t * B * H4, P.cseq[l] + (size_t)(t + 1) * BH,
@@ -395,7 +574,12 @@ int lm_pass(const mtl_lm_cfg& c, const LmLayout& L, int mode, const float* theta
       MTL_CHECK_LAUNCH();
     }
     MTL_TRY(k_zero(P.dc, BH, s));
-    for (int t = T - 1; t >= 0; --t) {
+    if (seq) {
+      lstm_seq_bwd_kernel<<<sgrid, LM_WARPS * 32, bwd_smem, s>>>(P.dy, P.whhT[l], P.gates[l], P.cseq[l], P.dgates, B, H, T,
+                                                                 P.bar + 2 * l + 1);
+      MTL_CHECK_LAUNCH();
+    }
+    for (int t = T - 1; t >= 0 && !seq; --t) {
       lstm_step_bwd_kernel<<<sgrid, LM_WARPS * 32, bwd_smem, s>>>(P.dy + (size_t)t * BH,
                                                                   t + 1 < T ? P.dgates + (size_t)(t + 1) * B * H4 : nullptr,
                                                                   P.whhT[l], P.gates[l] + (size_t)t * B * H4,

@@ -232,3 +232,15 @@ def test_lm_meta_step_with_ragged_blocks_matches_oracle():
     assert rel_err(hidden[0], hid_o[0]) < 5 * TOL
     r = res.cpu()
     assert all(abs(float(r[i, 8]) - vall[i]) < 5 * TOL * abs(vall[i]) for i in range(3))
+
+
+def test_lm_sequence_kernels_match_step_kernels():
+    """MTL_LM_SEQ=1: one persistent kernel per layer and direction (weights in registers, global-memory barrier between
+    time steps) instead of one launch per step -- same pass, checked against the oracle in a fresh process (the switch is
+    read once per process)."""
+    import subprocess
+    env = dict(os.environ, MTL_LM_SEQ="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-q", "-x", "-k",
+                        "cfg5_pass_matches_oracle or meta_step_matches_oracle"], capture_output=True, text=True, env=env, timeout=600,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0 and " passed" in r.stdout, r.stdout[-1500:] + r.stderr[-500:]
