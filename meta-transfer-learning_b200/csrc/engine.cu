@@ -442,15 +442,18 @@ static int wgrad_ctas() {
   return v;
 }
 // dx[M,K] = epi(dy[M,N] . W[N,K]) + beta*dx
+// atomic: other streams accumulate into dx at the same time -- at least two K slabs, i.e. the reduce-add epilogue
 static int lin_dgrad(Run& R, const float* dy, int ldy, const float* W, float* dx, int ldx, int M, int N, int Kd,
-                     float beta, int epi, const float* aux, bool dx_zeroed = false, int cls = MTL_OP_LIN_DGRAD) {
+                     float beta, int epi, const float* aux, bool dx_zeroed = false, int cls = MTL_OP_LIN_DGRAD,
+                     bool atomic = false) {
   GemmArgs g;
   memset(&g, 0, sizeof(g));
   g.A = dy; g.lda = ldy; g.transA = 0; g.B = W; g.ldb = Kd; g.transB = 0; g.C = dx; g.ldc = ldx;
   g.M = M; g.N = Kd; g.K = N; g.alpha = 1.f; g.beta = beta; g.epi = epi; g.aux = aux; g.split_k = 1;
-  if (beta == 1.f && epi == EPI_NONE)
+  if (beta == 1.f && epi == EPI_NONE) {
     g.split_k = slab_split((long long)mtl_cdiv(M, 128) * mtl_cdiv(Kd, Kd <= 64 ? 64 : 128), N, dgrad_ctas());
-  else if (dx_zeroed && beta == 0.f && (epi == EPI_NONE || epi == EPI_RELU_BWD)) {     // the ReLU mask is linear: masked slabs add up
+    if (atomic && g.split_k < 2) g.split_k = 2;
+  } else if (dx_zeroed && beta == 0.f && (epi == EPI_NONE || epi == EPI_RELU_BWD)) {     // the ReLU mask is linear: masked slabs add up
     const int sp = slab_split((long long)mtl_cdiv(M, 128) * mtl_cdiv(Kd, Kd <= 64 ? 64 : 128), N, zslab_ctas());
     if (sp > 1) { g.beta = 1.f; g.split_k = sp; }
   }
@@ -506,11 +509,12 @@ static int lowrank_bwd_head(Run& R, const LowRankAct& A, const float* dy, cudaEv
   }
   return MTL_OK;
 }
-static int lowrank_bwd_tail(Run& R, const LowRankAct& A, const LrBwd& h, float* dx, float beta_dx, cudaStream_t s_x) {
+static int lowrank_bwd_tail(Run& R, const LowRankAct& A, const LrBwd& h, float* dx, float beta_dx, cudaStream_t s_x,
+                            bool atomic = false) {
   const int r = R.S->cfg.rank;
   MTL_TRY(ev_wait(R, s_x, h.e_da));
   On on(R, s_x);
-  return lin_dgrad(R, h.da, r, R.theta + A.offA, dx, A.K, A.M, r, A.K, beta_dx, EPI_NONE, nullptr);
+  return lin_dgrad(R, h.da, r, R.theta + A.offA, dx, A.K, A.M, r, A.K, beta_dx, EPI_NONE, nullptr, false, MTL_OP_LIN_DGRAD, atomic);
 }
 
 // ----------------------------------------------------------------------------- fused low-rank projection pairs
@@ -859,12 +863,29 @@ static int attn_block_bwd(Run& R, const AttnAct& A, const float* dout, float* dx
     MTL_TRY(lowrank_bwd_head(R, A.q, dq, nullptr, R.main, R.wside(), &hq));
     MTL_TRY(lowrank_bwd_tail(R, A.q, hq, dxq, 1.f, R.main));
   } else {
-    MTL_TRY(lowrank_bwd_head(R, A.k, dkk, e_qkv, R.side(S_K), R.side(S_K), &hk));
-    MTL_TRY(lowrank_bwd_head(R, A.v, dvv, e_qkv, R.side(S_V), R.side(S_V), &hv));
-    MTL_TRY(lowrank_bwd_head(R, A.q, dq, nullptr, R.main, R.wside(), &hq));
-    MTL_TRY(lowrank_bwd_tail(R, A.q, hq, dxq, 1.f, R.main));
-    MTL_TRY(lowrank_bwd_tail(R, A.k, hk, dxkv, 1.f, R.main));
-    MTL_TRY(lowrank_bwd_tail(R, A.v, hv, dxkv, 1.f, R.main));
+    // the three input gradients reduce-add into the same dx (dxkv aliases dxq): they run side by side on main / S_K / S_V
+    // as K slabs (the L2 does the sum, order-free) instead of one after the other on the chain -- the chain of a
+    // self-attention backward ends [attention, da, dx] instead of [attention, da_q, dx_q, dx_k, dx_v] (13 us per block);
+    // the parameter gradients of k / v move to the parameter-gradient streams so that S_K / S_V hold nothing else
+    // Only for a pass running alone (latency-bound: 1 lane 10.73 -> 10.52 ms/step); with several lanes in flight the extra
+    // concurrency costs more than the shorter chain saves (6.23 -> 6.32 ms/step), so the tails stay on the chain there.
+    if (g_mtl_concurrency <= 1) {
+      MTL_TRY(lowrank_bwd_head(R, A.k, dkk, e_qkv, R.side(S_K), R.wside(), &hk));
+      MTL_TRY(lowrank_bwd_tail(R, A.k, hk, dxkv, 1.f, R.side(S_K), true));
+      MTL_TRY(lowrank_bwd_head(R, A.v, dvv, e_qkv, R.side(S_V), R.wside(), &hv));
+      MTL_TRY(lowrank_bwd_tail(R, A.v, hv, dxkv, 1.f, R.side(S_V), true));
+      MTL_TRY(lowrank_bwd_head(R, A.q, dq, nullptr, R.main, R.wside(), &hq));
+      MTL_TRY(lowrank_bwd_tail(R, A.q, hq, dxq, 1.f, R.main, true));
+      MTL_TRY(chain(R, R.side(S_K), R.main));
+      MTL_TRY(chain(R, R.side(S_V), R.main));
+    } else {
+      MTL_TRY(lowrank_bwd_head(R, A.k, dkk, e_qkv, R.side(S_K), R.side(S_K), &hk));
+      MTL_TRY(lowrank_bwd_head(R, A.v, dvv, e_qkv, R.side(S_V), R.side(S_V), &hv));
+      MTL_TRY(lowrank_bwd_head(R, A.q, dq, nullptr, R.main, R.wside(), &hq));
+      MTL_TRY(lowrank_bwd_tail(R, A.q, hq, dxq, 1.f, R.main));
+      MTL_TRY(lowrank_bwd_tail(R, A.k, hk, dxkv, 1.f, R.main));
+      MTL_TRY(lowrank_bwd_tail(R, A.v, hv, dxkv, 1.f, R.main));
+    }
   }
   return MTL_OK;
 }
