@@ -74,21 +74,37 @@ __global__ void __launch_bounds__(128) conv1_fwd64_kernel(const float* __restric
     xr[kh] = x + ((size_t)b * F + (rv[kh] ? ff : f)) * T;
   }
   float* o = out + (size_t)row * T * 64 + c4;
-#pragma unroll 4
-  for (int t = t0 + half; t < t1; t += 2) {
-    float4 acc = b4;
+  // the x taps of four pixels are fetched before the first FMA (explicit batches, see conv1_wgrad64_kernel)
+  constexpr int U = 4;
+  for (int t = t0 + half; t < t1; t += 2 * U) {
+    float xv[U][9];
 #pragma unroll
-    for (int kh = 0; kh < 3; ++kh)
+    for (int u = 0; u < U; ++u)
 #pragma unroll
-      for (int kw = 0; kw < 3; ++kw) {
-        const int tt = t + kw - 1;
-        if (!rv[kh] || tt < 0 || tt >= T) continue;        // the generic kernel skips padded taps too (no +0 term)
-        const float xv = __ldg(xr[kh] + tt);
-        acc.x += xv * wr[kh * 3 + kw][0]; acc.y += xv * wr[kh * 3 + kw][1];
-        acc.z += xv * wr[kh * 3 + kw][2]; acc.w += xv * wr[kh * 3 + kw][3];
-      }
-    acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f);
-    *reinterpret_cast<float4*>(o + (size_t)t * 64) = acc;
+      for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const int tt = t + 2 * u + kw - 1;
+          xv[u][kh * 3 + kw] = (t + 2 * u < t1 && rv[kh] && tt >= 0 && tt < T) ? __ldg(xr[kh] + tt) : 0.f;
+        }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int tu = t + 2 * u;
+      if (tu >= t1) break;
+      float4 acc = b4;
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const int tt = tu + kw - 1;
+          if (!rv[kh] || tt < 0 || tt >= T) continue;      // the generic kernel skips padded taps too (no +0 term)
+          const float v = xv[u][kh * 3 + kw];
+          acc.x += v * wr[kh * 3 + kw][0]; acc.y += v * wr[kh * 3 + kw][1];
+          acc.z += v * wr[kh * 3 + kw][2]; acc.w += v * wr[kh * 3 + kw][3];
+        }
+      acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f);
+      *reinterpret_cast<float4*>(o + (size_t)tu * 64) = acc;
+    }
   }
 }
 int k_conv1_fwd(const float* x, const float* w, const float* b, float* out, int B, int F, int T, int Cout,
@@ -182,19 +198,34 @@ __global__ void __launch_bounds__(128) conv1_wgrad64_kernel(const float* __restr
       xr[kh] = x + ((size_t)b * F + (rv[kh] ? ff : f)) * T;
     }
     const float* g = dout + (size_t)row * T * 64 + c4;
-#pragma unroll 4
-    for (int t = t0 + half; t < t1; t += 2) {
-      const float4 gv = __ldg(reinterpret_cast<const float4*>(g + (size_t)t * 64));
-      acc[9][0] += gv.x; acc[9][1] += gv.y; acc[9][2] += gv.z; acc[9][3] += gv.w;
+    // Four pixels per thread are fetched before the first FMA (explicit batches: with a plain `#pragma unroll` the compiler
+    // kept load -> FMA -> load order, i.e. ONE 512-byte request per warp in flight and 0.9 TB/s; ncu, profiles/r02_d_*)
+    constexpr int U = 4;
+    for (int t = t0 + half; t < t1; t += 2 * U) {
+      float4 gv[U];
+      float xv[U][9];
 #pragma unroll
-      for (int kh = 0; kh < 3; ++kh)
+      for (int u = 0; u < U; ++u) {
+        const int tu = t + 2 * u;
+        const bool ok = tu < t1;
+        gv[u] = ok ? __ldg(reinterpret_cast<const float4*>(g + (size_t)tu * 64)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int kw = 0; kw < 3; ++kw) {
-          const int tt = t + kw - 1;
-          const float xv = (rv[kh] && tt >= 0 && tt < T) ? __ldg(xr[kh] + tt) : 0.f;
-          acc[kh * 3 + kw][0] += xv * gv.x; acc[kh * 3 + kw][1] += xv * gv.y;
-          acc[kh * 3 + kw][2] += xv * gv.z; acc[kh * 3 + kw][3] += xv * gv.w;
+        for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+            const int tt = tu + kw - 1;
+            xv[u][kh * 3 + kw] = (ok && rv[kh] && tt >= 0 && tt < T) ? __ldg(xr[kh] + tt) : 0.f;
+          }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        acc[9][0] += gv[u].x; acc[9][1] += gv[u].y; acc[9][2] += gv[u].z; acc[9][3] += gv[u].w;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+          acc[k][0] += xv[u][k] * gv[u].x; acc[k][1] += xv[u][k] * gv[u].y;
+          acc[k][2] += xv[u][k] * gv[u].z; acc[k][3] += xv[u][k] * gv[u].w;
         }
+      }
     }
   }
 #pragma unroll
