@@ -305,6 +305,10 @@ int mtl_conv1_fwd(const float* x, const float* w, const float* b, float* out, in
  * 3xTF32 their tf32 hi and lo halves). */
 int mtl_conv3x3_relu_fwd(int mode, const float* x, const float* w, const float* b, float* col,
                          float* wg, float* out, int B, int F, int T, int Cin, int Cout, void* stream);
+/* the same with the following MaxPool2d(2, 2) (models/asr/transformer.py:51,58) written from the convolution's epilogue:
+ * out [B,F,T,Cout] as above (the backward needs it) and pool_out [B,F/2,T/2,Cout]; tensor-core engines, Cout % 32 == 0 */
+int mtl_conv3x3_relu_pool_fwd(int mode, const float* x, const float* w, const float* b, float* wg, float* out,
+                              float* pool_out, int B, int F, int T, int Cin, int Cout, void* stream);
 /* Backward of y = conv3x3(x) + b given dy (gradient w.r.t. the pre-ReLU output): dw += , db += ,
  * dx = (dgrad) masked by relu_aux > 0 when relu_aux != NULL (dx may be NULL). */
 long long mtl_conv3x3_bwd_scratch_floats(int mode, int B, int F, int T, int Cin, int Cout);

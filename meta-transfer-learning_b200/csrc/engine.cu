@@ -952,7 +952,9 @@ static int conv_weight_layouts(Run& R, Pass& P) {
   }
   return MTL_OK;
 }
-static int conv_fwd(Run& R, ConvAct& A, const float* x, int B, int F, int T, int widx) {
+// pool_out (nullable): 2x2 max-pooled copy of the output; *pooled says whether the convolution's epilogue produced it
+static int conv_fwd(Run& R, ConvAct& A, const float* x, int B, int F, int T, int widx, float* pool_out = nullptr,
+                    bool* pooled = nullptr) {
   const Layout& L = R.S->L;
   A.x = x; A.B = B; A.F = F; A.T = T; A.Cin = kConvCin[widx]; A.Cout = kConvCout[widx]; A.widx = widx;
   const size_t P = (size_t)B * F * T;
@@ -960,9 +962,12 @@ static int conv_fwd(Run& R, ConvAct& A, const float* x, int B, int F, int T, int
   const bool implicit = R.S->mode != MTL_GEMM_SIMT_FP32;      // tcgen05 implicit GEMM: no patch matrix
   A.col = implicit ? nullptr : R.ws.f(P * Kc);
   A.y = R.ws.f(P * A.Cout);
+  if (pooled) *pooled = false;
   if (implicit) {
-    K(k_conv3x3_tc(x, A.wg, R.theta + L.conv_b[widx], A.y, B, F, T, A.Cin, A.Cout, EPI_RELU, nullptr, op_mode(R.S, MTL_OP_CONV_FWD),
-                   k_conv3x3_w_split(op_mode(R.S, MTL_OP_CONV_FWD), A.Cout), R.st));
+    const int m = op_mode(R.S, MTL_OP_CONV_FWD), ws = k_conv3x3_w_split(m, A.Cout);
+    const bool fuse = pool_out && k_conv3x3_pool_fuse_default() && k_conv3x3_pool_fusable(m, A.Cout, ws);
+    if (pooled) *pooled = fuse;
+    K(k_conv3x3_tc(x, A.wg, R.theta + L.conv_b[widx], A.y, B, F, T, A.Cin, A.Cout, EPI_RELU, nullptr, m, ws, R.st, fuse ? pool_out : nullptr));
   } else {
     K(k_im2col3x3(x, A.col, B, F, T, A.Cin, R.st));
     MTL_TRY(lin_fwd(R, A.col, Kc, A.wg, R.theta + L.conv_b[widx], A.y, A.Cout, (int)P, A.Cout, Kc, EPI_RELU));
@@ -1063,13 +1068,16 @@ static int forward(Run& R, const mtl_batch& b, const float* pe_enc, const float*
   MTL_TRY(conv_weight_layouts(R, P));
   K(k_conv1_fwd(b.x, R.theta + L.conv_w[0], R.theta + L.conv_b[0], P.c1, B, P.F, P.T, 64, R.st));
   MTL_TRY(chain(R, R.side(S_AUX), R.main));
-  MTL_TRY(conv_fwd(R, P.cv[0], P.c1, B, P.F, P.T, 1));
+  // ReLU + MaxPool2d(2, 2) after conv.2 / conv.7 (transformer.py:51,58): from the convolution's own epilogue when the
+  // kw-box kernel runs it, else the stand-alone pooling kernel
+  bool pooled = false;
   P.p2 = R.ws.f((size_t)B * P.F2 * P.T2 * 64);
-  K(k_maxpool2_fwd(P.cv[0].y, P.p2, B, P.F, P.T, 64, R.st));
+  MTL_TRY(conv_fwd(R, P.cv[0], P.c1, B, P.F, P.T, 1, P.p2, &pooled));
+  if (!pooled) K(k_maxpool2_fwd(P.cv[0].y, P.p2, B, P.F, P.T, 64, R.st));
   MTL_TRY(conv_fwd(R, P.cv[1], P.p2, B, P.F2, P.T2, 2));
-  MTL_TRY(conv_fwd(R, P.cv[2], P.cv[1].y, B, P.F2, P.T2, 3));
   P.p4 = R.ws.f((size_t)B * P.F4 * P.T4 * 128);
-  K(k_maxpool2_fwd(P.cv[2].y, P.p4, B, P.F2, P.T2, 128, R.st));
+  MTL_TRY(conv_fwd(R, P.cv[2], P.cv[1].y, B, P.F2, P.T2, 3, P.p4, &pooled));
+  if (!pooled) K(k_maxpool2_fwd(P.cv[2].y, P.p4, B, P.F2, P.T2, 128, R.st));
   P.feat = R.ws.f((size_t)P.Me * P.d_in);
   K(k_feat_transpose(P.p4, P.feat, B, P.F4, P.T4, 128, R.st));
   }
@@ -1966,6 +1974,16 @@ extern "C" int mtl_conv3x3_relu_fwd(int mode, const float* x, const float* w, co
   g.A = col; g.lda = 9 * Cin; g.B = wg; g.ldb = 9 * Cin; g.transB = 1; g.C = out; g.ldc = Cout;
   g.M = B * F * T; g.N = Cout; g.K = 9 * Cin; g.alpha = 1.f; g.bias = b; g.epi = EPI_RELU; g.split_k = 1;
   return k_gemm(g, mode, st);
+}
+extern "C" int mtl_conv3x3_relu_pool_fwd(int mode, const float* x, const float* w, const float* b, float* wg, float* out,
+                                         float* pool_out, int B, int F, int T, int Cin, int Cout, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  MTL_REQUIRE(x && w && b && wg && out && pool_out, "null argument");
+  MTL_REQUIRE(mode == MTL_GEMM_TC_TF32 || mode == MTL_GEMM_TC_3XTF32, "the fused pooling epilogue runs on the tensor-core engines");
+  const int sg = k_conv3x3_w_split(mode, Cout);
+  MTL_REQUIRE(k_conv3x3_pool_fusable(mode, Cout, sg), "fused pooling needs the kw-box convolution kernel (Cout % 32 == 0)");
+  MTL_TRY(k_conv_w_fwd_layout(w, wg, Cout, Cin, sg, st));
+  return k_conv3x3_tc(x, wg, b, out, B, F, T, Cin, Cout, EPI_RELU, nullptr, mode, sg, st, pool_out);
 }
 extern "C" long long mtl_conv3x3_bwd_scratch_floats(int mode, int B, int F, int T, int Cin, int Cout) {
   const long long P = (long long)B * F * T, wsz = (long long)Cout * 9 * Cin + 64;

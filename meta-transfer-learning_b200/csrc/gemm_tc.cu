@@ -234,6 +234,7 @@ struct TcParams {
   int cluster_k;     // > 1: grid.z CTAs form one cluster that splits K and reduces over distributed shared memory
   int split_trunc;   // 3xTF32 splitter: 1 = truncating split (hi stays the raw tile), 0 = round-to-nearest hi written in place
   int lin_stages;    // > 0: plain GEMM on the small-footprint pipeline (this many stages; see lin_small_stages)
+  int pool;          // kw-box forward convolution: also store the 2x2 max-pooled tile (ReLU + MaxPool2d(2, 2)) through the tmX map
 };
 
 // ---- TMA epilogue (shared by the GEMM / tap-box convolution kernel and the kw-box convolution kernel).
@@ -243,7 +244,7 @@ struct TcParams {
 // and split-K slabs).  Row / column tails and the ragged edges of convolution pixel boxes are clipped by the TMA
 // unit, so there is no per-row address arithmetic at all.  stg_u / aux_u: 1024-aligned shared-memory addresses of
 // the staging tile and of the mask tile (both BN/32 boxes of 128 rows x 128 B); they alias dead operand buffers.
-template <int BN, bool SPLIT3>
+template <int BN, bool SPLIT3, bool POOL = false>
 __device__ __forceinline__ void tma_epilogue_rows(const TcParams& P, const CUtensorMap* tmC, const CUtensorMap* tmX,
                                                   uint32_t stg_u, uint32_t aux_u, uint64_t* tmem_full,
                                                   uint64_t* aux_full, const float* bias_s, uint32_t tmem_base, int warp,
@@ -272,6 +273,14 @@ __device__ __forceinline__ void tma_epilogue_rows(const TcParams& P, const CUten
   const uint32_t row_u = (uint32_t)row * 128u, sw = (uint32_t)(row & 7);
   const float alpha = g.alpha;
   const float lo = g.epi == EPI_RELU ? 0.f : -INFINITY;          // branch-free ReLU
+  // Fused 2x2 max-pool (models/asr/transformer.py:51,58): tile rows are pixels in (f, t) order, t fastest over 8, so the
+  // window partners of a row are lane ^ 1 (t) and lane ^ 8 (f); lanes with even t and even f park the pooled pixel in a
+  // second staging tile (32 rows = 8 f' x 4 t', where the unused mask tile would be) that goes out through tmX.  Floor
+  // pooling and ragged edges need no code: windows that reach past the image have pooled coordinates past F/2 or T/2 and
+  // are clipped by the TMA unit.
+  const bool pool = POOL && conv && !mask;       // compile-time: the GEMM / weight-gradient instantiations carry none of it
+  const uint32_t prow = (uint32_t)((((row >> 3) & 15) >> 1) * 4 + ((row & 7) >> 1));   // pooled row f' * 4 + t'
+  const bool pool_owner = (lane & 9) == 0;
   if (mask) mbar_wait(aux_full, aux_par);
 #pragma unroll 1
   for (int c = 0; c < nch; ++c) {
@@ -303,6 +312,17 @@ __device__ __forceinline__ void tma_epilogue_rows(const TcParams& P, const CUten
         o.z = a.z > 0.f ? o.z : 0.f; o.w = a.w > 0.f ? o.w : 0.f;
       }
       asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stg_u + slot), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
+      if (pool) {
+        float4 m = o;
+        m.x = fmaxf(m.x, __shfl_xor_sync(0xffffffffu, m.x, 1)); m.y = fmaxf(m.y, __shfl_xor_sync(0xffffffffu, m.y, 1));
+        m.z = fmaxf(m.z, __shfl_xor_sync(0xffffffffu, m.z, 1)); m.w = fmaxf(m.w, __shfl_xor_sync(0xffffffffu, m.w, 1));
+        m.x = fmaxf(m.x, __shfl_xor_sync(0xffffffffu, m.x, 8)); m.y = fmaxf(m.y, __shfl_xor_sync(0xffffffffu, m.y, 8));
+        m.z = fmaxf(m.z, __shfl_xor_sync(0xffffffffu, m.z, 8)); m.w = fmaxf(m.w, __shfl_xor_sync(0xffffffffu, m.w, 8));
+        if (pool_owner) {
+          const uint32_t pslot = (uint32_t)c * 4096u + prow * 128u + ((((uint32_t)j) ^ (prow & 7u)) << 4);
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(aux_u + pslot), "f"(m.x), "f"(m.y), "f"(m.z), "f"(m.w) : "memory");
+        }
+      }
     }
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staged rows -> visible to the TMA unit
@@ -313,6 +333,7 @@ __device__ __forceinline__ void tma_epilogue_rows(const TcParams& P, const CUten
     for (int c = 0; c < nch; ++c) {
       if (conv) tma_store_4d(tmC, stg_u + c * CHUNK_BYTES, n0 + c * 32, ct0, cf0, cb, add);
       else tma_store_2d(tmC, stg_u + c * CHUNK_BYTES, n0 + c * 32, m0, add);
+      if (pool) tma_store_4d(tmX, aux_u + c * 4096, n0 + c * 32, ct0 >> 1, cf0 >> 1, cb, false);
     }
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the staging boxes must outlive the reads
@@ -1013,9 +1034,14 @@ __global__ void __launch_bounds__(192) conv3x3_kw_kernel(const __grid_constant__
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("bar.sync 1, 128;" ::: "memory");
       }
-      tma_epilogue_rows<BN, SPLIT3>(P, &tmC, &tmX, base, base + Cfg::TILE, tmem_full, aux_full, bias_s,
-                                    tmem_base + (uint32_t)(mt * Cfg::ACC_COLS), warp, lane, 0, n0, true, ct0, cf0 + mt * KW_BF, cb,
-                                    (uint32_t)(n_mask & 1));
+      if (P.pool)
+        tma_epilogue_rows<BN, SPLIT3, true>(P, &tmC, &tmX, base, base + Cfg::TILE, tmem_full, aux_full, bias_s,
+                                            tmem_base + (uint32_t)(mt * Cfg::ACC_COLS), warp, lane, 0, n0, true, ct0, cf0 + mt * KW_BF,
+                                            cb, (uint32_t)(n_mask & 1));
+      else
+        tma_epilogue_rows<BN, SPLIT3, false>(P, &tmC, &tmX, base, base + Cfg::TILE, tmem_full, aux_full, bias_s,
+                                             tmem_base + (uint32_t)(mt * Cfg::ACC_COLS), warp, lane, 0, n0, true, ct0, cf0 + mt * KW_BF,
+                                             cb, (uint32_t)(n_mask & 1));
       ++n_mask;
     }
   }
@@ -1997,8 +2023,24 @@ int k_conv3x3_w_split(int precision_mode, int Cout) {
 // y[pixel, co] = epi(sum_{tap,ci} x[pixel+tap, ci] * wg[co, tap*Cin+ci] + bias[co])   (x NHWC [B,F,T,Cin], y [B*F*T, Cout])
 // w_split != 0: wg holds TWO matrices, hi = tf32(w) followed by lo = tf32(w - hi) (k_conv_w_*_layout with lo != null);
 // required by the kw-box kernel in 3xTF32, ignored otherwise.
+// ReLU + MaxPool2d(2, 2) from the convolution's epilogue.  MEASURED (cfg 2, 3 lanes): 2696 -> 2684 launches
+// per step and 6.22 -> 6.28 ms: the 64 shuffles + pooled staging per 32-column chunk lengthen every convolution tile's
+// epilogue (the part of a 3xTF32 tile that nothing overlaps), while the stand-alone pooling kernels (8 + 6 us per pass) hide
+// under the other lanes.  Bit-identical to the two-kernel path (tests/test_gpu_ops.py::test_conv3x3_relu_pool_fused);
+// MTL_CONV_POOL_FUSE=1 / mtl_conv3x3_relu_pool_fwd select it.
+static bool conv_pool_fuse_env() {
+  static int en = -1;
+  if (en < 0) { const char* e = getenv("MTL_CONV_POOL_FUSE"); en = (e && e[0] == '1') ? 1 : 0; }
+  return en != 0;
+}
+bool k_conv3x3_pool_fuse_default() { return conv_pool_fuse_env(); }
+bool k_conv3x3_pool_fusable(int precision_mode, int Cout, int w_split) {
+  const int en = 1;
+  const bool split3 = precision_mode == 2;
+  return en && precision_mode != 0 && k_conv3x3_kw_enabled() && Cout % 32 == 0 && (!split3 || w_split);
+}
 int k_conv3x3_tc(const float* x, const float* wg, const float* bias, float* y, int B, int F, int T, int Cin, int Cout,
-                 int epi, const float* aux, int precision_mode, int w_split, cudaStream_t s) {
+                 int epi, const float* aux, int precision_mode, int w_split, cudaStream_t s, float* pool_out) {
   MTL_REQUIRE(Cin % 32 == 0 && Cout % 4 == 0 && al16(x) && al16(wg) && al16(y), "conv3x3_tc: Cin % 32, Cout % 4, 16 B alignment");
   MTL_REQUIRE(epi != EPI_RELU_BWD || (aux && al16(aux)), "conv3x3_tc: aux");
   const bool split3 = precision_mode == 2, tf = !split3;
@@ -2039,6 +2081,12 @@ int k_conv3x3_tc(const float* x, const float* wg, const float* bias, float* y, i
     MTL_TRY(make_map_nhwc(y, B, F, T, Cout, KW_BT, KW_BF, false, false, &km.c));
     km.x = km.c;
     if (epi == EPI_RELU_BWD) MTL_TRY(make_map_nhwc(aux, B, F, T, Cout, KW_BT, KW_BF, false, false, &km.x));
+    if (pool_out) {
+      // 2x2 max-pooled copy [B, F/2, T/2, Cout] from the same epilogue: 4 (t') x 8 (f') pooled pixels per 128-pixel tile
+      MTL_REQUIRE(epi == EPI_RELU && al16(pool_out) && F >= 2 && T >= 2, "conv3x3_tc: fused pooling follows the ReLU forward");
+      MTL_TRY(make_map_nhwc(pool_out, B, F / 2, T / 2, Cout, KW_BT / 2, KW_BF / 2, false, false, &km.x));
+      P.pool = 1;
+    }
     dim3 grid(B * P.tiles_f * P.tiles_t, mtl_cdiv(Cout, bn), 1);
     if (mt == 1) {
       if (bn == 64) return split3 ? launch_kw<64, true, 1>(km, P, grid, s) : launch_kw<64, false, 1>(km, P, grid, s);
@@ -2047,6 +2095,7 @@ int k_conv3x3_tc(const float* x, const float* wg, const float* bias, float* y, i
     if (bn == 64) return split3 ? launch_kw<64, true, 2>(km, P, grid, s) : launch_kw<64, false, 2>(km, P, grid, s);
     return split3 ? launch_kw<128, true, 2>(km, P, grid, s) : launch_kw<128, false, 2>(km, P, grid, s);
   }
+  MTL_REQUIRE(!pool_out, "conv3x3_tc: fused pooling needs the kw-box kernel (k_conv3x3_pool_fusable)");
   P.bt_log2 = pick_bt_log2(BM, F, T, &P.tiles_t, &P.tiles_f);
   Maps tm;
   CUtensorMap& ta = tm.a;

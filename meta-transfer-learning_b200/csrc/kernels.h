@@ -64,8 +64,12 @@ int k_lowrank_pair(const LrPairArgs& a, int precision_mode, cudaStream_t s);
 //   dwgT[tap*Cin+ci, co] += sum_pixel x[pixel+tap,ci] * dy[pixel,co]                  (weight gradient, atomics)
 // w_split: wg holds [hi | lo] tf32 halves (2 x Cout*9*Cin floats, written by k_conv_w_*_layout with split = 1); the
 // 3xTF32 kw-box kernel needs it -- k_conv3x3_w_split(mode, Cout) says whether this build / environment uses it.
+// pool_out (nullable, forward with EPI_RELU only, when k_conv3x3_pool_fusable): the 2x2 floor-max-pooled output
+// [B, F/2, T/2, Cout] is written from the same epilogue (models/asr/transformer.py:51,58: ReLU -> MaxPool2d(2, 2))
 int k_conv3x3_tc(const float* x, const float* wg, const float* bias, float* y, int B, int F, int T, int Cin, int Cout,
-                 int epi, const float* aux, int precision_mode, int w_split, cudaStream_t s);
+                 int epi, const float* aux, int precision_mode, int w_split, cudaStream_t s, float* pool_out = nullptr);
+bool k_conv3x3_pool_fusable(int precision_mode, int Cout, int w_split);
+bool k_conv3x3_pool_fuse_default();   // MTL_CONV_POOL_FUSE=1: the engine uses the fused epilogue (measured slower: default off)
 int k_conv3x3_w_split(int precision_mode, int Cout);
 int k_conv3x3_wgrad_tc(const float* x, const float* dy, float* dwgT, int B, int F, int T, int Cin, int Cout,
                        int precision_mode, cudaStream_t s);

@@ -111,6 +111,7 @@ SIGNATURES = {
     "mtl_ce_bwd": (_I, [_P, _I, _P, _P, _P, _F, _F, _P, _I, _I, _P]),
     "mtl_conv1_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "mtl_conv3x3_relu_fwd": (_I, [_I, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "mtl_conv3x3_relu_pool_fwd": (_I, [_I, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "mtl_conv3x3_bwd_scratch_floats": (_LL, [_I, _I, _I, _I, _I, _I]),
     "mtl_conv3x3_bwd": (_I, [_I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "mtl_conv1_wgrad": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),

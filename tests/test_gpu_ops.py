@@ -361,6 +361,25 @@ def test_conv3x3_fwd_bwd(mode, B, Fq, T, cin, cout, masked):
     assert rel_err(dx, _nhwc(xr.grad * (xin > 0) if masked else xr.grad)) < tol
 
 
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("B,Fq,T,cin,cout", [(2, 21, 19, 64, 64), (2, 161, 101, 64, 64), (2, 80, 50, 128, 128), (1, 9, 140, 128, 128),
+                                             (3, 5, 4, 64, 128), (2, 32, 16, 64, 64), (1, 33, 17, 64, 128)])
+def test_conv3x3_relu_pool_fused(mode, B, Fq, T, cin, cout):
+    """conv -> ReLU -> MaxPool2d(2, 2) (models/asr/transformer.py:49-51,56-58) from ONE kernel: the pooled tensor must be
+    bit-identical to pooling the kernel's own un-pooled output (floor pooling: odd last rows / columns dropped)."""
+    x = torch.relu(_r(B, cin, Fq, T, seed=1))
+    w, b = _r(cout, cin, 3, 3, seed=2) * 0.05, _r(cout, seed=3) * 0.1
+    xd, wd, bd = _nhwc(x).contiguous().to(dev()), w.to(dev()), b.to(dev())
+    wg = torch.empty(2 * cout * 9 * cin + 64, device=dev())
+    out = torch.full((B, Fq, T, cout), 7.0, device=dev())
+    pool = torch.full((B, Fq // 2, T // 2, cout), 7.0, device=dev())
+    ok(lib().mtl_conv3x3_relu_pool_fwd(mode, P(xd), P(wd), P(bd), P(wg), P(out), P(pool), B, Fq, T, cin, cout, stream()))
+    ref = F.relu(F.conv2d(x.double(), w.double(), b.double(), padding=1))
+    assert rel_err(out, _nhwc(ref)) < CONV_TOL[mode]
+    own = F.max_pool2d(out.permute(0, 3, 1, 2), 2, stride=2).permute(0, 2, 3, 1).contiguous()
+    assert torch.equal(pool, own)
+
+
 @pytest.mark.parametrize("Fq,T", [(21, 19), (20, 18), (161, 101)])
 def test_maxpool_fwd_and_relu_pool_bwd(Fq, T):
     B, Cc = 2, 64

@@ -665,3 +665,15 @@ def test_precision_policy_classes():
         _session(cfg).set_op_mode(3, 7)
     with pytest.raises(mtl_b200.MtlError):
         _session(cfg).set_flag("no_such_flag", 1)
+
+
+def test_fused_pooling_epilogue_in_the_engine():
+    """MTL_CONV_POOL_FUSE=1: conv.2 / conv.7 write their max-pooled outputs from their own epilogues (no maxpool2_fwd launch);
+    the switch is read once per process, so the SMALL forward / backward parity test runs in a fresh one."""
+    import subprocess
+    import sys
+    env = dict(os.environ, MTL_CONV_POOL_FUSE="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-q", "-x", "-k",
+                        "small_fwd_bwd_vs_oracle or cfg2_fwd_bwd_golden"], capture_output=True, text=True, env=env, timeout=600,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0 and " passed" in r.stdout, r.stdout[-1500:] + r.stderr[-500:]
