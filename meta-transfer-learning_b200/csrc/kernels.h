@@ -83,6 +83,9 @@ int k_ln_fwd(const float* y, const float* res, const float* gamma, const float* 
 int k_ln_bwd(const float* dout, const float* xhat, const float* rstd, const float* gamma,
              const float* rowmask, MtlDrop drop, float* dy, float* dres, int dres_accumulate,
              float* dgamma, float* dbeta, int M, int d, cudaStream_t s);
+// dgamma / dbeta == null: only the activation gradient (the caller enqueues k_ln_param_grad where it wants it)
+int k_ln_param_grad(const float* dout, const float* xhat, const float* rowmask, float* dgamma, float* dbeta, int M, int d,
+                    cudaStream_t s);
 int k_colsum_acc(const float* x, int M, int N, int ld, float* out, cudaStream_t s);  // out[n] += sum_m x[m,n]
 int k_embed_fwd(const int* tok, const float* E, const float* pe, MtlDrop drop, float* out,
                 int B, int n, int d, cudaStream_t s);

@@ -188,6 +188,13 @@ int k_ln_bwd(const float* dout, const float* xhat, const float* rstd, const floa
   MTL_CHECK_CUDA(mtl_launch_pdl(ln_bwd_kernel, dim3(mtl_cdiv(M, 4)), dim3(128), 0, s, dout, xhat, rstd, gamma, rowmask, drop,
                                 dy, dres, dres_accumulate, M, d));
   ++g_mtl_launches;
+  if (!dgamma && !dbeta) return MTL_OK;             // the caller runs k_ln_param_grad itself (off the activation chain)
+  return k_ln_param_grad(dout, xhat, rowmask, dgamma, dbeta, M, d, s);
+}
+int k_ln_param_grad(const float* dout, const float* xhat, const float* rowmask, float* dgamma, float* dbeta, int M, int d,
+                    cudaStream_t s) {
+  MTL_REQUIRE(dgamma && dbeta, "null argument");
+  if (M == 0) return MTL_OK;
   // a (32 columns x 8 row-lanes) block walks its rows serially: slabs of 32 rows keep that walk 4 loads deep
   // (M = 264: 16 x 9 blocks instead of 16 blocks doing 33 dependent-latency steps each)
   const int slabs = M > 32 ? (mtl_cdiv(M, 32) < 512 ? mtl_cdiv(M, 32) : 512) : 1;
