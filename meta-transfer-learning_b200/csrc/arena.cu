@@ -43,6 +43,17 @@ struct SgdF { float* p; const float* g; float lr;
     reinterpret_cast<float4*>(p)[i] = u; }
   __device__ void one(size_t i) { p[i] -= lr * g[i]; } };
 
+// Inner SGD step out of place, with the clip coefficient folded in: g *= *coef (kept: the validation backward accumulates
+// onto the clipped gradient), out = in - lr * g.  Same fp32 operations as scale_by_dev + copy + sgd, two arena passes fewer.
+struct SgdOutF { float* out; const float* in; float* g; const float* coef; float lr;
+  __device__ void vec(size_t i) {
+    float4 w = reinterpret_cast<float4*>(g)[i];
+    if (coef) { const float c = *coef; w.x *= c; w.y *= c; w.z *= c; w.w *= c; reinterpret_cast<float4*>(g)[i] = w; }
+    float4 u = reinterpret_cast<const float4*>(in)[i];
+    u.x -= lr * w.x; u.y -= lr * w.y; u.z -= lr * w.z; u.w -= lr * w.w;
+    reinterpret_cast<float4*>(out)[i] = u; }
+  __device__ void one(size_t i) { float w = g[i]; if (coef) { w *= *coef; g[i] = w; } out[i] = in[i] - lr * w; } };
+
 struct AdamF {
   float* p; const float* g; float* m; float* v; const float* coef; float b2, omb1, omb2, eps;
   __device__ __forceinline__ void upd(float& pp, float gg, float& mm, float& vv, float step_size, float bc2s) {
@@ -77,6 +88,11 @@ int k_copy(float* d, const float* src, size_t n, cudaStream_t s) { MTL_REQUIRE(a
 int k_axpy(float* y, const float* x, float a, size_t n, cudaStream_t s) { MTL_REQUIRE(al16(y) && al16(x), "arena not 16B aligned"); AxpyF f{y, x, a}; LAUNCH_EW(f, n, s); }
 int k_scale_by_dev(float* y, const float* c, size_t n, cudaStream_t s) { MTL_REQUIRE(al16(y), "arena not 16B aligned"); ScaleDevF f{y, c}; LAUNCH_EW(f, n, s); }
 int k_sgd(float* p, const float* g, float lr, size_t n, cudaStream_t s) { MTL_REQUIRE(al16(p) && al16(g), "arena not 16B aligned"); SgdF f{p, g, lr}; LAUNCH_EW(f, n, s); }
+int k_sgd_out(float* out, const float* in, float* g, const float* coef_dev, float lr, size_t n, cudaStream_t s) {
+  MTL_REQUIRE(al16(out) && al16(in) && al16(g), "arena not 16B aligned");
+  SgdOutF f{out, in, g, coef_dev, lr};
+  LAUNCH_EW(f, n, s);
+}
 int k_adam(float* p, const float* g, float* m, float* v, const float* coef, double b1, double b2, double eps,
            size_t n, cudaStream_t s) {
   MTL_REQUIRE(al16(p) && al16(g) && al16(m) && al16(v), "arena not 16B aligned");

@@ -1593,7 +1593,9 @@ extern "C" int mtl_asr_greedy(mtl_session* s, const float* theta, const float* p
 static int task_body(mtl_session* s, Pass* pass, Branches* br, float* theta, float* grad, const float* pe_enc, const float* pe_dec,
                      void* workspace, long long workspace_bytes, const mtl_batch* train, const mtl_batch* val,
                      const mtl_meta_hparams* hp, SeedRef seed_tr, SeedRef seed_va, float* results16, cudaStream_t st,
-                     EarlyHook* early = nullptr) {
+                     EarlyHook* early = nullptr, const float* theta_src = nullptr) {
+  // theta_src (meta-step lanes): the train pass reads the SHARED weights and the inner step writes the lane's adapted copy
+  // out of place -- no deepcopy(state_dict) of 56 MB per task, and the clip scaling rides on the same kernel
   const size_t n = s->L.total;
   // scratch for the clip coefficient lives at the very end of the workspace
   const long long tail = (long long)((MTL_NORM_PARTIALS + 8) * sizeof(float) + 256);
@@ -1603,14 +1605,17 @@ static int task_body(mtl_session* s, Pass* pass, Branches* br, float* theta, flo
   mtl_batch tr = *train, va = *val;
   if (results16) { tr.ce_out = results16; va.ce_out = results16 + 8; }
   MTL_TRY(k_zero(grad, n, st));                                                     // inner_opt.zero_grad()
-  MTL_TRY(run_forward(s, pass, br, theta, pe_enc, pe_dec, workspace, ws_main, &tr, hp->dropout, seed_tr,
+  const float* th_tr = theta_src ? theta_src : theta;
+  MTL_TRY(run_forward(s, pass, br, th_tr, pe_enc, pe_dec, workspace, ws_main, &tr, hp->dropout, seed_tr,
                       hp->label_smoothing, st));
-  MTL_TRY(run_backward(s, pass, br, theta, grad, 1.f, nullptr, 0, st));             // tr_loss.backward()
-  if (hp->clip) {
-    MTL_TRY(k_clip_coef(grad, n, hp->max_norm, scratch, scratch + MTL_NORM_PARTIALS, st));
-    MTL_TRY(k_scale_by_dev(grad, scratch + MTL_NORM_PARTIALS + 1, n, st));
+  MTL_TRY(run_backward(s, pass, br, th_tr, grad, 1.f, nullptr, 0, st));             // tr_loss.backward()
+  if (hp->clip) MTL_TRY(k_clip_coef(grad, n, hp->max_norm, scratch, scratch + MTL_NORM_PARTIALS, st));
+  if (theta_src) {
+    MTL_TRY(k_sgd_out(theta, theta_src, grad, hp->clip ? scratch + MTL_NORM_PARTIALS + 1 : nullptr, hp->lr, n, st));
+  } else {
+    if (hp->clip) MTL_TRY(k_scale_by_dev(grad, scratch + MTL_NORM_PARTIALS + 1, n, st));
+    MTL_TRY(k_sgd(theta, grad, hp->lr, n, st));                                     // inner_opt.step()
   }
-  MTL_TRY(k_sgd(theta, grad, hp->lr, n, st));                                       // inner_opt.step()
   MTL_TRY(run_forward(s, pass, br, theta, pe_enc, pe_dec, workspace, ws_main, &va, hp->dropout, seed_va,
                       hp->label_smoothing, st));
   MTL_TRY(run_backward(s, pass, br, theta, grad, hp->val_scale, nullptr, 0, st, early));   // (val_loss/N).backward(), no zero_grad
@@ -1672,9 +1677,9 @@ static int meta_tasks_body(mtl_session* s, const mtl_meta_step_args* a, cudaStre
     const int l = t % a->n_lanes;
     Lane& ln = s->lanes[l];
     const mtl_lane& lb = a->lanes[l];
-    // adapted weights start from the shared theta (weights_original): the lane copy replaces
-    // deepcopy(state_dict) + load_state_dict (transient_trainer.py:160,237)
-    MTL_TRY(k_copy(lb.theta, a->theta, n, ln.st));
+    // adapted weights start from the shared theta (weights_original): the train pass reads it in place and the inner SGD
+    // step writes the lane's copy (task_body, theta_src) -- deepcopy(state_dict) + load_state_dict
+    // (transient_trainer.py:160,237) cost nothing
     mtl_batch va = *a->val;
     if (a->n_tasks > 1) { va.hyp_out = nullptr; va.gold_out = nullptr; }            // shared val batch: per-task outputs would race
     SeedRef s0, s1;
@@ -1702,7 +1707,7 @@ static int meta_tasks_body(mtl_session* s, const mtl_meta_step_args* a, cudaStre
     EarlyHook hook;
     hook.st = ln.col; hook.fn = acc_a; hook.ctx = &acc;
     MTL_TRY(task_body(s, &ln.pass, &ln.br, lb.theta, lb.grad, a->pe_enc, a->pe_dec, lb.workspace, lb.workspace_bytes,
-                      &a->train[t], &va, &a->hp, s0, s1, a->results ? a->results + 16 * t : nullptr, ln.st, &hook));
+                      &a->train[t], &va, &a->hp, s0, s1, a->results ? a->results + 16 * t : nullptr, ln.st, &hook, a->theta));
     if (hook.fired) {                                                               // the lane ends after its collector
       MTL_CHECK_CUDA(cudaEventRecord(ln.col_done, ln.col));
       MTL_CHECK_CUDA(cudaStreamWaitEvent(ln.st, ln.col_done, 0));

@@ -13,6 +13,8 @@ int k_copy(float* dst, const float* src, size_t n, cudaStream_t s);
 int k_axpy(float* y, const float* x, float a, size_t n, cudaStream_t s);            // y += a*x
 int k_scale_by_dev(float* y, const float* coef_dev, size_t n, cudaStream_t s);      // y *= *coef
 int k_sgd(float* p, const float* g, float lr, size_t n, cudaStream_t s);            // p -= lr*g
+// g *= *coef_dev (when non-null) ; out = in - lr*g   (inner step from the shared theta0 into a lane's adapted copy)
+int k_sgd_out(float* out, const float* in, float* g, const float* coef_dev, float lr, size_t n, cudaStream_t s);
 // clip_grad_norm_: writes total L2 norm to out[0] and coef=min(1,max_norm/(norm+1e-6)) to out[1].
 // `partial` must hold MTL_NORM_PARTIALS floats.
 #define MTL_NORM_PARTIALS 1024
