@@ -115,6 +115,26 @@ __global__ void lm_transpose_kernel(const float* __restrict__ W, float* __restri
 //   pre = xg[b, g*H + j] (x W_ih^T + b_ih, precomputed) + b_hh[g*H + j] + sum_k h_prev[b, k] * W_hh[g*H + j, k]
 //   c = sig(f) * c_prev + sig(i) * tanh(g);  h = sig(o) * tanh(c);  the four ACTIVATED gates are kept for the backward
 // (the first version, one thread per (b, j) walking K alone, ran 40 CTAs at ~25 us per step.)
+// One bulk copy (TMA, cp.async.bulk) of `bytes` (multiple of 16) global -> shared, completion on an mbarrier: the 64 KB gate-
+// gradient block of a backward step arrives in ONE round trip instead of four rounds of float4 loads per thread.
+__device__ __forceinline__ uint32_t lm_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void lm_bulk_load(float* dst, const float* src, uint32_t bytes, uint64_t* bar) {
+  const uint32_t b = lm_smem_u32(bar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(lm_smem_u32(dst)), "l"(src), "r"(bytes), "r"(b) : "memory");
+}
+__device__ __forceinline__ void lm_bar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t b = lm_smem_u32(bar);
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t done;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(b), "r"(parity) : "memory");
+    if (done) return;
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
 // global -> shared copy of n floats (n % 4 == 0, both 16 B aligned) with eight float4 loads per thread in flight at once:
 // the copy is one round trip to the L2 instead of one per element (a scalar loop here was most of the step kernels' time)
 __device__ __forceinline__ void fill_smem(float* __restrict__ dst, const float* __restrict__ src, int n) {
@@ -132,6 +152,24 @@ __device__ __forceinline__ void fill_smem(float* __restrict__ dst, const float* 
 #ifndef LM_WARPS_PER_CTA
 #define LM_WARPS_PER_CTA 4   // 8: 9.03, 4: 8.41, 2: 9.45 ms per meta-iteration (fewer shuffle reductions per SM vs. more state re-fills)
 #endif
+// Warp reduce-scatter by recursive halving: v[] holds N = 32 * PER per-lane partial sums; afterwards v[0 .. PER) of lane L is
+// the 32-lane total of entries [L * PER, (L + 1) * PER).  N - PER shuffles instead of 5 * N for N butterfly all-reduces
+// (124 instead of 480 for the 4 gates x 24 batch rows of a forward step).
+template <int PER>
+__device__ __forceinline__ void warp_reduce_scatter(float (&v)[32 * PER], int lane) {
+#pragma unroll
+  for (int s = 16, half = 16 * PER; s >= 1; s >>= 1, half >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < 16 * PER; ++i) {
+      if (i < half) {
+        const float send = up ? v[i] : v[i + half];
+        const float keep = up ? v[i + half] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+      }
+    }
+  }
+}
 constexpr int LM_BCH = 24, LM_WARPS = LM_WARPS_PER_CTA;      // batch rows per pass over the weights (the script's batch of 20 in one), warps per CTA
 constexpr int LM_KPF = 8, LM_KPB = 16;        // weight values per lane fetched together (all loads in flight before the first FMA)
 __global__ void __launch_bounds__(LM_WARPS * 32) lstm_step_fwd_kernel(const float* __restrict__ xg, const float* __restrict__ h_prev,
@@ -174,15 +212,14 @@ __global__ void __launch_bounds__(LM_WARPS * 32) lstm_step_fwd_kernel(const floa
         }
       }
     }
+    // lane b finishes batch row b0 + b: reduce-scatter with entry index b * 4 + gate, so lane b ends with its four gate sums
+    float v[128];
 #pragma unroll
-    for (int g = 0; g < 4; ++g)
+    for (int b = 0; b < 32; ++b)
 #pragma unroll
-      for (int b = 0; b < LM_BCH; ++b) acc[g][b] = warp_sum(acc[g][b]);
-    // lane b finishes batch row b0 + b (every lane holds every sum after the xor-reduction: pick without dynamic indexing)
-    float a4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int b = 0; b < LM_BCH; ++b)
-      if (lane == b) { a4[0] = acc[0][b]; a4[1] = acc[1][b]; a4[2] = acc[2][b]; a4[3] = acc[3][b]; }
+      for (int g = 0; g < 4; ++g) v[b * 4 + g] = b < LM_BCH ? acc[g][b < LM_BCH ? b : 0] : 0.f;
+    warp_reduce_scatter<4>(v, lane);
+    const float a4[4] = {v[0], v[1], v[2], v[3]};
     if (lane < nb) {
       const int b = b0 + lane;
       const float* x = xg + (size_t)b * H4;
@@ -206,17 +243,27 @@ __global__ void __launch_bounds__(LM_WARPS * 32) lstm_step_bwd_kernel(const floa
                                                                       const float* __restrict__ c_t, const float* __restrict__ c_prev,
                                                                       float* __restrict__ dc_carry, float* __restrict__ dgates, int B,
                                                                       int H) {
-  extern __shared__ float ds[];                   // dgates_next[b0 .. b0 + LM_BCH, :] (4H each)
+  extern __shared__ __align__(128) float ds[];    // dgates_next[b0 .. b0 + LM_BCH, :] (4H each)
+  __shared__ uint64_t fill_bar;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int j = blockIdx.x * LM_WARPS + warp;
   const int H4 = 4 * H;
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(lm_smem_u32(&fill_bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  uint32_t fill_phase = 0;
   for (int b0 = 0; b0 < B; b0 += LM_BCH) {
     const int nb = min(LM_BCH, B - b0);
     float rec = 0.f;
     if (dg_next) {
-      __syncthreads();
-      fill_smem(ds, dg_next + (size_t)b0 * H4, nb * H4);
-      __syncthreads();
+      __syncthreads();                               // barrier initialised / the previous chunk's readers are done
+      if (threadIdx.x == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic reads of ds before the async write
+        lm_bulk_load(ds, dg_next + (size_t)b0 * H4, (uint32_t)(nb * H4 * sizeof(float)), &fill_bar);
+      }
+      lm_bar_wait(&fill_bar, fill_phase);
+      fill_phase ^= 1u;
       if (j < H) {
         float acc[LM_BCH];
 #pragma unroll
@@ -234,11 +281,11 @@ __global__ void __launch_bounds__(LM_WARPS * 32) lstm_step_bwd_kernel(const floa
             for (int b = 0; b < LM_BCH; ++b) acc[b] = fmaf((b < nb && m < H4) ? ds[b * H4 + m] : 0.f, wv[i], acc[b]);
           }
         }
+        float v[32];
 #pragma unroll
-        for (int b = 0; b < LM_BCH; ++b) acc[b] = warp_sum(acc[b]);
-#pragma unroll
-        for (int b = 0; b < LM_BCH; ++b)
-          if (lane == b) rec = acc[b];
+        for (int b = 0; b < 32; ++b) v[b] = b < LM_BCH ? acc[b < LM_BCH ? b : 0] : 0.f;
+        warp_reduce_scatter<1>(v, lane);
+        rec = v[0];
       }
     }
     if (j >= H || lane >= nb) continue;
