@@ -31,10 +31,12 @@ class LMMetaTrainer(object):
         self.theta_work, self.grad, self.meta_grad = s.new_arena(), s.new_arena(), s.new_arena()
         self.hidden = s.new_hidden(args.batch_size)            # model.init_hidden(batch_size), carried across iterations
         self.lr = args.lr
+        self._results = None                                     # static loss-block buffer: part of the CUDA graph's identity
         self.use_graph = bool(getattr(args, "cuda_graph", True))   # replay the iteration from a CUDA graph (same shapes)
 
     def step(self, dataset, it: int, results: torch.Tensor = None):
-        """One meta-iteration on ``dataset`` (an ``LMDataset``); returns the (n_tasks, 16) device loss blocks."""
+        """One meta-iteration on ``dataset`` (an ``LMDataset``); returns the (n_tasks, 16) device loss blocks (a static
+        buffer unless ``results`` is given: clone it to keep it past the next iteration)."""
         a, s = self.args, self.model.session
         n = len(dataset.task_list)
         _, _, val_x, val_y = dataset.sample(-1, it)
@@ -43,7 +45,9 @@ class LMMetaTrainer(object):
             tr_x, tr_y, _, _ = dataset.sample(i, it)
             train.append((tr_x, tr_y))
         if results is None:
-            results = torch.zeros(n, 16, device=s.device)
+            if self._results is None or self._results.shape[0] != n:
+                self._results = torch.zeros(n, 16, device=s.device)
+            results = self._results                               # same pointer every iteration, so the captured graph replays
         seed = (int(getattr(a, "seed", 0)) * 1000003 + it) & 0x7FFFFFFFFFFF
         s.meta_step(self.theta, self.theta_work, self.grad, self.meta_grad, self.hidden, train, (val_x, val_y),
                     task_weights(n, a.ratio), self.lr, a.meta_lr_factor, a.clip if a.clip else 0.0,
@@ -72,7 +76,7 @@ class LMMetaTrainer(object):
         pending = []
         start = time.time()
         while it < num_it:
-            pending.append(self.step(dataset, it))
+            pending.append(self.step(dataset, it).clone())        # the static block is overwritten by the next iteration
             if it % log_interval == 0 and it > 0:
                 total += float(sum((r[:, 8] * w).sum() for r in pending))         # batch_loss = sum_i w_i val_loss_i
                 pending = []

@@ -244,3 +244,33 @@ def test_lm_sequence_kernels_match_step_kernels():
                         "cfg5_pass_matches_oracle or meta_step_matches_oracle"], capture_output=True, text=True, env=env, timeout=600,
                        cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert r.returncode == 0 and " passed" in r.stdout, r.stdout[-1500:] + r.stderr[-500:]
+
+
+def test_lm_trainer_replays_one_graph():
+    """LMMetaTrainer.step keeps every pointer of the iteration fixed (static token / loss buffers, device seed word): the
+    step is captured ONCE and replayed afterwards, and the replayed iterations keep training (loss blocks change)."""
+    pkg = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "meta-transfer-learning_b200")
+    if pkg not in sys.path:
+        sys.path.insert(0, pkg)
+    from lm.meta import LMMetaTrainer
+    from lm.model.rnn_model import RNNModel
+    from lm.util.data import LMDataset
+    torch.manual_seed(9)
+    V = 200
+    args = argparse.Namespace(bptt=5, batch_size=4, cuda=True, lr=1.0, meta_lr_factor=3.0, clip=0.25, dropout=0.2, ratio=0.8, seed=3)
+    gen = torch.Generator().manual_seed(5)
+    ds = LMDataset([torch.randint(0, V, (900,), generator=gen) for _ in range(3)], args)
+    model = RNNModel('LSTM', V, 32, 32, 2, dropout=0.2).cuda()
+    model.train()
+    tr = LMMetaTrainer(model, args)
+    graphs, losses = [], []
+    for it in range(6):
+        r = tr.step(ds, it)
+        losses.append(r[:, 8].clone())
+        g = getattr(model.session, "_graph", None)
+        graphs.append(None if g is None else g["graph"])
+    torch.cuda.synchronize()
+    assert graphs[0] is None and graphs[1] is not None            # eager first sighting, captured at the second
+    assert all(g is graphs[1] for g in graphs[2:])                # ... and replayed ever after
+    assert not torch.equal(losses[2], losses[5])
+    assert all(torch.isfinite(l).all() for l in losses)
