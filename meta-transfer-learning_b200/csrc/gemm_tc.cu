@@ -2034,10 +2034,10 @@ static bool conv_pool_fuse_env() {
   return en != 0;
 }
 bool k_conv3x3_pool_fuse_default() { return conv_pool_fuse_env(); }
+// can this convolution run on the kw-box kernel (the only one with the pooling epilogue)?
 bool k_conv3x3_pool_fusable(int precision_mode, int Cout, int w_split) {
-  const int en = 1;
   const bool split3 = precision_mode == 2;
-  return en && precision_mode != 0 && k_conv3x3_kw_enabled() && Cout % 32 == 0 && (!split3 || w_split);
+  return precision_mode != 0 && k_conv3x3_kw_enabled() && Cout % 32 == 0 && (!split3 || w_split);
 }
 int k_conv3x3_tc(const float* x, const float* wg, const float* bias, float* y, int B, int F, int T, int Cin, int Cout,
                  int epi, const float* aux, int precision_mode, int w_split, cudaStream_t s, float* pool_out) {
