@@ -117,3 +117,23 @@ def test_lm_model_api_surface():
         RNNModel('GRU', 10, 4, 4, 1)
     with pytest.raises(mtl_b200.MtlError):
         m(torch.zeros(3, 2, dtype=torch.long), m.init_hidden(2))      # no CPU path
+
+
+def test_lm_corpus_shares_one_dictionary_and_task_weights(tmp_path):
+    """The three corpora of lm/main_meta_transfer.py:130-139 extend ONE dictionary in reading order (`<eos>` closes every
+    line), and the validation losses are weighted (1 - ratio) / 2, (1 - ratio) / 2, ratio (lm/main_meta_transfer.py:346-349)."""
+    import sys
+    pkg = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "meta-transfer-learning_b200")
+    if pkg not in sys.path:
+        sys.path.insert(0, pkg)
+    from lm.meta import task_weights
+    from lm.util.data import Corpus
+    (tmp_path / "a.txt").write_text("x y\nz  x\n")
+    (tmp_path / "b.txt").write_text("y w\n")
+    a = Corpus(str(tmp_path / "a.txt"))
+    b = Corpus(str(tmp_path / "b.txt"), None, str(tmp_path / "a.txt"), a.dictionary)
+    assert a.train.tolist() == [0, 1, 2, 3, 0, 2]                     # x y <eos> z x <eos>
+    assert b.train.tolist() == [1, 4, 2] and b.test.tolist() == a.train.tolist() and b.valid is None
+    assert b.dictionary is a.dictionary and len(a.dictionary) == 5 and a.dictionary.idx2word[4] == "w"
+    w = task_weights(3, 0.8)
+    assert w == pytest.approx([0.1, 0.1, 0.8]) and sum(w) == pytest.approx(1.0)
